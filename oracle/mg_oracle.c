@@ -1,0 +1,680 @@
+/*
+ * mg_oracle.c — CPU restatement (plain C) of the reference's MiniGridEnv.step/reset/gen_obs.
+ *
+ * TEST INFRASTRUCTURE ONLY (see mg_oracle.h). It deliberately keeps the reference's own structure —
+ * an object grid, Grid.slice, (dir+1) x Grid.rotate_left, Grid.process_vis, Grid.encode — rather than
+ * the closed-form gather the CUDA kernels use, so that the two implementations are independent.
+ * All file:line citations are relative to /root/reference/minigrid/.
+ *
+ * Third-party arithmetic on the path (not under /root/reference, restated from the published
+ * algorithms and pinned by tests against numpy 2.3 itself and the reference doctest
+ * wrappers.py:26-41): numpy.random.SeedSequence, PCG64 (XSL-RR 128/64), Generator.integers
+ * (buffered 32-bit Lemire), Generator.shuffle (masked rejection), Generator.choice.
+ */
+#include "mg_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <time.h>
+#include <unistd.h>
+
+typedef unsigned __int128 u128;
+
+/* ---- core/constants.py:25-46 ---- */
+enum { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6, T_BOX = 7,
+       T_GOAL = 8, T_LAVA = 9, T_AGENT = 10 };
+enum { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5 };
+enum { S_OPEN = 0, S_CLOSED = 1, S_LOCKED = 2 };
+/* core/actions.py:7-20 */
+enum { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
+/* core/constants.py:49-58 DIR_TO_VEC */
+static const int DIR_X[4] = {1, 0, -1, 0};
+static const int DIR_Y[4] = {0, 1, 0, -1};
+
+#define VIEW 7 /* agent_view_size, minigrid_env.py:42 */
+
+/* A grid slot: the reference stores WorldObj|None (grid.py:35). `None` is type T_EMPTY here, which is
+ * also what Grid.encode emits for None (grid.py:258-261); an object is (type, colour, door state).
+ * Box.contains is always None in the four generators, so it is not modelled. */
+typedef struct { uint8_t type, color, state; } cell_t;
+static const cell_t CELL_NONE = {T_EMPTY, 0, 0};
+
+static int cell_is_none(cell_t c) { return c.type == T_EMPTY; }
+/* world_object.py:45-47,113,128,141,177 */
+static int can_overlap(cell_t c) {
+  return c.type == T_GOAL || c.type == T_FLOOR || c.type == T_LAVA || (c.type == T_DOOR && c.state == S_OPEN);
+}
+/* world_object.py:49-51,243,265,277 */
+static int can_pickup(cell_t c) { return c.type == T_KEY || c.type == T_BALL || c.type == T_BOX; }
+/* world_object.py:57-59,164,181 */
+static int see_behind(cell_t c) {
+  if (c.type == T_WALL) return 0;
+  if (c.type == T_DOOR) return c.state == S_OPEN;
+  return 1;
+}
+
+/* ---- numpy PCG64 + Generator restatement ---- */
+typedef struct { u128 state, inc; int has_uint32; uint32_t uinteger; } pcg64_t;
+
+static const u128 PCG_MULT = ((u128)0x2360ED051FC65DA4ULL << 64) | 0x4385DF649FCCF645ULL;
+
+static void pcg_step(pcg64_t *r) { r->state = r->state * PCG_MULT + r->inc; }
+static uint64_t rotr64(uint64_t v, unsigned rot) { return (v >> rot) | (v << ((-rot) & 63)); }
+static uint64_t pcg_next64(pcg64_t *r) {
+  pcg_step(r);
+  return rotr64((uint64_t)(r->state >> 64) ^ (uint64_t)r->state, (unsigned)(r->state >> 122));
+}
+static uint32_t pcg_next32(pcg64_t *r) {
+  if (r->has_uint32) { r->has_uint32 = 0; return r->uinteger; }
+  uint64_t n = pcg_next64(r);
+  r->has_uint32 = 1;
+  r->uinteger = (uint32_t)(n >> 32);
+  return (uint32_t)n;
+}
+static void pcg_srandom(pcg64_t *r, u128 initstate, u128 initseq) {
+  r->state = 0;
+  r->inc = (initseq << 1) | 1;
+  pcg_step(r);
+  r->state += initstate;
+  pcg_step(r);
+  r->has_uint32 = 0;
+  r->uinteger = 0;
+}
+
+/* numpy.random.SeedSequence(entropy=int).generate_state(8, uint32) */
+static uint32_t ss_hashmix(uint32_t value, uint32_t *hash_const) {
+  value ^= *hash_const;
+  *hash_const *= 0x931e8875u;
+  value *= *hash_const;
+  value ^= value >> 16;
+  return value;
+}
+static uint32_t ss_mix(uint32_t x, uint32_t y) {
+  uint32_t r = 0xca01f9ddu * x - 0x4973f715u * y;
+  r ^= r >> 16;
+  return r;
+}
+static void seed_sequence_pcg64(uint64_t seed, pcg64_t *r) {
+  uint32_t entropy[2];
+  int n_ent = 1;
+  entropy[0] = (uint32_t)seed;
+  entropy[1] = (uint32_t)(seed >> 32);
+  if (entropy[1] != 0) n_ent = 2;
+  uint32_t pool[4];
+  uint32_t hc = 0x43b0d7e5u;
+  for (int i = 0; i < 4; i++) pool[i] = ss_hashmix(i < n_ent ? entropy[i] : 0u, &hc);
+  for (int s = 0; s < 4; s++)
+    for (int d = 0; d < 4; d++)
+      if (s != d) pool[d] = ss_mix(pool[d], ss_hashmix(pool[s], &hc));
+  /* generate_state(4, uint64) == 8 uint32 words, little-endian pairs */
+  uint32_t out[8];
+  uint32_t hb = 0x8b51f9ddu;
+  for (int i = 0; i < 8; i++) {
+    uint32_t v = pool[i & 3];
+    v ^= hb;
+    hb *= 0x58f38dedu;
+    v *= hb;
+    v ^= v >> 16;
+    out[i] = v;
+  }
+  uint64_t w[4];
+  for (int i = 0; i < 4; i++) w[i] = (uint64_t)out[2 * i] | ((uint64_t)out[2 * i + 1] << 32);
+  /* pcg64_set_seed: state = (w0 high, w1 low), inc = (w2 high, w3 low) */
+  pcg_srandom(r, ((u128)w[0] << 64) | w[1], ((u128)w[2] << 64) | w[3]);
+}
+
+/* Generator.integers(low, high) for ranges < 2^32: zero draws when the range is one value */
+static int64_t rng_integers(pcg64_t *r, int64_t low, int64_t high) {
+  uint32_t rng = (uint32_t)(high - 1 - low);
+  if (rng == 0) return low;
+  uint32_t rng_excl = rng + 1;
+  uint64_t m = (uint64_t)pcg_next32(r) * rng_excl;
+  uint32_t leftover = (uint32_t)m;
+  if (leftover < rng_excl) {
+    uint32_t threshold = (0xFFFFFFFFu - rng) % rng_excl;
+    while (leftover < threshold) {
+      m = (uint64_t)pcg_next32(r) * rng_excl;
+      leftover = (uint32_t)m;
+    }
+  }
+  return low + (int64_t)(m >> 32);
+}
+/* random_interval(max): masked rejection, used by Generator.shuffle on a Python list */
+static uint32_t rng_interval(pcg64_t *r, uint32_t max) {
+  if (max == 0) return 0;
+  uint32_t mask = max;
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  uint32_t v;
+  while ((v = (pcg_next32(r) & mask)) > max) {}
+  return v;
+}
+
+/* ---- Grid (core/grid.py) ---- */
+typedef struct { int width, height; cell_t *cells; } grid_t;
+
+static cell_t grid_get(const grid_t *g, int i, int j) { return g->cells[j * g->width + i]; } /* grid.py:74-78 */
+static void grid_set(grid_t *g, int i, int j, cell_t v) { g->cells[j * g->width + i] = v; }   /* grid.py:65-72 */
+static const cell_t WALL_GREY = {T_WALL, C_GREY, 0};
+static void grid_horz_wall(grid_t *g, int x, int y, int length, cell_t obj) { /* grid.py:80-91 */
+  if (length < 0) length = g->width - x;
+  for (int i = 0; i < length; i++) grid_set(g, x + i, y, obj);
+}
+static void grid_vert_wall(grid_t *g, int x, int y, int length, cell_t obj) { /* grid.py:93-104 */
+  if (length < 0) length = g->height - y;
+  for (int j = 0; j < length; j++) grid_set(g, x, y + j, obj);
+}
+static void grid_wall_rect(grid_t *g, int x, int y, int w, int h) { /* grid.py:106-110 */
+  grid_horz_wall(g, x, y, w, WALL_GREY);
+  grid_horz_wall(g, x, y + h - 1, w, WALL_GREY);
+  grid_vert_wall(g, x, y, h, WALL_GREY);
+  grid_vert_wall(g, x + w - 1, y, h, WALL_GREY);
+}
+
+typedef struct { cell_t c[VIEW * VIEW]; } view_t; /* a 7x7 Grid, row-major j*7+i */
+static cell_t view_get(const view_t *v, int i, int j) { return v->c[j * VIEW + i]; }
+static void view_set(view_t *v, int i, int j, cell_t x) { v->c[j * VIEW + i] = x; }
+
+/* grid.py:124-143 */
+static void grid_slice(const grid_t *g, int topX, int topY, view_t *out) {
+  for (int j = 0; j < VIEW; j++)
+    for (int i = 0; i < VIEW; i++) {
+      int x = topX + i, y = topY + j;
+      cell_t v = (x >= 0 && x < g->width && y >= 0 && y < g->height) ? grid_get(g, x, y) : WALL_GREY;
+      view_set(out, i, j, v);
+    }
+}
+/* grid.py:110-122 (square view: width == height == 7) */
+static void view_rotate_left(const view_t *in, view_t *out) {
+  for (int i = 0; i < VIEW; i++)
+    for (int j = 0; j < VIEW; j++) view_set(out, j, VIEW - 1 - i, view_get(in, i, j));
+}
+/* grid.py:291-328; mask is [i][j] */
+static void view_process_vis(view_t *g, int ax, int ay, uint8_t mask[VIEW][VIEW]) {
+  memset(mask, 0, VIEW * VIEW);
+  mask[ax][ay] = 1;
+  for (int j = VIEW - 1; j >= 0; j--) {
+    for (int i = 0; i < VIEW - 1; i++) {
+      if (!mask[i][j]) continue;
+      cell_t c = view_get(g, i, j);
+      if (!cell_is_none(c) && !see_behind(c)) continue;
+      mask[i + 1][j] = 1;
+      if (j > 0) { mask[i + 1][j - 1] = 1; mask[i][j - 1] = 1; }
+    }
+    for (int i = VIEW - 1; i >= 1; i--) {
+      if (!mask[i][j]) continue;
+      cell_t c = view_get(g, i, j);
+      if (!cell_is_none(c) && !see_behind(c)) continue;
+      mask[i - 1][j] = 1;
+      if (j > 0) { mask[i - 1][j - 1] = 1; mask[i][j - 1] = 1; }
+    }
+  }
+  for (int j = 0; j < VIEW; j++)
+    for (int i = 0; i < VIEW; i++)
+      if (!mask[i][j]) view_set(g, i, j, CELL_NONE);
+}
+/* grid.py:244-268 + world_object.py:65-67,196-212; out is [i][j][3] C-order */
+static void encode_cell(cell_t c, uint8_t *o) {
+  if (cell_is_none(c)) { o[0] = T_EMPTY; o[1] = 0; o[2] = 0; }
+  else { o[0] = c.type; o[1] = c.color; o[2] = (c.type == T_DOOR) ? c.state : 0; }
+}
+
+/* ---- MiniGridEnv (minigrid_env.py) ---- */
+typedef struct {
+  grid_t grid;
+  int agent_x, agent_y, agent_dir;
+  int carrying;      /* bool */
+  cell_t carry;      /* valid iff carrying */
+  int step_count;
+  pcg64_t rng;
+  uint8_t pending_reset; /* SyncVectorEnv._autoreset_envs[i] */
+} env_t;
+
+struct mgo_vec {
+  int kind, width, height, max_steps, see_through;
+  int32_t params[8];
+  int n;
+  env_t *envs;
+  cell_t *arena;
+  /* scratch for rollout */
+  uint8_t *s_obs; int32_t *s_dir; double *s_rew; uint8_t *s_term, *s_trunc;
+};
+
+static int64_t rand_int(env_t *e, int64_t lo, int64_t hi) { return rng_integers(&e->rng, lo, hi); } /* :247-252 */
+
+/* minigrid_env.py:313-372 (reject_fn=None, max_tries=inf); obj == NULL places nothing (place_agent) */
+static void place_obj(env_t *e, const cell_t *obj, int top_x, int top_y, int size_w, int size_h, int *px, int *py) {
+  if (top_x < 0) top_x = 0;
+  if (top_y < 0) top_y = 0;
+  int hi_x = top_x + size_w < e->grid.width ? top_x + size_w : e->grid.width;
+  int hi_y = top_y + size_h < e->grid.height ? top_y + size_h : e->grid.height;
+  for (;;) {
+    int x = (int)rand_int(e, top_x, hi_x);
+    int y = (int)rand_int(e, top_y, hi_y);
+    if (!cell_is_none(grid_get(&e->grid, x, y))) continue;
+    if (x == e->agent_x && y == e->agent_y) continue;
+    *px = x; *py = y;
+    break;
+  }
+  if (obj) grid_set(&e->grid, *px, *py, *obj);
+}
+/* minigrid_env.py:383-397 */
+static void place_agent(env_t *e, int top_x, int top_y, int size_w, int size_h) {
+  e->agent_x = -1; e->agent_y = -1;
+  int x, y;
+  place_obj(e, NULL, top_x, top_y, size_w, size_h, &x, &y);
+  e->agent_x = x; e->agent_y = y;
+  e->agent_dir = (int)rand_int(e, 0, 4);
+}
+
+static void grid_clear(grid_t *g) { for (int k = 0; k < g->width * g->height; k++) g->cells[k] = CELL_NONE; }
+
+/* envs/empty.py:97-114 */
+static void gen_empty(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  grid_clear(&e->grid);
+  grid_wall_rect(&e->grid, 0, 0, W, H);
+  cell_t goal = {T_GOAL, C_GREEN, 0};
+  grid_set(&e->grid, W - 2, H - 2, goal);
+  if (!v->params[0]) { e->agent_x = v->params[1]; e->agent_y = v->params[2]; e->agent_dir = v->params[3]; }
+  else place_agent(e, 0, 0, W, H);
+}
+/* envs/doorkey.py:74-99 */
+static void gen_doorkey(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  grid_clear(&e->grid);
+  grid_wall_rect(&e->grid, 0, 0, W, H);
+  cell_t goal = {T_GOAL, C_GREEN, 0};
+  grid_set(&e->grid, W - 2, H - 2, goal);
+  int split = (int)rand_int(e, 2, W - 2);
+  grid_vert_wall(&e->grid, split, 0, -1, WALL_GREY);
+  place_agent(e, 0, 0, split, H);
+  int door_y = (int)rand_int(e, 1, H - 2);
+  cell_t door = {T_DOOR, C_YELLOW, S_LOCKED};
+  grid_set(&e->grid, split, door_y, door);
+  cell_t key = {T_KEY, C_YELLOW, 0};
+  int kx, ky;
+  place_obj(e, &key, 0, 0, split, H, &kx, &ky);
+}
+/* envs/crossing.py:131-188 */
+static void gen_crossing(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  int num_crossings = v->params[0];
+  cell_t obstacle = {(uint8_t)v->params[1], (uint8_t)(v->params[1] == T_LAVA ? C_RED : C_GREY), 0};
+  grid_clear(&e->grid);
+  grid_wall_rect(&e->grid, 0, 0, W, H);
+  e->agent_x = 1; e->agent_y = 1; e->agent_dir = 0;
+  cell_t goal = {T_GOAL, C_GREEN, 0};
+  grid_set(&e->grid, W - 2, H - 2, goal);
+  /* rivers = [(v, i) for i in range(2, height-2, 2)] + [(h, j) for j in range(2, width-2, 2)] */
+  int rdir[64], rpos[64], n = 0; /* dir: 0 = v, 1 = h */
+  for (int i = 2; i < H - 2; i += 2) { rdir[n] = 0; rpos[n] = i; n++; }
+  for (int j = 2; j < W - 2; j += 2) { rdir[n] = 1; rpos[n] = j; n++; }
+  for (int i = n - 1; i >= 1; i--) { /* np_random.shuffle(list) */
+    int j = (int)rng_interval(&e->rng, (uint32_t)i);
+    int td = rdir[i], tp = rpos[i]; rdir[i] = rdir[j]; rpos[i] = rpos[j]; rdir[j] = td; rpos[j] = tp;
+  }
+  if (num_crossings < n) n = num_crossings;
+  int rivers_v[64], nv = 0, rivers_h[64], nh = 0;
+  for (int k = 0; k < n; k++) { if (rdir[k] == 0) rivers_v[nv++] = rpos[k]; else rivers_h[nh++] = rpos[k]; }
+  /* sorted() */
+  for (int a = 1; a < nv; a++) { int t = rivers_v[a], b = a; while (b > 0 && rivers_v[b - 1] > t) { rivers_v[b] = rivers_v[b - 1]; b--; } rivers_v[b] = t; }
+  for (int a = 1; a < nh; a++) { int t = rivers_h[a], b = a; while (b > 0 && rivers_h[b - 1] > t) { rivers_h[b] = rivers_h[b - 1]; b--; } rivers_h[b] = t; }
+  /* itt.product(range(1, width-1), rivers_h) then itt.product(rivers_v, range(1, height-1)) */
+  for (int i = 1; i < W - 1; i++) for (int k = 0; k < nh; k++) grid_set(&e->grid, i, rivers_h[k], obstacle);
+  for (int k = 0; k < nv; k++) for (int j = 1; j < H - 1; j++) grid_set(&e->grid, rivers_v[k], j, obstacle);
+  /* path = [h]*len(rivers_v) + [v]*len(rivers_h); shuffle */
+  int path[128], np_ = 0;
+  for (int k = 0; k < nv; k++) path[np_++] = 1;
+  for (int k = 0; k < nh; k++) path[np_++] = 0;
+  for (int i = np_ - 1; i >= 1; i--) {
+    int j = (int)rng_interval(&e->rng, (uint32_t)i);
+    int t = path[i]; path[i] = path[j]; path[j] = t;
+  }
+  int limits_v[66], limits_h[66];
+  limits_v[0] = 0; for (int k = 0; k < nv; k++) limits_v[k + 1] = rivers_v[k]; limits_v[nv + 1] = H - 1;
+  limits_h[0] = 0; for (int k = 0; k < nh; k++) limits_h[k + 1] = rivers_h[k]; limits_h[nh + 1] = W - 1;
+  int room_i = 0, room_j = 0;
+  for (int k = 0; k < np_; k++) {
+    int i, j;
+    if (path[k] == 1) { /* h */
+      i = limits_v[room_i + 1];
+      int a = limits_h[room_j] + 1, b = limits_h[room_j + 1];
+      j = a + (int)rand_int(e, 0, b - a); /* np_random.choice(range(a, b)) */
+      room_i++;
+    } else {
+      int a = limits_v[room_i] + 1, b = limits_v[room_i + 1];
+      i = a + (int)rand_int(e, 0, b - a);
+      j = limits_h[room_j + 1];
+      room_j++;
+    }
+    grid_set(&e->grid, i, j, CELL_NONE);
+  }
+}
+/* envs/fourrooms.py:78-126 (agent_pos = goal_pos = None) */
+static void gen_fourrooms(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  grid_clear(&e->grid);
+  grid_horz_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_horz_wall(&e->grid, 0, H - 1, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, W - 1, 0, -1, WALL_GREY);
+  int room_w = W / 2, room_h = H / 2;
+  for (int j = 0; j < 2; j++)
+    for (int i = 0; i < 2; i++) {
+      int xL = i * room_w, yT = j * room_h, xR = xL + room_w, yB = yT + room_h;
+      if (i + 1 < 2) {
+        grid_vert_wall(&e->grid, xR, yT, room_h, WALL_GREY);
+        int py = (int)rand_int(e, yT + 1, yB);
+        grid_set(&e->grid, xR, py, CELL_NONE);
+      }
+      if (j + 1 < 2) {
+        grid_horz_wall(&e->grid, xL, yB, room_w, WALL_GREY);
+        int px = (int)rand_int(e, xL + 1, xR);
+        grid_set(&e->grid, px, yB, CELL_NONE);
+      }
+    }
+  place_agent(e, 0, 0, W, H);
+  cell_t goal = {T_GOAL, C_GREEN, 0};
+  int gx, gy;
+  place_obj(e, &goal, 0, 0, W, H, &gx, &gy);
+}
+
+/* minigrid_env.py:119-157 (without the gen_obs at the end) */
+static void env_reset(const mgo_vec *v, env_t *e) {
+  e->agent_x = -1; e->agent_y = -1; e->agent_dir = -1;
+  switch (v->kind) {
+    case MGO_EMPTY: gen_empty(v, e); break;
+    case MGO_DOORKEY: gen_doorkey(v, e); break;
+    case MGO_CROSSING: gen_crossing(v, e); break;
+    default: gen_fourrooms(v, e); break;
+  }
+  e->carrying = 0;
+  e->carry = CELL_NONE;
+  e->step_count = 0;
+}
+
+/* minigrid_env.py:597-650 */
+static void env_gen_obs(const mgo_vec *v, const env_t *e, uint8_t *image, int32_t *direction) {
+  int topX, topY; /* get_view_exts :453-484 */
+  switch (e->agent_dir) {
+    case 0: topX = e->agent_x; topY = e->agent_y - VIEW / 2; break;
+    case 1: topX = e->agent_x - VIEW / 2; topY = e->agent_y; break;
+    case 2: topX = e->agent_x - VIEW + 1; topY = e->agent_y - VIEW / 2; break;
+    default: topX = e->agent_x - VIEW / 2; topY = e->agent_y - VIEW + 1; break;
+  }
+  view_t a, b;
+  grid_slice(&e->grid, topX, topY, &a);
+  view_t *cur = &a, *other = &b;
+  for (int r = 0; r < e->agent_dir + 1; r++) { view_rotate_left(cur, other); view_t *t = cur; cur = other; other = t; }
+  uint8_t mask[VIEW][VIEW];
+  if (!v->see_through) view_process_vis(cur, VIEW / 2, VIEW - 1, mask);
+  else memset(mask, 1, sizeof(mask));
+  view_set(cur, VIEW / 2, VIEW - 1, e->carrying ? e->carry : CELL_NONE); /* :623-630 */
+  for (int i = 0; i < VIEW; i++)       /* Grid.encode(vis_mask) grid.py:244-268 */
+    for (int j = 0; j < VIEW; j++) {
+      uint8_t *o = image + (i * VIEW + j) * 3;
+      if (mask[i][j]) encode_cell(view_get(cur, i, j), o);
+      else { o[0] = 0; o[1] = 0; o[2] = 0; }
+    }
+  *direction = e->agent_dir;
+}
+
+/* minigrid_env.py:240-245; compiled with -ffp-contract=off so no FMA is formed */
+static double env_reward(const mgo_vec *v, const env_t *e) {
+  volatile double q = (double)e->step_count / (double)v->max_steps;
+  volatile double p = 0.9 * q;
+  return 1.0 - p;
+}
+
+/* minigrid_env.py:525-595 (transition only; the caller generates the obs). returns -1 on bad action */
+static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint8_t *terminated, uint8_t *truncated) {
+  e->step_count += 1;
+  *reward = 0; *terminated = 0; *truncated = 0;
+  int fx = e->agent_x + DIR_X[e->agent_dir], fy = e->agent_y + DIR_Y[e->agent_dir];
+  cell_t fwd = grid_get(&e->grid, fx, fy);
+  int fwd_none = cell_is_none(fwd);
+  switch (action) {
+    case A_LEFT: e->agent_dir -= 1; if (e->agent_dir < 0) e->agent_dir += 4; break;
+    case A_RIGHT: e->agent_dir = (e->agent_dir + 1) % 4; break;
+    case A_FORWARD:
+      if (fwd_none || can_overlap(fwd)) { e->agent_x = fx; e->agent_y = fy; }
+      if (!fwd_none && fwd.type == T_GOAL) { *terminated = 1; *reward = env_reward(v, e); }
+      if (!fwd_none && fwd.type == T_LAVA) *terminated = 1;
+      break;
+    case A_PICKUP:
+      if (!fwd_none && can_pickup(fwd) && !e->carrying) {
+        e->carrying = 1; e->carry = fwd;
+        grid_set(&e->grid, fx, fy, CELL_NONE);
+      }
+      break;
+    case A_DROP:
+      if (fwd_none && e->carrying) { grid_set(&e->grid, fx, fy, e->carry); e->carrying = 0; e->carry = CELL_NONE; }
+      break;
+    case A_TOGGLE:
+      if (!fwd_none) {
+        if (fwd.type == T_DOOR) { /* Door.toggle world_object.py:184-194 */
+          if (fwd.state == S_LOCKED) {
+            if (e->carrying && e->carry.type == T_KEY && e->carry.color == fwd.color) { fwd.state = S_OPEN; grid_set(&e->grid, fx, fy, fwd); }
+          } else { fwd.state = (fwd.state == S_OPEN) ? S_CLOSED : S_OPEN; grid_set(&e->grid, fx, fy, fwd); }
+        } else if (fwd.type == T_BOX) { /* Box.toggle :290-293, contains == None */
+          grid_set(&e->grid, fx, fy, CELL_NONE);
+        }
+      }
+      break;
+    case A_DONE: break;
+    default: e->step_count -= 1; return -1;
+  }
+  if (e->step_count >= v->max_steps) *truncated = 1;
+  return 0;
+}
+
+/* ---- vector level (gymnasium.vector.SyncVectorEnv semantics, restated) ---- */
+mgo_vec *mgo_vec_create(int kind, int width, int height, int max_steps, int see_through_walls,
+                        const int32_t *params, int n_params, int n_envs) {
+  mgo_vec *v = (mgo_vec *)calloc(1, sizeof(*v));
+  v->kind = kind; v->width = width; v->height = height; v->max_steps = max_steps; v->see_through = see_through_walls;
+  for (int i = 0; i < 8; i++) v->params[i] = (params && i < n_params) ? params[i] : 0;
+  v->n = n_envs;
+  v->envs = (env_t *)calloc((size_t)n_envs, sizeof(env_t));
+  v->arena = (cell_t *)malloc((size_t)n_envs * width * height * sizeof(cell_t));
+  for (int i = 0; i < n_envs; i++) {
+    env_t *e = &v->envs[i];
+    e->grid.width = width; e->grid.height = height;
+    e->grid.cells = v->arena + (size_t)i * width * height;
+    grid_clear(&e->grid);
+    e->agent_x = e->agent_y = -1; e->agent_dir = -1;
+    seed_sequence_pcg64((uint64_t)i, &e->rng);
+  }
+  return v;
+}
+void mgo_vec_destroy(mgo_vec *v) {
+  if (!v) return;
+  free(v->s_obs); free(v->s_dir); free(v->s_rew); free(v->s_term); free(v->s_trunc);
+  free(v->arena); free(v->envs); free(v);
+}
+void mgo_vec_seed(mgo_vec *v, const uint64_t *seeds) {
+  for (int i = 0; i < v->n; i++) seed_sequence_pcg64(seeds[i], &v->envs[i].rng);
+}
+int mgo_max_threads(void) {
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+static int clamp_threads(const mgo_vec *v, int n_threads) {
+  if (n_threads <= 0) n_threads = mgo_max_threads();
+  if (n_threads > v->n) n_threads = v->n;
+  return n_threads < 1 ? 1 : n_threads;
+}
+
+/* envs are independent, so a "thread" is just a contiguous slice of the vector (what a farm of
+ * SyncVectorEnv worker processes, one per core, amounts to) */
+typedef struct {
+  mgo_vec *v; int lo, hi; int op; /* 0 reset, 1 step, 2 rollout */
+  const int32_t *actions; uint8_t *obs; int32_t *dir; double *reward; uint8_t *term, *trunc;
+  int mode, n_steps, bad;
+} job_t;
+
+static void reset_range(mgo_vec *v, int lo, int hi, uint8_t *obs, int32_t *dir) {
+  for (int i = lo; i < hi; i++) {
+    env_t *e = &v->envs[i];
+    env_reset(v, e);
+    e->pending_reset = 0;
+    env_gen_obs(v, e, obs + (size_t)i * 147, dir + i);
+  }
+}
+static int step_range(mgo_vec *v, int lo, int hi, const int32_t *actions, uint8_t *obs, int32_t *dir,
+                      double *reward, uint8_t *terminated, uint8_t *truncated, int mode) {
+  int bad = 0;
+  for (int i = lo; i < hi; i++) {
+    env_t *e = &v->envs[i];
+    if (mode == MGO_AUTORESET_NEXT_STEP && e->pending_reset) {
+      env_reset(v, e); /* action ignored; unseeded reset: the RNG stream continues */
+      reward[i] = 0.0; terminated[i] = 0; truncated[i] = 0;
+      e->pending_reset = 0;
+    } else {
+      if (env_step(v, e, actions[i], &reward[i], &terminated[i], &truncated[i]) != 0) bad = 1;
+      int done = terminated[i] | truncated[i];
+      if (mode == MGO_AUTORESET_NEXT_STEP) e->pending_reset = (uint8_t)done;
+      else if (mode == MGO_AUTORESET_SAME_STEP && done) env_reset(v, e);
+    }
+    env_gen_obs(v, e, obs + (size_t)i * 147, dir + i);
+  }
+  return bad;
+}
+static void *job_main(void *arg) {
+  job_t *j = (job_t *)arg;
+  if (j->op == 0) reset_range(j->v, j->lo, j->hi, j->obs, j->dir);
+  else if (j->op == 1) j->bad = step_range(j->v, j->lo, j->hi, j->actions, j->obs, j->dir, j->reward, j->term, j->trunc, j->mode);
+  else
+    for (int t = 0; t < j->n_steps; t++)
+      j->bad |= step_range(j->v, j->lo, j->hi, j->actions + (size_t)t * j->v->n, j->obs, j->dir, j->reward, j->term, j->trunc, j->mode);
+  return NULL;
+}
+static int run_jobs(job_t proto, int nt) {
+  mgo_vec *v = proto.v;
+  if (nt == 1) { proto.lo = 0; proto.hi = v->n; job_main(&proto); return proto.bad; }
+  job_t *jobs = (job_t *)malloc(sizeof(job_t) * (size_t)nt);
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nt);
+  for (int k = 0; k < nt; k++) {
+    jobs[k] = proto;
+    jobs[k].lo = (int)((long long)v->n * k / nt);
+    jobs[k].hi = (int)((long long)v->n * (k + 1) / nt);
+    pthread_create(&th[k], NULL, job_main, &jobs[k]);
+  }
+  int bad = 0;
+  for (int k = 0; k < nt; k++) { pthread_join(th[k], NULL); bad |= jobs[k].bad; }
+  free(jobs); free(th);
+  return bad;
+}
+void mgo_vec_reset(mgo_vec *v, uint8_t *obs, int32_t *dir, int n_threads) {
+  job_t j; memset(&j, 0, sizeof(j));
+  j.v = v; j.op = 0; j.obs = obs; j.dir = dir;
+  run_jobs(j, clamp_threads(v, n_threads));
+}
+void mgo_vec_gen_obs(mgo_vec *v, uint8_t *obs, int32_t *dir) {
+  for (int i = 0; i < v->n; i++) env_gen_obs(v, &v->envs[i], obs + (size_t)i * 147, dir + i);
+}
+int mgo_vec_step(mgo_vec *v, const int32_t *actions, uint8_t *obs, int32_t *dir, double *reward,
+                 uint8_t *terminated, uint8_t *truncated, int mode, int n_threads) {
+  job_t j; memset(&j, 0, sizeof(j));
+  j.v = v; j.op = 1; j.actions = actions; j.obs = obs; j.dir = dir; j.reward = reward; j.term = terminated; j.trunc = truncated; j.mode = mode;
+  return run_jobs(j, clamp_threads(v, n_threads)) ? -1 : 0;
+}
+/* wrappers.py:419-426 */
+void mgo_vec_full_obs(mgo_vec *v, uint8_t *out) {
+  int W = v->width, H = v->height;
+  for (int n = 0; n < v->n; n++) {
+    env_t *e = &v->envs[n];
+    uint8_t *o = out + (size_t)n * W * H * 3;
+    for (int i = 0; i < W; i++)
+      for (int j = 0; j < H; j++) encode_cell(grid_get(&e->grid, i, j), o + (i * H + j) * 3);
+    uint8_t *a = o + (e->agent_x * H + e->agent_y) * 3;
+    a[0] = T_AGENT; a[1] = C_RED; a[2] = (uint8_t)e->agent_dir;
+  }
+}
+void mgo_vec_get_state(mgo_vec *v, uint8_t *grid, int32_t *agent, uint64_t *rng, uint8_t *pending) {
+  int W = v->width, H = v->height;
+  for (int n = 0; n < v->n; n++) {
+    env_t *e = &v->envs[n];
+    if (grid) {
+      uint8_t *o = grid + (size_t)n * W * H * 3;
+      for (int i = 0; i < W; i++)
+        for (int j = 0; j < H; j++) encode_cell(grid_get(&e->grid, i, j), o + (i * H + j) * 3);
+    }
+    if (agent) {
+      int32_t *a = agent + (size_t)n * 6;
+      a[0] = e->agent_x; a[1] = e->agent_y; a[2] = e->agent_dir;
+      a[3] = e->carrying ? e->carry.type : -1; a[4] = e->carrying ? e->carry.color : 0; a[5] = e->step_count;
+    }
+    if (rng) {
+      uint64_t *r = rng + (size_t)n * 6;
+      r[0] = (uint64_t)(e->rng.state >> 64); r[1] = (uint64_t)e->rng.state;
+      r[2] = (uint64_t)(e->rng.inc >> 64); r[3] = (uint64_t)e->rng.inc;
+      r[4] = (uint64_t)e->rng.has_uint32; r[5] = e->rng.uinteger;
+    }
+    if (pending) pending[n] = e->pending_reset;
+  }
+}
+void mgo_vec_set_state(mgo_vec *v, const uint8_t *grid, const int32_t *agent, const uint64_t *rng,
+                       const uint8_t *pending) {
+  int W = v->width, H = v->height;
+  for (int n = 0; n < v->n; n++) {
+    env_t *e = &v->envs[n];
+    if (grid) {
+      const uint8_t *o = grid + (size_t)n * W * H * 3;
+      for (int i = 0; i < W; i++)
+        for (int j = 0; j < H; j++) {
+          const uint8_t *c = o + (i * H + j) * 3;
+          cell_t x = {c[0], c[1], c[2]};
+          if (x.type == T_EMPTY || x.type == T_UNSEEN || x.type == T_AGENT) x = CELL_NONE; /* WorldObj.decode :77-78 */
+          grid_set(&e->grid, i, j, x);
+        }
+    }
+    if (agent) {
+      const int32_t *a = agent + (size_t)n * 6;
+      e->agent_x = a[0]; e->agent_y = a[1]; e->agent_dir = a[2];
+      e->carrying = a[3] >= 0;
+      e->carry = CELL_NONE;
+      if (e->carrying) { e->carry.type = (uint8_t)a[3]; e->carry.color = (uint8_t)a[4]; e->carry.state = 0; }
+      e->step_count = a[5];
+    }
+    if (rng) {
+      const uint64_t *r = rng + (size_t)n * 6;
+      e->rng.state = ((u128)r[0] << 64) | r[1];
+      e->rng.inc = ((u128)r[2] << 64) | r[3];
+      e->rng.has_uint32 = (int)r[4]; e->rng.uinteger = (uint32_t)r[5];
+    }
+    if (pending) e->pending_reset = pending[n];
+  }
+}
+
+int64_t mgo_rng_integers(mgo_vec *v, int i, int64_t low, int64_t high) { return rng_integers(&v->envs[i].rng, low, high); }
+uint32_t mgo_rng_next32(mgo_vec *v, int i) { return pcg_next32(&v->envs[i].rng); }
+void mgo_rng_shuffle_perm(mgo_vec *v, int i, int32_t *perm, int n) {
+  for (int k = n - 1; k >= 1; k--) {
+    int j = (int)rng_interval(&v->envs[i].rng, (uint32_t)k);
+    int32_t t = perm[k]; perm[k] = perm[j]; perm[j] = t;
+  }
+}
+
+double mgo_vec_rollout(mgo_vec *v, const int32_t *actions, int n_steps, int mode, int n_threads,
+                       uint64_t *checksum_out) {
+  size_t n = (size_t)v->n;
+  if (!v->s_obs) {
+    v->s_obs = (uint8_t *)malloc(n * 147); v->s_dir = (int32_t *)malloc(n * 4); v->s_rew = (double *)malloc(n * 8);
+    v->s_term = (uint8_t *)malloc(n); v->s_trunc = (uint8_t *)malloc(n);
+  }
+  job_t j; memset(&j, 0, sizeof(j));
+  j.v = v; j.op = 2; j.actions = actions; j.obs = v->s_obs; j.dir = v->s_dir; j.reward = v->s_rew;
+  j.term = v->s_term; j.trunc = v->s_trunc; j.mode = mode; j.n_steps = n_steps;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  run_jobs(j, clamp_threads(v, n_threads));
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (checksum_out) {
+    uint64_t h = 1469598103934665603ULL;
+    for (size_t k = 0; k < n * 147; k++) { h ^= v->s_obs[k]; h *= 1099511628211ULL; }
+    *checksum_out = h;
+  }
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

@@ -1,0 +1,176 @@
+"""ctypes front-end of the C oracle (oracle/mg_oracle.c). TEST INFRASTRUCTURE ONLY.
+
+`OracleVecEnv` mirrors a list of reference `MiniGridEnv` objects driven in lockstep with
+gymnasium.vector.SyncVectorEnv autoreset semantics (restated in mg_oracle.c:step_range).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmg_oracle.so")
+
+KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3}
+AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
+
+# id -> (kind, width, height, max_steps, see_through_walls, params); restated from
+# /root/reference/minigrid/__init__.py:25-28,106-109,159-162,183-185,214-216 and the env
+# constructors (empty.py:69-90, doorkey.py:62-68, crossing.py:89-116, fourrooms.py:55-67).
+ENV_SPECS = {
+    "MiniGrid-Empty-5x5-v0": ("empty", 5, 5, 100, True, [0, 1, 1, 0]),
+    "MiniGrid-Empty-8x8-v0": ("empty", 8, 8, 256, True, [0, 1, 1, 0]),
+    "MiniGrid-DoorKey-8x8-v0": ("doorkey", 8, 8, 640, False, []),
+    "MiniGrid-LavaCrossingS9N1-v0": ("crossing", 9, 9, 324, False, [1, 9]),
+    "MiniGrid-FourRooms-v0": ("fourrooms", 19, 19, 100, False, []),
+    # extra ids of the same four generators (wider parity coverage)
+    "MiniGrid-Empty-Random-6x6-v0": ("empty", 6, 6, 144, True, [1, 0, 0, 0]),
+    "MiniGrid-Empty-16x16-v0": ("empty", 16, 16, 1024, True, [0, 1, 1, 0]),
+    "MiniGrid-DoorKey-5x5-v0": ("doorkey", 5, 5, 250, False, []),
+    "MiniGrid-DoorKey-16x16-v0": ("doorkey", 16, 16, 2560, False, []),
+    "MiniGrid-LavaCrossingS9N3-v0": ("crossing", 9, 9, 324, False, [3, 9]),
+    "MiniGrid-LavaCrossingS11N5-v0": ("crossing", 11, 11, 484, False, [5, 9]),
+    "MiniGrid-SimpleCrossingS9N2-v0": ("crossing", 9, 9, 324, False, [2, 2]),
+}
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "mg_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libmg_oracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        p = C.c_void_p
+        L.mgo_vec_create.restype = p
+        L.mgo_vec_create.argtypes = [C.c_int] * 5 + [p, C.c_int, C.c_int]
+        L.mgo_vec_destroy.argtypes = [p]
+        L.mgo_vec_seed.argtypes = [p, p]
+        L.mgo_vec_reset.argtypes = [p, p, p, C.c_int]
+        L.mgo_vec_step.restype = C.c_int
+        L.mgo_vec_step.argtypes = [p] * 7 + [C.c_int, C.c_int]
+        L.mgo_vec_full_obs.argtypes = [p, p]
+        L.mgo_vec_gen_obs.argtypes = [p, p, p]
+        L.mgo_vec_get_state.argtypes = [p] * 5
+        L.mgo_vec_set_state.argtypes = [p] * 5
+        L.mgo_rng_integers.restype = C.c_int64
+        L.mgo_rng_integers.argtypes = [p, C.c_int, C.c_int64, C.c_int64]
+        L.mgo_rng_next32.restype = C.c_uint32
+        L.mgo_rng_next32.argtypes = [p, C.c_int]
+        L.mgo_rng_shuffle_perm.argtypes = [p, C.c_int, p, C.c_int]
+        L.mgo_vec_rollout.restype = C.c_double
+        L.mgo_vec_rollout.argtypes = [p, p, C.c_int, C.c_int, C.c_int, p]
+        L.mgo_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleVecEnv:
+    def __init__(self, env_id=None, num_envs=1, *, spec=None, autoreset="next_step", n_threads=1):
+        kind, W, H, max_steps, see_through, params = spec if spec is not None else ENV_SPECS[env_id]
+        self.kind, self.width, self.height = kind, W, H
+        self.max_steps, self.see_through, self.params = max_steps, see_through, list(params)
+        self.num_envs = int(num_envs)
+        self.mode = AUTORESET[autoreset]
+        self.n_threads = n_threads
+        prm = np.asarray(self.params, dtype=np.int32)
+        self._h = lib().mgo_vec_create(KIND[kind], W, H, max_steps, int(see_through), _ptr(prm), len(prm), self.num_envs)
+        n = self.num_envs
+        self.obs = np.zeros((n, 7, 7, 3), np.uint8)
+        self.dir = np.zeros(n, np.int32)
+        self.reward = np.zeros(n, np.float64)
+        self.terminated = np.zeros(n, np.uint8)
+        self.truncated = np.zeros(n, np.uint8)
+
+    def close(self):
+        if self._h:
+            lib().mgo_vec_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def seed(self, seeds):
+        s = np.ascontiguousarray(seeds, dtype=np.uint64)
+        assert s.shape == (self.num_envs,)
+        lib().mgo_vec_seed(self._h, _ptr(s))
+
+    def reset(self, seed=None):
+        if seed is not None:
+            seeds = np.arange(self.num_envs, dtype=np.uint64) + np.uint64(seed) if np.isscalar(seed) else seed
+            self.seed(seeds)
+        lib().mgo_vec_reset(self._h, _ptr(self.obs), _ptr(self.dir), self.n_threads)
+        return self.obs, self.dir
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        assert a.shape == (self.num_envs,)
+        rc = lib().mgo_vec_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.dir), _ptr(self.reward),
+                                _ptr(self.terminated), _ptr(self.truncated), self.mode, self.n_threads)
+        if rc != 0:
+            raise ValueError("Unknown action")
+        return self.obs, self.dir, self.reward, self.terminated.astype(bool), self.truncated.astype(bool)
+
+    def gen_obs(self):
+        lib().mgo_vec_gen_obs(self._h, _ptr(self.obs), _ptr(self.dir))
+        return self.obs, self.dir
+
+    def full_obs(self):
+        out = np.zeros((self.num_envs, self.width, self.height, 3), np.uint8)
+        lib().mgo_vec_full_obs(self._h, _ptr(out))
+        return out
+
+    def get_state(self):
+        n = self.num_envs
+        st = {
+            "grid": np.zeros((n, self.width, self.height, 3), np.uint8),
+            "agent": np.zeros((n, 6), np.int32),
+            "rng": np.zeros((n, 6), np.uint64),
+            "pending": np.zeros(n, np.uint8),
+        }
+        lib().mgo_vec_get_state(self._h, _ptr(st["grid"]), _ptr(st["agent"]), _ptr(st["rng"]), _ptr(st["pending"]))
+        return st
+
+    def set_state(self, grid=None, agent=None, rng=None, pending=None):
+        g = None if grid is None else np.ascontiguousarray(grid, np.uint8)
+        a = None if agent is None else np.ascontiguousarray(agent, np.int32)
+        r = None if rng is None else np.ascontiguousarray(rng, np.uint64)
+        p = None if pending is None else np.ascontiguousarray(pending, np.uint8)
+        lib().mgo_vec_set_state(self._h, _ptr(g), _ptr(a), _ptr(r), _ptr(p))
+
+    def rng_integers(self, i, low, high):
+        return int(lib().mgo_rng_integers(self._h, i, low, high))
+
+    def rng_next32(self, i):
+        return int(lib().mgo_rng_next32(self._h, i))
+
+    def rng_shuffle(self, i, n):
+        perm = np.arange(n, dtype=np.int32)
+        lib().mgo_rng_shuffle_perm(self._h, i, _ptr(perm), n)
+        return perm
+
+    def rollout(self, actions, n_threads=0):
+        """actions int32[T, N]; returns (seconds, checksum of the last obs batch)."""
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        assert a.ndim == 2 and a.shape[1] == self.num_envs
+        ck = C.c_uint64(0)
+        secs = lib().mgo_vec_rollout(self._h, _ptr(a), a.shape[0], self.mode, n_threads, C.byref(ck))
+        return float(secs), int(ck.value)
+
+
+def max_threads():
+    return int(lib().mgo_max_threads())

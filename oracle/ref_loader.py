@@ -1,0 +1,103 @@
+"""Import the UNMODIFIED Python reference (TEST INFRASTRUCTURE ONLY, build container only).
+
+/root/reference is read-only and exists only in the build container (never on the GPU box), so
+everything that uses this module is skipped when the tree is absent. gymnasium and pygame are not
+installed in the image: oracle/ref_shim supplies import stand-ins (our own code); a real gymnasium,
+if ever installed, takes precedence.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("MINIGRID_REFERENCE_ROOT", "/root/reference")
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shim")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "minigrid"))
+
+
+def load():
+    """Returns (gymnasium_module, minigrid_module) with the reference's envs registered."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    if importlib.util.find_spec("gymnasium") is None or importlib.util.find_spec("pygame") is None:
+        if _SHIM not in sys.path:
+            sys.path.append(_SHIM)  # appended: real packages win
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import gymnasium  # noqa: E402
+    import minigrid  # noqa: E402
+
+    return gymnasium, minigrid
+
+
+class ReferenceVecEnv:
+    """N reference MiniGridEnv objects stepped in lockstep with SyncVectorEnv autoreset rules
+    (gymnasium >= 1.0: NEXT_STEP default; SAME_STEP optional). Implemented here so the result does
+    not depend on which gymnasium (if any) is installed."""
+
+    def __init__(self, env_id, num_envs, autoreset="next_step", **kwargs):
+        import numpy as np
+
+        gym, _ = load()
+        self.np = np
+        self.envs = [gym.make(env_id, **kwargs).unwrapped for _ in range(num_envs)]
+        self.num_envs = num_envs
+        self.autoreset = autoreset
+        self.pending = [False] * num_envs
+
+    def reset(self, seed=None):
+        np = self.np
+        obs, dirs = [], []
+        for i, e in enumerate(self.envs):
+            s = None if seed is None else (int(seed) + i if np.isscalar(seed) else int(seed[i]))
+            o, _ = e.reset(seed=s)
+            obs.append(o["image"]); dirs.append(o["direction"])
+        self.pending = [False] * self.num_envs
+        return np.stack(obs), np.asarray(dirs, np.int32)
+
+    def step(self, actions):
+        np = self.np
+        obs, dirs, rew, term, trunc = [], [], [], [], []
+        for i, e in enumerate(self.envs):
+            if self.autoreset == "next_step" and self.pending[i]:
+                o, _ = e.reset()
+                r, te, tr = 0.0, False, False
+                self.pending[i] = False
+            else:
+                o, r, te, tr, _ = e.step(int(actions[i]))
+                done = te or tr
+                if self.autoreset == "next_step":
+                    self.pending[i] = done
+                elif self.autoreset == "same_step" and done:
+                    o, _ = e.reset()
+            obs.append(o["image"]); dirs.append(o["direction"]); rew.append(float(r)); term.append(te); trunc.append(tr)
+        return (np.stack(obs), np.asarray(dirs, np.int32), np.asarray(rew, np.float64),
+                np.asarray(term, bool), np.asarray(trunc, bool))
+
+    def get_state(self):
+        np = self.np
+        n = self.num_envs
+        e0 = self.envs[0]
+        grid = np.zeros((n, e0.width, e0.height, 3), np.uint8)
+        agent = np.zeros((n, 6), np.int32)
+        rng = np.zeros((n, 6), np.uint64)
+        for i, e in enumerate(self.envs):
+            grid[i] = e.grid.encode()
+            c = e.carrying
+            enc = c.encode() if c is not None else (-1, 0, 0)
+            agent[i] = [e.agent_pos[0], e.agent_pos[1], e.agent_dir, enc[0], enc[1], e.step_count]
+            st = e.np_random.bit_generator.state
+            s, inc = st["state"]["state"], st["state"]["inc"]
+            m = (1 << 64) - 1
+            rng[i] = [s >> 64, s & m, inc >> 64, inc & m, st["has_uint32"], st["uinteger"]]
+        return {"grid": grid, "agent": agent, "rng": rng, "pending": np.asarray(self.pending, np.uint8)}
+
+    def full_obs(self):
+        from minigrid.wrappers import FullyObsWrapper
+
+        np = self.np
+        return np.stack([FullyObsWrapper(e).observation({})["image"] for e in self.envs])
