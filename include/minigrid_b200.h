@@ -1,0 +1,118 @@
+/*
+ * minigrid_b200.h — C-ABI of the B200-native lockstep-batched Minigrid engine.
+ *
+ * The reference (Farama-Foundation/Minigrid, pure Python) has no FFI layer; the boundary it implements is
+ * the Gymnasium API (MiniGridEnv(gym.Env), minigrid/minigrid_env.py:24) and, batched, gymnasium.vector's
+ * VectorEnv as used in tests/test_envs.py:328-340. Each entry point below cites the reference interface
+ * it replaces for a whole batch of environments. All file:line citations are relative to
+ * /root/reference/minigrid/.
+ *
+ * Conventions
+ *  - plain C types only; every function returns MG_OK (0) or a negative MG_ERR_* code and records a
+ *    message retrievable with mg_last_error() (thread-local).
+ *  - `*_dev` pointers are device memory on the handle's GPU, owned by the caller (torch tensors in the
+ *    Python host layer); `*_host` pointers are host memory. The library owns only its state arena.
+ *  - device work is enqueued on the caller's `stream` (a cudaStream_t passed as void*) and is
+ *    asynchronous; the *_host entry points synchronise before returning.
+ *  - a handle is bound to one device; one host thread per handle. Distinct handles may run concurrently.
+ *  - device kernels cannot raise: an action outside 0..6 (ValueError at minigrid_env.py:584-585) sets a
+ *    sticky device error word, reported by mg_check_error() / the *_host calls.
+ */
+#ifndef MINIGRID_B200_H
+#define MINIGRID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_OK 0
+#define MG_ERR_INVALID_ARG (-1)
+#define MG_ERR_CUDA (-2)
+#define MG_ERR_INVALID_ACTION (-3)
+#define MG_ERR_NO_DEVICE (-4)
+
+/* generators (envs/empty.py, doorkey.py, crossing.py, fourrooms.py) */
+#define MG_KIND_EMPTY 0
+#define MG_KIND_DOORKEY 1
+#define MG_KIND_CROSSING 2
+#define MG_KIND_FOURROOMS 3
+
+/* gymnasium.vector.AutoresetMode */
+#define MG_AUTORESET_NEXT_STEP 0
+#define MG_AUTORESET_SAME_STEP 1
+#define MG_AUTORESET_DISABLED 2
+
+/* dtype of the action buffer handed to mg_step */
+#define MG_ACT_I32 0
+#define MG_ACT_I64 1
+#define MG_ACT_U8 2
+
+#define MG_VIEW 7                 /* agent_view_size (minigrid_env.py:42) */
+#define MG_OBS_BYTES (7 * 7 * 3)  /* one "image" (minigrid_env.py:72-77) */
+
+typedef struct mg_env mg_env;
+
+/* Replaces: constructing n_envs MiniGridEnv objects (minigrid_env.py:34-117) of one registered id
+ * (minigrid/__init__.py). kind/width/height/max_steps/see_through_walls are the constructor arguments;
+ * params: EMPTY {random_start, start_x, start_y, start_dir}; CROSSING {num_crossings, obstacle_type
+ * (9 lava | 2 wall)}; others none.
+ * device < 0 selects the current CUDA device. */
+int mg_create(int kind, int width, int height, int max_steps, int see_through_walls,
+              const int32_t *params, int n_params, int64_t n_envs, int autoreset_mode, int device,
+              mg_env **out);
+int mg_destroy(mg_env *env);
+const char *mg_last_error(void);
+
+int64_t mg_num_envs(const mg_env *env);
+/* total kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t mg_launch_count(const mg_env *env);
+
+/* Replaces: gym.Env.reset(seed=s) -> np_random = Generator(PCG64(SeedSequence(s))) (minigrid_env.py:125,
+ * gymnasium.utils.seeding.np_random). SeedSequence hashing runs on the device. seeds_host: uint64[n]. */
+int mg_seed(mg_env *env, const uint64_t *seeds_host, void *stream);
+/* env i gets seed base_seed + i (gymnasium.vector seed convention: reset(seed=int)) */
+int mg_seed_base(mg_env *env, uint64_t base_seed, void *stream);
+
+/* Replaces: MiniGridEnv.reset() for every env (minigrid_env.py:119-157): _gen_grid, carrying=None,
+ * step_count=0, gen_obs. RNG streams continue unless mg_seed* was called first.
+ * obs_dev: uint8[n][7][7][3]; dir_dev: int32[n]. Either may be NULL. */
+int mg_reset(mg_env *env, uint8_t *obs_dev, int32_t *dir_dev, void *stream);
+
+/* Replaces: MiniGridEnv.step(action) (minigrid_env.py:525-595) + gen_obs (:597-650) for every env, with
+ * gymnasium.vector.SyncVectorEnv autoreset semantics (mode given at mg_create).
+ * actions_dev: n actions of dtype action_dtype; obs_dev uint8[n][7][7][3]; dir_dev int32[n];
+ * reward_dev float64[n]; terminated_dev / truncated_dev uint8[n] (0/1). */
+int mg_step(mg_env *env, const void *actions_dev, int action_dtype, uint8_t *obs_dev, int32_t *dir_dev,
+            double *reward_dev, uint8_t *terminated_dev, uint8_t *truncated_dev, void *stream);
+
+/* Same two calls with HOST buffers (the end-to-end path: H2D of actions and D2H of every output happen
+ * inside the call, through pinned staging owned by the handle; returns after the results are on the host).
+ * actions_host: int32[n]. Returns MG_ERR_INVALID_ACTION if any action was outside 0..6. */
+int mg_reset_host(mg_env *env, uint8_t *obs_host, int32_t *dir_host);
+int mg_step_host(mg_env *env, const int32_t *actions_host, uint8_t *obs_host, int32_t *dir_host,
+                 double *reward_host, uint8_t *terminated_host, uint8_t *truncated_host);
+
+/* Replaces: FullyObsWrapper.observation (wrappers.py:419-426): grid.encode() with the agent cell set to
+ * (10, 0, agent_dir). out_dev: uint8[n][W][H][3]. */
+int mg_full_obs(mg_env *env, uint8_t *out_dev, void *stream);
+
+/* Replaces: pickling / inspecting env objects (tests/test_envs.py:185-195) and lets tests inject states.
+ * grid_dev: Grid.encode() uint8[n][W][H][3]; agent_dev: int32[n][6] {x, y, dir, carry_type (-1 none),
+ * carry_color, step_count}; rng_dev: uint64[n][6] {state_hi, state_lo, inc_hi, inc_lo, has_uint32,
+ * uinteger} (numpy PCG64 bit-generator state); pending_dev: uint8[n] NEXT_STEP autoreset flags.
+ * Any pointer may be NULL. */
+int mg_get_state(mg_env *env, uint8_t *grid_dev, int32_t *agent_dev, uint64_t *rng_dev,
+                 uint8_t *pending_dev, void *stream);
+int mg_set_state(mg_env *env, const uint8_t *grid_dev, const int32_t *agent_dev, const uint64_t *rng_dev,
+                 const uint8_t *pending_dev, void *stream);
+
+/* Synchronises `stream`, returns MG_ERR_INVALID_ACTION if a kernel saw an action outside 0..6 since the
+ * last check (and clears the flag), else MG_OK. */
+int mg_check_error(mg_env *env, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINIGRID_B200_H */

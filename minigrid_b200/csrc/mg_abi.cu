@@ -1,0 +1,351 @@
+// mg_abi.cu — the C-ABI of include/minigrid_b200.h: handle management, launch sequencing (autoreset
+// modes), and the host-buffer (end-to-end) entry points. No torch types cross this boundary.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/minigrid_b200.h"
+#include "mg_common.cuh"
+
+namespace mg {
+cudaError_t launch_step(const Params &p, const void *actions, int action_dtype, uint8_t *obs, int32_t *dir,
+                        double *reward, uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream);
+cudaError_t configure_step(const Params &p);
+cudaError_t launch_reset(const Params &p, const int *list, const int *count, uint8_t *obs, int32_t *dir,
+                         int set_fresh, cudaStream_t stream);
+cudaError_t launch_seed(const Params &p, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream);
+cudaError_t launch_full_obs(const Params &p, uint8_t *out, int with_agent, cudaStream_t stream);
+cudaError_t launch_get_state(const Params &p, uint8_t *grid, int32_t *agent, uint64_t *rng, uint8_t *pending,
+                             cudaStream_t stream);
+cudaError_t launch_set_state(const Params &p, const uint8_t *grid, const int32_t *agent, const uint64_t *rng,
+                             const uint8_t *pending, int cur, cudaStream_t stream);
+cudaError_t launch_init(const Params &p, cudaStream_t stream);
+}  // namespace mg
+
+using namespace mg;
+
+struct mg_env {
+  Params p;
+  int device;
+  int cur;           // the reset list the most recent step appended to
+  int64_t launches;
+  // device allocations owned by the handle
+  void *d_arena;     // grid | agent | rng | lists | counts | err | luts, one cudaMalloc
+  uint64_t *d_seeds;
+  // host path
+  cudaStream_t hstream;
+  int32_t *d_actions; uint8_t *d_out;  // device mirror of the host-facing buffers
+  int32_t *h_actions; uint8_t *h_out;  // pinned staging, used when the caller's buffers are pageable
+  int *h_err;
+};
+
+static thread_local std::string g_err;
+const char *mg_last_error(void) { return g_err.c_str(); }
+
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define MG_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return fail(MG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int mg_create(int kind, int width, int height, int max_steps, int see_through_walls, const int32_t *params,
+              int n_params, int64_t n_envs, int autoreset_mode, int device, mg_env **out) {
+  if (!out) return fail(MG_ERR_INVALID_ARG, "out is NULL");
+  *out = nullptr;
+  if (kind < 0 || kind > 3) return fail(MG_ERR_INVALID_ARG, "unknown kind");
+  if (width < 3 || height < 3 || width > MAX_DIM || height > MAX_DIM)
+    return fail(MG_ERR_INVALID_ARG, "width/height must be in [3, 26]");
+  if (max_steps < 1) return fail(MG_ERR_INVALID_ARG, "max_steps must be >= 1");
+  if (n_envs < 1 || n_envs > (int64_t)1 << 30) return fail(MG_ERR_INVALID_ARG, "n_envs out of range");
+  if (autoreset_mode < 0 || autoreset_mode > 2) return fail(MG_ERR_INVALID_ARG, "unknown autoreset mode");
+  if (kind == MG_KIND_CROSSING && (width % 2 == 0 || height % 2 == 0))
+    return fail(MG_ERR_INVALID_ARG, "crossing needs odd sizes (crossing.py:132)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(MG_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
+  if (device < 0) MG_CUDA(cudaGetDevice(&device));
+  if (device >= ndev) return fail(MG_ERR_INVALID_ARG, "device index out of range");
+  MG_CUDA(cudaSetDevice(device));
+
+  mg_env *h = new (std::nothrow) mg_env();
+  if (!h) return fail(MG_ERR_INVALID_ARG, "out of host memory");
+  memset(h, 0, sizeof(*h));
+  Params &p = h->p;
+  p.g = make_geom(width, height);
+  p.n_envs = (int)n_envs;
+  p.n_tiles = (int)((n_envs + TILE - 1) / TILE);
+  p.max_steps = max_steps;
+  p.see_through = see_through_walls ? 1 : 0;
+  p.mode = autoreset_mode;
+  p.kind = kind;
+  for (int i = 0; i < 8; ++i) p.kp[i] = (params && i < n_params) ? params[i] : 0;
+  if (kind == MG_KIND_EMPTY && !p.kp[0] && n_params < 4) { p.kp[1] = 1; p.kp[2] = 1; p.kp[3] = 0; }
+  if (kind == MG_KIND_CROSSING && n_params < 2) { p.kp[0] = 1; p.kp[1] = (int)T_LAVA; }
+  h->device = device;
+
+  const size_t n_pad = (size_t)p.n_tiles * TILE;
+  const size_t sz_grid = align_up((size_t)p.n_tiles * p.g.wpe * 128, 256);
+  const size_t sz_agent = align_up(n_pad * sizeof(uint4), 256);
+  const size_t sz_rng = align_up(n_pad * sizeof(RngRec), 256);
+  const size_t sz_list = align_up(n_pad * sizeof(int), 256);
+  const size_t sz_lut_r = align_up((size_t)(max_steps + 1) * sizeof(double), 256);
+  const size_t total = sz_grid + sz_agent + sz_rng + 2 * sz_list + 256 /*counts+err*/ + sz_lut_r + 1024;
+  cudaError_t e = cudaMalloc(&h->d_arena, total);
+  if (e != cudaSuccess) { delete h; return fail(MG_ERR_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); }
+  uint8_t *base = (uint8_t *)h->d_arena;
+  p.grid = (uint32_t *)base; base += sz_grid;
+  p.agent = (uint4 *)base; base += sz_agent;
+  p.rng = (RngRec *)base; base += sz_rng;
+  p.list[0] = (int *)base; base += sz_list;
+  p.list[1] = (int *)base; base += sz_list;
+  p.count[0] = (int *)base; p.count[1] = (int *)base + 1; p.err = (int *)base + 2; base += 256;
+  double *d_rl = (double *)base; base += sz_lut_r;
+  uint32_t *d_cl = (uint32_t *)base;
+  p.reward_lut = d_rl; p.cell_lut = d_cl;
+
+  // _reward(): 1 - 0.9 * (step_count / max_steps) in host IEEE double, never contracted (minigrid_env.py:245)
+  {
+    double *lut = (double *)malloc((size_t)(max_steps + 1) * sizeof(double));
+    for (int k = 0; k <= max_steps; ++k) {
+      volatile double q = (double)k / (double)max_steps;
+      volatile double m = 0.9 * q;
+      lut[k] = 1.0 - m;
+    }
+    e = cudaMemcpy(d_rl, lut, (size_t)(max_steps + 1) * sizeof(double), cudaMemcpyHostToDevice);
+    free(lut);
+    uint32_t cl[256];
+    for (uint32_t c = 0; c < 256; ++c) cl[c] = decode_cell(c);
+    if (e == cudaSuccess) e = cudaMemcpy(d_cl, cl, sizeof(cl), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(p.count[0], 0, 256);
+  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = configure_step(p);
+  if (e == cudaSuccess) e = launch_init(p, h->hstream);
+  if (e == cudaSuccess) e = launch_seed(p, nullptr, 0, h->hstream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->hstream);
+  if (e != cudaSuccess) {
+    std::string msg = std::string("mg_create: ") + cudaGetErrorString(e);
+    mg_destroy(h);
+    return fail(MG_ERR_CUDA, msg);
+  }
+  h->launches = 2;
+  *out = h;
+  return MG_OK;
+}
+
+int mg_destroy(mg_env *h) {
+  if (!h) return MG_OK;
+  cudaSetDevice(h->device);
+  if (h->hstream) { cudaStreamSynchronize(h->hstream); cudaStreamDestroy(h->hstream); }
+  cudaFree(h->d_arena);
+  cudaFree(h->d_seeds);
+  cudaFree(h->d_actions);
+  cudaFree(h->d_out);
+  cudaFreeHost(h->h_actions);
+  cudaFreeHost(h->h_out);
+  cudaFreeHost(h->h_err);
+  delete h;
+  return MG_OK;
+}
+
+int64_t mg_num_envs(const mg_env *h) { return h ? h->p.n_envs : 0; }
+int64_t mg_launch_count(const mg_env *h) { return h ? h->launches : 0; }
+
+int mg_seed(mg_env *h, const uint64_t *seeds_host, void *stream) {
+  if (!h || !seeds_host) return fail(MG_ERR_INVALID_ARG, "mg_seed: NULL argument");
+  MG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!h->d_seeds) MG_CUDA(cudaMalloc(&h->d_seeds, (size_t)h->p.n_envs * sizeof(uint64_t)));
+  MG_CUDA(cudaMemcpyAsync(h->d_seeds, seeds_host, (size_t)h->p.n_envs * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+  MG_CUDA(launch_seed(h->p, h->d_seeds, 0, s));
+  MG_CUDA(cudaStreamSynchronize(s));  // seeds_host may be pageable and freed by the caller
+  h->launches += 1;
+  return MG_OK;
+}
+
+int mg_seed_base(mg_env *h, uint64_t base_seed, void *stream) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_seed_base: NULL handle");
+  MG_CUDA(cudaSetDevice(h->device));
+  MG_CUDA(launch_seed(h->p, nullptr, base_seed, (cudaStream_t)stream));
+  h->launches += 1;
+  return MG_OK;
+}
+
+int mg_reset(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_reset: NULL handle");
+  MG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  MG_CUDA(cudaMemsetAsync(h->p.count[0], 0, 2 * sizeof(int), s));  // SyncVectorEnv.reset clears _autoreset_envs
+  MG_CUDA(launch_reset(h->p, nullptr, nullptr, obs_dev, dir_dev, 0, s));
+  h->launches += 1;
+  return MG_OK;
+}
+
+int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_dev, int32_t *dir_dev,
+            double *reward_dev, uint8_t *terminated_dev, uint8_t *truncated_dev, void *stream) {
+  if (!h || !actions_dev) return fail(MG_ERR_INVALID_ARG, "mg_step: NULL argument");
+  if (action_dtype < 0 || action_dtype > 2) return fail(MG_ERR_INVALID_ARG, "mg_step: unknown action dtype");
+  MG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const Params &p = h->p;
+  const int append = h->cur ^ 1;
+  if (p.mode == MG_AUTORESET_NEXT_STEP) {
+    // envs that finished last step are regenerated first; K1 then sees FLAG_FRESH, ignores their action and
+    // returns the reset observation with reward 0 / False / False
+    MG_CUDA(launch_reset(p, p.list[h->cur], p.count[h->cur], nullptr, nullptr, 1, s));
+    h->launches += 1;
+  }
+  MG_CUDA(launch_step(p, actions_dev, action_dtype, obs_dev, dir_dev, reward_dev, terminated_dev, truncated_dev, append, s));
+  h->launches += 1;
+  if (p.mode == MG_AUTORESET_SAME_STEP) {
+    MG_CUDA(launch_reset(p, p.list[append], p.count[append], obs_dev, dir_dev, 0, s));
+    h->launches += 1;
+  }
+  h->cur = append;
+  return MG_OK;
+}
+
+int mg_full_obs(mg_env *h, uint8_t *out_dev, void *stream) {
+  if (!h || !out_dev) return fail(MG_ERR_INVALID_ARG, "mg_full_obs: NULL argument");
+  MG_CUDA(cudaSetDevice(h->device));
+  MG_CUDA(launch_full_obs(h->p, out_dev, 1, (cudaStream_t)stream));
+  h->launches += 1;
+  return MG_OK;
+}
+
+int mg_get_state(mg_env *h, uint8_t *grid_dev, int32_t *agent_dev, uint64_t *rng_dev, uint8_t *pending_dev, void *stream) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_get_state: NULL handle");
+  MG_CUDA(cudaSetDevice(h->device));
+  MG_CUDA(launch_get_state(h->p, grid_dev, agent_dev, rng_dev, pending_dev, (cudaStream_t)stream));
+  h->launches += (grid_dev ? 1 : 0) + ((agent_dev || rng_dev || pending_dev) ? 1 : 0);
+  return MG_OK;
+}
+
+int mg_set_state(mg_env *h, const uint8_t *grid_dev, const int32_t *agent_dev, const uint64_t *rng_dev,
+                 const uint8_t *pending_dev, void *stream) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_set_state: NULL handle");
+  MG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pending_dev) MG_CUDA(cudaMemsetAsync(h->p.count[h->cur], 0, sizeof(int), s));
+  MG_CUDA(launch_set_state(h->p, grid_dev, agent_dev, rng_dev, pending_dev, h->cur, s));
+  h->launches += (grid_dev ? 1 : 0) + ((agent_dev || rng_dev || pending_dev) ? 1 : 0);
+  return MG_OK;
+}
+
+static int ensure_host_path(mg_env *h) {
+  if (h->h_err) return MG_OK;
+  const size_t n = (size_t)h->p.n_envs;
+  MG_CUDA(cudaMalloc(&h->d_actions, n * sizeof(int32_t)));
+  MG_CUDA(cudaMalloc(&h->d_out, align_up(n * OBS_BYTES, 256) + align_up(n * 8, 256) + align_up(n * 4, 256) + 2 * align_up(n, 256)));
+  MG_CUDA(cudaHostAlloc(&h->h_err, sizeof(int), cudaHostAllocDefault));
+  return MG_OK;
+}
+
+int mg_check_error(mg_env *h, void *stream) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_check_error: NULL handle");
+  MG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = ensure_host_path(h);
+  if (rc != MG_OK) return rc;
+  MG_CUDA(cudaMemcpyAsync(h->h_err, h->p.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  MG_CUDA(cudaStreamSynchronize(s));
+  if (*h->h_err) {
+    MG_CUDA(cudaMemsetAsync(h->p.err, 0, sizeof(int), s));
+    return fail(MG_ERR_INVALID_ACTION, "Unknown action: outside 0..6 (minigrid_env.py:584-585)");
+  }
+  return MG_OK;
+}
+
+static bool is_pinned(const void *ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// D2H of one output array: straight into the caller's buffer when it is page-locked, else through the
+// handle's pinned staging (copied out after the stream sync).
+struct PendingCopy { void *dst; const void *src; size_t bytes; };
+
+static int host_outputs(mg_env *h, uint8_t *obs_host, int32_t *dir_host, double *reward_host, uint8_t *term_host,
+                        uint8_t *trunc_host, uint8_t *d_obs, double *d_rew, int32_t *d_dir, uint8_t *d_term, uint8_t *d_trunc) {
+  const size_t n = (size_t)h->p.n_envs;
+  cudaStream_t s = h->hstream;
+  PendingCopy pend[5];
+  int np = 0;
+  size_t stage_off = 0;
+  auto copy_out = [&](void *host, const void *dev, size_t bytes) -> cudaError_t {
+    if (!host) return cudaSuccess;
+    if (is_pinned(host)) return cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s);
+    if (!h->h_out) {
+      cudaError_t e = cudaHostAlloc(&h->h_out, align_up(n * OBS_BYTES, 256) + align_up(n * 8, 256) + align_up(n * 4, 256) + 2 * align_up(n, 256),
+                                    cudaHostAllocDefault);
+      if (e != cudaSuccess) return e;
+    }
+    uint8_t *st = h->h_out + stage_off;
+    stage_off += align_up(bytes, 256);
+    pend[np++] = PendingCopy{host, st, bytes};
+    return cudaMemcpyAsync(st, dev, bytes, cudaMemcpyDeviceToHost, s);
+  };
+  MG_CUDA(copy_out(obs_host, d_obs, n * OBS_BYTES));
+  MG_CUDA(copy_out(reward_host, d_rew, n * 8));
+  MG_CUDA(copy_out(dir_host, d_dir, n * 4));
+  MG_CUDA(copy_out(term_host, d_term, n));
+  MG_CUDA(copy_out(trunc_host, d_trunc, n));
+  MG_CUDA(cudaMemcpyAsync(h->h_err, h->p.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  MG_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < np; ++i) memcpy(pend[i].dst, pend[i].src, pend[i].bytes);
+  if (*h->h_err) {
+    MG_CUDA(cudaMemsetAsync(h->p.err, 0, sizeof(int), s));
+    return fail(MG_ERR_INVALID_ACTION, "Unknown action: outside 0..6 (minigrid_env.py:584-585)");
+  }
+  return MG_OK;
+}
+
+static void host_dev_ptrs(mg_env *h, uint8_t **obs, double **rew, int32_t **dir, uint8_t **term, uint8_t **trunc) {
+  const size_t n = (size_t)h->p.n_envs;
+  uint8_t *b = h->d_out;
+  *obs = b; b += align_up(n * OBS_BYTES, 256);
+  *rew = (double *)b; b += align_up(n * 8, 256);
+  *dir = (int32_t *)b; b += align_up(n * 4, 256);
+  *term = b; b += align_up(n, 256);
+  *trunc = b;
+}
+
+int mg_reset_host(mg_env *h, uint8_t *obs_host, int32_t *dir_host) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_reset_host: NULL handle");
+  MG_CUDA(cudaSetDevice(h->device));
+  int rc = ensure_host_path(h);
+  if (rc != MG_OK) return rc;
+  uint8_t *d_obs, *d_term, *d_trunc; double *d_rew; int32_t *d_dir;
+  host_dev_ptrs(h, &d_obs, &d_rew, &d_dir, &d_term, &d_trunc);
+  rc = mg_reset(h, d_obs, d_dir, h->hstream);
+  if (rc != MG_OK) return rc;
+  return host_outputs(h, obs_host, dir_host, nullptr, nullptr, nullptr, d_obs, d_rew, d_dir, d_term, d_trunc);
+}
+
+int mg_step_host(mg_env *h, const int32_t *actions_host, uint8_t *obs_host, int32_t *dir_host, double *reward_host,
+                 uint8_t *terminated_host, uint8_t *truncated_host) {
+  if (!h || !actions_host) return fail(MG_ERR_INVALID_ARG, "mg_step_host: NULL argument");
+  MG_CUDA(cudaSetDevice(h->device));
+  int rc = ensure_host_path(h);
+  if (rc != MG_OK) return rc;
+  const size_t n = (size_t)h->p.n_envs;
+  const int32_t *src = actions_host;
+  if (!is_pinned(actions_host)) {
+    if (!h->h_actions) MG_CUDA(cudaHostAlloc(&h->h_actions, n * sizeof(int32_t), cudaHostAllocDefault));
+    memcpy(h->h_actions, actions_host, n * sizeof(int32_t));
+    src = h->h_actions;
+  }
+  MG_CUDA(cudaMemcpyAsync(h->d_actions, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->hstream));
+  uint8_t *d_obs, *d_term, *d_trunc; double *d_rew; int32_t *d_dir;
+  host_dev_ptrs(h, &d_obs, &d_rew, &d_dir, &d_term, &d_trunc);
+  rc = mg_step(h, h->d_actions, MG_ACT_I32, d_obs, d_dir, d_rew, d_term, d_trunc, h->hstream);
+  if (rc != MG_OK) return rc;
+  return host_outputs(h, obs_host, dir_host, reward_host, terminated_host, truncated_host, d_obs, d_rew, d_dir, d_term, d_trunc);
+}

@@ -1,0 +1,140 @@
+// mg_common.cuh — device data layout shared by every kernel of the engine.
+//
+// The reference's per-env object graph (Grid = list[WorldObj|None], minigrid/core/grid.py:35; WorldObj with
+// type/color/is_open/is_locked, core/world_object.py:27-43,171-176) becomes:
+//
+//   cell code (1 byte)   bits 0-3  t4     = OBJECT_TO_IDX type (core/constants.py:25-37) with the door state
+//                                           folded in: 4 door open, 11 door closed, 12 door locked
+//                        bits 4-6  colour = COLOR_TO_IDX (core/constants.py:20)
+//                        bit  7    opaque = !see_behind() (world_object.py:57,164,181), kept redundantly so
+//                                           that Grid.process_vis's transparency test is one bit
+//   grid tile            32 consecutive envs ("one warp-lane per environment"), word-interleaved:
+//                        tile[w][lane] uint32, w < wpe. Lane L's w-th word sits in shared-memory bank L, so
+//                        per-lane gathers at lane-specific offsets are conflict-free, and a tile is one
+//                        contiguous block that a single TMA bulk copy (cp.async.bulk) stages.
+//   per env words        array R: lines y = -1..H (row-major x bytes, ring lines are grey wall), then
+//                        array C: lines x = -1..W (column-major y bytes): every 7-cell run of the
+//                        egocentric view (Grid.slice + rotate_left, grid.py:110-143) is 7 consecutive
+//                        bytes of one line of R (facing +-x) or C (facing +-y).
+//   agent record         uint4 {x | y<<8, dir | flags<<8, carry code (0 none), step_count}
+//   rng record           numpy PCG64 bit-generator state (state, inc, has_uint32, uinteger)
+#pragma once
+#include <stdint.h>
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define MG_HD __host__ __device__ __forceinline__
+#define MG_D __device__ __forceinline__
+#else
+// Host build of the per-lane logic (tests/host_emu only: a CPU check of the device arithmetic before GPU time
+// is spent; never part of the product library). The shim supplies uint4 and the few intrinsics used below.
+#include "mg_host_shim.h"
+#define MG_HD inline
+#define MG_D inline
+#endif
+
+namespace mg {
+
+constexpr int VIEW = 7;
+constexpr int OBS_BYTES = 147;
+constexpr int TILE = 32;                    // envs per tile == lanes per warp
+constexpr int OBS_TILE_BYTES = OBS_BYTES * TILE;  // 4704, a multiple of 16
+constexpr int OBS_WORDS = 37;               // ceil(147 / 4)
+constexpr int MAX_DIM = 26;                 // W, H <= 26 (the OOB bit mask is built in 32 bits)
+
+// core/constants.py:25-37
+enum : uint32_t { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
+                  T_BOX = 7, T_GOAL = 8, T_LAVA = 9, T_AGENT = 10, T4_DOOR_CLOSED = 11, T4_DOOR_LOCKED = 12 };
+enum : uint32_t { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5 };
+// core/actions.py:7-20
+enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
+
+constexpr uint32_t OPAQUE_BIT = 0x80u;
+constexpr uint32_t CODE_EMPTY = T_EMPTY;
+constexpr uint32_t CODE_WALL = T_WALL | (C_GREY << 4) | OPAQUE_BIT;  // 0xD2, Wall() (world_object.py:160-162)
+constexpr uint32_t CODE_WALL4 = CODE_WALL * 0x01010101u;
+constexpr uint32_t CODE_GOAL = T_GOAL | (C_GREEN << 4);
+constexpr uint32_t CODE_LAVA = T_LAVA | (C_RED << 4);
+
+// agent flags (second word of the agent record, bits 8..)
+constexpr uint32_t FLAG_FRESH = 1u;    // state was just regenerated: the next step emits the reset obs
+constexpr uint32_t FLAG_PENDING = 2u;  // episode ended last step (SyncVectorEnv._autoreset_envs[i])
+
+enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS = 3 };
+enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
+
+// (type, colour, state) -> cell code. None/unseen/agent all mean "no object" (WorldObj.decode,
+// world_object.py:77-78) and encode as (1,0,0) (grid.py:258-261).
+MG_HD uint32_t encode_cell(uint32_t type, uint32_t color, uint32_t state) {
+  if (type == T_EMPTY || type == T_UNSEEN || type >= T_AGENT) return CODE_EMPTY;
+  uint32_t t4 = type, opaque = 0;
+  if (type == T_DOOR) {
+    t4 = state == 0 ? (uint32_t)T_DOOR : (state == 1 ? (uint32_t)T4_DOOR_CLOSED : (uint32_t)T4_DOOR_LOCKED);
+    opaque = state != 0;
+  } else if (type == T_WALL) {
+    opaque = 1;
+  }
+  return t4 | ((color & 7u) << 4) | (opaque << 7);
+}
+// cell code -> type | colour << 8 | state << 16 (WorldObj.encode / Door.encode, world_object.py:65-67,196-212)
+MG_HD uint32_t decode_cell(uint32_t code) {
+  uint32_t t4 = code & 15u, color = (code >> 4) & 7u;
+  if (t4 == T_UNSEEN) return 0;
+  if (t4 == T_EMPTY) return T_EMPTY;
+  if (t4 == T4_DOOR_CLOSED) return T_DOOR | (color << 8) | (1u << 16);
+  if (t4 == T4_DOOR_LOCKED) return T_DOOR | (color << 8) | (2u << 16);
+  return t4 | (color << 8);
+}
+
+struct Geom {
+  int W, H;
+  int lswR, lswC;  // words per line of R / C
+  int offC;        // word offset of array C inside an env
+  int wpe;         // words per env (tile = wpe * 32 words)
+};
+
+MG_HD Geom make_geom(int W, int H) {
+  Geom g;
+  g.W = W; g.H = H;
+  g.lswR = (W + 3) >> 2;
+  g.lswC = (H + 3) >> 2;
+  g.offC = (H + 2) * g.lswR;
+  g.wpe = g.offC + (W + 2) * g.lswC;
+  return g;
+}
+
+struct RngRec {  // 48 bytes, 16-byte aligned
+  uint64_t state_hi, state_lo, inc_hi, inc_lo;
+  uint32_t has_uint32, uinteger;
+  uint64_t pad;
+};
+
+struct Params {
+  Geom g;
+  int n_envs, n_tiles;
+  int max_steps, see_through, mode, kind;
+  int kp[8];                // generator parameters (see include/minigrid_b200.h)
+  uint32_t *grid;           // [n_tiles][wpe][32]
+  uint4 *agent;             // [n_tiles * 32]
+  RngRec *rng;              // [n_tiles * 32]
+  const double *reward_lut; // [max_steps + 1], 1 - 0.9 * (k / max_steps) computed on the host in IEEE double
+  const uint32_t *cell_lut; // [256] decode_cell()
+  int *err;                 // sticky error word
+  int *list[2];             // compacted env ids awaiting reset (ping-pong)
+  int *count[2];
+  int64_t first_env_index;
+};
+
+// word index of byte (line, pos) and helpers for the interleaved tile
+MG_HD int r_word(const Geom &g, int x, int y) { return (y + 1) * g.lswR + (x >> 2); }
+MG_HD int c_word(const Geom &g, int x, int y) { return g.offC + (x + 1) * g.lswC + (y >> 2); }
+
+MG_D uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+MG_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// bit i (i < 4) -> bit 8i
+MG_HD uint32_t spread4(uint32_t b) { return (b * 0x00204081u) & 0x01010101u; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+#endif
+
+}  // namespace mg

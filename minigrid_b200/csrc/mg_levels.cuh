@@ -1,0 +1,203 @@
+// mg_levels.cuh — the four level generators (_gen_grid) as "draw the integers, then evaluate a cell function".
+//   envs/empty.py:97-114, envs/doorkey.py:74-99, envs/crossing.py:131-188, envs/fourrooms.py:78-126,
+//   place_obj / place_agent rejection sampling: minigrid_env.py:313-397.
+// A finished level is a pure function of a handful of drawn integers, so generation is two phases:
+//   draw   the RNG calls in exactly the reference's order (rejection loops test the closed-form cell
+//          function instead of reading a half-built grid);
+//   fill   every word of the env's two arrays is computed from the cell function and stored once.
+#pragma once
+#include "mg_common.cuh"
+#include "mg_pcg64.cuh"
+
+namespace mg {
+
+struct Level {
+  int ax, ay, adir;
+  int a, b, c, d, e, f;        // kind-specific drawn integers
+  uint32_t rv, rh;             // crossing: river position bit masks (vertical = column x, horizontal = row y)
+  uint32_t open_row[MAX_DIM];  // crossing: openings, bit x of row y
+};
+
+// ---- cell functions: the finished grid of each generator ----
+MG_D bool on_border(const Geom &g, int x, int y) { return x == 0 || y == 0 || x == g.W - 1 || y == g.H - 1; }
+
+// envs/empty.py:97-114
+MG_D uint32_t cell_empty(const Geom &g, const Level &, int x, int y) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  if (x == g.W - 2 && y == g.H - 2) return CODE_GOAL;
+  return CODE_EMPTY;
+}
+// envs/doorkey.py:74-99: a = splitIdx, b = doorIdx, (c, d) = key position
+MG_D uint32_t cell_doorkey(const Geom &g, const Level &L, int x, int y) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  if (x == L.a) return y == L.b ? (T4_DOOR_LOCKED | (C_YELLOW << 4) | OPAQUE_BIT) : CODE_WALL;
+  if (x == L.c && y == L.d) return T_KEY | (C_YELLOW << 4);
+  if (x == g.W - 2 && y == g.H - 2) return CODE_GOAL;
+  return CODE_EMPTY;
+}
+// envs/crossing.py:131-188
+MG_D uint32_t cell_crossing(const Geom &g, const Level &L, int x, int y, uint32_t obstacle) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  if ((L.open_row[y] >> x) & 1u) return CODE_EMPTY;
+  if (((L.rv >> x) & 1u) || ((L.rh >> y) & 1u)) return obstacle;
+  if (x == g.W - 2 && y == g.H - 2) return CODE_GOAL;
+  return CODE_EMPTY;
+}
+// envs/fourrooms.py:78-126: gaps (9,a) (b,9) (c,9) (9,d) for the 19x19 layout; (e, f) = goal
+MG_D uint32_t cell_fourrooms_walls(const Geom &g, const Level &L, int x, int y) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  const int xm = g.W / 2, ym = g.H / 2;
+  if (x == xm && y < g.H - 1) return (y == L.a || y == L.d) ? CODE_EMPTY : CODE_WALL;
+  if (y == ym && x < g.W - 1) return (x == L.b || x == L.c) ? CODE_EMPTY : CODE_WALL;
+  return CODE_EMPTY;
+}
+MG_D uint32_t cell_fourrooms(const Geom &g, const Level &L, int x, int y) {
+  if (x == L.e && y == L.f) return CODE_GOAL;
+  return cell_fourrooms_walls(g, L, x, y);
+}
+
+template <int KIND>
+MG_D uint32_t cell_of(const Params &p, const Level &L, int x, int y) {
+  if (KIND == KIND_EMPTY) return cell_empty(p.g, L, x, y);
+  if (KIND == KIND_DOORKEY) return cell_doorkey(p.g, L, x, y);
+  if (KIND == KIND_CROSSING) {
+    const uint32_t obstacle = (p.kp[1] == (int)T_LAVA) ? CODE_LAVA : CODE_WALL;
+    return cell_crossing(p.g, L, x, y, obstacle);
+  }
+  return cell_fourrooms(p.g, L, x, y);
+}
+
+// ---- draw phase ----
+template <int KIND>
+MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
+  const Geom &g = p.g;
+  const int W = g.W, H = g.H;
+  L.a = L.b = L.c = L.d = L.e = L.f = -1;
+  L.rv = L.rh = 0;
+  if (KIND == KIND_EMPTY) {
+    if (!p.kp[0]) { L.ax = p.kp[1]; L.ay = p.kp[2]; L.adir = p.kp[3]; }
+    else {  // place_agent(): minigrid_env.py:383-397 over the whole grid
+      for (;;) {
+        const int x = rng_integers(r, 0, W), y = rng_integers(r, 0, H);
+        if (cell_empty(g, L, x, y) != CODE_EMPTY) continue;
+        L.ax = x; L.ay = y;
+        break;
+      }
+      L.adir = rng_integers(r, 0, 4);
+    }
+  } else if (KIND == KIND_DOORKEY) {
+    const int split = rng_integers(r, 2, W - 2);
+    L.a = split;
+    for (;;) {  // place_agent(size=(splitIdx, height)); door and key do not exist yet
+      const int x = rng_integers(r, 0, split), y = rng_integers(r, 0, H);
+      if (x == 0 || y == 0 || y == H - 1) continue;
+      L.ax = x; L.ay = y;
+      break;
+    }
+    L.adir = rng_integers(r, 0, 4);
+    L.b = rng_integers(r, 1, H - 2);
+    for (;;) {  // place_obj(Key, top=(0,0), size=(splitIdx, height)): empty cell that is not the agent's
+      const int x = rng_integers(r, 0, split), y = rng_integers(r, 0, H);
+      if (x == 0 || y == 0 || y == H - 1) continue;
+      if (x == L.ax && y == L.ay) continue;
+      L.c = x; L.d = y;
+      break;
+    }
+  } else if (KIND == KIND_CROSSING) {
+    L.ax = 1; L.ay = 1; L.adir = 0;
+    for (int y = 0; y < MAX_DIM; ++y) L.open_row[y] = 0;
+    // rivers = [(v, i) for i in range(2, H-2, 2)] + [(h, j) for j in range(2, W-2, 2)]; entry = pos | dir << 8
+    int riv[2 * MAX_DIM];
+    int n = 0;
+    for (int i = 2; i < H - 2; i += 2) riv[n++] = i;
+    for (int j = 2; j < W - 2; j += 2) riv[n++] = j | 256;
+    for (int i = n - 1; i >= 1; --i) {  // np_random.shuffle(list)
+      const int j = (int)rng_interval(r, (uint32_t)i);
+      const int t = riv[i]; riv[i] = riv[j]; riv[j] = t;
+    }
+    if (p.kp[0] < n) n = p.kp[0];
+    int nv = 0, nh = 0;
+    for (int k = 0; k < n; ++k) {
+      if (riv[k] & 256) { L.rh |= 1u << (riv[k] & 255); ++nh; } else { L.rv |= 1u << riv[k]; ++nv; }
+    }
+    // path = [h] * len(rivers_v) + [v] * len(rivers_h), shuffled; 1 = h
+    int path[2 * MAX_DIM];
+    const int np_ = nv + nh;
+    for (int k = 0; k < np_; ++k) path[k] = k < nv ? 1 : 0;
+    for (int i = np_ - 1; i >= 1; --i) {
+      const int j = (int)rng_interval(r, (uint32_t)i);
+      const int t = path[i]; path[i] = path[j]; path[j] = t;
+    }
+    // limits_v = [0] + sorted(rivers_v) + [H-1]: walk the sorted positions through the bit masks
+    int lim_v_lo = 0, lim_h_lo = 0;                    // limits_v[room_i], limits_h[room_j]
+    for (int k = 0; k < np_; ++k) {
+      // next limit above the current one
+      const uint32_t mv = L.rv & ~((2u << lim_v_lo) - 1u), mh = L.rh & ~((2u << lim_h_lo) - 1u);
+      const int lim_v_hi = mv ? (__ffs(mv) - 1) : H - 1;  // limits_v[room_i + 1]
+      const int lim_h_hi = mh ? (__ffs(mh) - 1) : W - 1;  // limits_h[room_j + 1]
+      int i, j;
+      if (path[k]) {  // h: cross the next vertical river at a random row of the current room
+        i = lim_v_hi;
+        j = lim_h_lo + 1 + rng_integers(r, 0, lim_h_hi - lim_h_lo - 1);  // choice(range(lo+1, hi))
+        lim_v_lo = lim_v_hi;
+      } else {
+        i = lim_v_lo + 1 + rng_integers(r, 0, lim_v_hi - lim_v_lo - 1);
+        j = lim_h_hi;
+        lim_h_lo = lim_h_hi;
+      }
+      L.open_row[j] |= 1u << i;
+    }
+  } else {  // FOURROOMS
+    const int rw = W / 2, rh = H / 2;
+    // loop order j (rows of rooms) then i: (0,0): vertical wall gap, horizontal wall gap; (1,0): horizontal;
+    // (0,1): vertical; (1,1): nothing   -> fourrooms.py:93-110
+    L.a = rng_integers(r, 1, rh);               // (xR=rw, y in [1, rh))
+    L.b = rng_integers(r, 1, rw);               // (x in [1, rw), yB=rh)
+    L.c = rng_integers(r, rw + 1, 2 * rw);      // (x in [rw+1, 2rw), yB=rh)
+    L.d = rng_integers(r, rh + 1, 2 * rh);      // (xR=rw, y in [rh+1, 2rh))
+    for (;;) {  // place_agent()
+      const int x = rng_integers(r, 0, W), y = rng_integers(r, 0, H);
+      if (cell_fourrooms_walls(g, L, x, y) != CODE_EMPTY) continue;
+      L.ax = x; L.ay = y;
+      break;
+    }
+    L.adir = rng_integers(r, 0, 4);
+    for (;;) {  // place_obj(Goal())
+      const int x = rng_integers(r, 0, W), y = rng_integers(r, 0, H);
+      if (cell_fourrooms_walls(g, L, x, y) != CODE_EMPTY) continue;
+      if (x == L.ax && y == L.ay) continue;
+      L.e = x; L.f = y;
+      break;
+    }
+  }
+}
+
+// fill phase: both arrays of one env; col points at the env's lane column of its tile (word w at col[w * 32])
+template <int KIND>
+MG_D void fill_level(const Params &p, const Level &L, uint32_t *col) {
+  const Geom &g = p.g;
+  for (int ly = -1; ly <= g.H; ++ly)
+    for (int wi = 0; wi < g.lswR; ++wi) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int x = 4 * wi + b;
+        const uint32_t c = (ly < 0 || ly >= g.H || x >= g.W) ? CODE_WALL : cell_of<KIND>(p, L, x, ly);
+        word |= c << (8 * b);
+      }
+      col[((ly + 1) * g.lswR + wi) * 32] = word;
+    }
+  for (int lx = -1; lx <= g.W; ++lx)
+    for (int wi = 0; wi < g.lswC; ++wi) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int y = 4 * wi + b;
+        const uint32_t c = (lx < 0 || lx >= g.W || y >= g.H) ? CODE_WALL : cell_of<KIND>(p, L, lx, y);
+        word |= c << (8 * b);
+      }
+      col[(g.offC + (lx + 1) * g.lswC + wi) * 32] = word;
+    }
+}
+
+}  // namespace mg

@@ -1,0 +1,162 @@
+// mg_obs.cuh — the egocentric 7x7x3 observation (MiniGridEnv.gen_obs, minigrid_env.py:597-650) for one
+// environment per lane, computed entirely in registers from the lane's interleaved grid tile.
+//
+// Reference pipeline                                   here
+//   get_view_exts + Grid.slice   (:453-484, grid.py:124)   closed form: world = agent + d*(6-vy) + r*(vx-3)
+//   (dir+1) x Grid.rotate_left   (grid.py:110-122)         -> a view column vx is 7 consecutive bytes of one
+//                                                          line of array R (dir 0/2) or C (dir 1/3), read
+//                                                          forwards or backwards: 3 word loads + 2 funnel
+//                                                          shifts + 2 byte permutes per column
+//   out of bounds -> Wall()      (grid.py:136-139)         ring lines + a per-step byte mask
+//   Grid.process_vis             (grid.py:291-328)         49-bit boards (byte = view row, bit = view column):
+//                                                          carry-chain fill rightwards, Kogge-Stone leftwards
+//   carry overlay                (minigrid_env.py:623-630) one byte permute
+//   Grid.encode(vis_mask)        (grid.py:244-268)         256-entry (type,colour,state) table + byte permutes
+//                                                          straight into the 147-byte C-order [vx][vy][c] stream
+#pragma once
+#include "mg_common.cuh"
+
+namespace mg {
+
+// one word of the lane's tile. base already points at this lane's column: word w is base[w * 32].
+template <bool SMEM>
+MG_D uint32_t tile_word(const uint32_t *base, int w) {
+#ifdef __CUDA_ARCH__
+  if (SMEM) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(base) + (uint32_t)(w << 7)));
+    return v;
+  }
+#endif
+  return base[w << 5];
+}
+
+// Grid.process_vis (grid.py:291-328) on bit boards. op*: opaque cells, v*: visible cells; byte j of
+// (lo, hi) is view row vy = j (hi holds rows 4..6), bit i is view column vx = i. The agent is at (3, 6).
+MG_D void process_vis(uint32_t oplo, uint32_t ophi, uint32_t &vlo, uint32_t &vhi) {
+  uint32_t m = 1u << 3;
+  vlo = 0; vhi = 0;
+#pragma unroll
+  for (int j = VIEW - 1; j >= 0; --j) {
+    const uint32_t op = ((j < 4) ? (oplo >> (8 * j)) : (ophi >> (8 * (j - 4)))) & 0x7Fu;
+    const uint32_t p = op ^ 0x7Fu;  // see_behind
+    // first sweep, i = 0..5 ascending: a visible transparent cell lights i+1 (and i, i+1 of the row above).
+    // That recurrence is the carry chain of g + p with generate g = v & p, propagate p.
+    const uint32_t g = m & p;
+    const uint32_t c = (g + p) ^ g ^ p;
+    const uint32_t v1 = (m | c) & 0x7Fu;
+    const uint32_t a1 = v1 & p & 0x3Fu;
+    // second sweep, i = 6..1 descending: prefix fill towards bit 0 (Kogge-Stone, 3 rounds cover 7 bits)
+    uint32_t f = v1 & p, q = p;
+    f |= q & (f >> 1); q &= q >> 1;
+    f |= q & (f >> 2); q &= q >> 2;
+    f |= q & (f >> 4);
+    const uint32_t v2 = v1 | (f >> 1);
+    const uint32_t a2 = f & 0x7Eu;  // == v2 & p on i = 1..6
+    if (j < 4) vlo |= v2 << (8 * j); else vhi |= v2 << (8 * (j - 4));
+    m = (a1 | (a1 << 1) | a2 | (a2 >> 1)) & 0x7Fu;  // the `if j > 0` writes into row j-1
+  }
+}
+
+// Produces the 147-byte image of one env as 37 little-endian words S (byte 147 is zero).
+//   base   lane's tile column (shared or global), lut: 256-entry decode table (shared or global)
+template <bool SEE_THROUGH, bool SMEM>
+MG_D void gen_obs_words(const Geom &g, const uint32_t *base, const uint32_t *lut,
+                                              int ax, int ay, int dir, uint32_t carry, uint32_t (&S)[OBS_WORDS]) {
+  const bool useC = dir & 1;
+  const bool rev = dir < 2;
+  const int lc = useC ? ax : ay;       // line coordinate of the agent in the chosen array
+  const int pc = useC ? ay : ax;       // position inside a line
+  const int lstep = (dir == 0 || dir == 3) ? 1 : -1;
+  const int nlines = useC ? g.W : g.H;
+  const int plen = useC ? g.H : g.W;
+  const int lsw = useC ? g.lswC : g.lswR;
+  const int abase = useC ? g.offC : 0;
+  const int p0 = rev ? pc : pc - 6;    // first byte position of every 7-byte run
+  const int wi0 = p0 >> 2;
+  const uint32_t sh = (uint32_t)(p0 & 3) * 8u;
+  const int k0 = clampi(wi0, 0, lsw - 1), k1 = clampi(wi0 + 1, 0, lsw - 1), k2 = clampi(wi0 + 2, 0, lsw - 1);
+  // bytes whose position falls outside [0, plen) read as grey wall (Grid.slice, grid.py:136-139)
+  uint32_t valid7 = ((((1u << plen) - 1u) << 6) >> (p0 + 6)) & 0x7Fu;
+  if (rev) valid7 = __brev(valid7) >> 25;
+  const uint32_t mlo = spread4(valid7 & 0xFu) * 0xFFu;
+  const uint32_t mhi = spread4(valid7 >> 4) * 0xFFu;
+  const uint32_t selLo = rev ? 0x3456u : 0x3210u;
+  const uint32_t selHi = rev ? 0x7012u : 0x7654u;
+
+  uint32_t clo[VIEW], chi[VIEW];
+  uint32_t oplo = 0, ophi = 0;
+#pragma unroll
+  for (int vx = 0; vx < VIEW; ++vx) {
+    const int l = clampi(lc + lstep * (vx - 3), -1, nlines) + 1;
+    const int rw = abase + l * lsw;
+    const uint32_t w0 = tile_word<SMEM>(base, rw + k0);
+    const uint32_t w1 = tile_word<SMEM>(base, rw + k1);
+    const uint32_t w2 = tile_word<SMEM>(base, rw + k2);
+    const uint32_t a = __funnelshift_r(w0, w1, sh);
+    const uint32_t b = __funnelshift_r(w1, w2, sh);
+    uint32_t lo = prmt(a, b, selLo);
+    uint32_t hi = prmt(a, b, selHi);
+    lo = (lo & mlo) | (CODE_WALL4 & ~mlo);
+    hi = (hi & mhi) | ((CODE_WALL4 & 0x00FFFFFFu) & ~mhi);
+    clo[vx] = lo; chi[vx] = hi;
+    if (!SEE_THROUGH) {
+      oplo |= ((lo >> 7) & 0x01010101u) << vx;
+      ophi |= ((hi >> 7) & 0x01010101u) << vx;
+    }
+  }
+  if (!SEE_THROUGH) {
+    uint32_t vlo, vhi;
+    process_vis(oplo, ophi, vlo, vhi);
+#pragma unroll
+    for (int vx = 0; vx < VIEW; ++vx) {
+      clo[vx] &= ((vlo >> vx) & 0x01010101u) * 0xFFu;  // unseen -> code 0 -> (0,0,0)
+      chi[vx] &= ((vhi >> vx) & 0x01010101u) * 0xFFu;
+    }
+  }
+  // the agent's own view cell (3,6) shows what it carries, else empty (minigrid_env.py:623-630)
+  chi[3] = prmt(chi[3], carry ? carry : CODE_EMPTY, 0x3410u);
+
+  // Grid.encode: image[vx][vy][c], i.e. triple q = 7*vx + vy occupies stream bytes 3q..3q+2
+  uint32_t T[VIEW * VIEW + 1];
+#pragma unroll
+  for (int vx = 0; vx < VIEW; ++vx) {
+#pragma unroll
+    for (int vy = 0; vy < VIEW; ++vy) {
+      const uint32_t word = (vy < 4) ? clo[vx] : chi[vx];
+      const uint32_t code = (word >> (8 * (vy & 3))) & 0xFFu;
+      T[vx * VIEW + vy] = lut[code];
+    }
+  }
+  T[VIEW * VIEW] = 0;
+#pragma unroll
+  for (int j = 0; j < OBS_WORDS; ++j) {
+    const int a = (4 * j) / 3, r = 4 * j - 3 * a;
+    S[j] = prmt(T[a], T[a + 1], r == 0 ? 0x4210u : (r == 1 ? 0x5421u : 0x6542u));
+  }
+}
+
+// Stage one warp's 32 images into shared memory exactly as they lie in the [n][7][7][3] output
+// (147-byte stride, so lane L starts at byte 147 L = word (147 L) / 4 plus (L & 3) bytes). Lane L skips its
+// first (L & 3) bytes; they travel in the last word written by lane L-1.
+// n0 is word 0 of lane L+1's stream (a warp shuffle on the device).
+MG_D void emit_obs_staged(uint32_t *stage, int lane, const uint32_t (&S)[OBS_WORDS], uint32_t n0) {
+  const uint32_t o8 = (uint32_t)(lane & 3) * 8u;
+  uint32_t *dst = stage + ((OBS_BYTES * lane + 3) >> 2);
+#pragma unroll
+  for (int i = 0; i < OBS_WORDS - 1; ++i) dst[i] = __funnelshift_r(S[i], S[i + 1], o8);
+  const uint32_t s36 = prmt(S[OBS_WORDS - 1], n0, 0x4210u);  // own bytes 144..146, then the next lane's byte 0
+  if ((lane & 3) != 3) dst[OBS_WORDS - 1] = __funnelshift_r(s36, n0 >> 8, o8);
+}
+
+// Slow emitter for the rare paths (reset kernel, partial tiles): plain byte stores.
+MG_D void emit_obs_bytes(uint8_t *dst, const uint32_t (&S)[OBS_WORDS]) {
+#pragma unroll
+  for (int w = 0; w < OBS_WORDS; ++w) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (4 * w + b < OBS_BYTES) dst[4 * w + b] = (uint8_t)(S[w] >> (8 * b));
+  }
+}
+
+}  // namespace mg

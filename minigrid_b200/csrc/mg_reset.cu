@@ -1,0 +1,71 @@
+// mg_reset.cu — K2: MiniGridEnv.reset (minigrid_env.py:119-157) = per-kind _gen_grid with numpy-exact RNG,
+// one lane per environment, driven either over every env (initial reset) or over the compacted list of
+// environments whose episode just ended (autoreset). Also the seeding kernel (SeedSequence -> PCG64).
+// The generators themselves live in mg_levels.cuh.
+#include "mg_common.cuh"
+#include "mg_obs.cuh"
+#include "mg_pcg64.cuh"
+#include "mg_levels.cuh"
+
+namespace mg {
+
+template <int KIND>
+__global__ void __launch_bounds__(128)
+k_reset(Params p, const int *__restrict__ list, const int *__restrict__ count, uint8_t *__restrict__ obs,
+        int32_t *__restrict__ dir_out, int set_fresh) {
+  const int n = list ? *count : p.n_envs;
+  const Geom &g = p.g;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int env = list ? list[idx] : idx;
+    Pcg r = load_rng(p.rng + env);
+    Level L;
+    draw_level<KIND>(p, r, L);
+    store_rng(p.rng + env, r);
+    uint32_t *col = p.grid + (size_t)(env >> 5) * g.wpe * 32 + (env & 31);
+    fill_level<KIND>(p, L, col);
+    uint4 rec;
+    rec.x = (uint32_t)L.ax | ((uint32_t)L.ay << 8);
+    rec.y = (uint32_t)L.adir | ((set_fresh ? FLAG_FRESH : 0u) << 8);
+    rec.z = 0;  // carrying = None
+    rec.w = 0;  // step_count = 0
+    p.agent[env] = rec;
+    if (dir_out) dir_out[env] = L.adir;
+    if (obs) {
+      uint32_t S[OBS_WORDS];
+      if (p.see_through) gen_obs_words<true, false>(g, col, p.cell_lut, L.ax, L.ay, L.adir, 0u, S);
+      else gen_obs_words<false, false>(g, col, p.cell_lut, L.ax, L.ay, L.adir, 0u, S);
+      emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
+    }
+  }
+}
+
+cudaError_t launch_reset(const Params &p, const int *list, const int *count, uint8_t *obs, int32_t *dir,
+                         int set_fresh, cudaStream_t stream) {
+  // the list length lives on the device: a fixed grid with a grid-stride loop needs no host round trip
+  const int threads = 128;
+  int blocks = list ? 148 * 4 : (p.n_envs + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;
+  switch (p.kind) {
+    case KIND_EMPTY: k_reset<KIND_EMPTY><<<blocks, threads, 0, stream>>>(p, list, count, obs, dir, set_fresh); break;
+    case KIND_DOORKEY: k_reset<KIND_DOORKEY><<<blocks, threads, 0, stream>>>(p, list, count, obs, dir, set_fresh); break;
+    case KIND_CROSSING: k_reset<KIND_CROSSING><<<blocks, threads, 0, stream>>>(p, list, count, obs, dir, set_fresh); break;
+    default: k_reset<KIND_FOURROOMS><<<blocks, threads, 0, stream>>>(p, list, count, obs, dir, set_fresh); break;
+  }
+  return cudaGetLastError();
+}
+
+// np_random = Generator(PCG64(SeedSequence(seed)))
+__global__ void k_seed(Params p, const uint64_t *__restrict__ seeds, uint64_t base) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.n_envs) return;
+  const uint64_t s = seeds ? seeds[env] : base + (uint64_t)p.first_env_index + (uint64_t)env;
+  const Pcg r = seed_pcg64(s);
+  store_rng(p.rng + env, r);
+}
+
+cudaError_t launch_seed(const Params &p, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream) {
+  k_seed<<<(p.n_envs + 127) / 128, 128, 0, stream>>>(p, seeds_dev, base);
+  return cudaGetLastError();
+}
+
+}  // namespace mg

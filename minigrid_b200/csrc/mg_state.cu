@@ -1,0 +1,134 @@
+// mg_state.cu — K3 (FullyObsWrapper.observation, wrappers.py:419-426) and the state exchange kernels
+// behind mg_get_state / mg_set_state (the checkpoint / parity-injection boundary).
+#include "mg_common.cuh"
+
+namespace mg {
+
+__device__ __forceinline__ uint32_t load_code(const Params &p, int env, int x, int y) {
+  const uint32_t *col = p.grid + (size_t)(env >> 5) * p.g.wpe * 32 + (env & 31);
+  return (col[c_word(p.g, x, y) * 32] >> (8 * (y & 3))) & 0xFFu;
+}
+
+// out[n][W][H][3] = grid.encode(), agent cell = (OBJECT_TO_IDX["agent"], COLOR_TO_IDX["red"], agent_dir).
+// One thread per (env, cell); array C is [x][y] ordered like the output.
+__global__ void k_full_obs(Params p, uint8_t *__restrict__ out, int with_agent) {
+  const int cells = p.g.W * p.g.H;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)p.n_envs * cells) return;
+  const int env = (int)(gid / cells), c = (int)(gid % cells);
+  const int x = c / p.g.H, y = c % p.g.H;
+  uint32_t t = __ldg(p.cell_lut + load_code(p, env, x, y));
+  if (with_agent) {
+    const uint4 rec = p.agent[env];
+    if ((int)(rec.x & 0xFF) == x && (int)((rec.x >> 8) & 0xFF) == y) t = T_AGENT | (C_RED << 8) | ((rec.y & 3u) << 16);
+  }
+  uint8_t *o = out + gid * 3;
+  o[0] = (uint8_t)t; o[1] = (uint8_t)(t >> 8); o[2] = (uint8_t)(t >> 16);
+}
+
+__global__ void k_get_agent(Params p, int32_t *__restrict__ agent, uint64_t *__restrict__ rng, uint8_t *__restrict__ pending) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.n_envs) return;
+  const uint4 rec = p.agent[env];
+  if (agent) {
+    int32_t *a = agent + (size_t)env * 6;
+    a[0] = rec.x & 0xFF; a[1] = (rec.x >> 8) & 0xFF; a[2] = rec.y & 3;
+    a[3] = rec.z ? (int32_t)(rec.z & 15u) : -1; a[4] = rec.z ? (int32_t)((rec.z >> 4) & 7u) : 0; a[5] = (int32_t)rec.w;
+  }
+  if (rng) {
+    const RngRec r = p.rng[env];
+    uint64_t *o = rng + (size_t)env * 6;
+    o[0] = r.state_hi; o[1] = r.state_lo; o[2] = r.inc_hi; o[3] = r.inc_lo; o[4] = r.has_uint32; o[5] = r.uinteger;
+  }
+  if (pending) pending[env] = ((rec.y >> 8) & FLAG_PENDING) ? 1 : 0;
+}
+
+// grid[n][W][H][3] -> both arrays of every env. One thread per (env, cell): two byte stores.
+__global__ void k_set_grid(Params p, const uint8_t *__restrict__ grid) {
+  const int cells = p.g.W * p.g.H;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)p.n_envs * cells) return;
+  const int env = (int)(gid / cells), c = (int)(gid % cells);
+  const int x = c / p.g.H, y = c % p.g.H;
+  const uint8_t *in = grid + gid * 3;
+  const uint8_t code = (uint8_t)encode_cell(in[0], in[1], in[2]);
+  uint8_t *col = reinterpret_cast<uint8_t *>(p.grid + (size_t)(env >> 5) * p.g.wpe * 32 + (env & 31));
+  col[(size_t)r_word(p.g, x, y) * 128 + (x & 3)] = code;
+  col[(size_t)c_word(p.g, x, y) * 128 + (y & 3)] = code;
+}
+
+// cur: the list the next mg_step will consume (NEXT_STEP). Rebuilt from the pending flags.
+__global__ void k_set_agent(Params p, const int32_t *__restrict__ agent, const uint64_t *__restrict__ rng,
+                            const uint8_t *__restrict__ pending, int cur) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.n_envs) return;
+  uint4 rec = p.agent[env];
+  if (agent) {
+    const int32_t *a = agent + (size_t)env * 6;
+    rec.x = (uint32_t)(a[0] & 0xFF) | ((uint32_t)(a[1] & 0xFF) << 8);
+    rec.y = (rec.y & ~3u) | (uint32_t)(a[2] & 3);
+    rec.z = a[3] >= 0 ? ((uint32_t)(a[3] & 15) | ((uint32_t)(a[4] & 7) << 4)) : 0u;
+    rec.w = (uint32_t)a[5];
+    rec.y &= ~(FLAG_FRESH << 8);
+  }
+  if (pending) {
+    uint32_t flags = (rec.y >> 8) & ~FLAG_PENDING;
+    if (pending[env]) {
+      flags |= FLAG_PENDING;
+      p.list[cur][atomicAdd(p.count[cur], 1)] = env;
+    }
+    rec.y = (rec.y & 0xFFu) | (flags << 8);
+  }
+  p.agent[env] = rec;
+  if (rng) {
+    const uint64_t *i = rng + (size_t)env * 6;
+    RngRec r;
+    r.state_hi = i[0]; r.state_lo = i[1]; r.inc_hi = i[2]; r.inc_lo = i[3];
+    r.has_uint32 = (uint32_t)i[4]; r.uinteger = (uint32_t)i[5]; r.pad = 0;
+    p.rng[env] = r;
+  }
+}
+
+// arena initialisation: every byte a grey wall (ring lines and line padding stay that way), agents parked
+// at (1,1) facing right so that padded lanes of a partial tile compute something harmless.
+__global__ void k_init(Params p) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long words = (long long)p.n_tiles * p.g.wpe * 32;
+  if (gid < words) p.grid[gid] = CODE_WALL4;
+  if (gid < (long long)p.n_tiles * 32) {
+    p.agent[gid] = make_uint4(1u | (1u << 8), 0u, 0u, 0u);
+    RngRec r;
+    r.state_hi = r.state_lo = r.inc_hi = 0; r.inc_lo = 1; r.has_uint32 = r.uinteger = 0; r.pad = 0;
+    p.rng[gid] = r;
+  }
+}
+
+cudaError_t launch_full_obs(const Params &p, uint8_t *out, int with_agent, cudaStream_t stream) {
+  const long long total = (long long)p.n_envs * p.g.W * p.g.H;
+  k_full_obs<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, out, with_agent);
+  return cudaGetLastError();
+}
+cudaError_t launch_get_state(const Params &p, uint8_t *grid, int32_t *agent, uint64_t *rng, uint8_t *pending, cudaStream_t stream) {
+  if (grid) {
+    cudaError_t e = launch_full_obs(p, grid, 0, stream);
+    if (e != cudaSuccess) return e;
+  }
+  if (agent || rng || pending) k_get_agent<<<(p.n_envs + 127) / 128, 128, 0, stream>>>(p, agent, rng, pending);
+  return cudaGetLastError();
+}
+cudaError_t launch_set_state(const Params &p, const uint8_t *grid, const int32_t *agent, const uint64_t *rng,
+                             const uint8_t *pending, int cur, cudaStream_t stream) {
+  if (grid) {
+    const long long total = (long long)p.n_envs * p.g.W * p.g.H;
+    k_set_grid<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, grid);
+  }
+  if (agent || rng || pending) k_set_agent<<<(p.n_envs + 127) / 128, 128, 0, stream>>>(p, agent, rng, pending, cur);
+  return cudaGetLastError();
+}
+cudaError_t launch_init(const Params &p, cudaStream_t stream) {
+  const long long words = (long long)p.n_tiles * p.g.wpe * 32;
+  k_init<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace mg

@@ -1,0 +1,215 @@
+// mg_step.cu — K1: MiniGridEnv.step (minigrid_env.py:525-595) fused with gen_obs (:597-650) for a batch.
+//
+// One warp = one tile of 32 environments, one lane per environment.
+//   1. lane 0 issues a TMA bulk copy (cp.async.bulk -> SASS UBLKCP) of the tile's interleaved grid words
+//      into shared memory and arms an mbarrier with the byte count; meanwhile every lane loads its
+//      action and 16-byte agent record with coalesced loads.
+//   2. transition: the 7-action rule on (agent, carrying, the one cell in front), predicated, with the
+//      rare cell mutation written to the staged tile and straight back to HBM (2 byte stores).
+//   3. observation in registers (mg_obs.cuh), staged to shared memory in output layout, then one TMA bulk
+//      store of the warp's 32 x 147 = 4704 contiguous bytes.
+//   4. coalesced stores of direction / reward / terminated / truncated and the agent record; environments
+//      whose episode ended are appended (warp-aggregated atomic) to the compacted reset list that K2 eats.
+#include "mg_common.cuh"
+#include "mg_obs.cuh"
+#include "mg_transition.cuh"
+
+namespace mg {
+
+constexpr int STEP_WARPS = 4;
+constexpr int STEP_THREADS = STEP_WARPS * 32;
+constexpr int STAGE_WORDS = 1184;  // 4704 B rounded up to a multiple of 128 B
+
+__host__ __device__ inline size_t step_smem_bytes(const Geom &g) {
+  return 1024 /*cell lut*/ + (size_t)STEP_WARPS * ((size_t)g.wpe * 128 + STAGE_WORDS * 4) + 64 /*mbarriers*/;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+template <typename ActT>
+__device__ __forceinline__ int load_action(const void *actions, int env) {
+  return (int)reinterpret_cast<const ActT *>(actions)[env];
+}
+
+template <bool SEE_THROUGH, typename ActT>
+__global__ void __launch_bounds__(STEP_THREADS)
+k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out,
+       double *__restrict__ reward_out, uint8_t *__restrict__ term_out, uint8_t *__restrict__ trunc_out,
+       int cur /*list this step appends to*/, int obs_tma_ok) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const Geom g = p.g;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x * STEP_WARPS + warp;
+  const uint32_t tile_bytes = (uint32_t)g.wpe * 128u;
+
+  uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);
+  uint32_t *gtile = reinterpret_cast<uint32_t *>(smem_raw + 1024 + (size_t)warp * tile_bytes);
+  uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * tile_bytes + (size_t)warp * STAGE_WORDS * 4);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * (tile_bytes + STAGE_WORDS * 4));
+  const uint32_t bar = smem_u32(bars + warp);
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.count[cur ^ 1] = 0;  // the list K2 consumed before this launch
+
+  const bool tile_ok = tile < p.n_tiles;
+  uint32_t *gsrc = p.grid + (size_t)(tile_ok ? tile : 0) * g.wpe * 32;
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (tile_ok) {
+      mbar_expect_tx(bar, tile_bytes);
+      tma_load_1d(smem_u32(gtile), gsrc, tile_bytes, bar);
+    }
+  }
+  for (int i = threadIdx.x; i < 256; i += STEP_THREADS) lut[i] = p.cell_lut[i];
+  __syncthreads();
+  if (!tile_ok) return;
+
+  const int env = tile * TILE + lane;
+  const bool active = env < p.n_envs;
+  uint4 rec = p.agent[env];
+  int ax = rec.x & 0xFF, ay = (rec.x >> 8) & 0xFF;
+  int dir = rec.y & 3;
+  uint32_t flags = rec.y >> 8;
+  uint32_t carry = rec.z;
+  int steps = (int)rec.w;
+  int action = (actions != nullptr && active) ? load_action<ActT>(actions, env) : A_DONE;
+
+  mbar_wait(bar, 0);
+
+  const uint32_t *base = gtile + lane;
+  double reward = 0.0;
+  uint32_t terminated = 0, truncated = 0;
+  const bool fresh = (flags & FLAG_FRESH) != 0;
+  if (actions != nullptr && !fresh) {
+    // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
+    steps += 1;
+    int fx, fy;
+    front_pos(g, ax, ay, dir, fx, fy);
+    const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
+    const uint32_t fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
+    const StepOut so = transition(action, fc, fx, fy, ax, ay, dir, carry);
+    const uint32_t newc = so.newc;
+    terminated = so.terminated;
+    if (so.goal)  // _reward(), minigrid_env.py:240-245: host-computed table, never an FMA
+      reward = steps <= p.max_steps ? p.reward_lut[steps]
+                                    : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
+    if (so.bad_action) atomicOr(p.err, 1);  // ValueError("Unknown action"), minigrid_env.py:584-585
+    if (newc != fc && active) {
+      uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
+      uint8_t *gb = reinterpret_cast<uint8_t *>(gsrc);
+      const size_t ro = ((size_t)rw * 32 + lane) * 4 + (fx & 3), co = ((size_t)cw * 32 + lane) * 4 + (fy & 3);
+      sb[ro] = (uint8_t)newc; sb[co] = (uint8_t)newc;
+      gb[ro] = (uint8_t)newc; gb[co] = (uint8_t)newc;
+    }
+    truncated = steps >= p.max_steps;
+  }
+  flags &= ~FLAG_FRESH;
+  const bool done = (terminated | truncated) != 0;
+  if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
+  if (p.mode != AUTORESET_DISABLED) {
+    const unsigned ball = __ballot_sync(0xFFFFFFFFu, done && active);
+    if (ball) {
+      int basei = 0;
+      if (lane == 0) basei = atomicAdd(p.count[cur], __popc(ball));
+      basei = __shfl_sync(0xFFFFFFFFu, basei, 0);
+      if (done && active) p.list[cur][basei + __popc(ball & ((1u << lane) - 1u))] = env;
+    }
+  }
+
+  // ---- gen_obs ----
+  if (obs != nullptr) {
+    uint32_t S[OBS_WORDS];
+    gen_obs_words<SEE_THROUGH, true>(g, base, lut, ax, ay, dir, carry, S);
+    const bool full = (tile + 1) * TILE <= p.n_envs;
+    if (full && obs_tma_ok) {
+      emit_obs_staged(stage, lane, S, __shfl_down_sync(0xFFFFFFFFu, S[0], 1));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_1d(obs + (size_t)tile * OBS_TILE_BYTES, smem_u32(stage), OBS_TILE_BYTES);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else if (active) {
+      emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
+    }
+  }
+  if (active) {
+    rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
+    rec.y = (uint32_t)dir | (flags << 8);
+    rec.z = carry;
+    rec.w = (uint32_t)steps;
+    p.agent[env] = rec;
+    if (dir_out) dir_out[env] = dir;
+    if (reward_out) reward_out[env] = reward;
+    if (term_out) term_out[env] = (uint8_t)terminated;
+    if (trunc_out) trunc_out[env] = (uint8_t)truncated;
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <bool ST, typename ActT>
+static cudaError_t launch_step_t(const Params &p, const void *actions, uint8_t *obs, int32_t *dir, double *reward,
+                                 uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream) {
+  const size_t smem = step_smem_bytes(p.g);
+  auto kern = k_step<ST, ActT>;
+  const int blocks = (p.n_tiles + STEP_WARPS - 1) / STEP_WARPS;
+  const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
+  kern<<<blocks, STEP_THREADS, smem, stream>>>(p, actions, obs, dir, reward, term, trunc, cur, tma_ok);
+  return cudaGetLastError();
+}
+
+template <bool ST, typename ActT>
+static cudaError_t configure_one(size_t smem) {
+  return cudaFuncSetAttribute(k_step<ST, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+// opt in to the tile-dependent dynamic shared memory once per handle
+cudaError_t configure_step(const Params &p) {
+  const size_t smem = step_smem_bytes(p.g);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = configure_one<true, int32_t>(smem);
+  if (e == cudaSuccess) e = configure_one<true, int64_t>(smem);
+  if (e == cudaSuccess) e = configure_one<true, uint8_t>(smem);
+  if (e == cudaSuccess) e = configure_one<false, int32_t>(smem);
+  if (e == cudaSuccess) e = configure_one<false, int64_t>(smem);
+  if (e == cudaSuccess) e = configure_one<false, uint8_t>(smem);
+  return e;
+}
+
+cudaError_t launch_step(const Params &p, const void *actions, int action_dtype, uint8_t *obs, int32_t *dir,
+                        double *reward, uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream) {
+#define MG_DISPATCH(ST)                                                                                         \
+  switch (action_dtype) {                                                                                       \
+    case 1: return launch_step_t<ST, int64_t>(p, actions, obs, dir, reward, term, trunc, cur, stream);          \
+    case 2: return launch_step_t<ST, uint8_t>(p, actions, obs, dir, reward, term, trunc, cur, stream);          \
+    default: return launch_step_t<ST, int32_t>(p, actions, obs, dir, reward, term, trunc, cur, stream);         \
+  }
+  if (p.see_through) { MG_DISPATCH(true) } else { MG_DISPATCH(false) }
+#undef MG_DISPATCH
+}
+
+}  // namespace mg

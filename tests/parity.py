@@ -1,0 +1,75 @@
+"""Shared parity drivers: replay a golden fixture / lockstep against the oracle on any engine object that
+exposes reset/step/gen_obs/full_obs/get_state/set_state (the CUDA engine through the C-ABI, or the host
+emulation of its device headers)."""
+import numpy as np
+
+
+def check_rollout_fixture(make_env, g):
+    n = g["actions"].shape[1]
+    e = make_env(g["env_id"], n, g["mode"])
+    obs, d = e.reset(seed=g["seed"])
+    np.testing.assert_array_equal(np.asarray(obs), g["obs0"])
+    np.testing.assert_array_equal(np.asarray(d), g["dir0"])
+    st = e.get_state()
+    np.testing.assert_array_equal(st["grid"], g["grid0"])
+    np.testing.assert_array_equal(st["agent"], g["agent0"])
+    np.testing.assert_array_equal(st["rng"], g["rng0"])
+    np.testing.assert_array_equal(e.full_obs(), g["full_obs0"])
+    for t in range(g["actions"].shape[0]):
+        obs, d, r, te, tr = e.step(g["actions"][t])
+        np.testing.assert_array_equal(np.asarray(obs), g["obs"][t], err_msg=f"obs t={t}")
+        np.testing.assert_array_equal(np.asarray(d), g["dir"][t], err_msg=f"dir t={t}")
+        assert np.asarray(r, np.float64).tobytes() == g["reward"][t].tobytes(), f"reward bits t={t}"
+        np.testing.assert_array_equal(np.asarray(te, bool), g["terminated"][t], err_msg=f"terminated t={t}")
+        np.testing.assert_array_equal(np.asarray(tr, bool), g["truncated"][t], err_msg=f"truncated t={t}")
+    st = e.get_state()
+    for k in ("grid", "agent", "rng", "pending"):
+        np.testing.assert_array_equal(st[k], g[k], err_msg=k)
+    np.testing.assert_array_equal(e.full_obs(), g["full_obs"])
+
+
+def check_inject_fixture(make_env, g):
+    n = g["actions"].shape[1]
+    e = make_env(g["env_id"], n, "disabled")
+    e.reset(seed=0)
+    e.set_state(grid=g["grid0"], agent=g["agent0"])
+    obs, _ = e.gen_obs()
+    np.testing.assert_array_equal(np.asarray(obs), g["obs0"])
+    for t in range(g["actions"].shape[0]):
+        obs, d, r, te, tr = e.step(g["actions"][t])
+        np.testing.assert_array_equal(np.asarray(obs), g["obs"][t], err_msg=f"obs t={t}")
+        np.testing.assert_array_equal(np.asarray(d), g["dir"][t])
+        assert np.asarray(r, np.float64).tobytes() == g["reward"][t].tobytes()
+        np.testing.assert_array_equal(np.asarray(te, bool), g["terminated"][t])
+        np.testing.assert_array_equal(np.asarray(tr, bool), g["truncated"][t])
+    st = e.get_state()
+    np.testing.assert_array_equal(st["grid"], g["grid"])
+    np.testing.assert_array_equal(st["agent"], g["agent"])
+
+
+def check_lockstep_vs_oracle(engine, oracle, n_steps, seed, action_seed=1234, check_state_every=0):
+    """engine and oracle are already constructed with the same spec/mode/num_envs."""
+    eo, ed = engine.reset(seed=seed)
+    oo, od = oracle.reset(seed=seed)
+    np.testing.assert_array_equal(np.asarray(eo), oo)
+    np.testing.assert_array_equal(np.asarray(ed), od)
+    rng = np.random.default_rng(action_seed)
+    n = oracle.num_envs
+    for t in range(n_steps):
+        a = rng.integers(0, 7, n).astype(np.int32)
+        e = engine.step(a)
+        o = oracle.step(a)
+        for x, y, name in zip(e, o, ["obs", "dir", "reward", "terminated", "truncated"]):
+            x = np.asarray(x); y = np.asarray(y)
+            if name == "reward":
+                assert x.astype(np.float64).tobytes() == y.tobytes(), f"reward bits t={t}"
+            else:
+                np.testing.assert_array_equal(x.astype(y.dtype), y, err_msg=f"{name} t={t}")
+        if check_state_every and (t + 1) % check_state_every == 0:
+            es, os_ = engine.get_state(), oracle.get_state()
+            for k in ("grid", "agent", "rng", "pending"):
+                np.testing.assert_array_equal(es[k], os_[k], err_msg=f"{k} t={t}")
+    es, os_ = engine.get_state(), oracle.get_state()
+    for k in ("grid", "agent", "rng", "pending"):
+        np.testing.assert_array_equal(es[k], os_[k], err_msg=k)
+    np.testing.assert_array_equal(engine.full_obs(), oracle.full_obs())
