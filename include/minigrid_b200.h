@@ -87,6 +87,10 @@ int mg_reset(mg_env *env, uint8_t *obs_dev, int32_t *dir_dev, void *stream);
 int mg_step(mg_env *env, const void *actions_dev, int action_dtype, uint8_t *obs_dev, int32_t *dir_dev,
             double *reward_dev, uint8_t *terminated_dev, uint8_t *truncated_dev, void *stream);
 
+/* Replaces: MiniGridEnv.gen_obs() (minigrid_env.py:634-650) for every env: the observation of the current
+ * state, no transition, state untouched. */
+int mg_gen_obs(mg_env *env, uint8_t *obs_dev, int32_t *dir_dev, void *stream);
+
 /* Same two calls with HOST buffers (the end-to-end path: H2D of actions and D2H of every output happen
  * inside the call, through pinned staging owned by the handle; returns after the results are on the host).
  * actions_host: int32[n]. Returns MG_ERR_INVALID_ACTION if any action was outside 0..6. */
@@ -107,6 +111,12 @@ int mg_get_state(mg_env *env, uint8_t *grid_dev, int32_t *agent_dev, uint64_t *r
                  uint8_t *pending_dev, void *stream);
 int mg_set_state(mg_env *env, const uint8_t *grid_dev, const int32_t *agent_dev, const uint64_t *rng_dev,
                  const uint8_t *pending_dev, void *stream);
+
+/* Measurement aid (no reference counterpart): while enabled, every K1 (step+obs) launch is bracketed by CUDA
+ * events on the launching stream; mg_profile_read synchronises them, returns the summed kernel milliseconds
+ * and the number of launches since the last read, and clears the list. */
+int mg_profile(mg_env *env, int enable);
+int mg_profile_read(mg_env *env, double *total_ms, int64_t *n_launches);
 
 /* Synchronises `stream`, returns MG_ERR_INVALID_ACTION if a kernel saw an action outside 0..6 since the
  * last check (and clears the flag), else MG_OK. */

@@ -1,0 +1,69 @@
+"""ctypes binding of the C-ABI in include/minigrid_b200.h. Fails loudly when the CUDA extension is missing:
+the engine has no CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+MG_OK = 0
+MG_ERR_INVALID_ACTION = -3
+
+_lib = None
+
+EXPORTS = [
+    "mg_create", "mg_destroy", "mg_last_error", "mg_num_envs", "mg_launch_count", "mg_seed", "mg_seed_base",
+    "mg_reset", "mg_step", "mg_gen_obs", "mg_reset_host", "mg_step_host", "mg_full_obs", "mg_get_state", "mg_set_state",
+    "mg_check_error", "mg_profile", "mg_profile_read",
+]
+
+
+class MinigridB200Error(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise MinigridB200Error(f"{path} is missing: run `python -m minigrid_b200._build` (needs nvcc)")
+        _build.build()
+    L = C.CDLL(path)
+    p, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+    L.mg_create.argtypes = [i32, i32, i32, i32, i32, p, i32, i64, i32, i32, C.POINTER(p)]
+    L.mg_destroy.argtypes = [p]
+    L.mg_last_error.restype = C.c_char_p
+    L.mg_num_envs.restype = i64
+    L.mg_num_envs.argtypes = [p]
+    L.mg_launch_count.restype = i64
+    L.mg_launch_count.argtypes = [p]
+    L.mg_seed.argtypes = [p, p, p]
+    L.mg_seed_base.argtypes = [p, u64, p]
+    L.mg_reset.argtypes = [p, p, p, p]
+    L.mg_step.argtypes = [p, p, i32, p, p, p, p, p, p]
+    L.mg_gen_obs.argtypes = [p, p, p, p]
+    L.mg_reset_host.argtypes = [p, p, p]
+    L.mg_step_host.argtypes = [p] * 7
+    L.mg_full_obs.argtypes = [p, p, p]
+    L.mg_get_state.argtypes = [p] * 6
+    L.mg_set_state.argtypes = [p] * 6
+    L.mg_check_error.argtypes = [p, p]
+    L.mg_profile.argtypes = [p, i32]
+    L.mg_profile_read.argtypes = [p, C.POINTER(C.c_double), C.POINTER(i64)]
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError here means the .so does not match include/minigrid_b200.h
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc == MG_OK:
+        return
+    msg = load().mg_last_error().decode()
+    if rc == MG_ERR_INVALID_ACTION:
+        raise ValueError(msg)  # the reference raises ValueError (minigrid_env.py:584-585)
+    raise MinigridB200Error(f"minigrid_b200 C-ABI error {rc}: {msg}")

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/minigrid_b200.h"
 #include "mg_common.cuh"
@@ -39,6 +40,9 @@ struct mg_env {
   int32_t *d_actions; uint8_t *d_out;  // device mirror of the host-facing buffers
   int32_t *h_actions; uint8_t *h_out;  // pinned staging, used when the caller's buffers are pageable
   int *h_err;
+  // optional per-launch timing of K1 (bench.py's roofline leg)
+  int profiling;
+  std::vector<cudaEvent_t> *prof_events;  // start/stop pairs
 };
 
 static thread_local std::string g_err;
@@ -150,6 +154,10 @@ int mg_destroy(mg_env *h) {
   cudaFreeHost(h->h_actions);
   cudaFreeHost(h->h_out);
   cudaFreeHost(h->h_err);
+  if (h->prof_events) {
+    for (cudaEvent_t e : *h->prof_events) cudaEventDestroy(e);
+    delete h->prof_events;
+  }
   delete h;
   return MG_OK;
 }
@@ -201,13 +209,56 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
     MG_CUDA(launch_reset(p, p.list[h->cur], p.count[h->cur], nullptr, nullptr, 1, s));
     h->launches += 1;
   }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (h->profiling) {
+    MG_CUDA(cudaEventCreate(&ev0));
+    MG_CUDA(cudaEventCreate(&ev1));
+    MG_CUDA(cudaEventRecord(ev0, s));
+  }
   MG_CUDA(launch_step(p, actions_dev, action_dtype, obs_dev, dir_dev, reward_dev, terminated_dev, truncated_dev, append, s));
   h->launches += 1;
+  if (h->profiling) {
+    MG_CUDA(cudaEventRecord(ev1, s));
+    h->prof_events->push_back(ev0);
+    h->prof_events->push_back(ev1);
+  }
   if (p.mode == MG_AUTORESET_SAME_STEP) {
     MG_CUDA(launch_reset(p, p.list[append], p.count[append], obs_dev, dir_dev, 0, s));
     h->launches += 1;
   }
   h->cur = append;
+  return MG_OK;
+}
+
+int mg_gen_obs(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_gen_obs: NULL handle");
+  MG_CUDA(cudaSetDevice(h->device));
+  MG_CUDA(launch_step(h->p, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr, h->cur, (cudaStream_t)stream));
+  h->launches += 1;
+  return MG_OK;
+}
+
+int mg_profile(mg_env *h, int enable) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_profile: NULL handle");
+  if (!h->prof_events) h->prof_events = new std::vector<cudaEvent_t>();
+  h->profiling = enable ? 1 : 0;
+  return MG_OK;
+}
+
+int mg_profile_read(mg_env *h, double *total_ms, int64_t *n_launches) {
+  if (!h || !total_ms || !n_launches) return fail(MG_ERR_INVALID_ARG, "mg_profile_read: NULL argument");
+  *total_ms = 0.0; *n_launches = 0;
+  if (!h->prof_events) return MG_OK;
+  MG_CUDA(cudaSetDevice(h->device));
+  std::vector<cudaEvent_t> &ev = *h->prof_events;
+  for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+    MG_CUDA(cudaEventSynchronize(ev[i + 1]));
+    float ms = 0.f;
+    MG_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    *total_ms += ms; *n_launches += 1;
+    cudaEventDestroy(ev[i]); cudaEventDestroy(ev[i + 1]);
+  }
+  ev.clear();
   return MG_OK;
 }
 

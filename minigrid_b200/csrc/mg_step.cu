@@ -72,7 +72,8 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * (tile_bytes + STAGE_WORDS * 4));
   const uint32_t bar = smem_u32(bars + warp);
 
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.count[cur ^ 1] = 0;  // the list K2 consumed before this launch
+  const bool stepping = actions != nullptr;  // nullptr: observation-only pass (MiniGridEnv.gen_obs), state untouched
+  if (stepping && blockIdx.x == 0 && threadIdx.x == 0) *p.count[cur ^ 1] = 0;  // the list K2 consumed before this launch
 
   const bool tile_ok = tile < p.n_tiles;
   uint32_t *gsrc = p.grid + (size_t)(tile_ok ? tile : 0) * g.wpe * 32;
@@ -96,7 +97,7 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
   uint32_t flags = rec.y >> 8;
   uint32_t carry = rec.z;
   int steps = (int)rec.w;
-  int action = (actions != nullptr && active) ? load_action<ActT>(actions, env) : A_DONE;
+  const int action = (stepping && active) ? load_action<ActT>(actions, env) : A_DONE;
 
   mbar_wait(bar, 0);
 
@@ -104,7 +105,7 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
   double reward = 0.0;
   uint32_t terminated = 0, truncated = 0;
   const bool fresh = (flags & FLAG_FRESH) != 0;
-  if (actions != nullptr && !fresh) {
+  if (stepping && !fresh) {
     // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
     steps += 1;
     int fx, fy;
@@ -127,10 +128,12 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
     }
     truncated = steps >= p.max_steps;
   }
-  flags &= ~FLAG_FRESH;
   const bool done = (terminated | truncated) != 0;
-  if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
-  if (p.mode != AUTORESET_DISABLED) {
+  if (stepping) {
+    flags &= ~FLAG_FRESH;
+    if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
+  }
+  if (stepping && p.mode != AUTORESET_DISABLED) {
     const unsigned ball = __ballot_sync(0xFFFFFFFFu, done && active);
     if (ball) {
       int basei = 0;
@@ -158,11 +161,13 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
     }
   }
   if (active) {
-    rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
-    rec.y = (uint32_t)dir | (flags << 8);
-    rec.z = carry;
-    rec.w = (uint32_t)steps;
-    p.agent[env] = rec;
+    if (stepping) {
+      rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
+      rec.y = (uint32_t)dir | (flags << 8);
+      rec.z = carry;
+      rec.w = (uint32_t)steps;
+      p.agent[env] = rec;
+    }
     if (dir_out) dir_out[env] = dir;
     if (reward_out) reward_out[env] = reward;
     if (term_out) term_out[env] = (uint8_t)terminated;

@@ -1,0 +1,81 @@
+"""Registered ids -> constructor arguments of the four generators the engine implements.
+
+Restated from the reference's registry and constructors (no code copied; citations relative to
+/root/reference/minigrid/): __init__.py:25-28 (LavaCrossingS9N1), :106-109 (DoorKey-8x8), :159-162
+(Empty-5x5), :183-185 (Empty-8x8), :214-216 (FourRooms); defaults empty.py:69-90 (max_steps 4*size^2,
+see_through_walls=True), doorkey.py:62-68 (10*size^2), crossing.py:89-116 (4*size^2), fourrooms.py:55-67
+(19x19, max_steps 100).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+KIND_EMPTY, KIND_DOORKEY, KIND_CROSSING, KIND_FOURROOMS = 0, 1, 2, 3
+T_WALL, T_LAVA = 2, 9
+
+
+@dataclass(frozen=True)
+class EnvSpec:
+    kind: int
+    width: int
+    height: int
+    max_steps: int
+    see_through_walls: bool
+    params: tuple = field(default_factory=tuple)
+    mission: str = ""
+
+
+def empty(size=8, agent_start_pos=(1, 1), agent_start_dir=0, max_steps=None):
+    random_start = agent_start_pos is None
+    sx, sy = (0, 0) if random_start else agent_start_pos
+    return EnvSpec(KIND_EMPTY, size, size, max_steps or 4 * size * size, True,
+                   (int(random_start), sx, sy, agent_start_dir), "get to the green goal square")
+
+
+def doorkey(size=8, max_steps=None):
+    return EnvSpec(KIND_DOORKEY, size, size, max_steps or 10 * size * size, False, (),
+                   "use the key to open the door and then get to the goal")
+
+
+def crossing(size=9, num_crossings=1, obstacle_type="lava", max_steps=None):
+    lava = obstacle_type == "lava"
+    return EnvSpec(KIND_CROSSING, size, size, max_steps or 4 * size * size, False,
+                   (num_crossings, T_LAVA if lava else T_WALL),
+                   "avoid the lava and get to the green goal square" if lava
+                   else "find the opening and get to the green goal square")
+
+
+def fourrooms(max_steps=100):
+    return EnvSpec(KIND_FOURROOMS, 19, 19, max_steps, False, (), "reach the goal")
+
+
+REGISTRY = {
+    # BASELINE.json configs
+    "MiniGrid-Empty-5x5-v0": empty(size=5),
+    "MiniGrid-Empty-8x8-v0": empty(size=8),
+    "MiniGrid-DoorKey-8x8-v0": doorkey(size=8),
+    "MiniGrid-LavaCrossingS9N1-v0": crossing(9, 1, "lava"),
+    "MiniGrid-FourRooms-v0": fourrooms(),
+    # other registered ids of the same generators (__init__.py:31-74,94-116,159-192)
+    "MiniGrid-Empty-Random-5x5-v0": empty(size=5, agent_start_pos=None),
+    "MiniGrid-Empty-6x6-v0": empty(size=6),
+    "MiniGrid-Empty-Random-6x6-v0": empty(size=6, agent_start_pos=None),
+    "MiniGrid-Empty-16x16-v0": empty(size=16),
+    "MiniGrid-DoorKey-5x5-v0": doorkey(size=5),
+    "MiniGrid-DoorKey-6x6-v0": doorkey(size=6),
+    "MiniGrid-DoorKey-16x16-v0": doorkey(size=16),
+    "MiniGrid-LavaCrossingS9N2-v0": crossing(9, 2, "lava"),
+    "MiniGrid-LavaCrossingS9N3-v0": crossing(9, 3, "lava"),
+    "MiniGrid-LavaCrossingS11N5-v0": crossing(11, 5, "lava"),
+    "MiniGrid-SimpleCrossingS9N1-v0": crossing(9, 1, "wall"),
+    "MiniGrid-SimpleCrossingS9N2-v0": crossing(9, 2, "wall"),
+    "MiniGrid-SimpleCrossingS9N3-v0": crossing(9, 3, "wall"),
+    "MiniGrid-SimpleCrossingS11N5-v0": crossing(11, 5, "wall"),
+}
+
+
+def get(env_id: str) -> EnvSpec:
+    try:
+        return REGISTRY[env_id]
+    except KeyError:
+        raise KeyError(f"{env_id!r} is not one of the ids this engine implements: {sorted(REGISTRY)}") from None

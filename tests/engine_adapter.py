@@ -1,0 +1,60 @@
+"""Drives the CUDA engine (through the Python host layer -> C-ABI) with the same surface as
+oracle.OracleVecEnv, returning numpy arrays, so tests/parity.py can compare the two."""
+import numpy as np
+import torch
+
+from minigrid_b200 import MinigridVecEnv, specs
+
+
+class EngineAdapter:
+    def __init__(self, env_id=None, num_envs=1, mode="next_step", spec=None, host=False, action_dtype=torch.int32):
+        self.e = MinigridVecEnv(env_id, num_envs, spec=spec, autoreset_mode=mode)
+        self.num_envs = num_envs
+        self.host = host
+        self.action_dtype = action_dtype
+
+    @staticmethod
+    def _np(t):
+        return t.cpu().numpy() if isinstance(t, torch.Tensor) else t
+
+    def reset(self, seed=None):
+        if self.host:
+            obs, _ = self.e.reset_host(seed=seed)
+        else:
+            obs, _ = self.e.reset(seed=seed)
+        return self._np(obs["image"]).copy(), self._np(obs["direction"]).copy()
+
+    def step(self, actions):
+        if self.host:
+            obs, r, te, tr, _ = self.e.step_host(np.asarray(actions, np.int32))
+        else:
+            a = torch.as_tensor(np.asarray(actions)).to(device=self.e.device, dtype=self.action_dtype)
+            obs, r, te, tr, _ = self.e.step(a)
+            self.e.check_actions()
+        return (self._np(obs["image"]).copy(), self._np(obs["direction"]).copy(), self._np(r).copy(),
+                self._np(te).copy(), self._np(tr).copy())
+
+    def gen_obs(self):
+        obs = self.e.gen_obs()
+        return self._np(obs["image"]).copy(), self._np(obs["direction"]).copy()
+
+    def full_obs(self):
+        return self.e.full_obs().cpu().numpy()
+
+    def get_state(self):
+        st = {k: v.cpu().numpy() for k, v in self.e.get_state().items()}
+        st["rng"] = st["rng"].view(np.uint64)
+        return st
+
+    def set_state(self, grid=None, agent=None, rng=None, pending=None):
+        self.e.set_state(grid=grid, agent=agent, rng=rng, pending=pending)
+
+
+def make_engine(env_id, n, mode):
+    return EngineAdapter(env_id, n, mode)
+
+
+def spec_tuple(env_id):
+    s = specs.get(env_id)
+    kind = ["empty", "doorkey", "crossing", "fourrooms"][s.kind]
+    return (kind, s.width, s.height, s.max_steps, s.see_through_walls, list(s.params))

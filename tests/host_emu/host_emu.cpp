@@ -68,7 +68,8 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
                        uint8_t *term_out, uint8_t *trunc_out, int cur) {  // k_step body
   Params &p = e->p;
   const Geom g = p.g;
-  e->count[cur ^ 1] = 0;
+  const bool stepping = actions != nullptr;
+  if (stepping) e->count[cur ^ 1] = 0;
   std::vector<uint32_t> gtile((size_t)g.wpe * 32), stage(1184);
   for (int tile = 0; tile < p.n_tiles; ++tile) {
     uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
@@ -87,7 +88,7 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
       double reward = 0.0;
       uint32_t terminated = 0, truncated = 0;
       const bool fresh = (flags & FLAG_FRESH) != 0;
-      if (actions && !fresh) {
+      if (stepping && !fresh) {
         steps += 1;
         int fx, fy;
         front_pos(g, ax, ay, dir, fx, fy);
@@ -109,19 +110,23 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
         }
         truncated = steps >= p.max_steps;
       }
-      flags &= ~FLAG_FRESH;
       const bool done = (terminated | truncated) != 0;
-      if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
-      if (p.mode != AUTORESET_DISABLED && done && active) e->list[cur][e->count[cur]++] = env;
+      if (stepping) {
+        flags &= ~FLAG_FRESH;
+        if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
+      }
+      if (stepping && p.mode != AUTORESET_DISABLED && done && active) e->list[cur][e->count[cur]++] = env;
       if (obs) {
         gen_obs_words<ST, true>(g, base, p.cell_lut, ax, ay, dir, carry, S[lane]);
         if (!full && active) emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S[lane]);
       }
       if (active) {
-        rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
-        rec.y = (uint32_t)dir | (flags << 8);
-        rec.z = carry; rec.w = (uint32_t)steps;
-        p.agent[env] = rec;
+        if (stepping) {
+          rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
+          rec.y = (uint32_t)dir | (flags << 8);
+          rec.z = carry; rec.w = (uint32_t)steps;
+          p.agent[env] = rec;
+        }
         if (dir_out) dir_out[env] = dir;
         if (reward_out) reward_out[env] = reward;
         if (term_out) term_out[env] = (uint8_t)terminated;
@@ -174,6 +179,11 @@ void emu_reset(void *h, uint8_t *obs, int32_t *dir) {
 }
 int emu_step(void *h, const int32_t *actions, uint8_t *obs, int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc) {
   Emu *e = (Emu *)h;
+  if (!actions) {  // mg_gen_obs
+    if (e->p.see_through) step_tiles<true>(e, nullptr, obs, dir, nullptr, nullptr, nullptr, e->cur);
+    else step_tiles<false>(e, nullptr, obs, dir, nullptr, nullptr, nullptr, e->cur);
+    return 0;
+  }
   const int append = e->cur ^ 1;
   if (e->p.mode == AUTORESET_NEXT_STEP) reset_list(e, e->cur, nullptr, nullptr, 1);
   if (e->p.see_through) step_tiles<true>(e, actions, obs, dir, reward, term, trunc, append);
