@@ -28,7 +28,8 @@ class EngineAdapter:
         if self.host:
             obs, r, te, tr, _ = self.e.step_host(np.asarray(actions, np.int32))
         else:
-            a = torch.as_tensor(np.asarray(actions)).to(device=self.e.device, dtype=self.action_dtype)
+            a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
+            a = a.to(device=self.e.device, dtype=self.action_dtype)
             obs, r, te, tr, _ = self.e.step(a)
             self.e.check_actions()
         return (self._np(obs["image"]).copy(), self._np(obs["direction"]).copy(), self._np(r).copy(),
