@@ -121,7 +121,7 @@ struct Params {
   int *err;                 // sticky error word
   int *list[2];             // compacted env ids awaiting reset (ping-pong)
   int *count[2];
-  int64_t first_env_index;
+  int *tile_ctr[2];         // dynamic tile scheduler of K1 (ping-pong between launches)
 };
 
 // word index of byte (line, pos) and helpers for the interleaved tile

@@ -10,8 +10,10 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {  // P
   const uint64_t ab = ((uint64_t)b << 32) | a;
   uint32_t r = 0;
   for (int i = 0; i < 4; ++i) {
-    const uint32_t n = (sel >> (4 * i)) & 7u;
-    r |= (uint32_t)((ab >> (8 * n)) & 0xFFu) << (8 * i);
+    const uint32_t n = (sel >> (4 * i)) & 15u;
+    uint32_t byte = (uint32_t)((ab >> (8 * (n & 7u))) & 0xFFu);
+    if (n & 8u) byte = (byte & 0x80u) ? 0xFFu : 0x00u;  // replicate the sign bit
+    r |= byte << (8 * i);
   }
   return r;
 }

@@ -110,8 +110,9 @@ MG_D void gen_obs_words(const Geom &g, const uint32_t *base, const uint32_t *lut
     process_vis(oplo, ophi, vlo, vhi);
 #pragma unroll
     for (int vx = 0; vx < VIEW; ++vx) {
-      clo[vx] &= ((vlo >> vx) & 0x01010101u) * 0xFFu;  // unseen -> code 0 -> (0,0,0)
-      chi[vx] &= ((vhi >> vx) & 0x01010101u) * 0xFFu;
+      // bit vx of every row byte -> bit 7, then prmt's sign-replicate mode turns it into a 0x00/0xFF byte mask
+      clo[vx] &= prmt(vlo << (7 - vx), 0u, 0xBA98u);  // unseen -> code 0 -> (0,0,0)
+      chi[vx] &= prmt(vhi << (7 - vx), 0u, 0xBA98u);
     }
   }
   // the agent's own view cell (3,6) shows what it carries, else empty (minigrid_env.py:623-630)

@@ -58,7 +58,7 @@ cudaError_t launch_reset(const Params &p, const int *list, const int *count, uin
 __global__ void k_seed(Params p, const uint64_t *__restrict__ seeds, uint64_t base) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= p.n_envs) return;
-  const uint64_t s = seeds ? seeds[env] : base + (uint64_t)p.first_env_index + (uint64_t)env;
+  const uint64_t s = seeds ? seeds[env] : base + (uint64_t)env;
   const Pcg r = seed_pcg64(s);
   store_rng(p.rng + env, r);
 }

@@ -3,7 +3,8 @@
 // One warp = one tile of 32 environments, one lane per environment.
 //   1. lane 0 issues a TMA bulk copy (cp.async.bulk -> SASS UBLKCP) of the tile's interleaved grid words
 //      into shared memory and arms an mbarrier with the byte count; meanwhile every lane loads its
-//      action and 16-byte agent record with coalesced loads.
+//      action and 16-byte agent record with coalesced loads. Warps are persistent and double-buffered:
+//      the copy for the next tile is issued before the current one is processed.
 //   2. transition: the 7-action rule on (agent, carrying, the one cell in front), predicated, with the
 //      rare cell mutation written to the staged tile and straight back to HBM (2 byte stores).
 //   3. observation in registers (mg_obs.cuh), staged to shared memory in output layout, then one TMA bulk
@@ -18,10 +19,16 @@ namespace mg {
 
 constexpr int STEP_WARPS = 4;
 constexpr int STEP_THREADS = STEP_WARPS * 32;
-constexpr int STAGE_WORDS = 1184;  // 4704 B rounded up to a multiple of 128 B
 
+// per-warp buffer: holds the staged tile, then (once the gather has consumed it) the warp's 4704-byte
+// observation block in output layout. Two of them per warp: compute on one while TMA fills the other.
+__host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
+  uint32_t b = (uint32_t)g.wpe * 128u;
+  if (b < (uint32_t)OBS_TILE_BYTES) b = OBS_TILE_BYTES;
+  return (b + 127u) & ~127u;
+}
 __host__ __device__ inline size_t step_smem_bytes(const Geom &g) {
-  return 1024 /*cell lut*/ + (size_t)STEP_WARPS * ((size_t)g.wpe * 128 + STAGE_WORDS * 4) + 64 /*mbarriers*/;
+  return 1024 /*cell table*/ + (size_t)STEP_WARPS * 2 * step_buf_bytes(g) + 128 /*mbarriers*/;
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -55,163 +62,225 @@ __device__ __forceinline__ int load_action(const void *actions, int env) {
   return (int)reinterpret_cast<const ActT *>(actions)[env];
 }
 
+// Persistent warps: every warp owns two shared-memory buffers and walks tiles handed out by a device-side
+// counter. While tile i is being processed out of one buffer, the TMA bulk load of tile i+1 (and the
+// coalesced loads of its agent records / actions) is already in flight into the other, and the index of
+// tile i+2 is being fetched. par selects this launch's tile counter (the other one is re-armed for the next).
 template <bool SEE_THROUGH, typename ActT>
 __global__ void __launch_bounds__(STEP_THREADS)
 k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out,
        double *__restrict__ reward_out, uint8_t *__restrict__ term_out, uint8_t *__restrict__ trunc_out,
-       int cur /*list this step appends to*/, int obs_tma_ok) {
+       int cur /*list this step appends to*/, int par, int obs_tma_ok) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const Geom g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile = blockIdx.x * STEP_WARPS + warp;
   const uint32_t tile_bytes = (uint32_t)g.wpe * 128u;
+  const uint32_t buf_bytes = step_buf_bytes(g);
 
   uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);
-  uint32_t *gtile = reinterpret_cast<uint32_t *>(smem_raw + 1024 + (size_t)warp * tile_bytes);
-  uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * tile_bytes + (size_t)warp * STAGE_WORDS * 4);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * (tile_bytes + STAGE_WORDS * 4));
-  const uint32_t bar = smem_u32(bars + warp);
+  uint8_t *bufs = smem_raw + 1024 + (size_t)warp * 2 * buf_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * 2 * buf_bytes);
+  const uint32_t bar0 = smem_u32(bars + 2 * warp);
 
   const bool stepping = actions != nullptr;  // nullptr: observation-only pass (MiniGridEnv.gen_obs), state untouched
-  if (stepping && blockIdx.x == 0 && threadIdx.x == 0) *p.count[cur ^ 1] = 0;  // the list K2 consumed before this launch
-
-  const bool tile_ok = tile < p.n_tiles;
-  uint32_t *gsrc = p.grid + (size_t)(tile_ok ? tile : 0) * g.wpe * 32;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (stepping) *p.count[cur ^ 1] = 0;  // the reset list K2 consumed before this launch
+    *p.tile_ctr[par ^ 1] = 0;             // re-arm the other tile counter for the next launch
+  }
+  const int total_warps = gridDim.x * STEP_WARPS;
+  int tile = blockIdx.x * STEP_WARPS + warp;
+  int next = p.n_tiles;
+  uint4 rec = make_uint4(0, 0, 0, 0);
+  int action = A_DONE;
   if (lane == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (tile_ok) {
-      mbar_expect_tx(bar, tile_bytes);
-      tma_load_1d(smem_u32(gtile), gsrc, tile_bytes, bar);
-    }
   }
-  for (int i = threadIdx.x; i < 256; i += STEP_THREADS) lut[i] = p.cell_lut[i];
+  __syncwarp();
+  if (tile < p.n_tiles) {
+    if (lane == 0) {
+      mbar_expect_tx(bar0, tile_bytes);
+      tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
+      next = atomicAdd(p.tile_ctr[par], 1) + total_warps;
+    }
+    const int env = tile * TILE + lane;
+    rec = p.agent[env];
+    if (stepping && env < p.n_envs) action = load_action<ActT>(actions, env);
+  }
+  // the 256-entry (type, colour, state) table is pure arithmetic: no global load on the critical path
+  for (int i = threadIdx.x; i < 256; i += STEP_THREADS) lut[i] = decode_cell((uint32_t)i);
   __syncthreads();
-  if (!tile_ok) return;
+  next = __shfl_sync(0xFFFFFFFFu, next, 0);
 
-  const int env = tile * TILE + lane;
-  const bool active = env < p.n_envs;
-  uint4 rec = p.agent[env];
-  int ax = rec.x & 0xFF, ay = (rec.x >> 8) & 0xFF;
-  int dir = rec.y & 3;
-  uint32_t flags = rec.y >> 8;
-  uint32_t carry = rec.z;
-  int steps = (int)rec.w;
-  const int action = (stepping && active) ? load_action<ActT>(actions, env) : A_DONE;
-
-  mbar_wait(bar, 0);
-
-  const uint32_t *base = gtile + lane;
-  double reward = 0.0;
-  uint32_t terminated = 0, truncated = 0;
-  const bool fresh = (flags & FLAG_FRESH) != 0;
-  if (stepping && !fresh) {
-    // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
-    steps += 1;
-    int fx, fy;
-    front_pos(g, ax, ay, dir, fx, fy);
-    const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
-    const uint32_t fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
-    const StepOut so = transition(action, fc, fx, fy, ax, ay, dir, carry);
-    const uint32_t newc = so.newc;
-    terminated = so.terminated;
-    if (so.goal)  // _reward(), minigrid_env.py:240-245: host-computed table, never an FMA
-      reward = steps <= p.max_steps ? p.reward_lut[steps]
-                                    : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
-    if (so.bad_action) atomicOr(p.err, 1);  // ValueError("Unknown action"), minigrid_env.py:584-585
-    if (newc != fc && active) {
-      uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
-      uint8_t *gb = reinterpret_cast<uint8_t *>(gsrc);
-      const size_t ro = ((size_t)rw * 32 + lane) * 4 + (fx & 3), co = ((size_t)cw * 32 + lane) * 4 + (fy & 3);
-      sb[ro] = (uint8_t)newc; sb[co] = (uint8_t)newc;
-      gb[ro] = (uint8_t)newc; gb[co] = (uint8_t)newc;
-    }
-    truncated = steps >= p.max_steps;
-  }
-  const bool done = (terminated | truncated) != 0;
-  if (stepping) {
-    flags &= ~FLAG_FRESH;
-    if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
-  }
-  if (stepping && p.mode != AUTORESET_DISABLED) {
-    const unsigned ball = __ballot_sync(0xFFFFFFFFu, done && active);
-    if (ball) {
-      int basei = 0;
-      if (lane == 0) basei = atomicAdd(p.count[cur], __popc(ball));
-      basei = __shfl_sync(0xFFFFFFFFu, basei, 0);
-      if (done && active) p.list[cur][basei + __popc(ball & ((1u << lane) - 1u))] = env;
-    }
-  }
-
-  // ---- gen_obs ----
-  if (obs != nullptr) {
-    uint32_t S[OBS_WORDS];
-    gen_obs_words<SEE_THROUGH, true>(g, base, lut, ax, ay, dir, carry, S);
-    const bool full = (tile + 1) * TILE <= p.n_envs;
-    if (full && obs_tma_ok) {
-      emit_obs_staged(stage, lane, S, __shfl_down_sync(0xFFFFFFFFu, S[0], 1));
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
+  uint32_t phase = 0;  // bit b = parity to wait for on buffer b
+  int b = 0;
+  while (tile < p.n_tiles) {
+    // ---- prefetch tile `next` into the other buffer, and the index of the tile after it ----
+    uint4 rec_n = make_uint4(0, 0, 0, 0);
+    int action_n = A_DONE, nn = p.n_tiles;
+    if (next < p.n_tiles) {
       if (lane == 0) {
-        tma_store_1d(obs + (size_t)tile * OBS_TILE_BYTES, smem_u32(stage), OBS_TILE_BYTES);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the obs block staged there two tiles ago
+        const uint32_t nb = bar0 + 8u * (uint32_t)(b ^ 1);
+        mbar_expect_tx(nb, tile_bytes);
+        tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
+        nn = atomicAdd(p.tile_ctr[par], 1) + total_warps;
       }
-    } else if (active) {
-      emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
+      const int env_n = next * TILE + lane;
+      rec_n = p.agent[env_n];
+      if (stepping && env_n < p.n_envs) action_n = load_action<ActT>(actions, env_n);
     }
-  }
-  if (active) {
+
+    uint32_t *gtile = reinterpret_cast<uint32_t *>(bufs + (size_t)b * buf_bytes);
+    uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
+    const int env = tile * TILE + lane;
+    const bool active = env < p.n_envs;
+    int ax = rec.x & 0xFF, ay = (rec.x >> 8) & 0xFF;
+    int dir = rec.y & 3;
+    uint32_t flags = rec.y >> 8;
+    uint32_t carry = rec.z;
+    int steps = (int)rec.w;
+
+    mbar_wait(bar0 + 8u * (uint32_t)b, (phase >> b) & 1u);
+    phase ^= 1u << b;
+
+    const uint32_t *base = gtile + lane;
+    double reward = 0.0;
+    uint32_t terminated = 0, truncated = 0;
+    const bool fresh = (flags & FLAG_FRESH) != 0;
+    if (stepping && !fresh) {
+      // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
+      steps += 1;
+      int fx, fy;
+      front_pos(g, ax, ay, dir, fx, fy);
+      const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
+      const uint32_t fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
+      const StepOut so = transition(action, fc, fx, fy, ax, ay, dir, carry);
+      const uint32_t newc = so.newc;
+      terminated = so.terminated;
+      if (so.goal)  // _reward(), minigrid_env.py:240-245: host-computed table, never an FMA
+        reward = steps <= p.max_steps ? p.reward_lut[steps]
+                                      : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
+      if (so.bad_action) atomicOr(p.err, 1);  // ValueError("Unknown action"), minigrid_env.py:584-585
+      if (newc != fc && active) {
+        uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
+        uint8_t *gb = reinterpret_cast<uint8_t *>(gsrc);
+        const size_t ro = ((size_t)rw * 32 + lane) * 4 + (fx & 3), co = ((size_t)cw * 32 + lane) * 4 + (fy & 3);
+        sb[ro] = (uint8_t)newc; sb[co] = (uint8_t)newc;
+        gb[ro] = (uint8_t)newc; gb[co] = (uint8_t)newc;
+      }
+      truncated = steps >= p.max_steps;
+    }
+    const bool done = (terminated | truncated) != 0;
     if (stepping) {
-      rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
-      rec.y = (uint32_t)dir | (flags << 8);
-      rec.z = carry;
-      rec.w = (uint32_t)steps;
-      p.agent[env] = rec;
+      flags &= ~FLAG_FRESH;
+      if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
     }
-    if (dir_out) dir_out[env] = dir;
-    if (reward_out) reward_out[env] = reward;
-    if (term_out) term_out[env] = (uint8_t)terminated;
-    if (trunc_out) trunc_out[env] = (uint8_t)truncated;
+    if (stepping && p.mode != AUTORESET_DISABLED) {
+      const unsigned ball = __ballot_sync(0xFFFFFFFFu, done && active);
+      if (ball) {
+        int basei = 0;
+        if (lane == 0) basei = atomicAdd(p.count[cur], __popc(ball));
+        basei = __shfl_sync(0xFFFFFFFFu, basei, 0);
+        if (done && active) p.list[cur][basei + __popc(ball & ((1u << lane) - 1u))] = env;
+      }
+    }
+
+    // ---- gen_obs ----
+    if (obs != nullptr) {
+      uint32_t S[OBS_WORDS];
+      gen_obs_words<SEE_THROUGH, true>(g, base, lut, ax, ay, dir, carry, S);
+      const bool full = (tile + 1) * TILE <= p.n_envs;
+      if (full && obs_tma_ok) {
+        const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);  // also: every lane is past its tile reads
+        emit_obs_staged(gtile, lane, S, n0);                         // the consumed tile buffer becomes the stage
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_1d(obs + (size_t)tile * OBS_TILE_BYTES, smem_u32(gtile), OBS_TILE_BYTES);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else if (active) {
+        emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
+      }
+    }
+    if (active) {
+      if (stepping) {
+        rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
+        rec.y = (uint32_t)dir | (flags << 8);
+        rec.z = carry;
+        rec.w = (uint32_t)steps;
+        p.agent[env] = rec;
+      }
+      if (dir_out) dir_out[env] = dir;
+      if (reward_out) reward_out[env] = reward;
+      if (term_out) term_out[env] = (uint8_t)terminated;
+      if (trunc_out) trunc_out[env] = (uint8_t)truncated;
+    }
+    __syncwarp();  // lanes may still be reading this buffer (partial-tile path) before it is refilled
+    tile = next;
+    next = __shfl_sync(0xFFFFFFFFu, nn, 0);
+    rec = rec_n;
+    action = action_n;
+    b ^= 1;
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 template <bool ST, typename ActT>
-static cudaError_t launch_step_t(const Params &p, const void *actions, uint8_t *obs, int32_t *dir, double *reward,
-                                 uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream) {
+static cudaError_t launch_step_t(const Params &p, int grid, const void *actions, uint8_t *obs, int32_t *dir,
+                                 double *reward, uint8_t *term, uint8_t *trunc, int cur, int par, cudaStream_t stream) {
   const size_t smem = step_smem_bytes(p.g);
-  auto kern = k_step<ST, ActT>;
-  const int blocks = (p.n_tiles + STEP_WARPS - 1) / STEP_WARPS;
   const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
-  kern<<<blocks, STEP_THREADS, smem, stream>>>(p, actions, obs, dir, reward, term, trunc, cur, tma_ok);
+  k_step<ST, ActT><<<grid, STEP_THREADS, smem, stream>>>(p, actions, obs, dir, reward, term, trunc, cur, par, tma_ok);
   return cudaGetLastError();
 }
 
 template <bool ST, typename ActT>
-static cudaError_t configure_one(size_t smem) {
-  return cudaFuncSetAttribute(k_step<ST, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-// opt in to the tile-dependent dynamic shared memory once per handle
-cudaError_t configure_step(const Params &p) {
-  const size_t smem = step_smem_bytes(p.g);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = configure_one<true, int32_t>(smem);
-  if (e == cudaSuccess) e = configure_one<true, int64_t>(smem);
-  if (e == cudaSuccess) e = configure_one<true, uint8_t>(smem);
-  if (e == cudaSuccess) e = configure_one<false, int32_t>(smem);
-  if (e == cudaSuccess) e = configure_one<false, int64_t>(smem);
-  if (e == cudaSuccess) e = configure_one<false, uint8_t>(smem);
+static cudaError_t configure_one(size_t smem, int *ctas_per_sm) {
+  cudaError_t e = cudaFuncSetAttribute(k_step<ST, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int n = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_step<ST, ActT>, STEP_THREADS, smem);
+  if (e == cudaSuccess && n < *ctas_per_sm) *ctas_per_sm = n;
   return e;
 }
+// opt in to the tile-dependent dynamic shared memory once per handle and size the persistent grid:
+// one CTA slot per resident CTA, never more CTAs than there are groups of STEP_WARPS tiles
+cudaError_t configure_step(const Params &p, int *grid_out) {
+  const size_t smem = step_smem_bytes(p.g);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  int ctas = 32;
+  cudaError_t e = cudaSuccess;
+  if (p.see_through) {
+    if (e == cudaSuccess) e = configure_one<true, int32_t>(smem, &ctas);
+    if (e == cudaSuccess) e = configure_one<true, int64_t>(smem, &ctas);
+    if (e == cudaSuccess) e = configure_one<true, uint8_t>(smem, &ctas);
+  } else {
+    if (e == cudaSuccess) e = configure_one<false, int32_t>(smem, &ctas);
+    if (e == cudaSuccess) e = configure_one<false, int64_t>(smem, &ctas);
+    if (e == cudaSuccess) e = configure_one<false, uint8_t>(smem, &ctas);
+  }
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (ctas < 1) return cudaErrorInvalidValue;
+  const long long want = ((long long)p.n_tiles + STEP_WARPS - 1) / STEP_WARPS;
+  long long grid = (long long)sms * ctas;
+  if (grid > want) grid = want;
+  *grid_out = (int)(grid < 1 ? 1 : grid);
+  return cudaSuccess;
+}
 
-cudaError_t launch_step(const Params &p, const void *actions, int action_dtype, uint8_t *obs, int32_t *dir,
-                        double *reward, uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream) {
-#define MG_DISPATCH(ST)                                                                                         \
-  switch (action_dtype) {                                                                                       \
-    case 1: return launch_step_t<ST, int64_t>(p, actions, obs, dir, reward, term, trunc, cur, stream);          \
-    case 2: return launch_step_t<ST, uint8_t>(p, actions, obs, dir, reward, term, trunc, cur, stream);          \
-    default: return launch_step_t<ST, int32_t>(p, actions, obs, dir, reward, term, trunc, cur, stream);         \
+cudaError_t launch_step(const Params &p, int grid, const void *actions, int action_dtype, uint8_t *obs, int32_t *dir,
+                        double *reward, uint8_t *term, uint8_t *trunc, int cur, int par, cudaStream_t stream) {
+#define MG_DISPATCH(ST)                                                                                              \
+  switch (action_dtype) {                                                                                            \
+    case 1: return launch_step_t<ST, int64_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, par, stream);    \
+    case 2: return launch_step_t<ST, uint8_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, par, stream);    \
+    default: return launch_step_t<ST, int32_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, par, stream);   \
   }
   if (p.see_through) { MG_DISPATCH(true) } else { MG_DISPATCH(false) }
 #undef MG_DISPATCH
