@@ -12,7 +12,7 @@
 
 namespace mg {
 cudaError_t launch_step(const Params &p, int grid, const void *actions, int action_dtype, uint8_t *obs, int32_t *dir,
-                        double *reward, uint8_t *term, uint8_t *trunc, int cur, int par, cudaStream_t stream);
+                        double *reward, uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream);
 cudaError_t configure_step(const Params &p, int *grid_out);
 cudaError_t launch_reset(const Params &p, const int *list, const int *count, uint8_t *obs, int32_t *dir,
                          int set_fresh, cudaStream_t stream);
@@ -31,7 +31,6 @@ struct mg_env {
   Params p;
   int device;
   int cur;           // the reset list the most recent step appended to
-  int par;           // tile-counter parity of the next K1 launch
   int step_grid;     // persistent grid of K1
   int64_t launches;
   // device allocations owned by the handle
@@ -110,8 +109,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   p.rng = (RngRec *)base; base += sz_rng;
   p.list[0] = (int *)base; base += sz_list;
   p.list[1] = (int *)base; base += sz_list;
-  p.count[0] = (int *)base; p.count[1] = (int *)base + 1; p.err = (int *)base + 2;
-  p.tile_ctr[0] = (int *)base + 3; p.tile_ctr[1] = (int *)base + 4; base += 256;
+  p.count[0] = (int *)base; p.count[1] = (int *)base + 1; p.err = (int *)base + 2; base += 256;
   double *d_rl = (double *)base; base += sz_lut_r;
   uint32_t *d_cl = (uint32_t *)base;
   p.reward_lut = d_rl; p.cell_lut = d_cl;
@@ -219,8 +217,7 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
     MG_CUDA(cudaEventRecord(ev0, s));
   }
   MG_CUDA(launch_step(p, h->step_grid, actions_dev, action_dtype, obs_dev, dir_dev, reward_dev, terminated_dev, truncated_dev,
-                      append, h->par, s));
-  h->par ^= 1;
+                      append, s));
   h->launches += 1;
   if (h->profiling) {
     MG_CUDA(cudaEventRecord(ev1, s));
@@ -238,9 +235,8 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
 int mg_gen_obs(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_gen_obs: NULL handle");
   MG_CUDA(cudaSetDevice(h->device));
-  MG_CUDA(launch_step(h->p, h->step_grid, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr, h->cur, h->par,
+  MG_CUDA(launch_step(h->p, h->step_grid, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr, h->cur,
                       (cudaStream_t)stream));
-  h->par ^= 1;
   h->launches += 1;
   return MG_OK;
 }

@@ -121,14 +121,23 @@ struct Params {
   int *err;                 // sticky error word
   int *list[2];             // compacted env ids awaiting reset (ping-pong)
   int *count[2];
-  int *tile_ctr[2];         // dynamic tile scheduler of K1 (ping-pong between launches)
 };
 
 // word index of byte (line, pos) and helpers for the interleaved tile
 MG_HD int r_word(const Geom &g, int x, int y) { return (y + 1) * g.lswR + (x >> 2); }
 MG_HD int c_word(const Geom &g, int x, int y) { return g.offC + (x + 1) * g.lswC + (y >> 2); }
 
-MG_D uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+// PTX prmt.b32 (generic mode): selector nibble bits 0-2 pick one of the 8 source bytes, bit 3 replicates that
+// byte's sign bit instead. CUDA's __byte_perm() only honours the low 3 bits, hence the inline PTX.
+MG_D uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+#else
+  return __byte_perm(a, b, sel);
+#endif
+}
 MG_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 // bit i (i < 4) -> bit 8i
 MG_HD uint32_t spread4(uint32_t b) { return (b * 0x00204081u) & 0x01010101u; }

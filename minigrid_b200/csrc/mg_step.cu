@@ -62,15 +62,16 @@ __device__ __forceinline__ int load_action(const void *actions, int env) {
   return (int)reinterpret_cast<const ActT *>(actions)[env];
 }
 
-// Persistent warps: every warp owns two shared-memory buffers and walks tiles handed out by a device-side
-// counter. While tile i is being processed out of one buffer, the TMA bulk load of tile i+1 (and the
-// coalesced loads of its agent records / actions) is already in flight into the other, and the index of
-// tile i+2 is being fetched. par selects this launch's tile counter (the other one is re-armed for the next).
+// Persistent warps: the grid is one wave of CTAs; CTA c owns the contiguous tile range [c T/G, (c+1) T/G)
+// (so every SM gets the same share) and its warps pull tiles from a shared-memory counter (so a CTA's warps
+// stay balanced). Every warp owns two shared-memory buffers: while tile i is processed out of one, the TMA
+// bulk load of tile i+1 (and the coalesced loads of its agent records / actions) is already in flight into
+// the other, and the index of tile i+2 has been fetched.
 template <bool SEE_THROUGH, typename ActT>
 __global__ void __launch_bounds__(STEP_THREADS)
 k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out,
        double *__restrict__ reward_out, uint8_t *__restrict__ term_out, uint8_t *__restrict__ trunc_out,
-       int cur /*list this step appends to*/, int par, int obs_tma_ok) {
+       int cur /*list this step appends to*/, int obs_tma_ok) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const Geom g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -81,15 +82,17 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
   uint8_t *bufs = smem_raw + 1024 + (size_t)warp * 2 * buf_bytes;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * 2 * buf_bytes);
   const uint32_t bar0 = smem_u32(bars + 2 * warp);
+  int *s_next = reinterpret_cast<int *>(bars + 2 * STEP_WARPS);
 
   const bool stepping = actions != nullptr;  // nullptr: observation-only pass (MiniGridEnv.gen_obs), state untouched
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (stepping) *p.count[cur ^ 1] = 0;  // the reset list K2 consumed before this launch
-    *p.tile_ctr[par ^ 1] = 0;             // re-arm the other tile counter for the next launch
-  }
-  const int total_warps = gridDim.x * STEP_WARPS;
-  int tile = blockIdx.x * STEP_WARPS + warp;
-  int next = p.n_tiles;
+  if (stepping && blockIdx.x == 0 && threadIdx.x == 0) *p.count[cur ^ 1] = 0;  // the reset list K2 consumed before this launch
+  const int t_lo = (int)(((long long)p.n_tiles * blockIdx.x) / gridDim.x);
+  const int t_hi = (int)(((long long)p.n_tiles * (blockIdx.x + 1)) / gridDim.x);
+  if (threadIdx.x == 0) *s_next = t_lo + 2 * STEP_WARPS;  // warps start on t_lo + warp and t_lo + STEP_WARPS + warp
+  int tile = t_lo + warp;
+  int next = t_lo + STEP_WARPS + warp;
+  if (tile >= t_hi) tile = p.n_tiles;
+  if (next >= t_hi) next = p.n_tiles;
   uint4 rec = make_uint4(0, 0, 0, 0);
   int action = A_DONE;
   if (lane == 0) {
@@ -102,7 +105,6 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
     if (lane == 0) {
       mbar_expect_tx(bar0, tile_bytes);
       tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
-      next = atomicAdd(p.tile_ctr[par], 1) + total_warps;
     }
     const int env = tile * TILE + lane;
     rec = p.agent[env];
@@ -111,7 +113,6 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
   // the 256-entry (type, colour, state) table is pure arithmetic: no global load on the critical path
   for (int i = threadIdx.x; i < 256; i += STEP_THREADS) lut[i] = decode_cell((uint32_t)i);
   __syncthreads();
-  next = __shfl_sync(0xFFFFFFFFu, next, 0);
 
   uint32_t phase = 0;  // bit b = parity to wait for on buffer b
   int b = 0;
@@ -125,7 +126,8 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
         const uint32_t nb = bar0 + 8u * (uint32_t)(b ^ 1);
         mbar_expect_tx(nb, tile_bytes);
         tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
-        nn = atomicAdd(p.tile_ctr[par], 1) + total_warps;
+        nn = atomicAdd(s_next, 1);  // shared-memory atomic: tens of cycles, consumed one tile later
+        if (nn >= t_hi) nn = p.n_tiles;
       }
       const int env_n = next * TILE + lane;
       rec_n = p.agent[env_n];
@@ -230,10 +232,10 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
 
 template <bool ST, typename ActT>
 static cudaError_t launch_step_t(const Params &p, int grid, const void *actions, uint8_t *obs, int32_t *dir,
-                                 double *reward, uint8_t *term, uint8_t *trunc, int cur, int par, cudaStream_t stream) {
+                                 double *reward, uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream) {
   const size_t smem = step_smem_bytes(p.g);
   const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
-  k_step<ST, ActT><<<grid, STEP_THREADS, smem, stream>>>(p, actions, obs, dir, reward, term, trunc, cur, par, tma_ok);
+  k_step<ST, ActT><<<grid, STEP_THREADS, smem, stream>>>(p, actions, obs, dir, reward, term, trunc, cur, tma_ok);
   return cudaGetLastError();
 }
 
@@ -275,12 +277,12 @@ cudaError_t configure_step(const Params &p, int *grid_out) {
 }
 
 cudaError_t launch_step(const Params &p, int grid, const void *actions, int action_dtype, uint8_t *obs, int32_t *dir,
-                        double *reward, uint8_t *term, uint8_t *trunc, int cur, int par, cudaStream_t stream) {
+                        double *reward, uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream) {
 #define MG_DISPATCH(ST)                                                                                              \
   switch (action_dtype) {                                                                                            \
-    case 1: return launch_step_t<ST, int64_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, par, stream);    \
-    case 2: return launch_step_t<ST, uint8_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, par, stream);    \
-    default: return launch_step_t<ST, int32_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, par, stream);   \
+    case 1: return launch_step_t<ST, int64_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, stream);    \
+    case 2: return launch_step_t<ST, uint8_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, stream);    \
+    default: return launch_step_t<ST, int32_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, stream);   \
   }
   if (p.see_through) { MG_DISPATCH(true) } else { MG_DISPATCH(false) }
 #undef MG_DISPATCH
