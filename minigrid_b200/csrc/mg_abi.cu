@@ -11,17 +11,16 @@
 #include "mg_common.cuh"
 
 namespace mg {
-cudaError_t launch_step(const Params &p, int grid, const void *actions, int action_dtype, uint8_t *obs, int32_t *dir,
-                        double *reward, uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream);
-cudaError_t configure_step(const Params &p, int *grid_out);
-cudaError_t launch_reset(const Params &p, const int *list, const int *count, uint8_t *obs, int32_t *dir,
-                         int set_fresh, cudaStream_t stream);
+cudaError_t launch_step(const Params &p, int nbuf, int grid, const void *actions, int action_dtype, uint8_t *obs,
+                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream);
+cudaError_t configure_step(const Params &p, int nbuf_request, int *nbuf_out, int *grid_out);
+cudaError_t launch_reset(const Params &p, uint8_t *obs, int32_t *dir, cudaStream_t stream);
 cudaError_t launch_seed(const Params &p, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream);
 cudaError_t launch_full_obs(const Params &p, uint8_t *out, int with_agent, cudaStream_t stream);
 cudaError_t launch_get_state(const Params &p, uint8_t *grid, int32_t *agent, uint64_t *rng, uint8_t *pending,
                              cudaStream_t stream);
 cudaError_t launch_set_state(const Params &p, const uint8_t *grid, const int32_t *agent, const uint64_t *rng,
-                             const uint8_t *pending, int cur, cudaStream_t stream);
+                             const uint8_t *pending, cudaStream_t stream);
 cudaError_t launch_init(const Params &p, cudaStream_t stream);
 }  // namespace mg
 
@@ -30,8 +29,8 @@ using namespace mg;
 struct mg_env {
   Params p;
   int device;
-  int cur;           // the reset list the most recent step appended to
-  int step_grid;     // persistent grid of K1
+  int step_grid;     // persistent grid of K1 (one wave)
+  int step_nbuf;     // 1 or 2 tile buffers per warp
   int64_t launches;
   // device allocations owned by the handle
   void *d_arena;     // grid | agent | rng | lists | counts | err | luts, one cudaMalloc
@@ -98,18 +97,15 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   const size_t sz_grid = align_up((size_t)p.n_tiles * p.g.wpe * 128, 256);
   const size_t sz_agent = align_up(n_pad * sizeof(uint4), 256);
   const size_t sz_rng = align_up(n_pad * sizeof(RngRec), 256);
-  const size_t sz_list = align_up(n_pad * sizeof(int), 256);
   const size_t sz_lut_r = align_up((size_t)(max_steps + 1) * sizeof(double), 256);
-  const size_t total = sz_grid + sz_agent + sz_rng + 2 * sz_list + 256 /*counts+err*/ + sz_lut_r + 1024;
+  const size_t total = sz_grid + sz_agent + sz_rng + 256 /*err*/ + sz_lut_r + 1024;
   cudaError_t e = cudaMalloc(&h->d_arena, total);
   if (e != cudaSuccess) { delete h; return fail(MG_ERR_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); }
   uint8_t *base = (uint8_t *)h->d_arena;
   p.grid = (uint32_t *)base; base += sz_grid;
   p.agent = (uint4 *)base; base += sz_agent;
   p.rng = (RngRec *)base; base += sz_rng;
-  p.list[0] = (int *)base; base += sz_list;
-  p.list[1] = (int *)base; base += sz_list;
-  p.count[0] = (int *)base; p.count[1] = (int *)base + 1; p.err = (int *)base + 2; base += 256;
+  p.err = (int *)base; base += 256;
   double *d_rl = (double *)base; base += sz_lut_r;
   uint32_t *d_cl = (uint32_t *)base;
   p.reward_lut = d_rl; p.cell_lut = d_cl;
@@ -127,10 +123,13 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     uint32_t cl[256];
     for (uint32_t c = 0; c < 256; ++c) cl[c] = decode_cell(c);
     if (e == cudaSuccess) e = cudaMemcpy(d_cl, cl, sizeof(cl), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(p.count[0], 0, 256);
+    if (e == cudaSuccess) e = cudaMemset(p.err, 0, 256);
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = configure_step(p, &h->step_grid);
+  if (e == cudaSuccess) {
+    const char *nb = getenv("MINIGRID_B200_NBUF");  // tuning knob: force 1 or 2 tile buffers per warp
+    e = configure_step(p, nb ? atoi(nb) : 0, &h->step_nbuf, &h->step_grid);
+  }
   if (e == cudaSuccess) e = launch_init(p, h->hstream);
   if (e == cudaSuccess) e = launch_seed(p, nullptr, 0, h->hstream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->hstream);
@@ -190,8 +189,7 @@ int mg_reset(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_reset: NULL handle");
   MG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  MG_CUDA(cudaMemsetAsync(h->p.count[0], 0, 2 * sizeof(int), s));  // SyncVectorEnv.reset clears _autoreset_envs
-  MG_CUDA(launch_reset(h->p, nullptr, nullptr, obs_dev, dir_dev, 0, s));
+  MG_CUDA(launch_reset(h->p, obs_dev, dir_dev, s));
   h->launches += 1;
   return MG_OK;
 }
@@ -203,39 +201,28 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
   MG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const Params &p = h->p;
-  const int append = h->cur ^ 1;
-  if (p.mode == MG_AUTORESET_NEXT_STEP) {
-    // envs that finished last step are regenerated first; K1 then sees FLAG_FRESH, ignores their action and
-    // returns the reset observation with reward 0 / False / False
-    MG_CUDA(launch_reset(p, p.list[h->cur], p.count[h->cur], nullptr, nullptr, 1, s));
-    h->launches += 1;
-  }
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (h->profiling) {
     MG_CUDA(cudaEventCreate(&ev0));
     MG_CUDA(cudaEventCreate(&ev1));
     MG_CUDA(cudaEventRecord(ev0, s));
   }
-  MG_CUDA(launch_step(p, h->step_grid, actions_dev, action_dtype, obs_dev, dir_dev, reward_dev, terminated_dev, truncated_dev,
-                      append, s));
+  // one launch: transition + autoreset (either mode) + observation
+  MG_CUDA(launch_step(p, h->step_nbuf, h->step_grid, actions_dev, action_dtype, obs_dev, dir_dev, reward_dev, terminated_dev,
+                      truncated_dev, s));
   h->launches += 1;
   if (h->profiling) {
     MG_CUDA(cudaEventRecord(ev1, s));
     h->prof_events->push_back(ev0);
     h->prof_events->push_back(ev1);
   }
-  if (p.mode == MG_AUTORESET_SAME_STEP) {
-    MG_CUDA(launch_reset(p, p.list[append], p.count[append], obs_dev, dir_dev, 0, s));
-    h->launches += 1;
-  }
-  h->cur = append;
   return MG_OK;
 }
 
 int mg_gen_obs(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_gen_obs: NULL handle");
   MG_CUDA(cudaSetDevice(h->device));
-  MG_CUDA(launch_step(h->p, h->step_grid, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr, h->cur,
+  MG_CUDA(launch_step(h->p, h->step_nbuf, h->step_grid, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr,
                       (cudaStream_t)stream));
   h->launches += 1;
   return MG_OK;
@@ -286,8 +273,7 @@ int mg_set_state(mg_env *h, const uint8_t *grid_dev, const int32_t *agent_dev, c
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_set_state: NULL handle");
   MG_CUDA(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  if (pending_dev) MG_CUDA(cudaMemsetAsync(h->p.count[h->cur], 0, sizeof(int), s));
-  MG_CUDA(launch_set_state(h->p, grid_dev, agent_dev, rng_dev, pending_dev, h->cur, s));
+  MG_CUDA(launch_set_state(h->p, grid_dev, agent_dev, rng_dev, pending_dev, s));
   h->launches += (grid_dev ? 1 : 0) + ((agent_dev || rng_dev || pending_dev) ? 1 : 0);
   return MG_OK;
 }

@@ -56,8 +56,7 @@ constexpr uint32_t CODE_GOAL = T_GOAL | (C_GREEN << 4);
 constexpr uint32_t CODE_LAVA = T_LAVA | (C_RED << 4);
 
 // agent flags (second word of the agent record, bits 8..)
-constexpr uint32_t FLAG_FRESH = 1u;    // state was just regenerated: the next step emits the reset obs
-constexpr uint32_t FLAG_PENDING = 2u;  // episode ended last step (SyncVectorEnv._autoreset_envs[i])
+constexpr uint32_t FLAG_PENDING = 2u;  // episode ended last step (SyncVectorEnv._autoreset_envs[i], NEXT_STEP)
 
 enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS = 3 };
 enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
@@ -119,8 +118,6 @@ struct Params {
   const double *reward_lut; // [max_steps + 1], 1 - 0.9 * (k / max_steps) computed on the host in IEEE double
   const uint32_t *cell_lut; // [256] decode_cell()
   int *err;                 // sticky error word
-  int *list[2];             // compacted env ids awaiting reset (ping-pong)
-  int *count[2];
 };
 
 // word index of byte (line, pos) and helpers for the interleaved tile

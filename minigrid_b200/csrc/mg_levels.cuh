@@ -172,32 +172,29 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
   }
 }
 
-// fill phase: both arrays of one env; col points at the env's lane column of its tile (word w at col[w * 32])
+// fill phase. Word w of an env (w < wpe): 4 consecutive bytes of one line of array R (w < offC) or C.
+template <int KIND>
+MG_D uint32_t level_word(const Params &p, const Level &L, int w) {
+  const Geom &g = p.g;
+  const bool inC = w >= g.offC;
+  const int lw = inC ? g.lswC : g.lswR;
+  const int rel = inC ? w - g.offC : w;
+  const int line = rel / lw - 1, wi = rel - (line + 1) * lw;
+  const int nlines = inC ? g.W : g.H, plen = inC ? g.H : g.W;
+  uint32_t word = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int pos = 4 * wi + b;
+    uint32_t c = CODE_WALL;
+    if (line >= 0 && line < nlines && pos < plen) c = inC ? cell_of<KIND>(p, L, line, pos) : cell_of<KIND>(p, L, pos, line);
+    word |= c << (8 * b);
+  }
+  return word;
+}
+// both arrays of one env; col points at the env's lane column of its tile (word w at col[w * 32])
 template <int KIND>
 MG_D void fill_level(const Params &p, const Level &L, uint32_t *col) {
-  const Geom &g = p.g;
-  for (int ly = -1; ly <= g.H; ++ly)
-    for (int wi = 0; wi < g.lswR; ++wi) {
-      uint32_t word = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int x = 4 * wi + b;
-        const uint32_t c = (ly < 0 || ly >= g.H || x >= g.W) ? CODE_WALL : cell_of<KIND>(p, L, x, ly);
-        word |= c << (8 * b);
-      }
-      col[((ly + 1) * g.lswR + wi) * 32] = word;
-    }
-  for (int lx = -1; lx <= g.W; ++lx)
-    for (int wi = 0; wi < g.lswC; ++wi) {
-      uint32_t word = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int y = 4 * wi + b;
-        const uint32_t c = (lx < 0 || lx >= g.W || y >= g.H) ? CODE_WALL : cell_of<KIND>(p, L, lx, y);
-        word |= c << (8 * b);
-      }
-      col[(g.offC + (lx + 1) * g.lswC + wi) * 32] = word;
-    }
+  for (int w = 0; w < p.g.wpe; ++w) col[w * 32] = level_word<KIND>(p, L, w);
 }
 
 }  // namespace mg

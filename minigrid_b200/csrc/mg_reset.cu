@@ -1,6 +1,6 @@
-// mg_reset.cu — K2: MiniGridEnv.reset (minigrid_env.py:119-157) = per-kind _gen_grid with numpy-exact RNG,
-// one lane per environment, driven either over every env (initial reset) or over the compacted list of
-// environments whose episode just ended (autoreset). Also the seeding kernel (SeedSequence -> PCG64).
+// mg_reset.cu — K2: MiniGridEnv.reset (minigrid_env.py:119-157) = per-kind _gen_grid with numpy-exact RNG for
+// EVERY environment (the explicit VectorEnv.reset()), one lane per environment; autoreset of individual
+// environments happens inside K1 (mg_step.cu). Also the seeding kernel (SeedSequence -> PCG64).
 // The generators themselves live in mg_levels.cuh.
 #include "mg_common.cuh"
 #include "mg_obs.cuh"
@@ -11,12 +11,9 @@ namespace mg {
 
 template <int KIND>
 __global__ void __launch_bounds__(128)
-k_reset(Params p, const int *__restrict__ list, const int *__restrict__ count, uint8_t *__restrict__ obs,
-        int32_t *__restrict__ dir_out, int set_fresh) {
-  const int n = list ? *count : p.n_envs;
+k_reset(Params p, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out) {
   const Geom &g = p.g;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    const int env = list ? list[idx] : idx;
+  for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < p.n_envs; env += gridDim.x * blockDim.x) {
     Pcg r = load_rng(p.rng + env);
     Level L;
     draw_level<KIND>(p, r, L);
@@ -25,7 +22,7 @@ k_reset(Params p, const int *__restrict__ list, const int *__restrict__ count, u
     fill_level<KIND>(p, L, col);
     uint4 rec;
     rec.x = (uint32_t)L.ax | ((uint32_t)L.ay << 8);
-    rec.y = (uint32_t)L.adir | ((set_fresh ? FLAG_FRESH : 0u) << 8);
+    rec.y = (uint32_t)L.adir;  // flags cleared: SyncVectorEnv.reset() clears _autoreset_envs
     rec.z = 0;  // carrying = None
     rec.w = 0;  // step_count = 0
     p.agent[env] = rec;
@@ -39,17 +36,14 @@ k_reset(Params p, const int *__restrict__ list, const int *__restrict__ count, u
   }
 }
 
-cudaError_t launch_reset(const Params &p, const int *list, const int *count, uint8_t *obs, int32_t *dir,
-                         int set_fresh, cudaStream_t stream) {
-  // the list length lives on the device: a fixed grid with a grid-stride loop needs no host round trip
+cudaError_t launch_reset(const Params &p, uint8_t *obs, int32_t *dir, cudaStream_t stream) {
   const int threads = 128;
-  int blocks = list ? 148 * 4 : (p.n_envs + threads - 1) / threads;
-  if (blocks < 1) blocks = 1;
+  const int blocks = (p.n_envs + threads - 1) / threads;
   switch (p.kind) {
-    case KIND_EMPTY: k_reset<KIND_EMPTY><<<blocks, threads, 0, stream>>>(p, list, count, obs, dir, set_fresh); break;
-    case KIND_DOORKEY: k_reset<KIND_DOORKEY><<<blocks, threads, 0, stream>>>(p, list, count, obs, dir, set_fresh); break;
-    case KIND_CROSSING: k_reset<KIND_CROSSING><<<blocks, threads, 0, stream>>>(p, list, count, obs, dir, set_fresh); break;
-    default: k_reset<KIND_FOURROOMS><<<blocks, threads, 0, stream>>>(p, list, count, obs, dir, set_fresh); break;
+    case KIND_EMPTY: k_reset<KIND_EMPTY><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_DOORKEY: k_reset<KIND_DOORKEY><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_CROSSING: k_reset<KIND_CROSSING><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    default: k_reset<KIND_FOURROOMS><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
   }
   return cudaGetLastError();
 }

@@ -57,9 +57,8 @@ __global__ void k_set_grid(Params p, const uint8_t *__restrict__ grid) {
   col[(size_t)c_word(p.g, x, y) * 128 + (y & 3)] = code;
 }
 
-// cur: the list the next mg_step will consume (NEXT_STEP). Rebuilt from the pending flags.
 __global__ void k_set_agent(Params p, const int32_t *__restrict__ agent, const uint64_t *__restrict__ rng,
-                            const uint8_t *__restrict__ pending, int cur) {
+                            const uint8_t *__restrict__ pending) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= p.n_envs) return;
   uint4 rec = p.agent[env];
@@ -69,14 +68,10 @@ __global__ void k_set_agent(Params p, const int32_t *__restrict__ agent, const u
     rec.y = (rec.y & ~3u) | (uint32_t)(a[2] & 3);
     rec.z = a[3] >= 0 ? ((uint32_t)(a[3] & 15) | ((uint32_t)(a[4] & 7) << 4)) : 0u;
     rec.w = (uint32_t)a[5];
-    rec.y &= ~(FLAG_FRESH << 8);
   }
   if (pending) {
     uint32_t flags = (rec.y >> 8) & ~FLAG_PENDING;
-    if (pending[env]) {
-      flags |= FLAG_PENDING;
-      p.list[cur][atomicAdd(p.count[cur], 1)] = env;
-    }
+    if (pending[env]) flags |= FLAG_PENDING;
     rec.y = (rec.y & 0xFFu) | (flags << 8);
   }
   p.agent[env] = rec;
@@ -117,12 +112,12 @@ cudaError_t launch_get_state(const Params &p, uint8_t *grid, int32_t *agent, uin
   return cudaGetLastError();
 }
 cudaError_t launch_set_state(const Params &p, const uint8_t *grid, const int32_t *agent, const uint64_t *rng,
-                             const uint8_t *pending, int cur, cudaStream_t stream) {
+                             const uint8_t *pending, cudaStream_t stream) {
   if (grid) {
     const long long total = (long long)p.n_envs * p.g.W * p.g.H;
     k_set_grid<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, grid);
   }
-  if (agent || rng || pending) k_set_agent<<<(p.n_envs + 127) / 128, 128, 0, stream>>>(p, agent, rng, pending, cur);
+  if (agent || rng || pending) k_set_agent<<<(p.n_envs + 127) / 128, 128, 0, stream>>>(p, agent, rng, pending);
   return cudaGetLastError();
 }
 cudaError_t launch_init(const Params &p, cudaStream_t stream) {

@@ -1,18 +1,23 @@
-// mg_step.cu — K1: MiniGridEnv.step (minigrid_env.py:525-595) fused with gen_obs (:597-650) for a batch.
+// mg_step.cu — K1: MiniGridEnv.step (minigrid_env.py:525-595) fused with gen_obs (:597-650) and with the
+// vector-level autoreset (MiniGridEnv.reset, :119-157) for a batch: ONE launch per vector step.
 //
 // One warp = one tile of 32 environments, one lane per environment.
 //   1. lane 0 issues a TMA bulk copy (cp.async.bulk -> SASS UBLKCP) of the tile's interleaved grid words
 //      into shared memory and arms an mbarrier with the byte count; meanwhile every lane loads its
-//      action and 16-byte agent record with coalesced loads. Warps are persistent and double-buffered:
-//      the copy for the next tile is issued before the current one is processed.
-//   2. transition: the 7-action rule on (agent, carrying, the one cell in front), predicated, with the
+//      action and 16-byte agent record with coalesced loads. Warps are persistent; with NBUF == 2 they are
+//      double-buffered (the copy for the next tile is issued before the current one is processed).
+//   2. autoreset (NEXT_STEP: envs flagged last step, before the transition; SAME_STEP: envs that just ended,
+//      after it): rare, so the whole warp regenerates one environment at a time — every lane replays the
+//      numpy-exact RNG draws (uniform control flow) and fills a 1/32 share of the level's words.
+//   3. transition: the 7-action rule on (agent, carrying, the one cell in front), predicated, with the
 //      rare cell mutation written to the staged tile and straight back to HBM (2 byte stores).
-//   3. observation in registers (mg_obs.cuh), staged to shared memory in output layout, then one TMA bulk
-//      store of the warp's 32 x 147 = 4704 contiguous bytes.
-//   4. coalesced stores of direction / reward / terminated / truncated and the agent record; environments
-//      whose episode ended are appended (warp-aggregated atomic) to the compacted reset list that K2 eats.
+//   4. observation in registers (mg_obs.cuh), staged into the consumed tile buffer in output layout, then one
+//      TMA bulk store of the warp's 32 x 147 = 4704 contiguous bytes.
+//   5. coalesced stores of direction / reward / terminated / truncated and the agent record.
 #include "mg_common.cuh"
+#include "mg_levels.cuh"
 #include "mg_obs.cuh"
+#include "mg_pcg64.cuh"
 #include "mg_transition.cuh"
 
 namespace mg {
@@ -21,14 +26,14 @@ constexpr int STEP_WARPS = 4;
 constexpr int STEP_THREADS = STEP_WARPS * 32;
 
 // per-warp buffer: holds the staged tile, then (once the gather has consumed it) the warp's 4704-byte
-// observation block in output layout. Two of them per warp: compute on one while TMA fills the other.
+// observation block in output layout.
 __host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
   uint32_t b = (uint32_t)g.wpe * 128u;
   if (b < (uint32_t)OBS_TILE_BYTES) b = OBS_TILE_BYTES;
   return (b + 127u) & ~127u;
 }
-__host__ __device__ inline size_t step_smem_bytes(const Geom &g) {
-  return 1024 /*cell table*/ + (size_t)STEP_WARPS * 2 * step_buf_bytes(g) + 128 /*mbarriers*/;
+__host__ __device__ inline size_t step_smem_bytes(const Geom &g, int nbuf) {
+  return 1024 /*cell table*/ + (size_t)STEP_WARPS * nbuf * step_buf_bytes(g) + 128 /*mbarriers + tile counter*/;
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -57,21 +62,47 @@ __device__ __forceinline__ void tma_store_1d(void *dst, uint32_t src, uint32_t b
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
-template <typename ActT>
-__device__ __forceinline__ int load_action(const void *actions, int env) {
-  return (int)reinterpret_cast<const ActT *>(actions)[env];
+__device__ __forceinline__ int load_action(const void *actions, int dtype, int env) {
+  if (dtype == 1) return (int)reinterpret_cast<const long long *>(actions)[env];
+  if (dtype == 2) return (int)reinterpret_cast<const uint8_t *>(actions)[env];
+  return reinterpret_cast<const int *>(actions)[env];
 }
 
-// Persistent warps: the grid is one wave of CTAs; CTA c owns the contiguous tile range [c T/G, (c+1) T/G)
-// (so every SM gets the same share) and its warps pull tiles from a shared-memory counter (so a CTA's warps
-// stay balanced). Every warp owns two shared-memory buffers: while tile i is processed out of one, the TMA
-// bulk load of tile i+1 (and the coalesced loads of its agent records / actions) is already in flight into
-// the other, and the index of tile i+2 has been fetched.
-template <bool SEE_THROUGH, typename ActT>
+// MiniGridEnv.reset() for the lanes in `pend`, one environment at a time with the whole warp: all lanes
+// replay the draws (same RNG state, uniform control flow), lane L fills words L, L+32, ... of the level into
+// the staged tile and HBM, and the owning lane takes the new agent state. Out of line: it is the rare path
+// and must not cost the hot loop registers.
+struct ResetOut { int ax, ay, dir; };
+
+template <int KIND>
+__device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int tile, uint32_t *gtile, int lane) {
+  ResetOut out = {0, 0, 0};
+  const Geom &g = p.g;
+  uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
+  while (pend) {
+    const int src = __ffs(pend) - 1;
+    pend &= pend - 1;
+    const int env = tile * TILE + src;
+    Pcg r = load_rng(p.rng + env);
+    Level L;
+    draw_level<KIND>(p, r, L);
+    if (lane == 0) store_rng(p.rng + env, r);
+    for (int w = lane; w < g.wpe; w += 32) {
+      const uint32_t word = level_word<KIND>(p, L, w);
+      gtile[w * 32 + src] = word;
+      gsrc[w * 32 + src] = word;
+    }
+    if (lane == src) { out.ax = L.ax; out.ay = L.ay; out.dir = L.adir; }
+  }
+  __syncwarp();
+  return out;
+}
+
+template <int KIND, bool SEE_THROUGH, int NBUF>
 __global__ void __launch_bounds__(STEP_THREADS)
-k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out,
-       double *__restrict__ reward_out, uint8_t *__restrict__ term_out, uint8_t *__restrict__ trunc_out,
-       int cur /*list this step appends to*/, int obs_tma_ok) {
+k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
+       int32_t *__restrict__ dir_out, double *__restrict__ reward_out, uint8_t *__restrict__ term_out,
+       uint8_t *__restrict__ trunc_out, int obs_tma_ok) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const Geom g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -79,18 +110,18 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
   const uint32_t buf_bytes = step_buf_bytes(g);
 
   uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);
-  uint8_t *bufs = smem_raw + 1024 + (size_t)warp * 2 * buf_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * 2 * buf_bytes);
+  uint8_t *bufs = smem_raw + 1024 + (size_t)warp * NBUF * buf_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * NBUF * buf_bytes);
   const uint32_t bar0 = smem_u32(bars + 2 * warp);
   int *s_next = reinterpret_cast<int *>(bars + 2 * STEP_WARPS);
 
   const bool stepping = actions != nullptr;  // nullptr: observation-only pass (MiniGridEnv.gen_obs), state untouched
-  if (stepping && blockIdx.x == 0 && threadIdx.x == 0) *p.count[cur ^ 1] = 0;  // the reset list K2 consumed before this launch
+  // one wave of persistent CTAs; CTA c owns tiles [c T/G, (c+1) T/G), its warps pull from a shared counter
   const int t_lo = (int)(((long long)p.n_tiles * blockIdx.x) / gridDim.x);
   const int t_hi = (int)(((long long)p.n_tiles * (blockIdx.x + 1)) / gridDim.x);
-  if (threadIdx.x == 0) *s_next = t_lo + 2 * STEP_WARPS;  // warps start on t_lo + warp and t_lo + STEP_WARPS + warp
+  if (threadIdx.x == 0) *s_next = t_lo + NBUF * STEP_WARPS;
   int tile = t_lo + warp;
-  int next = t_lo + STEP_WARPS + warp;
+  int next = (NBUF == 2) ? t_lo + STEP_WARPS + warp : p.n_tiles;
   if (tile >= t_hi) tile = p.n_tiles;
   if (next >= t_hi) next = p.n_tiles;
   uint4 rec = make_uint4(0, 0, 0, 0);
@@ -101,14 +132,14 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  if (tile < p.n_tiles) {
+  if (NBUF == 2 && tile < p.n_tiles) {
     if (lane == 0) {
       mbar_expect_tx(bar0, tile_bytes);
       tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
     }
     const int env = tile * TILE + lane;
     rec = p.agent[env];
-    if (stepping && env < p.n_envs) action = load_action<ActT>(actions, env);
+    if (stepping && env < p.n_envs) action = load_action(actions, act_dtype, env);
   }
   // the 256-entry (type, colour, state) table is pure arithmetic: no global load on the critical path
   for (int i = threadIdx.x; i < 256; i += STEP_THREADS) lut[i] = decode_cell((uint32_t)i);
@@ -117,21 +148,34 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
   uint32_t phase = 0;  // bit b = parity to wait for on buffer b
   int b = 0;
   while (tile < p.n_tiles) {
-    // ---- prefetch tile `next` into the other buffer, and the index of the tile after it ----
     uint4 rec_n = make_uint4(0, 0, 0, 0);
     int action_n = A_DONE, nn = p.n_tiles;
-    if (next < p.n_tiles) {
+    if (NBUF == 2) {
+      // ---- prefetch tile `next` into the other buffer, and the index of the tile after it ----
+      if (next < p.n_tiles) {
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the obs block staged there two tiles ago
+          const uint32_t nb = bar0 + 8u * (uint32_t)(b ^ 1);
+          mbar_expect_tx(nb, tile_bytes);
+          tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
+          nn = atomicAdd(s_next, 1);  // shared-memory atomic, consumed one tile later
+          if (nn >= t_hi) nn = p.n_tiles;
+        }
+        const int env_n = next * TILE + lane;
+        rec_n = p.agent[env_n];
+        if (stepping && env_n < p.n_envs) action_n = load_action(actions, act_dtype, env_n);
+      }
+    } else {
       if (lane == 0) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the obs block staged there two tiles ago
-        const uint32_t nb = bar0 + 8u * (uint32_t)(b ^ 1);
-        mbar_expect_tx(nb, tile_bytes);
-        tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
-        nn = atomicAdd(s_next, 1);  // shared-memory atomic: tens of cycles, consumed one tile later
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left the buffer
+        mbar_expect_tx(bar0, tile_bytes);
+        tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
+        nn = atomicAdd(s_next, 1);
         if (nn >= t_hi) nn = p.n_tiles;
       }
-      const int env_n = next * TILE + lane;
-      rec_n = p.agent[env_n];
-      if (stepping && env_n < p.n_envs) action_n = load_action<ActT>(actions, env_n);
+      const int env0 = tile * TILE + lane;
+      rec = p.agent[env0];
+      action = (stepping && env0 < p.n_envs) ? load_action(actions, act_dtype, env0) : A_DONE;
     }
 
     uint32_t *gtile = reinterpret_cast<uint32_t *>(bufs + (size_t)b * buf_bytes);
@@ -150,7 +194,17 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
     const uint32_t *base = gtile + lane;
     double reward = 0.0;
     uint32_t terminated = 0, truncated = 0;
-    const bool fresh = (flags & FLAG_FRESH) != 0;
+    // NEXT_STEP autoreset (gymnasium >= 1.0 SyncVectorEnv): an env that ended last step ignores its action,
+    // is reset now, and returns the reset obs with reward 0 / False / False
+    bool fresh = false;
+    if (stepping && p.mode == AUTORESET_NEXT_STEP) {
+      fresh = active && (flags & FLAG_PENDING);
+      const unsigned pend = __ballot_sync(0xFFFFFFFFu, fresh);
+      if (pend) {
+        const ResetOut ro = warp_reset<KIND>(p, pend, tile, gtile, lane);
+        if (fresh) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; flags &= ~FLAG_PENDING; }
+      }
+    }
     if (stepping && !fresh) {
       // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
       steps += 1;
@@ -173,19 +227,16 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
         gb[ro] = (uint8_t)newc; gb[co] = (uint8_t)newc;
       }
       truncated = steps >= p.max_steps;
-    }
-    const bool done = (terminated | truncated) != 0;
-    if (stepping) {
-      flags &= ~FLAG_FRESH;
+      const bool done = (terminated | truncated) != 0;
       if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
     }
-    if (stepping && p.mode != AUTORESET_DISABLED) {
-      const unsigned ball = __ballot_sync(0xFFFFFFFFu, done && active);
-      if (ball) {
-        int basei = 0;
-        if (lane == 0) basei = atomicAdd(p.count[cur], __popc(ball));
-        basei = __shfl_sync(0xFFFFFFFFu, basei, 0);
-        if (done && active) p.list[cur][basei + __popc(ball & ((1u << lane) - 1u))] = env;
+    // SAME_STEP autoreset: the env is reset inside the step that ended it and the reset obs is returned
+    if (stepping && p.mode == AUTORESET_SAME_STEP) {
+      const bool again = active && ((terminated | truncated) != 0);
+      const unsigned pend = __ballot_sync(0xFFFFFFFFu, again);
+      if (pend) {
+        const ResetOut ro = warp_reset<KIND>(p, pend, tile, gtile, lane);
+        if (again) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; }
       }
     }
 
@@ -221,71 +272,74 @@ k_step(Params p, const void *__restrict__ actions, uint8_t *__restrict__ obs, in
       if (trunc_out) trunc_out[env] = (uint8_t)truncated;
     }
     __syncwarp();  // lanes may still be reading this buffer (partial-tile path) before it is refilled
-    tile = next;
-    next = __shfl_sync(0xFFFFFFFFu, nn, 0);
-    rec = rec_n;
-    action = action_n;
-    b ^= 1;
+    if (NBUF == 2) {
+      tile = next;
+      next = __shfl_sync(0xFFFFFFFFu, nn, 0);
+      rec = rec_n;
+      action = action_n;
+      b ^= 1;
+    } else {
+      tile = __shfl_sync(0xFFFFFFFFu, nn, 0);
+    }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
-template <bool ST, typename ActT>
-static cudaError_t launch_step_t(const Params &p, int grid, const void *actions, uint8_t *obs, int32_t *dir,
-                                 double *reward, uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream) {
-  const size_t smem = step_smem_bytes(p.g);
-  const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
-  k_step<ST, ActT><<<grid, STEP_THREADS, smem, stream>>>(p, actions, obs, dir, reward, term, trunc, cur, tma_ok);
-  return cudaGetLastError();
+typedef void (*StepKernel)(Params, const void *, int, uint8_t *, int32_t *, double *, uint8_t *, uint8_t *, int);
+
+template <int NBUF>
+static StepKernel pick_kernel(int kind, int see_through) {
+#define MG_K(K) (see_through ? (StepKernel)k_step<K, true, NBUF> : (StepKernel)k_step<K, false, NBUF>)
+  switch (kind) {
+    case KIND_EMPTY: return MG_K(KIND_EMPTY);
+    case KIND_DOORKEY: return MG_K(KIND_DOORKEY);
+    case KIND_CROSSING: return MG_K(KIND_CROSSING);
+    default: return MG_K(KIND_FOURROOMS);
+  }
+#undef MG_K
+}
+static StepKernel step_kernel(const Params &p, int nbuf) {
+  return nbuf == 2 ? pick_kernel<2>(p.kind, p.see_through) : pick_kernel<1>(p.kind, p.see_through);
 }
 
-template <bool ST, typename ActT>
-static cudaError_t configure_one(size_t smem, int *ctas_per_sm) {
-  cudaError_t e = cudaFuncSetAttribute(k_step<ST, ActT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  int n = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_step<ST, ActT>, STEP_THREADS, smem);
-  if (e == cudaSuccess && n < *ctas_per_sm) *ctas_per_sm = n;
-  return e;
-}
-// opt in to the tile-dependent dynamic shared memory once per handle and size the persistent grid:
-// one CTA slot per resident CTA, never more CTAs than there are groups of STEP_WARPS tiles
-cudaError_t configure_step(const Params &p, int *grid_out) {
-  const size_t smem = step_smem_bytes(p.g);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  int ctas = 32;
-  cudaError_t e = cudaSuccess;
-  if (p.see_through) {
-    if (e == cudaSuccess) e = configure_one<true, int32_t>(smem, &ctas);
-    if (e == cudaSuccess) e = configure_one<true, int64_t>(smem, &ctas);
-    if (e == cudaSuccess) e = configure_one<true, uint8_t>(smem, &ctas);
-  } else {
-    if (e == cudaSuccess) e = configure_one<false, int32_t>(smem, &ctas);
-    if (e == cudaSuccess) e = configure_one<false, int64_t>(smem, &ctas);
-    if (e == cudaSuccess) e = configure_one<false, uint8_t>(smem, &ctas);
-  }
-  if (e != cudaSuccess) return e;
+// opt in to the tile-dependent dynamic shared memory once per handle, choose single or double buffering
+// (double buffering needs twice the shared memory per warp) and size the persistent grid: one wave of CTAs,
+// never more CTAs than there are groups of STEP_WARPS tiles
+cudaError_t configure_step(const Params &p, int nbuf_request, int *nbuf_out, int *grid_out) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (ctas < 1) return cudaErrorInvalidValue;
+  int best_nbuf = 0, best_ctas = 0;
+  for (int nbuf = 2; nbuf >= 1; --nbuf) {
+    if (nbuf_request && nbuf != nbuf_request) continue;
+    const size_t smem = step_smem_bytes(p.g, nbuf);
+    if (smem > 227 * 1024) continue;
+    StepKernel k = step_kernel(p, nbuf);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k, STEP_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    if (ctas < 1) continue;
+    // prefer double buffering unless it leaves fewer than 4 CTAs (16 warps) per SM and single buffering has more
+    if (best_nbuf == 0 || (best_ctas < 4 && ctas > best_ctas)) { best_nbuf = nbuf; best_ctas = ctas; }
+  }
+  if (best_nbuf == 0) return cudaErrorInvalidValue;
   const long long want = ((long long)p.n_tiles + STEP_WARPS - 1) / STEP_WARPS;
-  long long grid = (long long)sms * ctas;
+  long long grid = (long long)sms * best_ctas;
   if (grid > want) grid = want;
   *grid_out = (int)(grid < 1 ? 1 : grid);
+  *nbuf_out = best_nbuf;
   return cudaSuccess;
 }
 
-cudaError_t launch_step(const Params &p, int grid, const void *actions, int action_dtype, uint8_t *obs, int32_t *dir,
-                        double *reward, uint8_t *term, uint8_t *trunc, int cur, cudaStream_t stream) {
-#define MG_DISPATCH(ST)                                                                                              \
-  switch (action_dtype) {                                                                                            \
-    case 1: return launch_step_t<ST, int64_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, stream);    \
-    case 2: return launch_step_t<ST, uint8_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, stream);    \
-    default: return launch_step_t<ST, int32_t>(p, grid, actions, obs, dir, reward, term, trunc, cur, stream);   \
-  }
-  if (p.see_through) { MG_DISPATCH(true) } else { MG_DISPATCH(false) }
-#undef MG_DISPATCH
+cudaError_t launch_step(const Params &p, int nbuf, int grid, const void *actions, int action_dtype, uint8_t *obs,
+                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream) {
+  const size_t smem = step_smem_bytes(p.g, nbuf);
+  const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
+  StepKernel k = step_kernel(p, nbuf);
+  k<<<grid, STEP_THREADS, smem, stream>>>(p, actions, action_dtype, obs, dir, reward, term, trunc, tma_ok);
+  return cudaGetLastError();
 }
 
 }  // namespace mg

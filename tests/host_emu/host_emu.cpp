@@ -16,6 +16,8 @@
 
 using namespace mg;
 
+static size_t step_words(const Geom &g) { size_t w = (size_t)g.wpe * 32; return w < 1184 ? 1184 : w; }
+
 struct Emu {
   Params p;
   std::vector<uint32_t> grid;
@@ -23,14 +25,11 @@ struct Emu {
   std::vector<RngRec> rng;
   std::vector<double> reward_lut;
   std::vector<uint32_t> cell_lut;
-  std::vector<int> list[2];
-  int count[2];
-  int cur;
   int err;
 };
 
 template <int KIND>
-static void reset_env(Emu *e, int env, uint8_t *obs, int32_t *dir_out, int set_fresh) {  // k_reset body
+static void reset_env(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {  // k_reset body
   Params &p = e->p;
   Pcg r = load_rng(&e->rng[env]);
   Level L;
@@ -40,7 +39,7 @@ static void reset_env(Emu *e, int env, uint8_t *obs, int32_t *dir_out, int set_f
   fill_level<KIND>(p, L, col);
   uint4 rec;
   rec.x = (uint32_t)L.ax | ((uint32_t)L.ay << 8);
-  rec.y = (uint32_t)L.adir | ((set_fresh ? FLAG_FRESH : 0u) << 8);
+  rec.y = (uint32_t)L.adir;
   rec.z = 0; rec.w = 0;
   p.agent[env] = rec;
   if (dir_out) dir_out[env] = L.adir;
@@ -51,92 +50,145 @@ static void reset_env(Emu *e, int env, uint8_t *obs, int32_t *dir_out, int set_f
     emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
   }
 }
-static void reset_one(Emu *e, int env, uint8_t *obs, int32_t *dir_out, int set_fresh) {
+static void reset_one(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {
   switch (e->p.kind) {
-    case KIND_EMPTY: reset_env<KIND_EMPTY>(e, env, obs, dir_out, set_fresh); break;
-    case KIND_DOORKEY: reset_env<KIND_DOORKEY>(e, env, obs, dir_out, set_fresh); break;
-    case KIND_CROSSING: reset_env<KIND_CROSSING>(e, env, obs, dir_out, set_fresh); break;
-    default: reset_env<KIND_FOURROOMS>(e, env, obs, dir_out, set_fresh); break;
+    case KIND_EMPTY: reset_env<KIND_EMPTY>(e, env, obs, dir_out); break;
+    case KIND_DOORKEY: reset_env<KIND_DOORKEY>(e, env, obs, dir_out); break;
+    case KIND_CROSSING: reset_env<KIND_CROSSING>(e, env, obs, dir_out); break;
+    default: reset_env<KIND_FOURROOMS>(e, env, obs, dir_out); break;
   }
 }
-static void reset_list(Emu *e, int which, uint8_t *obs, int32_t *dir, int set_fresh) {
-  for (int i = 0; i < e->count[which]; ++i) reset_one(e, e->list[which][i], obs, dir, set_fresh);
+// warp_reset body: the lanes in `pend` are regenerated one at a time; every "lane" fills its share of words
+struct ResetOut { int ax, ay, dir; };
+template <int KIND>
+static void warp_reset_k(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOut out[32]) {
+  Params &p = e->p;
+  uint32_t *gsrc = p.grid + (size_t)tile * p.g.wpe * 32;
+  while (pend) {
+    const int src = __ffs(pend) - 1;
+    pend &= pend - 1;
+    const int env = tile * TILE + src;
+    Pcg r = load_rng(&e->rng[env]);
+    Level L;
+    draw_level<KIND>(p, r, L);
+    store_rng(&e->rng[env], r);
+    for (int w = 0; w < p.g.wpe; ++w) {
+      const uint32_t word = level_word<KIND>(p, L, w);
+      gtile[w * 32 + src] = word;
+      gsrc[w * 32 + src] = word;
+    }
+    out[src].ax = L.ax; out[src].ay = L.ay; out[src].dir = L.adir;
+  }
+}
+static void warp_reset(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOut out[32]) {
+  switch (e->p.kind) {
+    case KIND_EMPTY: warp_reset_k<KIND_EMPTY>(e, pend, tile, gtile, out); break;
+    case KIND_DOORKEY: warp_reset_k<KIND_DOORKEY>(e, pend, tile, gtile, out); break;
+    case KIND_CROSSING: warp_reset_k<KIND_CROSSING>(e, pend, tile, gtile, out); break;
+    default: warp_reset_k<KIND_FOURROOMS>(e, pend, tile, gtile, out); break;
+  }
 }
 
 template <bool ST>
 static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *dir_out, double *reward_out,
-                       uint8_t *term_out, uint8_t *trunc_out, int cur) {  // k_step body
+                       uint8_t *term_out, uint8_t *trunc_out) {  // k_step body, phase by phase over the 32 lanes
   Params &p = e->p;
   const Geom g = p.g;
   const bool stepping = actions != nullptr;
-  if (stepping) e->count[cur ^ 1] = 0;
-  std::vector<uint32_t> gtile((size_t)g.wpe * 32), stage(1184);
+  std::vector<uint32_t> gtile((size_t)step_words(g)), S_all(32 * OBS_WORDS);
   for (int tile = 0; tile < p.n_tiles; ++tile) {
     uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
     memcpy(gtile.data(), gsrc, (size_t)g.wpe * 128);  // the TMA bulk load
-    uint32_t S[32][OBS_WORDS];
     const bool full = (tile + 1) * TILE <= p.n_envs;
+    int ax[32], ay[32], dir[32], steps[32];
+    uint32_t flags[32], carry[32], terminated[32] = {0}, truncated[32] = {0};
+    double reward[32] = {0};
+    bool active[32], fresh[32] = {false};
+    uint4 rec[32];
     for (int lane = 0; lane < 32; ++lane) {
       const int env = tile * TILE + lane;
-      const bool active = env < p.n_envs;
-      uint4 rec = p.agent[env];
-      int ax = rec.x & 0xFF, ay = (rec.x >> 8) & 0xFF, dir = rec.y & 3;
-      uint32_t flags = rec.y >> 8, carry = rec.z;
-      int steps = (int)rec.w;
-      const int action = (actions && active) ? actions[env] : A_DONE;
-      const uint32_t *base = gtile.data() + lane;
-      double reward = 0.0;
-      uint32_t terminated = 0, truncated = 0;
-      const bool fresh = (flags & FLAG_FRESH) != 0;
-      if (stepping && !fresh) {
-        steps += 1;
-        int fx, fy;
-        front_pos(g, ax, ay, dir, fx, fy);
-        const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
-        const uint32_t fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
-        const StepOut so = transition(action, fc, fx, fy, ax, ay, dir, carry);
-        terminated = so.terminated;
-        if (so.goal) {
-          if (steps <= p.max_steps) reward = p.reward_lut[steps];
-          else { volatile double q = (double)steps / (double)p.max_steps; volatile double m = 0.9 * q; reward = 1.0 - m; }
-        }
-        if (so.bad_action) e->err |= 1;
-        if (so.newc != fc && active) {
-          uint8_t *sb = reinterpret_cast<uint8_t *>(gtile.data());
-          uint8_t *gb = reinterpret_cast<uint8_t *>(gsrc);
-          const size_t ro = ((size_t)rw * 32 + lane) * 4 + (fx & 3), co = ((size_t)cw * 32 + lane) * 4 + (fy & 3);
-          sb[ro] = (uint8_t)so.newc; sb[co] = (uint8_t)so.newc;
-          gb[ro] = (uint8_t)so.newc; gb[co] = (uint8_t)so.newc;
-        }
-        truncated = steps >= p.max_steps;
-      }
-      const bool done = (terminated | truncated) != 0;
-      if (stepping) {
-        flags &= ~FLAG_FRESH;
-        if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
-      }
-      if (stepping && p.mode != AUTORESET_DISABLED && done && active) e->list[cur][e->count[cur]++] = env;
-      if (obs) {
-        gen_obs_words<ST, true>(g, base, p.cell_lut, ax, ay, dir, carry, S[lane]);
-        if (!full && active) emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S[lane]);
-      }
-      if (active) {
-        if (stepping) {
-          rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
-          rec.y = (uint32_t)dir | (flags << 8);
-          rec.z = carry; rec.w = (uint32_t)steps;
-          p.agent[env] = rec;
-        }
-        if (dir_out) dir_out[env] = dir;
-        if (reward_out) reward_out[env] = reward;
-        if (term_out) term_out[env] = (uint8_t)terminated;
-        if (trunc_out) trunc_out[env] = (uint8_t)truncated;
+      active[lane] = env < p.n_envs;
+      rec[lane] = p.agent[env];
+      ax[lane] = rec[lane].x & 0xFF; ay[lane] = (rec[lane].x >> 8) & 0xFF; dir[lane] = rec[lane].y & 3;
+      flags[lane] = rec[lane].y >> 8; carry[lane] = rec[lane].z; steps[lane] = (int)rec[lane].w;
+    }
+    if (stepping && p.mode == AUTORESET_NEXT_STEP) {
+      unsigned pend = 0;
+      for (int lane = 0; lane < 32; ++lane) { fresh[lane] = active[lane] && (flags[lane] & FLAG_PENDING); if (fresh[lane]) pend |= 1u << lane; }
+      if (pend) {
+        ResetOut ro[32];
+        warp_reset(e, pend, tile, gtile.data(), ro);
+        for (int lane = 0; lane < 32; ++lane)
+          if (fresh[lane]) { ax[lane] = ro[lane].ax; ay[lane] = ro[lane].ay; dir[lane] = ro[lane].dir; carry[lane] = 0; steps[lane] = 0; flags[lane] &= ~FLAG_PENDING; }
       }
     }
-    if (obs && full) {
-      for (int lane = 0; lane < 32; ++lane)
-        emit_obs_staged(stage.data(), lane, S[lane], lane < 31 ? S[lane + 1][0] : S[lane][0]);
-      memcpy(obs + (size_t)tile * OBS_TILE_BYTES, stage.data(), OBS_TILE_BYTES);  // the TMA bulk store
+    for (int lane = 0; lane < 32; ++lane) {
+      if (!(stepping && !fresh[lane])) continue;
+      const int env = tile * TILE + lane;
+      const int action = active[lane] ? actions[env] : A_DONE;
+      const uint32_t *base = gtile.data() + lane;
+      steps[lane] += 1;
+      int fx, fy;
+      front_pos(g, ax[lane], ay[lane], dir[lane], fx, fy);
+      const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
+      const uint32_t fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
+      const StepOut so = transition(action, fc, fx, fy, ax[lane], ay[lane], dir[lane], carry[lane]);
+      terminated[lane] = so.terminated;
+      if (so.goal) {
+        if (steps[lane] <= p.max_steps) reward[lane] = p.reward_lut[steps[lane]];
+        else { volatile double q = (double)steps[lane] / (double)p.max_steps; volatile double m = 0.9 * q; reward[lane] = 1.0 - m; }
+      }
+      if (so.bad_action) e->err |= 1;
+      if (so.newc != fc && active[lane]) {
+        uint8_t *sb = reinterpret_cast<uint8_t *>(gtile.data());
+        uint8_t *gb = reinterpret_cast<uint8_t *>(gsrc);
+        const size_t ro = ((size_t)rw * 32 + lane) * 4 + (fx & 3), co = ((size_t)cw * 32 + lane) * 4 + (fy & 3);
+        sb[ro] = (uint8_t)so.newc; sb[co] = (uint8_t)so.newc;
+        gb[ro] = (uint8_t)so.newc; gb[co] = (uint8_t)so.newc;
+      }
+      truncated[lane] = steps[lane] >= p.max_steps;
+      const bool done = (terminated[lane] | truncated[lane]) != 0;
+      if (p.mode == AUTORESET_NEXT_STEP) flags[lane] = done ? (flags[lane] | FLAG_PENDING) : (flags[lane] & ~FLAG_PENDING);
+    }
+    if (stepping && p.mode == AUTORESET_SAME_STEP) {
+      unsigned pend = 0;
+      bool again[32];
+      for (int lane = 0; lane < 32; ++lane) { again[lane] = active[lane] && ((terminated[lane] | truncated[lane]) != 0); if (again[lane]) pend |= 1u << lane; }
+      if (pend) {
+        ResetOut ro[32];
+        warp_reset(e, pend, tile, gtile.data(), ro);
+        for (int lane = 0; lane < 32; ++lane)
+          if (again[lane]) { ax[lane] = ro[lane].ax; ay[lane] = ro[lane].ay; dir[lane] = ro[lane].dir; carry[lane] = 0; steps[lane] = 0; }
+      }
+    }
+    if (obs) {
+      for (int lane = 0; lane < 32; ++lane) {
+        uint32_t(&S)[OBS_WORDS] = *reinterpret_cast<uint32_t(*)[OBS_WORDS]>(&S_all[lane * OBS_WORDS]);
+        gen_obs_words<ST, true>(g, gtile.data() + lane, p.cell_lut, ax[lane], ay[lane], dir[lane], carry[lane], S);
+        if (!full && active[lane]) emit_obs_bytes(obs + (size_t)(tile * TILE + lane) * OBS_BYTES, S);
+      }
+      if (full) {  // the consumed tile buffer becomes the stage
+        for (int lane = 0; lane < 32; ++lane) {
+          uint32_t(&S)[OBS_WORDS] = *reinterpret_cast<uint32_t(*)[OBS_WORDS]>(&S_all[lane * OBS_WORDS]);
+          emit_obs_staged(gtile.data(), lane, S, S_all[(lane < 31 ? lane + 1 : lane) * OBS_WORDS]);
+        }
+        memcpy(obs + (size_t)tile * OBS_TILE_BYTES, gtile.data(), OBS_TILE_BYTES);  // the TMA bulk store
+      }
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+      if (!active[lane]) continue;
+      const int env = tile * TILE + lane;
+      if (stepping) {
+        uint4 r = rec[lane];
+        r.x = (uint32_t)ax[lane] | ((uint32_t)ay[lane] << 8);
+        r.y = (uint32_t)dir[lane] | (flags[lane] << 8);
+        r.z = carry[lane]; r.w = (uint32_t)steps[lane];
+        p.agent[env] = r;
+      }
+      if (dir_out) dir_out[env] = dir[lane];
+      if (reward_out) reward_out[env] = reward[lane];
+      if (term_out) term_out[env] = (uint8_t)terminated[lane];
+      if (trunc_out) trunc_out[env] = (uint8_t)truncated[lane];
     }
   }
 }
@@ -161,8 +213,7 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
   for (int k = 0; k <= max_steps; ++k) { volatile double q = (double)k / (double)max_steps; volatile double m = 0.9 * q; e->reward_lut[k] = 1.0 - m; }
   e->cell_lut.resize(256);
   for (uint32_t c = 0; c < 256; ++c) e->cell_lut[c] = decode_cell(c);
-  e->list[0].resize(n_pad); e->list[1].resize(n_pad);
-  e->count[0] = e->count[1] = 0; e->cur = 0; e->err = 0;
+  e->err = 0;
   p.grid = e->grid.data(); p.agent = e->agent.data(); p.rng = e->rng.data();
   p.reward_lut = e->reward_lut.data(); p.cell_lut = e->cell_lut.data();
   return e;
@@ -174,22 +225,12 @@ void emu_seed(void *h, const uint64_t *seeds) {
 }
 void emu_reset(void *h, uint8_t *obs, int32_t *dir) {
   Emu *e = (Emu *)h;
-  e->count[0] = e->count[1] = 0;
-  for (int i = 0; i < e->p.n_envs; ++i) reset_one(e, i, obs, dir, 0);
+  for (int i = 0; i < e->p.n_envs; ++i) reset_one(e, i, obs, dir);
 }
 int emu_step(void *h, const int32_t *actions, uint8_t *obs, int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc) {
-  Emu *e = (Emu *)h;
-  if (!actions) {  // mg_gen_obs
-    if (e->p.see_through) step_tiles<true>(e, nullptr, obs, dir, nullptr, nullptr, nullptr, e->cur);
-    else step_tiles<false>(e, nullptr, obs, dir, nullptr, nullptr, nullptr, e->cur);
-    return 0;
-  }
-  const int append = e->cur ^ 1;
-  if (e->p.mode == AUTORESET_NEXT_STEP) reset_list(e, e->cur, nullptr, nullptr, 1);
-  if (e->p.see_through) step_tiles<true>(e, actions, obs, dir, reward, term, trunc, append);
-  else step_tiles<false>(e, actions, obs, dir, reward, term, trunc, append);
-  if (e->p.mode == AUTORESET_SAME_STEP) reset_list(e, append, obs, dir, 0);
-  e->cur = append;
+  Emu *e = (Emu *)h;  // mg_step / mg_gen_obs (actions == NULL): one K1 launch
+  if (e->p.see_through) step_tiles<true>(e, actions, obs, dir, reward, term, trunc);
+  else step_tiles<false>(e, actions, obs, dir, reward, term, trunc);
   const int bad = e->err; e->err = 0;
   return bad ? -1 : 0;
 }
