@@ -14,6 +14,8 @@
 //   4. observation in registers (mg_obs.cuh), staged into the consumed tile buffer in output layout, then one
 //      TMA bulk store of the warp's 32 x 147 = 4704 contiguous bytes.
 //   5. coalesced stores of direction / reward / terminated / truncated and the agent record.
+#include <cstdlib>
+
 #include "mg_common.cuh"
 #include "mg_levels.cuh"
 #include "mg_obs.cuh"
@@ -115,6 +117,9 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
   const uint32_t bar0 = smem_u32(bars + 2 * warp);
   int *s_next = reinterpret_cast<int *>(bars + 2 * STEP_WARPS);
 
+  // Programmatic dependent launch: let the next kernel in the stream start its prologue while this grid drains,
+  // and do our own prologue (no global memory touched) before waiting for the previous grid to complete.
+  asm volatile("griddepcontrol.launch_dependents;");
   const bool stepping = actions != nullptr;  // nullptr: observation-only pass (MiniGridEnv.gen_obs), state untouched
   // one wave of persistent CTAs; CTA c owns tiles [c T/G, (c+1) T/G), its warps pull from a shared counter
   const int t_lo = (int)(((long long)p.n_tiles * blockIdx.x) / gridDim.x);
@@ -131,7 +136,10 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+  // the 256-entry (type, colour, state) table is pure arithmetic: no global load anywhere near the critical path
+  for (int i = threadIdx.x; i < 256; i += STEP_THREADS) lut[i] = decode_cell((uint32_t)i);
+  __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads state the previous step wrote
   if (NBUF == 2 && tile < p.n_tiles) {
     if (lane == 0) {
       mbar_expect_tx(bar0, tile_bytes);
@@ -141,9 +149,6 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     rec = p.agent[env];
     if (stepping && env < p.n_envs) action = load_action(actions, act_dtype, env);
   }
-  // the 256-entry (type, colour, state) table is pure arithmetic: no global load on the critical path
-  for (int i = threadIdx.x; i < 256; i += STEP_THREADS) lut[i] = decode_cell((uint32_t)i);
-  __syncthreads();
 
   uint32_t phase = 0;  // bit b = parity to wait for on buffer b
   int b = 0;
@@ -338,8 +343,18 @@ cudaError_t launch_step(const Params &p, int nbuf, int grid, const void *actions
   const size_t smem = step_smem_bytes(p.g, nbuf);
   const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
   StepKernel k = step_kernel(p, nbuf);
-  k<<<grid, STEP_THREADS, smem, stream>>>(p, actions, action_dtype, obs, dir, reward, term, trunc, tma_ok);
-  return cudaGetLastError();
+  static const bool use_pdl = []() { const char *e = getenv("MINIGRID_B200_PDL"); return !e || atoi(e) != 0; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(STEP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, p, actions, action_dtype, obs, dir, reward, term, trunc, tma_ok);
 }
 
 }  // namespace mg
