@@ -9,11 +9,12 @@
 
 #include "../../include/minigrid_b200.h"
 #include "mg_common.cuh"
+#include "mg_obs.cuh"
 
 namespace mg {
-cudaError_t launch_step(const Params &p, int nbuf, int grid, const void *actions, int action_dtype, uint8_t *obs,
+cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
                         int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream);
-cudaError_t configure_step(const Params &p, int nbuf_request, int *nbuf_out, int *grid_out);
+cudaError_t configure_step(const Params &p, StepPlan *plan);
 cudaError_t launch_reset(const Params &p, uint8_t *obs, int32_t *dir, cudaStream_t stream);
 cudaError_t launch_seed(const Params &p, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream);
 cudaError_t launch_full_obs(const Params &p, uint8_t *out, int with_agent, cudaStream_t stream);
@@ -29,8 +30,7 @@ using namespace mg;
 struct mg_env {
   Params p;
   int device;
-  int step_grid;     // persistent grid of K1 (one wave)
-  int step_nbuf;     // 1 or 2 tile buffers per warp
+  StepPlan plan;     // launch shape of K1
   int64_t launches;
   // device allocations owned by the handle
   void *d_arena;     // grid | agent | rng | lists | counts | err | luts, one cudaMalloc
@@ -98,7 +98,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   const size_t sz_agent = align_up(n_pad * sizeof(uint4), 256);
   const size_t sz_rng = align_up(n_pad * sizeof(RngRec), 256);
   const size_t sz_lut_r = align_up((size_t)(max_steps + 1) * sizeof(double), 256);
-  const size_t total = sz_grid + sz_agent + sz_rng + 256 /*err*/ + sz_lut_r + 1024;
+  const size_t total = sz_grid + sz_agent + sz_rng + 256 /*err*/ + sz_lut_r + 1024 + VIS_TBL_BYTES;
   cudaError_t e = cudaMalloc(&h->d_arena, total);
   if (e != cudaSuccess) { delete h; return fail(MG_ERR_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); }
   uint8_t *base = (uint8_t *)h->d_arena;
@@ -107,8 +107,9 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   p.rng = (RngRec *)base; base += sz_rng;
   p.err = (int *)base; base += 256;
   double *d_rl = (double *)base; base += sz_lut_r;
-  uint32_t *d_cl = (uint32_t *)base;
-  p.reward_lut = d_rl; p.cell_lut = d_cl;
+  uint32_t *d_cl = (uint32_t *)base; base += 1024;
+  uint16_t *d_vt = (uint16_t *)base;
+  p.reward_lut = d_rl; p.cell_lut = d_cl; p.vis_tbl = d_vt;
 
   // _reward(): 1 - 0.9 * (step_count / max_steps) in host IEEE double, never contracted (minigrid_env.py:245)
   {
@@ -124,12 +125,13 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     for (uint32_t c = 0; c < 256; ++c) cl[c] = decode_cell(c);
     if (e == cudaSuccess) e = cudaMemcpy(d_cl, cl, sizeof(cl), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(p.err, 0, 256);
+    uint16_t *vt = (uint16_t *)malloc(VIS_TBL_BYTES);
+    build_vis_table(vt);
+    if (e == cudaSuccess) e = cudaMemcpy(d_vt, vt, VIS_TBL_BYTES, cudaMemcpyHostToDevice);
+    free(vt);
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) {
-    const char *nb = getenv("MINIGRID_B200_NBUF");  // tuning knob: force 1 or 2 tile buffers per warp
-    e = configure_step(p, nb ? atoi(nb) : 0, &h->step_nbuf, &h->step_grid);
-  }
+  if (e == cudaSuccess) e = configure_step(p, &h->plan);
   if (e == cudaSuccess) e = launch_init(p, h->hstream);
   if (e == cudaSuccess) e = launch_seed(p, nullptr, 0, h->hstream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->hstream);
@@ -208,7 +210,7 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
     MG_CUDA(cudaEventRecord(ev0, s));
   }
   // one launch: transition + autoreset (either mode) + observation
-  MG_CUDA(launch_step(p, h->step_nbuf, h->step_grid, actions_dev, action_dtype, obs_dev, dir_dev, reward_dev, terminated_dev,
+  MG_CUDA(launch_step(p, h->plan, actions_dev, action_dtype, obs_dev, dir_dev, reward_dev, terminated_dev,
                       truncated_dev, s));
   h->launches += 1;
   if (h->profiling) {
@@ -222,7 +224,7 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
 int mg_gen_obs(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_gen_obs: NULL handle");
   MG_CUDA(cudaSetDevice(h->device));
-  MG_CUDA(launch_step(h->p, h->step_nbuf, h->step_grid, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr,
+  MG_CUDA(launch_step(h->p, h->plan, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr,
                       (cudaStream_t)stream));
   h->launches += 1;
   return MG_OK;

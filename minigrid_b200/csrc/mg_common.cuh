@@ -117,7 +117,13 @@ struct Params {
   RngRec *rng;              // [n_tiles * 32]
   const double *reward_lut; // [max_steps + 1], 1 - 0.9 * (k / max_steps) computed on the host in IEEE double
   const uint32_t *cell_lut; // [256] decode_cell()
+  const uint16_t *vis_tbl;  // [128 * 128] process_vis row table (mg_obs.cuh: build_vis_table)
   int *err;                 // sticky error word
+};
+
+struct StepPlan {  // launch shape of K1, chosen once per handle (mg_step.cu: configure_step)
+  int warps, vis, ctas_per_sm, grid;
+  size_t smem;
 };
 
 // word index of byte (line, pos) and helpers for the interleaved tile

@@ -31,38 +31,76 @@ MG_D uint32_t tile_word(const uint32_t *base, int w) {
   return base[w << 5];
 }
 
-// Grid.process_vis (grid.py:291-328) on bit boards. op*: opaque cells, v*: visible cells; byte j of
-// (lo, hi) is view row vy = j (hi holds rows 4..6), bit i is view column vx = i. The agent is at (3, 6).
+// One row of Grid.process_vis (grid.py:291-328) on 7-bit masks (bit i = view column i): m = cells of this row
+// already visible, p = transparent cells (see_behind). Returns the row's final visibility v2 and the mask `up`
+// it lights in the row above.
+MG_HD void vis_row(uint32_t m, uint32_t p, uint32_t &v2, uint32_t &up) {
+  // first sweep, i = 0..5 ascending: a visible transparent cell lights i+1 (and i, i+1 of the row above).
+  // That recurrence is the carry chain of g + p with generate g = m & p, propagate p.
+  const uint32_t g = m & p;
+  const uint32_t c = (g + p) ^ g ^ p;
+  const uint32_t v1 = (m | c) & 0x7Fu;
+  const uint32_t a1 = v1 & p & 0x3Fu;
+  // second sweep, i = 6..1 descending: prefix fill towards bit 0 (Kogge-Stone, 3 rounds cover 7 bits)
+  uint32_t f = v1 & p, q = p;
+  f |= q & (f >> 1); q &= q >> 1;
+  f |= q & (f >> 2); q &= q >> 2;
+  f |= q & (f >> 4);
+  v2 = v1 | (f >> 1);
+  const uint32_t a2 = f & 0x7Eu;  // == v2 & p on i = 1..6
+  up = (a1 | (a1 << 1) | a2 | (a2 >> 1)) & 0x7Fu;  // the `if j > 0` writes into row j-1
+}
+
+// Grid.process_vis on bit boards. op*: opaque cells, v*: visible cells; byte j of (lo, hi) is view row vy = j
+// (hi holds rows 4..6), bit i is view column vx = i. The agent is at (3, 6).
 MG_D void process_vis(uint32_t oplo, uint32_t ophi, uint32_t &vlo, uint32_t &vhi) {
   uint32_t m = 1u << 3;
   vlo = 0; vhi = 0;
 #pragma unroll
   for (int j = VIEW - 1; j >= 0; --j) {
     const uint32_t op = ((j < 4) ? (oplo >> (8 * j)) : (ophi >> (8 * (j - 4)))) & 0x7Fu;
-    const uint32_t p = op ^ 0x7Fu;  // see_behind
-    // first sweep, i = 0..5 ascending: a visible transparent cell lights i+1 (and i, i+1 of the row above).
-    // That recurrence is the carry chain of g + p with generate g = v & p, propagate p.
-    const uint32_t g = m & p;
-    const uint32_t c = (g + p) ^ g ^ p;
-    const uint32_t v1 = (m | c) & 0x7Fu;
-    const uint32_t a1 = v1 & p & 0x3Fu;
-    // second sweep, i = 6..1 descending: prefix fill towards bit 0 (Kogge-Stone, 3 rounds cover 7 bits)
-    uint32_t f = v1 & p, q = p;
-    f |= q & (f >> 1); q &= q >> 1;
-    f |= q & (f >> 2); q &= q >> 2;
-    f |= q & (f >> 4);
-    const uint32_t v2 = v1 | (f >> 1);
-    const uint32_t a2 = f & 0x7Eu;  // == v2 & p on i = 1..6
+    uint32_t v2, up;
+    vis_row(m, op ^ 0x7Fu, v2, up);
     if (j < 4) vlo |= v2 << (8 * j); else vhi |= v2 << (8 * (j - 4));
-    m = (a1 | (a1 << 1) | a2 | (a2 >> 1)) & 0x7Fu;  // the `if j > 0` writes into row j-1
+    m = up;
+  }
+}
+
+// Table-driven form: vis_row for all 128 x 128 (m, p) pairs, 2 bytes each = 32 KB that K1 keeps in shared
+// memory. Entry at byte offset 2m + 256p: low byte v2, high byte up << 1 (i.e. the next row's 2m), so a row
+// costs a shift, an and-or, one 16-bit shared load, a shift and a byte insert.
+constexpr int VIS_TBL_BYTES = 128 * 128 * 2;
+inline void build_vis_table(uint16_t *tbl) {
+  for (uint32_t p = 0; p < 128; ++p)
+    for (uint32_t m = 0; m < 128; ++m) {
+      uint32_t v2, up;
+      vis_row(m, p, v2, up);
+      tbl[m + 128 * p] = (uint16_t)(v2 | (up << 9));
+    }
+}
+MG_D void process_vis_tbl(const uint16_t *tbl, uint32_t oplo, uint32_t ophi, uint32_t &vlo, uint32_t &vhi) {
+  const uint32_t plo = ~oplo & 0x7F7F7F7Fu, phi = ~ophi & 0x007F7F7Fu;
+  const uint8_t *t8 = reinterpret_cast<const uint8_t *>(tbl);
+  uint32_t m2 = (1u << 3) << 1;
+  vlo = 0; vhi = 0;
+#pragma unroll
+  for (int j = VIEW - 1; j >= 0; --j) {
+    const uint32_t pj8 = (j < 4) ? ((j == 0 ? plo << 8 : plo >> (8 * j - 8)) & 0x7F00u)
+                                 : ((j == 4 ? phi << 8 : phi >> (8 * (j - 4) - 8)) & 0x7F00u);
+    const uint32_t e = *reinterpret_cast<const uint16_t *>(t8 + (m2 | pj8));
+    if (j < 4) vlo = prmt(vlo, e, 0x3210u ^ (0x4u << (4 * j)) ^ ((uint32_t)j << (4 * j)));
+    else vhi = prmt(vhi, e, 0x3210u ^ (0x4u << (4 * (j - 4))) ^ ((uint32_t)(j - 4) << (4 * (j - 4))));
+    m2 = e >> 8;
   }
 }
 
 // Produces the 147-byte image of one env as 37 little-endian words S (byte 147 is zero).
 //   base   lane's tile column (shared or global), lut: 256-entry decode table (shared or global)
-template <bool SEE_THROUGH, bool SMEM>
-MG_D void gen_obs_words(const Geom &g, const uint32_t *base, const uint32_t *lut,
-                                              int ax, int ay, int dir, uint32_t carry, uint32_t (&S)[OBS_WORDS]) {
+//   VIS    VIS_NONE: see_through_walls (minigrid_env.py:616-621); VIS_ALU: bit tricks; VIS_TBL: vis_tbl lookups
+constexpr int VIS_NONE = 0, VIS_ALU = 1, VIS_TBL = 2;
+template <int VIS, bool SMEM>
+MG_D void gen_obs_words(const Geom &g, const uint32_t *base, const uint32_t *lut, const uint16_t *vis_tbl,
+                        int ax, int ay, int dir, uint32_t carry, uint32_t (&S)[OBS_WORDS]) {
   const bool useC = dir & 1;
   const bool rev = dir < 2;
   const int lc = useC ? ax : ay;       // line coordinate of the agent in the chosen array
@@ -100,14 +138,15 @@ MG_D void gen_obs_words(const Geom &g, const uint32_t *base, const uint32_t *lut
     lo = (lo & mlo) | (CODE_WALL4 & ~mlo);
     hi = (hi & mhi) | ((CODE_WALL4 & 0x00FFFFFFu) & ~mhi);
     clo[vx] = lo; chi[vx] = hi;
-    if (!SEE_THROUGH) {
+    if (VIS != VIS_NONE) {
       oplo |= ((lo >> 7) & 0x01010101u) << vx;
       ophi |= ((hi >> 7) & 0x01010101u) << vx;
     }
   }
-  if (!SEE_THROUGH) {
+  if (VIS != VIS_NONE) {
     uint32_t vlo, vhi;
-    process_vis(oplo, ophi, vlo, vhi);
+    if (VIS == VIS_TBL) process_vis_tbl(vis_tbl, oplo, ophi, vlo, vhi);
+    else process_vis(oplo, ophi, vlo, vhi);
 #pragma unroll
     for (int vx = 0; vx < VIEW; ++vx) {
       // bit vx of every row byte -> bit 7, then prmt's sign-replicate mode turns it into a 0x00/0xFF byte mask

@@ -29,8 +29,8 @@ k_reset(Params p, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out) {
     if (dir_out) dir_out[env] = L.adir;
     if (obs) {
       uint32_t S[OBS_WORDS];
-      if (p.see_through) gen_obs_words<true, false>(g, col, p.cell_lut, L.ax, L.ay, L.adir, 0u, S);
-      else gen_obs_words<false, false>(g, col, p.cell_lut, L.ax, L.ay, L.adir, 0u, S);
+      if (p.see_through) gen_obs_words<VIS_NONE, false>(g, col, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
+      else gen_obs_words<VIS_ALU, false>(g, col, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
       emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
     }
   }

@@ -4,8 +4,8 @@
 // One warp = one tile of 32 environments, one lane per environment.
 //   1. lane 0 issues a TMA bulk copy (cp.async.bulk -> SASS UBLKCP) of the tile's interleaved grid words
 //      into shared memory and arms an mbarrier with the byte count; meanwhile every lane loads its
-//      action and 16-byte agent record with coalesced loads. Warps are persistent; with NBUF == 2 they are
-//      double-buffered (the copy for the next tile is issued before the current one is processed).
+//      action and 16-byte agent record with coalesced loads. Warps are persistent (one wave of CTAs); other
+//      resident warps cover the copy's latency (double-buffering per warp measured slower: it halves occupancy).
 //   2. autoreset (NEXT_STEP: envs flagged last step, before the transition; SAME_STEP: envs that just ended,
 //      after it): rare, so the whole warp regenerates one environment at a time — every lane replays the
 //      numpy-exact RNG draws (uniform control flow) and fills a 1/32 share of the level's words.
@@ -14,6 +14,7 @@
 //   4. observation in registers (mg_obs.cuh), staged into the consumed tile buffer in output layout, then one
 //      TMA bulk store of the warp's 32 x 147 = 4704 contiguous bytes.
 //   5. coalesced stores of direction / reward / terminated / truncated and the agent record.
+#include <cstdio>
 #include <cstdlib>
 
 #include "mg_common.cuh"
@@ -24,9 +25,6 @@
 
 namespace mg {
 
-constexpr int STEP_WARPS = 4;
-constexpr int STEP_THREADS = STEP_WARPS * 32;
-
 // per-warp buffer: holds the staged tile, then (once the gather has consumed it) the warp's 4704-byte
 // observation block in output layout.
 __host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
@@ -34,8 +32,9 @@ __host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
   if (b < (uint32_t)OBS_TILE_BYTES) b = OBS_TILE_BYTES;
   return (b + 127u) & ~127u;
 }
-__host__ __device__ inline size_t step_smem_bytes(const Geom &g, int nbuf) {
-  return 1024 /*cell table*/ + (size_t)STEP_WARPS * nbuf * step_buf_bytes(g) + 128 /*mbarriers + tile counter*/;
+// [cell table 1 KB][visibility table 32 KB, VIS_TBL only][warps x buffer][mbarriers: one per warp + table][tile counter]
+__host__ __device__ inline size_t step_smem_bytes(const Geom &g, int vis, int warps) {
+  return 1024 + (vis == VIS_TBL ? VIS_TBL_BYTES : 0) + (size_t)warps * step_buf_bytes(g) + 8 * (size_t)warps + 16;
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -100,8 +99,8 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
   return out;
 }
 
-template <int KIND, bool SEE_THROUGH, int NBUF>
-__global__ void __launch_bounds__(STEP_THREADS)
+template <int KIND, int VIS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)  // 1024 threads / SM  =>  at most 64 registers
 k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
        int32_t *__restrict__ dir_out, double *__restrict__ reward_out, uint8_t *__restrict__ term_out,
        uint8_t *__restrict__ trunc_out, int obs_tma_ok) {
@@ -110,91 +109,66 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t tile_bytes = (uint32_t)g.wpe * 128u;
   const uint32_t buf_bytes = step_buf_bytes(g);
+  constexpr uint32_t TBL = (VIS == VIS_TBL) ? (uint32_t)VIS_TBL_BYTES : 0u;
 
   uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);
-  uint8_t *bufs = smem_raw + 1024 + (size_t)warp * NBUF * buf_bytes;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + (size_t)STEP_WARPS * NBUF * buf_bytes);
-  const uint32_t bar0 = smem_u32(bars + 2 * warp);
-  int *s_next = reinterpret_cast<int *>(bars + 2 * STEP_WARPS);
+  const uint16_t *vis_tbl = reinterpret_cast<const uint16_t *>(smem_raw + 1024);
+  uint32_t *gtile = reinterpret_cast<uint32_t *>(smem_raw + 1024 + TBL + (size_t)warp * buf_bytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + TBL + (size_t)WARPS * buf_bytes);
+  const uint32_t bar = smem_u32(bars + warp), tbl_bar = smem_u32(bars + WARPS);
+  int *s_next = reinterpret_cast<int *>(bars + WARPS + 1);
 
   // Programmatic dependent launch: let the next kernel in the stream start its prologue while this grid drains,
-  // and do our own prologue (no global memory touched) before waiting for the previous grid to complete.
+  // and do our own prologue (nothing the previous step wrote is touched) before waiting for it to complete.
   asm volatile("griddepcontrol.launch_dependents;");
   const bool stepping = actions != nullptr;  // nullptr: observation-only pass (MiniGridEnv.gen_obs), state untouched
   // one wave of persistent CTAs; CTA c owns tiles [c T/G, (c+1) T/G), its warps pull from a shared counter
   const int t_lo = (int)(((long long)p.n_tiles * blockIdx.x) / gridDim.x);
   const int t_hi = (int)(((long long)p.n_tiles * (blockIdx.x + 1)) / gridDim.x);
-  if (threadIdx.x == 0) *s_next = t_lo + NBUF * STEP_WARPS;
+  if (threadIdx.x == 0) {
+    *s_next = t_lo + WARPS;
+    if (VIS == VIS_TBL) {  // the table is immutable after mg_create: its copy may run ahead of griddepcontrol.wait
+      mbar_init(tbl_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(tbl_bar, TBL);
+      tma_load_1d(smem_u32(vis_tbl), p.vis_tbl, TBL, tbl_bar);
+    }
+  }
   int tile = t_lo + warp;
-  int next = (NBUF == 2) ? t_lo + STEP_WARPS + warp : p.n_tiles;
   if (tile >= t_hi) tile = p.n_tiles;
-  if (next >= t_hi) next = p.n_tiles;
-  uint4 rec = make_uint4(0, 0, 0, 0);
-  int action = A_DONE;
   if (lane == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // the 256-entry (type, colour, state) table is pure arithmetic: no global load anywhere near the critical path
-  for (int i = threadIdx.x; i < 256; i += STEP_THREADS) lut[i] = decode_cell((uint32_t)i);
+  for (int i = threadIdx.x; i < 256; i += WARPS * 32) lut[i] = decode_cell((uint32_t)i);
   __syncthreads();
+  if (VIS == VIS_TBL) mbar_wait(tbl_bar, 0);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads state the previous step wrote
-  if (NBUF == 2 && tile < p.n_tiles) {
-    if (lane == 0) {
-      mbar_expect_tx(bar0, tile_bytes);
-      tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
-    }
-    const int env = tile * TILE + lane;
-    rec = p.agent[env];
-    if (stepping && env < p.n_envs) action = load_action(actions, act_dtype, env);
-  }
 
-  uint32_t phase = 0;  // bit b = parity to wait for on buffer b
-  int b = 0;
+  uint32_t phase = 0;
   while (tile < p.n_tiles) {
-    uint4 rec_n = make_uint4(0, 0, 0, 0);
-    int action_n = A_DONE, nn = p.n_tiles;
-    if (NBUF == 2) {
-      // ---- prefetch tile `next` into the other buffer, and the index of the tile after it ----
-      if (next < p.n_tiles) {
-        if (lane == 0) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the obs block staged there two tiles ago
-          const uint32_t nb = bar0 + 8u * (uint32_t)(b ^ 1);
-          mbar_expect_tx(nb, tile_bytes);
-          tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
-          nn = atomicAdd(s_next, 1);  // shared-memory atomic, consumed one tile later
-          if (nn >= t_hi) nn = p.n_tiles;
-        }
-        const int env_n = next * TILE + lane;
-        rec_n = p.agent[env_n];
-        if (stepping && env_n < p.n_envs) action_n = load_action(actions, act_dtype, env_n);
-      }
-    } else {
-      if (lane == 0) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left the buffer
-        mbar_expect_tx(bar0, tile_bytes);
-        tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
-        nn = atomicAdd(s_next, 1);
-        if (nn >= t_hi) nn = p.n_tiles;
-      }
-      const int env0 = tile * TILE + lane;
-      rec = p.agent[env0];
-      action = (stepping && env0 < p.n_envs) ? load_action(actions, act_dtype, env0) : A_DONE;
+    int nn = p.n_tiles;
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left the buffer
+      mbar_expect_tx(bar, tile_bytes);
+      tma_load_1d(smem_u32(gtile), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar);
+      nn = atomicAdd(s_next, 1);  // shared-memory atomic, consumed at the end of this tile
+      if (nn >= t_hi) nn = p.n_tiles;
     }
-
-    uint32_t *gtile = reinterpret_cast<uint32_t *>(bufs + (size_t)b * buf_bytes);
     uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
     const int env = tile * TILE + lane;
     const bool active = env < p.n_envs;
+    uint4 rec = p.agent[env];
+    const int action = (stepping && active) ? load_action(actions, act_dtype, env) : A_DONE;
     int ax = rec.x & 0xFF, ay = (rec.x >> 8) & 0xFF;
     int dir = rec.y & 3;
     uint32_t flags = rec.y >> 8;
     uint32_t carry = rec.z;
     int steps = (int)rec.w;
 
-    mbar_wait(bar0 + 8u * (uint32_t)b, (phase >> b) & 1u);
-    phase ^= 1u << b;
+    mbar_wait(bar, phase);
+    phase ^= 1u;
 
     const uint32_t *base = gtile + lane;
     double reward = 0.0;
@@ -248,7 +222,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     // ---- gen_obs ----
     if (obs != nullptr) {
       uint32_t S[OBS_WORDS];
-      gen_obs_words<SEE_THROUGH, true>(g, base, lut, ax, ay, dir, carry, S);
+      gen_obs_words<VIS, true>(g, base, lut, vis_tbl, ax, ay, dir, carry, S);
       const bool full = (tile + 1) * TILE <= p.n_envs;
       if (full && obs_tma_ok) {
         const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);  // also: every lane is past its tile reads
@@ -277,77 +251,83 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       if (trunc_out) trunc_out[env] = (uint8_t)truncated;
     }
     __syncwarp();  // lanes may still be reading this buffer (partial-tile path) before it is refilled
-    if (NBUF == 2) {
-      tile = next;
-      next = __shfl_sync(0xFFFFFFFFu, nn, 0);
-      rec = rec_n;
-      action = action_n;
-      b ^= 1;
-    } else {
-      tile = __shfl_sync(0xFFFFFFFFu, nn, 0);
-    }
+    tile = __shfl_sync(0xFFFFFFFFu, nn, 0);
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 typedef void (*StepKernel)(Params, const void *, int, uint8_t *, int32_t *, double *, uint8_t *, uint8_t *, int);
 
-template <int NBUF>
-static StepKernel pick_kernel(int kind, int see_through) {
-#define MG_K(K) (see_through ? (StepKernel)k_step<K, true, NBUF> : (StepKernel)k_step<K, false, NBUF>)
+template <int VIS, int WARPS>
+static StepKernel pick_kind(int kind) {
   switch (kind) {
-    case KIND_EMPTY: return MG_K(KIND_EMPTY);
-    case KIND_DOORKEY: return MG_K(KIND_DOORKEY);
-    case KIND_CROSSING: return MG_K(KIND_CROSSING);
-    default: return MG_K(KIND_FOURROOMS);
+    case KIND_EMPTY: return (StepKernel)k_step<KIND_EMPTY, VIS, WARPS>;
+    case KIND_DOORKEY: return (StepKernel)k_step<KIND_DOORKEY, VIS, WARPS>;
+    case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS, WARPS>;
+    default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, WARPS>;
   }
-#undef MG_K
 }
-static StepKernel step_kernel(const Params &p, int nbuf) {
-  return nbuf == 2 ? pick_kernel<2>(p.kind, p.see_through) : pick_kernel<1>(p.kind, p.see_through);
+template <int WARPS>
+static StepKernel pick_vis(int kind, int vis) {
+  if (vis == VIS_NONE) return pick_kind<VIS_NONE, WARPS>(kind);
+  if (vis == VIS_ALU) return pick_kind<VIS_ALU, WARPS>(kind);
+  return pick_kind<VIS_TBL, WARPS>(kind);
+}
+static StepKernel step_kernel(int kind, int vis, int warps) {
+  if (warps == 16) return pick_vis<16>(kind, vis);
+  if (warps == 8) return pick_vis<8>(kind, vis);
+  return pick_vis<4>(kind, vis);
 }
 
-// opt in to the tile-dependent dynamic shared memory once per handle, choose single or double buffering
-// (double buffering needs twice the shared memory per warp) and size the persistent grid: one wave of CTAs,
-// never more CTAs than there are groups of STEP_WARPS tiles
-cudaError_t configure_step(const Params &p, int nbuf_request, int *nbuf_out, int *grid_out) {
+// Choose the CTA shape once per handle: among {16, 8, 4} warps per CTA and (for envs with occlusion) the
+// table-driven or the ALU process_vis, take the variant that keeps the most warps resident per SM (ties: table,
+// then wider CTA), opt in to its dynamic shared memory, and size the persistent grid to one wave of CTAs.
+// MINIGRID_B200_CFG="warps,vis" (vis: 1 ALU, 2 table) overrides the choice (tuning knob).
+cudaError_t configure_step(const Params &p, StepPlan *plan) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int best_nbuf = 0, best_ctas = 0;
-  for (int nbuf = 2; nbuf >= 1; --nbuf) {
-    if (nbuf_request && nbuf != nbuf_request) continue;
-    const size_t smem = step_smem_bytes(p.g, nbuf);
-    if (smem > 227 * 1024) continue;
-    StepKernel k = step_kernel(p, nbuf);
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int ctas = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k, STEP_THREADS, smem);
-    if (e != cudaSuccess) return e;
-    if (ctas < 1) continue;
-    // prefer double buffering unless it leaves fewer than 4 CTAs (16 warps) per SM and single buffering has more
-    if (best_nbuf == 0 || (best_ctas < 4 && ctas > best_ctas)) { best_nbuf = nbuf; best_ctas = ctas; }
+  int want_warps = 0, want_vis = 0;
+  if (const char *cfg = getenv("MINIGRID_B200_CFG")) sscanf(cfg, "%d,%d", &want_warps, &want_vis);
+  int best_resident = 0;
+  plan->warps = 0;
+  const int vis_opts[2] = {VIS_TBL, VIS_ALU};
+  for (int vi = 0; vi < (p.see_through ? 1 : 2); ++vi) {
+    const int vis = p.see_through ? VIS_NONE : vis_opts[vi];
+    if (!p.see_through && want_vis && vis != want_vis) continue;
+    for (int warps = 16; warps >= 4; warps >>= 1) {
+      if (want_warps && warps != want_warps) continue;
+      const size_t smem = step_smem_bytes(p.g, vis, warps);
+      if (smem > 227 * 1024) continue;
+      StepKernel k = step_kernel(p.kind, vis, warps);
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      int ctas = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k, warps * 32, smem);
+      if (e != cudaSuccess) return e;
+      if (ctas * warps > best_resident) {
+        best_resident = ctas * warps;
+        plan->warps = warps; plan->vis = vis; plan->ctas_per_sm = ctas; plan->smem = smem;
+      }
+    }
   }
-  if (best_nbuf == 0) return cudaErrorInvalidValue;
-  const long long want = ((long long)p.n_tiles + STEP_WARPS - 1) / STEP_WARPS;
-  long long grid = (long long)sms * best_ctas;
+  if (plan->warps == 0) return cudaErrorInvalidValue;
+  const long long want = ((long long)p.n_tiles + plan->warps - 1) / plan->warps;
+  long long grid = (long long)sms * plan->ctas_per_sm;
   if (grid > want) grid = want;
-  *grid_out = (int)(grid < 1 ? 1 : grid);
-  *nbuf_out = best_nbuf;
+  plan->grid = (int)(grid < 1 ? 1 : grid);
   return cudaSuccess;
 }
 
-cudaError_t launch_step(const Params &p, int nbuf, int grid, const void *actions, int action_dtype, uint8_t *obs,
+cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
                         int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream) {
-  const size_t smem = step_smem_bytes(p.g, nbuf);
   const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
-  StepKernel k = step_kernel(p, nbuf);
+  StepKernel k = step_kernel(p.kind, plan.vis, plan.warps);
   static const bool use_pdl = []() { const char *e = getenv("MINIGRID_B200_PDL"); return !e || atoi(e) != 0; }();
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(STEP_THREADS);
-  cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3((unsigned)plan.warps * 32);
+  cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -20,30 +20,37 @@ MG_HD void front_pos(const Geom &g, int ax, int ay, int dir, int &fx, int &fy) {
   fy = clampi(ay + dy, 0, g.H - 1);
 }
 
+// Straight-line (select-based) form: every lane runs the same instructions whatever its action, so a warp of
+// 32 environments with 32 different actions does not diverge.
 MG_HD StepOut transition(int action, uint32_t fc, int fx, int fy, int &ax, int &ay, int &dir, uint32_t &carry) {
   StepOut o;
-  o.newc = fc; o.terminated = 0; o.goal = 0; o.bad_action = 0;
   const uint32_t t4 = fc & 15u, col = (fc >> 4) & 7u;
-  if (action == A_LEFT) dir = (dir + 3) & 3;                 // :541-544
-  else if (action == A_RIGHT) dir = (dir + 1) & 3;           // :547-548
-  else if (action == A_FORWARD) {                            // :551-558
-    // can_overlap: None, Goal, Floor, Lava, open Door (world_object.py:45,113,128,141,177)
-    if ((0x031Au >> t4) & 1u) { ax = fx; ay = fy; }
-    if (t4 == T_GOAL) { o.terminated = 1; o.goal = 1; }
-    if (t4 == T_LAVA) o.terminated = 1;
-  } else if (action == A_PICKUP) {                           // :561-566, can_pickup: Key, Ball, Box
-    if (t4 >= T_KEY && t4 <= T_BOX && carry == 0) { carry = fc & 0x7Fu; o.newc = CODE_EMPTY; }
-  } else if (action == A_DROP) {                             // :569-573
-    if (t4 == T_EMPTY && carry != 0) { o.newc = carry; carry = 0; }
-  } else if (action == A_TOGGLE) {                           // :576-578
-    if (t4 == T4_DOOR_LOCKED) {                              // Door.toggle, world_object.py:184-194
-      if ((carry & 15u) == T_KEY && ((carry >> 4) & 7u) == col) o.newc = T_DOOR | (col << 4);
-    } else if (t4 == T_DOOR) o.newc = T4_DOOR_CLOSED | (col << 4) | OPAQUE_BIT;
-    else if (t4 == T4_DOOR_CLOSED) o.newc = T_DOOR | (col << 4);
-    else if (t4 == T_BOX) o.newc = CODE_EMPTY;               // Box.toggle, contains == None (:290-293)
-  } else if (action != A_DONE) {
-    o.bad_action = 1;
-  }
+  const bool isF = action == A_FORWARD, isP = action == A_PICKUP, isD = action == A_DROP, isT = action == A_TOGGLE;
+  // left / right: agent_dir = (dir -/+ 1) mod 4                                           :541-548
+  dir = (dir + (action == A_LEFT ? 3 : 0) + (action == A_RIGHT ? 1 : 0)) & 3;
+  // forward: can_overlap = None, Goal, Floor, Lava, open Door (world_object.py:45,113,128,141,177)   :551-558
+  const bool mv = isF && ((0x031Au >> t4) & 1u);
+  ax = mv ? fx : ax;
+  ay = mv ? fy : ay;
+  o.goal = (isF && t4 == T_GOAL) ? 1u : 0u;
+  o.terminated = (isF && (t4 == T_GOAL || t4 == T_LAVA)) ? 1u : 0u;
+  // pickup: can_pickup = Key, Ball, Box, and nothing carried                               :561-566
+  const bool pick = isP && t4 >= T_KEY && t4 <= T_BOX && carry == 0;
+  // drop: front cell is None and something is carried                                      :569-573
+  const bool drop = isD && t4 == T_EMPTY && carry != 0;
+  // toggle: Door.toggle (world_object.py:184-194), Box.toggle with contains == None (:290-293)   :576-578
+  const bool unlock = t4 == T4_DOOR_LOCKED && (carry & 15u) == T_KEY && ((carry >> 4) & 7u) == col;
+  const bool opens = isT && (t4 == T4_DOOR_CLOSED || unlock);
+  const bool closes = isT && t4 == T_DOOR;
+  const bool unbox = isT && t4 == T_BOX;
+  uint32_t newc = fc;
+  newc = (pick || unbox) ? CODE_EMPTY : newc;
+  newc = drop ? carry : newc;
+  newc = opens ? (T_DOOR | (col << 4)) : newc;
+  newc = closes ? (T4_DOOR_CLOSED | (col << 4) | OPAQUE_BIT) : newc;
+  carry = pick ? (fc & 0x7Fu) : (drop ? 0u : carry);
+  o.newc = newc;
+  o.bad_action = ((unsigned)action > (unsigned)A_DONE) ? 1u : 0u;  // ValueError, :584-585
   return o;
 }
 

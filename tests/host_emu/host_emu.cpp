@@ -25,6 +25,8 @@ struct Emu {
   std::vector<RngRec> rng;
   std::vector<double> reward_lut;
   std::vector<uint32_t> cell_lut;
+  std::vector<uint16_t> vis_tbl;
+  int use_tbl;
   int err;
 };
 
@@ -45,8 +47,8 @@ static void reset_env(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {  // k_r
   if (dir_out) dir_out[env] = L.adir;
   if (obs) {
     uint32_t S[OBS_WORDS];
-    if (p.see_through) gen_obs_words<true, false>(p.g, col, p.cell_lut, L.ax, L.ay, L.adir, 0u, S);
-    else gen_obs_words<false, false>(p.g, col, p.cell_lut, L.ax, L.ay, L.adir, 0u, S);
+    if (p.see_through) gen_obs_words<VIS_NONE, false>(p.g, col, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
+    else gen_obs_words<VIS_ALU, false>(p.g, col, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
     emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
   }
 }
@@ -89,7 +91,7 @@ static void warp_reset(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOu
   }
 }
 
-template <bool ST>
+template <int VIS>
 static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *dir_out, double *reward_out,
                        uint8_t *term_out, uint8_t *trunc_out) {  // k_step body, phase by phase over the 32 lanes
   Params &p = e->p;
@@ -164,7 +166,7 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
     if (obs) {
       for (int lane = 0; lane < 32; ++lane) {
         uint32_t(&S)[OBS_WORDS] = *reinterpret_cast<uint32_t(*)[OBS_WORDS]>(&S_all[lane * OBS_WORDS]);
-        gen_obs_words<ST, true>(g, gtile.data() + lane, p.cell_lut, ax[lane], ay[lane], dir[lane], carry[lane], S);
+        gen_obs_words<VIS, true>(g, gtile.data() + lane, p.cell_lut, p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], S);
         if (!full && active[lane]) emit_obs_bytes(obs + (size_t)(tile * TILE + lane) * OBS_BYTES, S);
       }
       if (full) {  // the consumed tile buffer becomes the stage
@@ -213,6 +215,10 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
   for (int k = 0; k <= max_steps; ++k) { volatile double q = (double)k / (double)max_steps; volatile double m = 0.9 * q; e->reward_lut[k] = 1.0 - m; }
   e->cell_lut.resize(256);
   for (uint32_t c = 0; c < 256; ++c) e->cell_lut[c] = decode_cell(c);
+  e->vis_tbl.resize(128 * 128);
+  build_vis_table(e->vis_tbl.data());
+  p.vis_tbl = e->vis_tbl.data();
+  e->use_tbl = (n_envs % 2) == 0;  // exercise both process_vis forms across the test matrix
   e->err = 0;
   p.grid = e->grid.data(); p.agent = e->agent.data(); p.rng = e->rng.data();
   p.reward_lut = e->reward_lut.data(); p.cell_lut = e->cell_lut.data();
@@ -229,8 +235,9 @@ void emu_reset(void *h, uint8_t *obs, int32_t *dir) {
 }
 int emu_step(void *h, const int32_t *actions, uint8_t *obs, int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc) {
   Emu *e = (Emu *)h;  // mg_step / mg_gen_obs (actions == NULL): one K1 launch
-  if (e->p.see_through) step_tiles<true>(e, actions, obs, dir, reward, term, trunc);
-  else step_tiles<false>(e, actions, obs, dir, reward, term, trunc);
+  if (e->p.see_through) step_tiles<VIS_NONE>(e, actions, obs, dir, reward, term, trunc);
+  else if (e->use_tbl) step_tiles<VIS_TBL>(e, actions, obs, dir, reward, term, trunc);
+  else step_tiles<VIS_ALU>(e, actions, obs, dir, reward, term, trunc);
   const int bad = e->err; e->err = 0;
   return bad ? -1 : 0;
 }
