@@ -99,14 +99,15 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
   return out;
 }
 
-template <int KIND, int VIS, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)  // 1024 threads / SM  =>  at most 64 registers
+template <int KIND, int VIS>
+__global__ void __launch_bounds__(1024, 1)  // up to 32 warps per CTA, one CTA per SM  =>  at most 64 registers
 k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
        int32_t *__restrict__ dir_out, double *__restrict__ reward_out, uint8_t *__restrict__ term_out,
        uint8_t *__restrict__ trunc_out, int obs_tma_ok) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const Geom g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int WARPS = blockDim.x >> 5;
   const uint32_t tile_bytes = (uint32_t)g.wpe * 128u;
   const uint32_t buf_bytes = step_buf_bytes(g);
   constexpr uint32_t TBL = (VIS == VIS_TBL) ? (uint32_t)VIS_TBL_BYTES : 0u;
@@ -141,7 +142,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // the 256-entry (type, colour, state) table is pure arithmetic: no global load anywhere near the critical path
-  for (int i = threadIdx.x; i < 256; i += WARPS * 32) lut[i] = decode_cell((uint32_t)i);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = decode_cell((uint32_t)i);
   __syncthreads();
   if (VIS == VIS_TBL) mbar_wait(tbl_bar, 0);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads state the previous step wrote
@@ -258,56 +259,63 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
 
 typedef void (*StepKernel)(Params, const void *, int, uint8_t *, int32_t *, double *, uint8_t *, uint8_t *, int);
 
-template <int VIS, int WARPS>
+template <int VIS>
 static StepKernel pick_kind(int kind) {
   switch (kind) {
-    case KIND_EMPTY: return (StepKernel)k_step<KIND_EMPTY, VIS, WARPS>;
-    case KIND_DOORKEY: return (StepKernel)k_step<KIND_DOORKEY, VIS, WARPS>;
-    case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS, WARPS>;
-    default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, WARPS>;
+    case KIND_EMPTY: return (StepKernel)k_step<KIND_EMPTY, VIS>;
+    case KIND_DOORKEY: return (StepKernel)k_step<KIND_DOORKEY, VIS>;
+    case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS>;
+    default: return (StepKernel)k_step<KIND_FOURROOMS, VIS>;
   }
 }
-template <int WARPS>
-static StepKernel pick_vis(int kind, int vis) {
-  if (vis == VIS_NONE) return pick_kind<VIS_NONE, WARPS>(kind);
-  if (vis == VIS_ALU) return pick_kind<VIS_ALU, WARPS>(kind);
-  return pick_kind<VIS_TBL, WARPS>(kind);
-}
-static StepKernel step_kernel(int kind, int vis, int warps) {
-  if (warps == 16) return pick_vis<16>(kind, vis);
-  if (warps == 8) return pick_vis<8>(kind, vis);
-  return pick_vis<4>(kind, vis);
+static StepKernel step_kernel(int kind, int vis) {
+  if (vis == VIS_NONE) return pick_kind<VIS_NONE>(kind);
+  if (vis == VIS_ALU) return pick_kind<VIS_ALU>(kind);
+  return pick_kind<VIS_TBL>(kind);
 }
 
-// Choose the CTA shape once per handle: among {16, 8, 4} warps per CTA and (for envs with occlusion) the
-// table-driven or the ALU process_vis, take the variant that keeps the most warps resident per SM (ties: table,
-// then wider CTA), opt in to its dynamic shared memory, and size the persistent grid to one wave of CTAs.
-// MINIGRID_B200_CFG="warps,vis" (vis: 1 ALU, 2 table) overrides the choice (tuning knob).
+// Choose the CTA shape once per handle. One persistent CTA of W <= 32 warps per SM (a second CTA per SM when
+// the tiles are small enough that both fit); W is taken from the upper half of what shared memory allows so
+// that tiles_per_SM / W lands just below an integer (the last round of tiles is then full: 8192 tiles on
+// 148 SMs is 55.35 per SM, and 28 warps finish in 1.98 rounds where 32 would need 2 with the second 73 % full).
+// The table-driven process_vis costs 32 KB per CTA and is preferred unless it costs more than a quarter of the
+// resident warps. MINIGRID_B200_CFG="warps,vis" (vis: 1 ALU, 2 table) overrides the choice (tuning knob).
 cudaError_t configure_step(const Params &p, StepPlan *plan) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int want_warps = 0, want_vis = 0;
   if (const char *cfg = getenv("MINIGRID_B200_CFG")) sscanf(cfg, "%d,%d", &want_warps, &want_vis);
-  int best_resident = 0;
+  const double tiles_per_sm = (double)p.n_tiles / sms;
+  double best_score = -1.0;
   plan->warps = 0;
   const int vis_opts[2] = {VIS_TBL, VIS_ALU};
   for (int vi = 0; vi < (p.see_through ? 1 : 2); ++vi) {
     const int vis = p.see_through ? VIS_NONE : vis_opts[vi];
     if (!p.see_through && want_vis && vis != want_vis) continue;
-    for (int warps = 16; warps >= 4; warps >>= 1) {
-      if (want_warps && warps != want_warps) continue;
-      const size_t smem = step_smem_bytes(p.g, vis, warps);
-      if (smem > 227 * 1024) continue;
-      StepKernel k = step_kernel(p.kind, vis, warps);
-      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
+    StepKernel k = step_kernel(p.kind, vis);
+    // the most warps one CTA can hold
+    int wmax = 0;
+    for (int w = 32; w >= 1; --w)
+      if (step_smem_bytes(p.g, vis, w) <= 227 * 1024 - 1024) { wmax = w; break; }
+    if (wmax == 0) continue;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes(p.g, vis, wmax));
+    if (e != cudaSuccess) return e;
+    for (int w = wmax; w >= (want_warps ? 1 : (wmax + 1) / 2); --w) {
+      if (want_warps && w != want_warps) continue;
+      const size_t smem = step_smem_bytes(p.g, vis, w);
       int ctas = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k, warps * 32, smem);
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k, w * 32, smem);
       if (e != cudaSuccess) return e;
-      if (ctas * warps > best_resident) {
-        best_resident = ctas * warps;
-        plan->warps = warps; plan->vis = vis; plan->ctas_per_sm = ctas; plan->smem = smem;
+      if (ctas < 1) continue;
+      if (ctas * w > 32) ctas = 32 / w;  // 64-register kernels: 1024 threads per SM at most
+      const int resident = ctas * w;
+      const double rounds = tiles_per_sm / resident;
+      const double fill = rounds <= 1.0 ? 1.0 : rounds / (double)(long long)(rounds + 0.999999);  // last-round efficiency
+      const double score = resident * fill * (vis == VIS_TBL ? 1.3 : 1.0);
+      if (score > best_score + 1e-9) {
+        best_score = score;
+        plan->warps = w; plan->vis = vis; plan->ctas_per_sm = ctas; plan->smem = smem;
       }
     }
   }
@@ -322,7 +330,7 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
 cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
                         int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream) {
   const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
-  StepKernel k = step_kernel(p.kind, plan.vis, plan.warps);
+  StepKernel k = step_kernel(p.kind, plan.vis);
   static const bool use_pdl = []() { const char *e = getenv("MINIGRID_B200_PDL"); return !e || atoi(e) != 0; }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)plan.grid);
