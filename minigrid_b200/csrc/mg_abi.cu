@@ -133,8 +133,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = configure_step(p, &h->plan);
   if (e == cudaSuccess && getenv("MINIGRID_B200_VERBOSE"))
-    fprintf(stderr, "[minigrid_b200] K1 plan: %d warps/CTA, vis=%d, %d CTA/SM, grid=%d, smem=%zu B, tiles=%d\n", h->plan.warps,
-            h->plan.vis, h->plan.ctas_per_sm, h->plan.grid, h->plan.smem, p.n_tiles);
+    fprintf(stderr, "[minigrid_b200] K1 plan: %d warps/CTA, vis=%d, nbuf=%d, %d CTA/SM, grid=%d, smem=%zu B, tiles=%d\n", h->plan.warps,
+            h->plan.vis, h->plan.nbuf, h->plan.ctas_per_sm, h->plan.grid, h->plan.smem, p.n_tiles);
   if (e == cudaSuccess) e = launch_init(p, h->hstream);
   if (e == cudaSuccess) e = launch_seed(p, nullptr, 0, h->hstream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->hstream);

@@ -122,7 +122,7 @@ struct Params {
 };
 
 struct StepPlan {  // launch shape of K1, chosen once per handle (mg_step.cu: configure_step)
-  int warps, vis, ctas_per_sm, grid;
+  int warps, vis, nbuf, ctas_per_sm, grid;
   size_t smem;
 };
 

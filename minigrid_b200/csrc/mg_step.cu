@@ -33,8 +33,8 @@ __host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
   return (b + 127u) & ~127u;
 }
 // [cell table 1 KB][visibility table 32 KB, VIS_TBL only][warps x buffer][mbarriers: one per warp + table][tile counter]
-__host__ __device__ inline size_t step_smem_bytes(const Geom &g, int vis, int warps) {
-  return 1024 + (vis == VIS_TBL ? VIS_TBL_BYTES : 0) + (size_t)warps * step_buf_bytes(g) + 8 * (size_t)warps + 16;
+__host__ __device__ inline size_t step_smem_bytes(const Geom &g, int vis, int warps, int nbuf) {
+  return 1024 + (vis == VIS_TBL ? VIS_TBL_BYTES : 0) + (size_t)warps * nbuf * step_buf_bytes(g) + 16 * (size_t)warps + 16;
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -99,8 +99,10 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
   return out;
 }
 
-template <int KIND, int VIS>
-__global__ void __launch_bounds__(1024, 1)  // up to 32 warps per CTA, one CTA per SM  =>  at most 64 registers
+// NBUF == 2: each warp owns two buffers and prefetches its next tile (TMA + agent records + actions) before it
+// processes the current one, so HBM transfers overlap compute instead of alternating with it in GPU-wide bursts.
+template <int KIND, int VIS, int NBUF>
+__global__ void __launch_bounds__(NBUF == 2 ? 640 : 1024, 1)  // one CTA per SM: <= 20 warps (96 regs) or <= 32 (64 regs)
 k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
        int32_t *__restrict__ dir_out, double *__restrict__ reward_out, uint8_t *__restrict__ term_out,
        uint8_t *__restrict__ trunc_out, int obs_tma_ok) {
@@ -114,10 +116,10 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
 
   uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);
   const uint16_t *vis_tbl = reinterpret_cast<const uint16_t *>(smem_raw + 1024);
-  uint32_t *gtile = reinterpret_cast<uint32_t *>(smem_raw + 1024 + TBL + (size_t)warp * buf_bytes);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + TBL + (size_t)WARPS * buf_bytes);
-  const uint32_t bar = smem_u32(bars + warp), tbl_bar = smem_u32(bars + WARPS);
-  int *s_next = reinterpret_cast<int *>(bars + WARPS + 1);
+  uint8_t *bufs = smem_raw + 1024 + TBL + (size_t)warp * NBUF * buf_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + TBL + (size_t)WARPS * NBUF * buf_bytes);
+  const uint32_t bar0 = smem_u32(bars + 2 * warp), tbl_bar = smem_u32(bars + 2 * WARPS);
+  int *s_next = reinterpret_cast<int *>(bars + 2 * WARPS + 1);
 
   // Programmatic dependent launch: let the next kernel in the stream start its prologue while this grid drains,
   // and do our own prologue (nothing the previous step wrote is touched) before waiting for it to complete.
@@ -127,7 +129,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
   const int t_lo = (int)(((long long)p.n_tiles * blockIdx.x) / gridDim.x);
   const int t_hi = (int)(((long long)p.n_tiles * (blockIdx.x + 1)) / gridDim.x);
   if (threadIdx.x == 0) {
-    *s_next = t_lo + WARPS;
+    *s_next = t_lo + NBUF * WARPS;
     if (VIS == VIS_TBL) {  // the table is immutable after mg_create: its copy may run ahead of griddepcontrol.wait
       mbar_init(tbl_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,9 +138,12 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     }
   }
   int tile = t_lo + warp;
+  int next = (NBUF == 2) ? t_lo + WARPS + warp : p.n_tiles;
   if (tile >= t_hi) tile = p.n_tiles;
+  if (next >= t_hi) next = p.n_tiles;
   if (lane == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // the 256-entry (type, colour, state) table is pure arithmetic: no global load anywhere near the critical path
@@ -147,29 +152,61 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
   if (VIS == VIS_TBL) mbar_wait(tbl_bar, 0);
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads state the previous step wrote
 
-  uint32_t phase = 0;
-  while (tile < p.n_tiles) {
-    int nn = p.n_tiles;
+  uint4 rec = make_uint4(0, 0, 0, 0);
+  int action = A_DONE;
+  if (NBUF == 2 && tile < p.n_tiles) {
     if (lane == 0) {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left the buffer
-      mbar_expect_tx(bar, tile_bytes);
-      tma_load_1d(smem_u32(gtile), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar);
-      nn = atomicAdd(s_next, 1);  // shared-memory atomic, consumed at the end of this tile
-      if (nn >= t_hi) nn = p.n_tiles;
+      mbar_expect_tx(bar0, tile_bytes);
+      tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
     }
+    const int env0 = tile * TILE + lane;
+    rec = p.agent[env0];
+    if (stepping && env0 < p.n_envs) action = load_action(actions, act_dtype, env0);
+  }
+
+  uint32_t phase = 0;  // bit b = parity to wait for on buffer b
+  int b = 0;
+  while (tile < p.n_tiles) {
+    uint4 rec_n = make_uint4(0, 0, 0, 0);
+    int action_n = A_DONE, nn = p.n_tiles;
+    if (NBUF == 2) {
+      if (next < p.n_tiles) {  // prefetch the next tile into the other buffer, and the index of the one after it
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the obs block staged there two tiles ago
+          const uint32_t nb = bar0 + 8u * (uint32_t)(b ^ 1);
+          mbar_expect_tx(nb, tile_bytes);
+          tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
+          nn = atomicAdd(s_next, 1);  // shared-memory atomic, consumed one tile later
+          if (nn >= t_hi) nn = p.n_tiles;
+        }
+        const int env_n = next * TILE + lane;
+        rec_n = p.agent[env_n];
+        if (stepping && env_n < p.n_envs) action_n = load_action(actions, act_dtype, env_n);
+      }
+    } else {
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left the buffer
+        mbar_expect_tx(bar0, tile_bytes);
+        tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
+        nn = atomicAdd(s_next, 1);  // consumed at the end of this tile
+        if (nn >= t_hi) nn = p.n_tiles;
+      }
+      const int env0 = tile * TILE + lane;
+      rec = p.agent[env0];
+      action = (stepping && env0 < p.n_envs) ? load_action(actions, act_dtype, env0) : A_DONE;
+    }
+    uint32_t *gtile = reinterpret_cast<uint32_t *>(bufs + (size_t)b * buf_bytes);
     uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
     const int env = tile * TILE + lane;
     const bool active = env < p.n_envs;
-    uint4 rec = p.agent[env];
-    const int action = (stepping && active) ? load_action(actions, act_dtype, env) : A_DONE;
     int ax = rec.x & 0xFF, ay = (rec.x >> 8) & 0xFF;
     int dir = rec.y & 3;
     uint32_t flags = rec.y >> 8;
     uint32_t carry = rec.z;
     int steps = (int)rec.w;
 
-    mbar_wait(bar, phase);
-    phase ^= 1u;
+    mbar_wait(bar0 + 8u * (uint32_t)b, (phase >> b) & 1u);
+    phase ^= 1u << b;
 
     const uint32_t *base = gtile + lane;
     double reward = 0.0;
@@ -252,26 +289,38 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       if (trunc_out) trunc_out[env] = (uint8_t)truncated;
     }
     __syncwarp();  // lanes may still be reading this buffer (partial-tile path) before it is refilled
-    tile = __shfl_sync(0xFFFFFFFFu, nn, 0);
+    if (NBUF == 2) {
+      tile = next;
+      next = __shfl_sync(0xFFFFFFFFu, nn, 0);
+      rec = rec_n;
+      action = action_n;
+      b ^= 1;
+    } else {
+      tile = __shfl_sync(0xFFFFFFFFu, nn, 0);
+    }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 typedef void (*StepKernel)(Params, const void *, int, uint8_t *, int32_t *, double *, uint8_t *, uint8_t *, int);
 
-template <int VIS>
+template <int VIS, int NBUF>
 static StepKernel pick_kind(int kind) {
   switch (kind) {
-    case KIND_EMPTY: return (StepKernel)k_step<KIND_EMPTY, VIS>;
-    case KIND_DOORKEY: return (StepKernel)k_step<KIND_DOORKEY, VIS>;
-    case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS>;
-    default: return (StepKernel)k_step<KIND_FOURROOMS, VIS>;
+    case KIND_EMPTY: return (StepKernel)k_step<KIND_EMPTY, VIS, NBUF>;
+    case KIND_DOORKEY: return (StepKernel)k_step<KIND_DOORKEY, VIS, NBUF>;
+    case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS, NBUF>;
+    default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, NBUF>;
   }
 }
-static StepKernel step_kernel(int kind, int vis) {
-  if (vis == VIS_NONE) return pick_kind<VIS_NONE>(kind);
-  if (vis == VIS_ALU) return pick_kind<VIS_ALU>(kind);
-  return pick_kind<VIS_TBL>(kind);
+template <int NBUF>
+static StepKernel pick_vis(int kind, int vis) {
+  if (vis == VIS_NONE) return pick_kind<VIS_NONE, NBUF>(kind);
+  if (vis == VIS_ALU) return pick_kind<VIS_ALU, NBUF>(kind);
+  return pick_kind<VIS_TBL, NBUF>(kind);
+}
+static StepKernel step_kernel(int kind, int vis, int nbuf) {
+  return nbuf == 2 ? pick_vis<2>(kind, vis) : pick_vis<1>(kind, vis);
 }
 
 // Choose the CTA shape once per handle. One persistent CTA of W <= 32 warps per SM (a second CTA per SM when
@@ -284,8 +333,8 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int want_warps = 0, want_vis = 0;
-  if (const char *cfg = getenv("MINIGRID_B200_CFG")) sscanf(cfg, "%d,%d", &want_warps, &want_vis);
+  int want_warps = 0, want_vis = 0, want_nbuf = 0;
+  if (const char *cfg = getenv("MINIGRID_B200_CFG")) sscanf(cfg, "%d,%d,%d", &want_warps, &want_vis, &want_nbuf);
   const double tiles_per_sm = (double)p.n_tiles / sms;
   double best_score = -1.0;
   plan->warps = 0;
@@ -293,29 +342,35 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
   for (int vi = 0; vi < (p.see_through ? 1 : 2); ++vi) {
     const int vis = p.see_through ? VIS_NONE : vis_opts[vi];
     if (!p.see_through && want_vis && vis != want_vis) continue;
-    StepKernel k = step_kernel(p.kind, vis);
-    // the most warps one CTA can hold
-    int wmax = 0;
-    for (int w = 32; w >= 1; --w)
-      if (step_smem_bytes(p.g, vis, w) <= 227 * 1024 - 1024) { wmax = w; break; }
-    if (wmax == 0) continue;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem_bytes(p.g, vis, wmax));
-    if (e != cudaSuccess) return e;
-    for (int w = wmax; w >= (want_warps ? 1 : (wmax + 1) / 2); --w) {
-      if (want_warps && w != want_warps) continue;
-      const size_t smem = step_smem_bytes(p.g, vis, w);
-      int ctas = 0;
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k, w * 32, smem);
+    for (int nbuf = 2; nbuf >= 1; --nbuf) {
+      if (want_nbuf && nbuf != want_nbuf) continue;
+      StepKernel k = step_kernel(p.kind, vis, nbuf);
+      const int wcap = nbuf == 2 ? 20 : 32;  // __launch_bounds__ of the two variants
+      int wmax = 0;
+      for (int w = wcap; w >= 1; --w)
+        if (step_smem_bytes(p.g, vis, w, nbuf) <= 227 * 1024 - 1024) { wmax = w; break; }
+      if (wmax == 0) continue;
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)step_smem_bytes(p.g, vis, wmax, nbuf));
       if (e != cudaSuccess) return e;
-      if (ctas < 1) continue;
-      if (ctas * w > 32) ctas = 32 / w;  // 64-register kernels: 1024 threads per SM at most
-      const int resident = ctas * w;
-      const double rounds = tiles_per_sm / resident;
-      const double fill = rounds <= 1.0 ? 1.0 : rounds / (double)(long long)(rounds + 0.999999);  // last-round efficiency
-      const double score = resident * fill * (vis == VIS_TBL ? 1.3 : 1.0);
-      if (score > best_score + 1e-9) {
-        best_score = score;
-        plan->warps = w; plan->vis = vis; plan->ctas_per_sm = ctas; plan->smem = smem;
+      for (int w = wmax; w >= (want_warps ? 1 : (wmax + 1) / 2); --w) {
+        if (want_warps && w != want_warps) continue;
+        const size_t smem = step_smem_bytes(p.g, vis, w, nbuf);
+        int ctas = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k, w * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (ctas < 1) continue;
+        if (ctas * w > wcap) ctas = wcap / w;
+        if (ctas < 1) continue;
+        const int resident = ctas * w;
+        const double rounds = tiles_per_sm / resident;
+        const double fill = rounds <= 1.0 ? 1.0 : rounds / (double)(long long)(rounds + 0.999999);  // last-round efficiency
+        // measured on DoorKey-8x8 x 262144 (profiles/r01_sweep_*): prefetching beats occupancy, table beats ALU
+        const double score = (resident < 20 ? resident : 20) * fill * (vis == VIS_TBL ? 1.3 : 1.0) * (nbuf == 2 ? 1.25 : 1.0);
+        if (score > best_score + 1e-9) {
+          best_score = score;
+          plan->warps = w; plan->vis = vis; plan->nbuf = nbuf; plan->ctas_per_sm = ctas; plan->smem = smem;
+        }
       }
     }
   }
@@ -330,7 +385,7 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
 cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
                         int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream) {
   const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
-  StepKernel k = step_kernel(p.kind, plan.vis);
+  StepKernel k = step_kernel(p.kind, plan.vis, plan.nbuf);
   static const bool use_pdl = []() { const char *e = getenv("MINIGRID_B200_PDL"); return !e || atoi(e) != 0; }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)plan.grid);
