@@ -45,6 +45,7 @@ def load(build_if_missing: bool = True):
     L.mg_seed_base.argtypes = [p, u64, p]
     L.mg_reset.argtypes = [p, p, p, p]
     L.mg_step.argtypes = [p, p, i32, p, p, p, p, p, p]
+    L.mg_step.restype = i32
     L.mg_gen_obs.argtypes = [p, p, p, p]
     L.mg_reset_host.argtypes = [p, p, p]
     L.mg_step_host.argtypes = [p] * 7
