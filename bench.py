@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--graph", type=int, default=1, help="replay the step loop as CUDA graphs of this many steps x rotate (0 = eager launches)")
     return ap.parse_args()
 
 
@@ -225,6 +226,40 @@ def main():
 
     run(W)
     barrier()
+    # The step loop is launch-bound for small batches (one ~20 us kernel per step vs ~8 us of Python + driver per
+    # launch), so it is captured once as a CUDA graph through the same public step() calls and replayed. K steps
+    # are still exactly K kernel launches on the device.
+    graph = None
+    G = 0
+    if args.graph:
+        G = R * max(1, min(T // R, 128 // R))  # steps per graph: every batch and a run of distinct action rows
+        if G > K:
+            G = 0
+    if G:
+        try:
+            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(cap_stream):
+                run(G)  # warm the capture stream
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=cap_stream):
+                    run(G)
+            torch.cuda.current_stream(dev).wait_stream(cap_stream)
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001  (fall back to eager launches, and say so)
+            graph = None
+            G = 0
+            graph_error = repr(exc)
+            torch.cuda.synchronize()
+    eager_run = run
+    if graph is not None:
+        def run(steps, first=0):  # noqa: F811
+            for _ in range(steps // G):
+                graph.replay()
+            if steps % G:
+                eager_run(steps % G, first)
+        run(G)
+        barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = sum(b.launch_count for b in batches)
@@ -239,6 +274,8 @@ def main():
     clocks = sampler.stop()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = sum(b.launch_count for b in batches) - l0
+    if graph is not None:
+        launches += (K // G) * G  # launches replayed by the graphs (each captured step() is one kernel node)
     for b in batches:
         b.check_actions()
     value = total * K / (ms * 1e-3)
@@ -248,13 +285,13 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for t in range(K):
+    for t in range(K):  # eager launches, one batch: shows the launch-bound regime next to the graph number
         step_fns[0](act_rows[t % T])
     e1.record()
     torch.cuda.synchronize()
     ms_res = max_over_ranks(e0.elapsed_time(e1))
 
-    # dominant kernel: a vector step is exactly ONE K1 launch (launches == K is asserted below), so the CUDA events
+    # dominant kernel: a vector step is exactly ONE K1 launch (launches == K), so the CUDA events
     # that bracket the timed region measure K back-to-back k_step launches on the launching stream; ms / K is the
     # average launch duration including launch gaps (conservative)
     kstep_ms = ms / K if launches == K else None
@@ -306,7 +343,8 @@ def main():
             "config": {"workload": f"{args.env}, {n} envs per GPU ({total} total), uniform random actions, NEXT_STEP autoreset",
                        "env": args.env, "envs_per_gpu": n, "total_envs": total, "autoreset": "next_step",
                        "l2": f"{R} independent env batches cycled, working set {R * ws / 1e6:.0f} MB per GPU > 126 MB L2 (inputs larger than L2)",
-                       "parallelism": f"env-sharded x{world}, no collective on the step path"},
+                       "parallelism": f"env-sharded x{world}, no collective on the step path",
+                       "launch": (f"CUDA graph replay, {G} steps per graph" if graph is not None else "eager launches")},
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
             "gpu_launches": int(launches),
