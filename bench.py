@@ -116,6 +116,22 @@ class ClockSampler:
         return out
 
 
+def usable_cores():
+    """Host threads this process can actually run at once: min(online CPUs, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(np.ceil(int(quota) / int(period)))))
+    except Exception:
+        pass
+    return n
+
+
 def run_reference(args, rank, world):
     """The reference algorithm on the host CPUs: the oracle port (C restatement of MiniGridEnv.step/gen_obs,
     validated against the Python reference), one env slice per host thread. The Python reference itself cannot
@@ -125,19 +141,19 @@ def run_reference(args, rank, world):
     from oracle.oracle import OracleVecEnv, max_threads
 
     n = args.envs_per_gpu
-    cores = max_threads()
-    env = OracleVecEnv(args.env, n, autoreset="next_step", n_threads=0)
+    cores = min(max_threads(), usable_cores())
+    env = OracleVecEnv(args.env, n, autoreset="next_step", n_threads=cores)
     env.reset(seed=0)
     rng = np.random.default_rng(1234)
     # bounded sample: keep the whole run to a few minutes whatever the core count
     probe_steps = 2
-    secs, _ = env.rollout(rng.integers(0, 7, (probe_steps, n)).astype(np.int32), n_threads=0)
+    secs, _ = env.rollout(rng.integers(0, 7, (probe_steps, n)).astype(np.int32), n_threads=cores)
     per_step = max(secs / probe_steps, 1e-6)
     budget = 120.0
     steps = int(max(3, min(args.steps, budget / per_step)))
     warm = int(max(1, min(args.warmup, 10.0 / per_step)))
-    env.rollout(rng.integers(0, 7, (warm, n)).astype(np.int32), n_threads=0)
-    secs, _ = env.rollout(rng.integers(0, 7, (steps, n)).astype(np.int32), n_threads=0)
+    env.rollout(rng.integers(0, 7, (warm, n)).astype(np.int32), n_threads=cores)
+    secs, _ = env.rollout(rng.integers(0, 7, (steps, n)).astype(np.int32), n_threads=cores)
     value = n * steps / secs
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
@@ -156,16 +172,17 @@ def run_reference(args, rank, world):
 def cpu_baseline(args):
     from oracle.oracle import OracleVecEnv, max_threads
 
-    cores = max_threads()
+    cores = min(max_threads(), usable_cores())
     n = 65536
-    env = OracleVecEnv(args.env, n, autoreset="next_step", n_threads=0)
+    env = OracleVecEnv(args.env, n, autoreset="next_step", n_threads=cores)
     env.reset(seed=0)
     rng = np.random.default_rng(1234)
-    secs, _ = env.rollout(rng.integers(0, 7, (2, n)).astype(np.int32), n_threads=0)
+    secs, _ = env.rollout(rng.integers(0, 7, (2, n)).astype(np.int32), n_threads=cores)
     steps = int(max(4, min(2000, args.cpu_seconds / max(secs / 2, 1e-6))))
-    secs, _ = env.rollout(rng.integers(0, 7, (steps, n)).astype(np.int32), n_threads=0)
+    secs, _ = env.rollout(rng.integers(0, 7, (steps, n)).astype(np.int32), n_threads=cores)
     return {"value": n * steps / secs, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n} envs x {steps} lockstep steps of {args.env} ({secs:.1f} s), oracle C port on {cores} host threads"}
+            "sample": f"{n} envs x {steps} lockstep steps of {args.env} ({secs:.1f} s), oracle C port on {cores} host threads "
+                      f"(os.cpu_count()={os.cpu_count()}, cgroup CPU quota respected)"}
 
 
 def main():

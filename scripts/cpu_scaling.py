@@ -1,3 +1,5 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, time
 from oracle.oracle import OracleVecEnv, max_threads
 print("max_threads", max_threads())
