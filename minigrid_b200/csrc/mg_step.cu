@@ -63,10 +63,25 @@ __device__ __forceinline__ void tma_store_1d(void *dst, uint32_t src, uint32_t b
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
+// volatile asm loads: they stay where they are written (ahead of the mbarrier wait), so a prefetch really is one
+__device__ __forceinline__ uint4 ldg_rec(const uint4 *ptr) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
 __device__ __forceinline__ int load_action(const void *actions, int dtype, int env) {
-  if (dtype == 1) return (int)reinterpret_cast<const long long *>(actions)[env];
-  if (dtype == 2) return (int)reinterpret_cast<const uint8_t *>(actions)[env];
-  return reinterpret_cast<const int *>(actions)[env];
+  int v;
+  if (dtype == 1) {
+    long long w;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(w) : "l"(reinterpret_cast<const long long *>(actions) + env));
+    return (int)w;
+  }
+  if (dtype == 2) {
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const uint8_t *>(actions) + env));
+    return v;
+  }
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const int *>(actions) + env));
+  return v;
 }
 
 // MiniGridEnv.reset() for the lanes in `pend`, one environment at a time with the whole warp: all lanes
@@ -160,7 +175,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
     }
     const int env0 = tile * TILE + lane;
-    rec = p.agent[env0];
+    rec = ldg_rec(p.agent + env0);
     if (stepping && env0 < p.n_envs) action = load_action(actions, act_dtype, env0);
   }
 
@@ -180,7 +195,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
           if (nn >= t_hi) nn = p.n_tiles;
         }
         const int env_n = next * TILE + lane;
-        rec_n = p.agent[env_n];
+        rec_n = ldg_rec(p.agent + env_n);
         if (stepping && env_n < p.n_envs) action_n = load_action(actions, act_dtype, env_n);
       }
     } else {
@@ -192,7 +207,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
         if (nn >= t_hi) nn = p.n_tiles;
       }
       const int env0 = tile * TILE + lane;
-      rec = p.agent[env0];
+      rec = ldg_rec(p.agent + env0);
       action = (stepping && env0 < p.n_envs) ? load_action(actions, act_dtype, env0) : A_DONE;
     }
     uint32_t *gtile = reinterpret_cast<uint32_t *>(bufs + (size_t)b * buf_bytes);
