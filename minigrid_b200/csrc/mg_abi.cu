@@ -23,6 +23,7 @@ cudaError_t launch_get_state(const Params &p, uint8_t *grid, int32_t *agent, uin
 cudaError_t launch_set_state(const Params &p, const uint8_t *grid, const int32_t *agent, const uint64_t *rng,
                              const uint8_t *pending, cudaStream_t stream);
 cudaError_t launch_init(const Params &p, cudaStream_t stream);
+cudaError_t launch_template(const Params &p, uint32_t *tmpl, cudaStream_t stream);
 }  // namespace mg
 
 using namespace mg;
@@ -98,7 +99,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   const size_t sz_agent = align_up(n_pad * sizeof(uint4), 256);
   const size_t sz_rng = align_up(n_pad * sizeof(RngRec), 256);
   const size_t sz_lut_r = align_up((size_t)(max_steps + 1) * sizeof(double), 256);
-  const size_t total = sz_grid + sz_agent + sz_rng + 256 /*err*/ + sz_lut_r + 1024 + VIS_TBL_BYTES;
+  const size_t sz_tmpl = align_up((size_t)p.g.wpe * 4, 256);
+  const size_t total = sz_grid + sz_agent + sz_rng + 256 /*err*/ + sz_lut_r + 1024 + VIS_TBL_BYTES + sz_tmpl;
   cudaError_t e = cudaMalloc(&h->d_arena, total);
   if (e != cudaSuccess) { delete h; return fail(MG_ERR_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); }
   uint8_t *base = (uint8_t *)h->d_arena;
@@ -108,8 +110,9 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   p.err = (int *)base; base += 256;
   double *d_rl = (double *)base; base += sz_lut_r;
   uint32_t *d_cl = (uint32_t *)base; base += 1024;
-  uint16_t *d_vt = (uint16_t *)base;
-  p.reward_lut = d_rl; p.cell_lut = d_cl; p.vis_tbl = d_vt;
+  uint16_t *d_vt = (uint16_t *)base; base += VIS_TBL_BYTES;
+  uint32_t *d_tm = (uint32_t *)base;
+  p.reward_lut = d_rl; p.cell_lut = d_cl; p.vis_tbl = d_vt; p.tmpl = d_tm;
 
   // _reward(): 1 - 0.9 * (step_count / max_steps) in host IEEE double, never contracted (minigrid_env.py:245)
   {
@@ -136,6 +139,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     fprintf(stderr, "[minigrid_b200] K1 plan: %d warps/CTA, vis=%d, nbuf=%d, %d CTA/SM, grid=%d, smem=%zu B, tiles=%d\n", h->plan.warps,
             h->plan.vis, h->plan.nbuf, h->plan.ctas_per_sm, h->plan.grid, h->plan.smem, p.n_tiles);
   if (e == cudaSuccess) e = launch_init(p, h->hstream);
+  if (e == cudaSuccess) e = launch_template(p, d_tm, h->hstream);
   if (e == cudaSuccess) e = launch_seed(p, nullptr, 0, h->hstream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->hstream);
   if (e != cudaSuccess) {
@@ -143,7 +147,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     mg_destroy(h);
     return fail(MG_ERR_CUDA, msg);
   }
-  h->launches = 2;
+  h->launches = 3;
   *out = h;
   return MG_OK;
 }

@@ -118,6 +118,7 @@ struct Params {
   const double *reward_lut; // [max_steps + 1], 1 - 0.9 * (k / max_steps) computed on the host in IEEE double
   const uint32_t *cell_lut; // [256] decode_cell()
   const uint16_t *vis_tbl;  // [128 * 128] process_vis row table (mg_obs.cuh: build_vis_table)
+  const uint32_t *tmpl;     // [wpe] level template: the words of a blank draw (mg_levels.cuh)
   int *err;                 // sticky error word
 };
 

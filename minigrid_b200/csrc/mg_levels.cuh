@@ -197,4 +197,38 @@ MG_D void fill_level(const Params &p, const Level &L, uint32_t *col) {
   for (int w = 0; w < p.g.wpe; ++w) col[w * 32] = level_word<KIND>(p, L, w);
 }
 
+// ---- template + patch form of the fill (the in-step autoreset of K1) ----
+// Most of a level never changes between episodes. The template is the level of a "blank" draw (no split wall,
+// key, rivers, gaps or goal where those are drawn); a freshly drawn level differs from it only on a few lines,
+// whose cells are re-evaluated with the same cell function and written as bytes.
+MG_D Level blank_level() {
+  Level L;
+  L.ax = L.ay = 1; L.adir = 0;
+  L.a = L.b = L.c = L.d = L.e = L.f = -1;
+  L.rv = L.rh = 0;
+  for (int y = 0; y < MAX_DIM; ++y) L.open_row[y] = 0;
+  return L;
+}
+// calls put(x, y) for this lane's share of the cells that may differ from the template
+template <int KIND, class Put>
+MG_D void patch_level(const Params &p, const Level &L, int lane, Put &&put) {
+  const Geom &g = p.g;
+  if (KIND == KIND_DOORKEY) {
+    if (lane >= 1 && lane <= g.H - 2) put(L.a, lane);  // the split column (door included)
+    if (lane == 31) put(L.c, L.d);                      // the key
+  } else if (KIND == KIND_CROSSING) {
+    for (uint32_t m = L.rv; m; m &= m - 1)              // river columns (openings lie on rivers)
+      if (lane >= 1 && lane <= g.H - 2) put(__ffs(m) - 1, lane);
+    for (uint32_t m = L.rh; m; m &= m - 1)              // river rows
+      if (lane >= 1 && lane <= g.W - 2) put(lane, __ffs(m) - 1);
+  } else if (KIND == KIND_FOURROOMS) {
+    const int xm = g.W / 2, ym = g.H / 2;
+    if (lane == 0) put(xm, L.a);
+    if (lane == 1) put(L.b, ym);
+    if (lane == 2) put(L.c, ym);
+    if (lane == 3) put(xm, L.d);
+    if (lane == 4) put(L.e, L.f);
+  }
+}
+
 }  // namespace mg

@@ -48,6 +48,25 @@ cudaError_t launch_reset(const Params &p, uint8_t *obs, int32_t *dir, cudaStream
   return cudaGetLastError();
 }
 
+// the level template (words of a blank draw), once per handle
+template <int KIND>
+__global__ void k_template(Params p, uint32_t *tmpl) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= p.g.wpe) return;
+  const Level L = blank_level();
+  tmpl[w] = level_word<KIND>(p, L, w);
+}
+cudaError_t launch_template(const Params &p, uint32_t *tmpl, cudaStream_t stream) {
+  const int blocks = (p.g.wpe + 63) / 64;
+  switch (p.kind) {
+    case KIND_EMPTY: k_template<KIND_EMPTY><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_DOORKEY: k_template<KIND_DOORKEY><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_CROSSING: k_template<KIND_CROSSING><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    default: k_template<KIND_FOURROOMS><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+  }
+  return cudaGetLastError();
+}
+
 // np_random = Generator(PCG64(SeedSequence(seed)))
 __global__ void k_seed(Params p, const uint64_t *__restrict__ seeds, uint64_t base) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;

@@ -84,31 +84,50 @@ __device__ __forceinline__ int load_action(const void *actions, int dtype, int e
   return v;
 }
 
-// MiniGridEnv.reset() for the lanes in `pend`, one environment at a time with the whole warp: all lanes
-// replay the draws (same RNG state, uniform control flow), lane L fills words L, L+32, ... of the level into
-// the staged tile and HBM, and the owning lane takes the new agent state. Out of line: it is the rare path
-// and must not cost the hot loop registers.
+// MiniGridEnv.reset() for the lanes in `pend`. Phase 1: every pending lane replays the numpy-exact draws of ITS
+// environment (lane per env; only the rejection loops diverge). Phase 2, one environment at a time with the whole
+// warp: the owner's drawn integers are broadcast, lane L copies words L, L+32, ... of the level template into the
+// staged tile and HBM, then the few cells that depend on the draw are re-evaluated and written as bytes.
+// Out of line: it is the rare path and must not cost the hot loop registers.
 struct ResetOut { int ax, ay, dir; };
 
 template <int KIND>
 __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int tile, uint32_t *gtile, int lane) {
-  ResetOut out = {0, 0, 0};
   const Geom &g = p.g;
   uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
+  Level L = blank_level();
+  if ((pend >> lane) & 1u) {
+    RngRec *rr = p.rng + (size_t)tile * TILE + lane;
+    Pcg r = load_rng(rr);
+    draw_level<KIND>(p, r, L);
+    store_rng(rr, r);
+  }
+  const ResetOut out = {L.ax, L.ay, L.adir};
+  __syncwarp();
   while (pend) {
     const int src = __ffs(pend) - 1;
     pend &= pend - 1;
-    const int env = tile * TILE + src;
-    Pcg r = load_rng(p.rng + env);
-    Level L;
-    draw_level<KIND>(p, r, L);
-    if (lane == 0) store_rng(p.rng + env, r);
+    Level B;  // the owner's draw, broadcast
+    B.ax = B.ay = B.adir = 0;
+    B.a = __shfl_sync(0xFFFFFFFFu, L.a, src); B.b = __shfl_sync(0xFFFFFFFFu, L.b, src);
+    B.c = __shfl_sync(0xFFFFFFFFu, L.c, src); B.d = __shfl_sync(0xFFFFFFFFu, L.d, src);
+    B.e = __shfl_sync(0xFFFFFFFFu, L.e, src); B.f = __shfl_sync(0xFFFFFFFFu, L.f, src);
+    B.rv = __shfl_sync(0xFFFFFFFFu, L.rv, src); B.rh = __shfl_sync(0xFFFFFFFFu, L.rh, src);
+    if (KIND == KIND_CROSSING)
+      for (int y = 0; y < g.H; ++y) B.open_row[y] = __shfl_sync(0xFFFFFFFFu, L.open_row[y], src);
     for (int w = lane; w < g.wpe; w += 32) {
-      const uint32_t word = level_word<KIND>(p, L, w);
+      const uint32_t word = __ldg(p.tmpl + w);
       gtile[w * 32 + src] = word;
       gsrc[w * 32 + src] = word;
     }
-    if (lane == src) { out.ax = L.ax; out.ay = L.ay; out.dir = L.adir; }
+    __syncwarp();  // template words land before the byte patches other lanes write into them
+    uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(gsrc);
+    patch_level<KIND>(p, B, lane, [&](int x, int y) {
+      const uint8_t code = (uint8_t)cell_of<KIND>(p, B, x, y);
+      const size_t ro = ((size_t)r_word(g, x, y) * 32 + src) * 4 + (x & 3), co = ((size_t)c_word(g, x, y) * 32 + src) * 4 + (y & 3);
+      sb[ro] = code; sb[co] = code;
+      gb[ro] = code; gb[co] = code;
+    });
   }
   __syncwarp();
   return out;

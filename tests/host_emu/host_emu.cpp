@@ -26,6 +26,7 @@ struct Emu {
   std::vector<double> reward_lut;
   std::vector<uint32_t> cell_lut;
   std::vector<uint16_t> vis_tbl;
+  std::vector<uint32_t> tmpl;
   int use_tbl;
   int err;
 };
@@ -60,26 +61,35 @@ static void reset_one(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {
     default: reset_env<KIND_FOURROOMS>(e, env, obs, dir_out); break;
   }
 }
-// warp_reset body: the lanes in `pend` are regenerated one at a time; every "lane" fills its share of words
+// warp_reset body: phase 1 lane-per-env draws, phase 2 template copy + byte patches per environment
 struct ResetOut { int ax, ay, dir; };
 template <int KIND>
 static void warp_reset_k(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOut out[32]) {
   Params &p = e->p;
-  uint32_t *gsrc = p.grid + (size_t)tile * p.g.wpe * 32;
+  const Geom &g = p.g;
+  uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
+  std::vector<Level> Ls(32, blank_level());
+  for (int lane = 0; lane < 32; ++lane)
+    if ((pend >> lane) & 1u) {
+      const int env = tile * TILE + lane;
+      Pcg r = load_rng(&e->rng[env]);
+      draw_level<KIND>(p, r, Ls[lane]);
+      store_rng(&e->rng[env], r);
+    }
+  for (int lane = 0; lane < 32; ++lane) { out[lane].ax = Ls[lane].ax; out[lane].ay = Ls[lane].ay; out[lane].dir = Ls[lane].adir; }
   while (pend) {
     const int src = __ffs(pend) - 1;
     pend &= pend - 1;
-    const int env = tile * TILE + src;
-    Pcg r = load_rng(&e->rng[env]);
-    Level L;
-    draw_level<KIND>(p, r, L);
-    store_rng(&e->rng[env], r);
-    for (int w = 0; w < p.g.wpe; ++w) {
-      const uint32_t word = level_word<KIND>(p, L, w);
-      gtile[w * 32 + src] = word;
-      gsrc[w * 32 + src] = word;
-    }
-    out[src].ax = L.ax; out[src].ay = L.ay; out[src].dir = L.adir;
+    const Level &B = Ls[src];
+    for (int w = 0; w < g.wpe; ++w) { gtile[w * 32 + src] = e->tmpl[w]; gsrc[w * 32 + src] = e->tmpl[w]; }
+    uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(gsrc);
+    for (int lane = 0; lane < 32; ++lane)
+      patch_level<KIND>(p, B, lane, [&](int x, int y) {
+        const uint8_t code = (uint8_t)cell_of<KIND>(p, B, x, y);
+        const size_t ro = ((size_t)r_word(g, x, y) * 32 + src) * 4 + (x & 3), co = ((size_t)c_word(g, x, y) * 32 + src) * 4 + (y & 3);
+        sb[ro] = code; sb[co] = code;
+        gb[ro] = code; gb[co] = code;
+      });
   }
 }
 static void warp_reset(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOut out[32]) {
@@ -218,7 +228,19 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
   e->vis_tbl.resize(128 * 128);
   build_vis_table(e->vis_tbl.data());
   p.vis_tbl = e->vis_tbl.data();
-  e->use_tbl = (n_envs % 2) == 0;  // exercise both process_vis forms across the test matrix
+  e->use_tbl = (n_envs % 2) == 0;
+  e->tmpl.resize(p.g.wpe);
+  {  // k_template body
+    const Level L = blank_level();
+    for (int w = 0; w < p.g.wpe; ++w)
+      switch (kind) {
+        case KIND_EMPTY: e->tmpl[w] = level_word<KIND_EMPTY>(p, L, w); break;
+        case KIND_DOORKEY: e->tmpl[w] = level_word<KIND_DOORKEY>(p, L, w); break;
+        case KIND_CROSSING: e->tmpl[w] = level_word<KIND_CROSSING>(p, L, w); break;
+        default: e->tmpl[w] = level_word<KIND_FOURROOMS>(p, L, w); break;
+      }
+    p.tmpl = e->tmpl.data();
+  }  // exercise both process_vis forms across the test matrix
   e->err = 0;
   p.grid = e->grid.data(); p.agent = e->agent.data(); p.rng = e->rng.data();
   p.reward_lut = e->reward_lut.data(); p.cell_lut = e->cell_lut.data();
