@@ -15,7 +15,9 @@ struct Level {
   int ax, ay, adir;
   int a, b, c, d, e, f;        // kind-specific drawn integers
   uint32_t rv, rh;             // crossing: river position bit masks (vertical = column x, horizontal = row y)
-  uint32_t open_row[MAX_DIM];  // crossing: openings, bit x of row y
+  // crossing: every river is crossed exactly once (crossing.py:170-188). 5-bit fields, one per river in
+  // ascending position order: the open row y of each vertical river / the open column x of each horizontal river.
+  unsigned long long ov, oh;
 };
 
 // ---- cell functions: the finished grid of each generator ----
@@ -38,8 +40,10 @@ MG_D uint32_t cell_doorkey(const Geom &g, const Level &L, int x, int y) {
 // envs/crossing.py:131-188
 MG_D uint32_t cell_crossing(const Geom &g, const Level &L, int x, int y, uint32_t obstacle) {
   if (on_border(g, x, y)) return CODE_WALL;
-  if ((L.open_row[y] >> x) & 1u) return CODE_EMPTY;
-  if (((L.rv >> x) & 1u) || ((L.rh >> y) & 1u)) return obstacle;
+  const bool on_v = (L.rv >> x) & 1u, on_h = (L.rh >> y) & 1u;
+  if (on_v && (int)((L.ov >> (5 * __popc(L.rv & ((1u << x) - 1u)))) & 31u) == y) return CODE_EMPTY;
+  if (on_h && (int)((L.oh >> (5 * __popc(L.rh & ((1u << y) - 1u)))) & 31u) == x) return CODE_EMPTY;
+  if (on_v || on_h) return obstacle;
   if (x == g.W - 2 && y == g.H - 2) return CODE_GOAL;
   return CODE_EMPTY;
 }
@@ -74,6 +78,7 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
   const int W = g.W, H = g.H;
   L.a = L.b = L.c = L.d = L.e = L.f = -1;
   L.rv = L.rh = 0;
+  L.ov = L.oh = 0;
   if (KIND == KIND_EMPTY) {
     if (!p.kp[0]) { L.ax = p.kp[1]; L.ay = p.kp[2]; L.adir = p.kp[3]; }
     else {  // place_agent(): minigrid_env.py:383-397 over the whole grid
@@ -105,47 +110,53 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
     }
   } else if (KIND == KIND_CROSSING) {
     L.ax = 1; L.ay = 1; L.adir = 0;
-    for (int y = 0; y < MAX_DIM; ++y) L.open_row[y] = 0;
-    // rivers = [(v, i) for i in range(2, H-2, 2)] + [(h, j) for j in range(2, W-2, 2)]; entry = pos | dir << 8
-    int riv[2 * MAX_DIM];
+    // rivers = [(v, i) for i in range(2, H-2, 2)] + [(h, j) for j in range(2, W-2, 2)]. Kept in registers: up to 32
+    // one-byte entries (pos | dir << 7) in two 128-bit words, so the rare path needs no local-memory arrays.
+    u128 r_lo = 0, r_hi = 0;
+    auto rget = [&](int i) -> uint32_t { return (uint32_t)(((i < 16) ? r_lo : r_hi) >> (8 * (i & 15))) & 0xFFu; };
+    auto rset = [&](int i, uint32_t v) {
+      const u128 m = (u128)0xFF << (8 * (i & 15)), val = (u128)v << (8 * (i & 15));
+      if (i < 16) r_lo = (r_lo & ~m) | val; else r_hi = (r_hi & ~m) | val;
+    };
     int n = 0;
-    for (int i = 2; i < H - 2; i += 2) riv[n++] = i;
-    for (int j = 2; j < W - 2; j += 2) riv[n++] = j | 256;
+    for (int i = 2; i < H - 2; i += 2) rset(n++, (uint32_t)i);
+    for (int j = 2; j < W - 2; j += 2) rset(n++, (uint32_t)j | 128u);
     for (int i = n - 1; i >= 1; --i) {  // np_random.shuffle(list)
       const int j = (int)rng_interval(r, (uint32_t)i);
-      const int t = riv[i]; riv[i] = riv[j]; riv[j] = t;
+      const uint32_t a = rget(i), b = rget(j);
+      rset(i, b); rset(j, a);
     }
     if (p.kp[0] < n) n = p.kp[0];
     int nv = 0, nh = 0;
     for (int k = 0; k < n; ++k) {
-      if (riv[k] & 256) { L.rh |= 1u << (riv[k] & 255); ++nh; } else { L.rv |= 1u << riv[k]; ++nv; }
+      const uint32_t e = rget(k);
+      if (e & 128u) { L.rh |= 1u << (e & 127u); ++nh; } else { L.rv |= 1u << e; ++nv; }
     }
-    // path = [h] * len(rivers_v) + [v] * len(rivers_h), shuffled; 1 = h
-    int path[2 * MAX_DIM];
+    // path = [h] * len(rivers_v) + [v] * len(rivers_h), shuffled; bit k of `path` set = h
     const int np_ = nv + nh;
-    for (int k = 0; k < np_; ++k) path[k] = k < nv ? 1 : 0;
+    uint32_t path = (nv >= 32) ? 0xFFFFFFFFu : ((1u << nv) - 1u);
     for (int i = np_ - 1; i >= 1; --i) {
       const int j = (int)rng_interval(r, (uint32_t)i);
-      const int t = path[i]; path[i] = path[j]; path[j] = t;
+      const uint32_t bi = (path >> i) & 1u, bj = (path >> j) & 1u;
+      path = (path & ~((1u << i) | (1u << j))) | (bj << i) | (bi << j);
     }
     // limits_v = [0] + sorted(rivers_v) + [H-1]: walk the sorted positions through the bit masks
-    int lim_v_lo = 0, lim_h_lo = 0;                    // limits_v[room_i], limits_h[room_j]
+    int lim_v_lo = 0, lim_h_lo = 0;  // limits_v[room_i], limits_h[room_j]
+    int room_i = 0, room_j = 0;
+    L.ov = 0; L.oh = 0;
     for (int k = 0; k < np_; ++k) {
-      // next limit above the current one
       const uint32_t mv = L.rv & ~((2u << lim_v_lo) - 1u), mh = L.rh & ~((2u << lim_h_lo) - 1u);
       const int lim_v_hi = mv ? (__ffs(mv) - 1) : H - 1;  // limits_v[room_i + 1]
       const int lim_h_hi = mh ? (__ffs(mh) - 1) : W - 1;  // limits_h[room_j + 1]
-      int i, j;
-      if (path[k]) {  // h: cross the next vertical river at a random row of the current room
-        i = lim_v_hi;
-        j = lim_h_lo + 1 + rng_integers(r, 0, lim_h_hi - lim_h_lo - 1);  // choice(range(lo+1, hi))
-        lim_v_lo = lim_v_hi;
+      if ((path >> k) & 1u) {  // h: cross the next vertical river at a random row of the current room
+        const int j = lim_h_lo + 1 + rng_integers(r, 0, lim_h_hi - lim_h_lo - 1);  // choice(range(lo+1, hi))
+        L.ov |= (unsigned long long)j << (5 * room_i);
+        lim_v_lo = lim_v_hi; ++room_i;
       } else {
-        i = lim_v_lo + 1 + rng_integers(r, 0, lim_v_hi - lim_v_lo - 1);
-        j = lim_h_hi;
-        lim_h_lo = lim_h_hi;
+        const int i = lim_v_lo + 1 + rng_integers(r, 0, lim_v_hi - lim_v_lo - 1);
+        L.oh |= (unsigned long long)i << (5 * room_j);
+        lim_h_lo = lim_h_hi; ++room_j;
       }
-      L.open_row[j] |= 1u << i;
     }
   } else {  // FOURROOMS
     const int rw = W / 2, rh = H / 2;
@@ -206,7 +217,7 @@ MG_D Level blank_level() {
   L.ax = L.ay = 1; L.adir = 0;
   L.a = L.b = L.c = L.d = L.e = L.f = -1;
   L.rv = L.rh = 0;
-  for (int y = 0; y < MAX_DIM; ++y) L.open_row[y] = 0;
+  L.ov = L.oh = 0;
   return L;
 }
 // calls put(x, y) for this lane's share of the cells that may differ from the template

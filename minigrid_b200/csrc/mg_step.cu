@@ -113,8 +113,7 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
     B.c = __shfl_sync(0xFFFFFFFFu, L.c, src); B.d = __shfl_sync(0xFFFFFFFFu, L.d, src);
     B.e = __shfl_sync(0xFFFFFFFFu, L.e, src); B.f = __shfl_sync(0xFFFFFFFFu, L.f, src);
     B.rv = __shfl_sync(0xFFFFFFFFu, L.rv, src); B.rh = __shfl_sync(0xFFFFFFFFu, L.rh, src);
-    if (KIND == KIND_CROSSING)
-      for (int y = 0; y < g.H; ++y) B.open_row[y] = __shfl_sync(0xFFFFFFFFu, L.open_row[y], src);
+    B.ov = __shfl_sync(0xFFFFFFFFu, L.ov, src); B.oh = __shfl_sync(0xFFFFFFFFu, L.oh, src);
     for (int w = lane; w < g.wpe; w += 32) {
       const uint32_t word = __ldg(p.tmpl + w);
       gtile[w * 32 + src] = word;
