@@ -63,7 +63,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
               int n_params, int64_t n_envs, int autoreset_mode, int device, mg_env **out) {
   if (!out) return fail(MG_ERR_INVALID_ARG, "out is NULL");
   *out = nullptr;
-  if (kind < 0 || kind > 3) return fail(MG_ERR_INVALID_ARG, "unknown kind");
+  if (kind < 0 || kind >= KIND_COUNT) return fail(MG_ERR_INVALID_ARG, "unknown kind");
   if (width < 3 || height < 3 || width > MAX_DIM || height > MAX_DIM)
     return fail(MG_ERR_INVALID_ARG, "width/height must be in [3, 26]");
   if (max_steps < 1) return fail(MG_ERR_INVALID_ARG, "max_steps must be >= 1");
@@ -92,6 +92,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   for (int i = 0; i < 8; ++i) p.kp[i] = (params && i < n_params) ? params[i] : 0;
   if (kind == MG_KIND_EMPTY && !p.kp[0] && n_params < 4) { p.kp[1] = 1; p.kp[2] = 1; p.kp[3] = 0; }
   if (kind == MG_KIND_CROSSING && n_params < 2) { p.kp[0] = 1; p.kp[1] = (int)T_LAVA; }
+  if (kind == MG_KIND_LAVAGAP && n_params < 1) p.kp[0] = (int)T_LAVA;
+  if (kind == MG_KIND_DISTSHIFT && n_params < 4) { if (n_params < 1) p.kp[0] = 2; p.kp[1] = 1; p.kp[2] = 1; p.kp[3] = 0; }
   h->device = device;
 
   const size_t n_pad = (size_t)p.n_tiles * TILE;

@@ -60,8 +60,25 @@ MG_D uint32_t cell_fourrooms(const Geom &g, const Level &L, int x, int y) {
   return cell_fourrooms_walls(g, L, x, y);
 }
 
+// envs/lavagap.py:100-135: (a, b) = gap position; the obstacle column spans y = 1..H-2
+MG_D uint32_t cell_lavagap(const Geom &g, const Level &L, int x, int y, uint32_t obstacle) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  if (x == L.a) return y == L.b ? CODE_EMPTY : obstacle;
+  if (x == g.W - 2 && y == g.H - 2) return CODE_GOAL;
+  return CODE_EMPTY;
+}
+// envs/distshift.py:98-120: lava strips on rows 1 and strip2_row, x = 3..W-4; goal at (W-2, 1); no draws
+MG_D uint32_t cell_distshift(const Geom &g, int strip2_row, int x, int y) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  if (x == g.W - 2 && y == 1) return CODE_GOAL;
+  if (x >= 3 && x < g.W - 3 && (y == 1 || y == strip2_row)) return CODE_LAVA;
+  return CODE_EMPTY;
+}
+
 template <int KIND>
 MG_D uint32_t cell_of(const Params &p, const Level &L, int x, int y) {
+  if (KIND == KIND_LAVAGAP) return cell_lavagap(p.g, L, x, y, (p.kp[0] == (int)T_WALL) ? CODE_WALL : CODE_LAVA);
+  if (KIND == KIND_DISTSHIFT) return cell_distshift(p.g, p.kp[0], x, y);
   if (KIND == KIND_EMPTY) return cell_empty(p.g, L, x, y);
   if (KIND == KIND_DOORKEY) return cell_doorkey(p.g, L, x, y);
   if (KIND == KIND_CROSSING) {
@@ -90,6 +107,12 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
       }
       L.adir = rng_integers(r, 0, 4);
     }
+  } else if (KIND == KIND_LAVAGAP) {
+    L.ax = 1; L.ay = 1; L.adir = 0;
+    L.a = rng_integers(r, 2, W - 2);
+    L.b = rng_integers(r, 1, H - 1);
+  } else if (KIND == KIND_DISTSHIFT) {
+    L.ax = p.kp[1]; L.ay = p.kp[2]; L.adir = p.kp[3];
   } else if (KIND == KIND_DOORKEY) {
     const int split = rng_integers(r, 2, W - 2);
     L.a = split;
@@ -224,7 +247,9 @@ MG_D Level blank_level() {
 template <int KIND, class Put>
 MG_D void patch_level(const Params &p, const Level &L, int lane, Put &&put) {
   const Geom &g = p.g;
-  if (KIND == KIND_DOORKEY) {
+  if (KIND == KIND_LAVAGAP) {
+    if (lane >= 1 && lane <= g.H - 2) put(L.a, lane);  // the obstacle column (gap included)
+  } else if (KIND == KIND_DOORKEY) {
     if (lane >= 1 && lane <= g.H - 2) put(L.a, lane);  // the split column (door included)
     if (lane == 31) put(L.c, L.d);                      // the key
   } else if (KIND == KIND_CROSSING) {

@@ -343,6 +343,8 @@ static StepKernel pick_kind(int kind) {
     case KIND_EMPTY: return (StepKernel)k_step<KIND_EMPTY, VIS, NBUF>;
     case KIND_DOORKEY: return (StepKernel)k_step<KIND_DOORKEY, VIS, NBUF>;
     case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS, NBUF>;
+    case KIND_LAVAGAP: return (StepKernel)k_step<KIND_LAVAGAP, VIS, NBUF>;
+    case KIND_DISTSHIFT: return (StepKernel)k_step<KIND_DISTSHIFT, VIS, NBUF>;
     default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, NBUF>;
   }
 }

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
-KIND_EMPTY, KIND_DOORKEY, KIND_CROSSING, KIND_FOURROOMS = 0, 1, 2, 3
+KIND_EMPTY, KIND_DOORKEY, KIND_CROSSING, KIND_FOURROOMS, KIND_LAVAGAP, KIND_DISTSHIFT = 0, 1, 2, 3, 4, 5
 T_WALL, T_LAVA = 2, 9
 
 
@@ -49,6 +49,20 @@ def fourrooms(max_steps=100):
     return EnvSpec(KIND_FOURROOMS, 19, 19, max_steps, False, (), "reach the goal")
 
 
+def lavagap(size, obstacle_type="lava", max_steps=None):
+    """envs/lavagap.py:68-91 (4*size^2 steps, see_through_walls=False)."""
+    lava = obstacle_type == "lava"
+    return EnvSpec(KIND_LAVAGAP, size, size, max_steps or 4 * size * size, False, (T_LAVA if lava else T_WALL,),
+                   "avoid the lava and get to the green goal square" if lava
+                   else "find the opening and get to the green goal square")
+
+
+def distshift(width=9, height=7, strip2_row=2, agent_start_pos=(1, 1), agent_start_dir=0, max_steps=None):
+    """envs/distshift.py:63-92 (4*width*height steps, see_through_walls=True, fixed agent start)."""
+    return EnvSpec(KIND_DISTSHIFT, width, height, max_steps or 4 * width * height, True,
+                   (strip2_row, agent_start_pos[0], agent_start_pos[1], agent_start_dir), "get to the green goal square")
+
+
 REGISTRY = {
     # BASELINE.json configs
     "MiniGrid-Empty-5x5-v0": empty(size=5),
@@ -71,6 +85,12 @@ REGISTRY = {
     "MiniGrid-SimpleCrossingS9N2-v0": crossing(9, 2, "wall"),
     "MiniGrid-SimpleCrossingS9N3-v0": crossing(9, 3, "wall"),
     "MiniGrid-SimpleCrossingS11N5-v0": crossing(11, 5, "wall"),
+    # round-1 widening: base-step-only generators, __init__.py:79-88,295-310
+    "MiniGrid-LavaGapS5-v0": lavagap(5),
+    "MiniGrid-LavaGapS6-v0": lavagap(6),
+    "MiniGrid-LavaGapS7-v0": lavagap(7),
+    "MiniGrid-DistShift1-v0": distshift(strip2_row=2),
+    "MiniGrid-DistShift2-v0": distshift(strip2_row=5),
 }
 
 

@@ -34,6 +34,10 @@ ROLLOUTS = {  # id -> (N, T, seed)
     "MiniGrid-DoorKey-16x16-v0": (4, 200, 3),
     "MiniGrid-LavaCrossingS11N5-v0": (4, 200, 9),
     "MiniGrid-SimpleCrossingS9N2-v0": (4, 350, 21),
+    "MiniGrid-LavaGapS5-v0": (4, 200, 13),
+    "MiniGrid-LavaGapS7-v0": (4, 300, 17),
+    "MiniGrid-DistShift1-v0": (4, 300, 19),
+    "MiniGrid-DistShift2-v0": (4, 300, 23),
 }
 INJECTS = {  # id (host env whose size/see_through/max_steps are used) -> (N, T)
     "MiniGrid-DoorKey-8x8-v0": (16, 120),
@@ -41,6 +45,7 @@ INJECTS = {  # id (host env whose size/see_through/max_steps are used) -> (N, T)
     "MiniGrid-LavaCrossingS9N1-v0": (8, 80),
     "MiniGrid-FourRooms-v0": (8, 80),
     "MiniGrid-Empty-5x5-v0": (8, 60),
+    "MiniGrid-DistShift1-v0": (8, 80),  # 9 x 7: width != height
 }
 
 

@@ -380,6 +380,36 @@ static void gen_fourrooms(const mgo_vec *v, env_t *e) {
   place_obj(e, &goal, 0, 0, W, H, &gx, &gy);
 }
 
+/* envs/lavagap.py:100-135 */
+static void gen_lavagap(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  cell_t obstacle = {(uint8_t)v->params[0], (uint8_t)(v->params[0] == T_LAVA ? C_RED : C_GREY), 0};
+  grid_clear(&e->grid);
+  grid_wall_rect(&e->grid, 0, 0, W, H);
+  e->agent_x = 1; e->agent_y = 1; e->agent_dir = 0;
+  cell_t goal = {T_GOAL, C_GREEN, 0};
+  grid_set(&e->grid, W - 2, H - 2, goal);
+  int gap_x = (int)rand_int(e, 2, W - 2);
+  int gap_y = (int)rand_int(e, 1, H - 1);
+  grid_vert_wall(&e->grid, gap_x, 1, H - 2, obstacle);
+  grid_set(&e->grid, gap_x, gap_y, CELL_NONE);
+}
+/* envs/distshift.py:98-120 (agent_start_pos given) */
+static void gen_distshift(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  int strip2_row = v->params[0];
+  grid_clear(&e->grid);
+  grid_wall_rect(&e->grid, 0, 0, W, H);
+  cell_t goal = {T_GOAL, C_GREEN, 0};
+  grid_set(&e->grid, W - 2, 1, goal);
+  cell_t lava = {T_LAVA, C_RED, 0};
+  for (int i = 0; i < W - 6; i++) {
+    grid_set(&e->grid, 3 + i, 1, lava);
+    grid_set(&e->grid, 3 + i, strip2_row, lava);
+  }
+  e->agent_x = v->params[1]; e->agent_y = v->params[2]; e->agent_dir = v->params[3];
+}
+
 /* minigrid_env.py:119-157 (without the gen_obs at the end) */
 static void env_reset(const mgo_vec *v, env_t *e) {
   e->agent_x = -1; e->agent_y = -1; e->agent_dir = -1;
@@ -387,6 +417,8 @@ static void env_reset(const mgo_vec *v, env_t *e) {
     case MGO_EMPTY: gen_empty(v, e); break;
     case MGO_DOORKEY: gen_doorkey(v, e); break;
     case MGO_CROSSING: gen_crossing(v, e); break;
+    case MGO_LAVAGAP: gen_lavagap(v, e); break;
+    case MGO_DISTSHIFT: gen_distshift(v, e); break;
     default: gen_fourrooms(v, e); break;
   }
   e->carrying = 0;

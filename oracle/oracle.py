@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmg_oracle.so")
 
-KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3}
+KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 
 # id -> (kind, width, height, max_steps, see_through_walls, params); restated from
@@ -34,6 +34,11 @@ ENV_SPECS = {
     "MiniGrid-LavaCrossingS9N3-v0": ("crossing", 9, 9, 324, False, [3, 9]),
     "MiniGrid-LavaCrossingS11N5-v0": ("crossing", 11, 11, 484, False, [5, 9]),
     "MiniGrid-SimpleCrossingS9N2-v0": ("crossing", 9, 9, 324, False, [2, 2]),
+    # round-1 widening: lavagap.py:68-135 (__init__.py:295-310), distshift.py:63-120 (__init__.py:79-88)
+    "MiniGrid-LavaGapS5-v0": ("lavagap", 5, 5, 100, False, [9]),
+    "MiniGrid-LavaGapS7-v0": ("lavagap", 7, 7, 196, False, [9]),
+    "MiniGrid-DistShift1-v0": ("distshift", 9, 7, 252, True, [2, 1, 1, 0]),
+    "MiniGrid-DistShift2-v0": ("distshift", 9, 7, 252, True, [5, 1, 1, 0]),
 }
 
 
