@@ -26,9 +26,9 @@ sys.path.insert(0, ROOT)
 ALGO_BYTES_PER_STEP = 348  # action 4 + patch 147 + obs 147 + reward 8 + flags 2 + agent 20 r + 20 w
 L2_BYTES = 126e6
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch from the committed ncu --set full capture
-# (profiles/r01_kstep_v3_ncu_details.txt: 47.24 MB read + 11.92 MB written; obs writes mostly stay in L2)
-TRAFFIC_BYTES_PER_LAUNCH = 59.2e6
-TRAFFIC_SOURCE = "ncu --set full, profiles/r01_kstep_v3 (DoorKey-8x8 x 262144; applies to the default workload only)"
+# (profiles/r01_kstep_v10_summary.txt: 47.27 MB read + 12.3-13.8 MB written; obs writes mostly stay in L2)
+TRAFFIC_BYTES_PER_LAUNCH = 60.3e6
+TRAFFIC_SOURCE = "ncu --set full, profiles/r01_kstep_v10 (DoorKey-8x8 x 262144; applies to the default workload only)"
 
 
 def parse_args():
@@ -317,7 +317,7 @@ def main():
     try:
         for b in batches:
             b.profile_kernels(True)
-        run(min(K, 200), W)
+        eager_run(min(K, 200), W)  # graph replays bypass the C-ABI call that records the events
         torch.cuda.synchronize()
         tot, cnt = 0.0, 0
         for b in batches:
