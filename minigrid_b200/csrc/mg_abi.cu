@@ -82,7 +82,12 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   if (!h) return fail(MG_ERR_INVALID_ARG, "out of host memory");
   memset(h, 0, sizeof(*h));
   Params &p = h->p;
-  p.g = make_geom(width, height);
+  {
+    // small grids: whole tiles through TMA; large grids: env-major lines and per-lane view windows (mg_common.cuh)
+    int layout = make_geom(width, height, LAYOUT_TILED).wpe * 4 > 512 ? LAYOUT_WINDOW : LAYOUT_TILED;
+    if (const char *e = getenv("MINIGRID_B200_LAYOUT")) layout = atoi(e) ? LAYOUT_WINDOW : LAYOUT_TILED;  // tuning / test knob
+    p.g = make_geom(width, height, layout);
+  }
   p.n_envs = (int)n_envs;
   p.n_tiles = (int)((n_envs + TILE - 1) / TILE);
   p.max_steps = max_steps;
@@ -97,7 +102,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   h->device = device;
 
   const size_t n_pad = (size_t)p.n_tiles * TILE;
-  const size_t sz_grid = align_up((size_t)p.n_tiles * p.g.wpe * 128, 256);
+  const size_t sz_grid = align_up((size_t)p.n_tiles * p.g.wpe * 128, 256) + 256;  // + slack: window copies read 224 B from a line start
   const size_t sz_agent = align_up(n_pad * sizeof(uint4), 256);
   const size_t sz_rng = align_up(n_pad * sizeof(RngRec), 256);
   const size_t sz_lut_r = align_up((size_t)(max_steps + 1) * sizeof(double), 256);
@@ -138,7 +143,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = configure_step(p, &h->plan);
   if (e == cudaSuccess && getenv("MINIGRID_B200_VERBOSE"))
-    fprintf(stderr, "[minigrid_b200] K1 plan: %d warps/CTA, vis=%d, nbuf=%d, %d CTA/SM, grid=%d, smem=%zu B, tiles=%d\n", h->plan.warps,
+    fprintf(stderr, "[minigrid_b200] K1 plan: layout=%d, %d warps/CTA, vis=%d, nbuf=%d, %d CTA/SM, grid=%d, smem=%zu B, tiles=%d\n", p.g.layout, h->plan.warps,
             h->plan.vis, h->plan.nbuf, h->plan.ctas_per_sm, h->plan.grid, h->plan.smem, p.n_tiles);
   if (e == cudaSuccess) e = launch_init(p, h->hstream);
   if (e == cudaSuccess) e = launch_template(p, d_tm, h->hstream);

@@ -12,8 +12,8 @@
 //                        tile[w][lane] uint32, w < wpe. Lane L's w-th word sits in shared-memory bank L, so
 //                        per-lane gathers at lane-specific offsets are conflict-free, and a tile is one
 //                        contiguous block that a single TMA bulk copy (cp.async.bulk) stages.
-//   per env words        array R: lines y = -1..H (row-major x bytes, ring lines are grey wall), then
-//                        array C: lines x = -1..W (column-major y bytes): every 7-cell run of the
+//   per env words        array R: lines y = -ring..H+ring-1 (row-major x bytes, ring lines are grey wall), then
+//                        array C: lines x = -ring..W+ring-1 (column-major y bytes): every 7-cell run of the
 //                        egocentric view (Grid.slice + rotate_left, grid.py:110-143) is 7 consecutive
 //                        bytes of one line of R (facing +-x) or C (facing +-y).
 //   agent record         uint4 {x | y<<8, dir | flags<<8, carry code (0 none), step_count}
@@ -85,21 +85,38 @@ MG_HD uint32_t decode_cell(uint32_t code) {
   return t4 | (color << 8);
 }
 
+// Two HBM layouts of the per-env words (same words, same r_word / c_word indices):
+//   LAYOUT_TILED   tile[w][lane] for 32 consecutive envs (small grids): one TMA bulk copy stages a whole tile and
+//                  per-lane gathers are bank-conflict free.
+//   LAYOUT_WINDOW  env-major, 32-byte lines, 3 ring lines (large grids): a step only touches the 7 lines of the
+//                  egocentric view, 224 contiguous bytes of one array, which each lane copies with cp.async;
+//                  HBM traffic per env-step no longer grows with the grid.
+enum : int { LAYOUT_TILED = 0, LAYOUT_WINDOW = 1 };
+constexpr int WIN_LINE_WORDS = 8;   // 32-byte lines (W, H <= 26)
+constexpr int WIN_BYTES = 7 * 32;   // the 7 view lines
+constexpr int WIN_LANE_BYTES = 240; // per-lane shared-memory stride (16-byte aligned, 60 words: 4-way bank spread)
+
 struct Geom {
   int W, H;
   int lswR, lswC;  // words per line of R / C
+  int ring;        // wall lines stored before line 0 and after the last line of each array
   int offC;        // word offset of array C inside an env
-  int wpe;         // words per env (tile = wpe * 32 words)
+  int wpe;         // words per env
+  int layout;
 };
 
-MG_HD Geom make_geom(int W, int H) {
+MG_HD Geom make_geom(int W, int H, int layout) {
   Geom g;
-  g.W = W; g.H = H;
-  g.lswR = (W + 3) >> 2;
-  g.lswC = (H + 3) >> 2;
-  g.offC = (H + 2) * g.lswR;
-  g.wpe = g.offC + (W + 2) * g.lswC;
+  g.W = W; g.H = H; g.layout = layout;
+  if (layout == LAYOUT_TILED) { g.lswR = (W + 3) >> 2; g.lswC = (H + 3) >> 2; g.ring = 1; }
+  else { g.lswR = WIN_LINE_WORDS; g.lswC = WIN_LINE_WORDS; g.ring = 3; }
+  g.offC = (H + 2 * g.ring) * g.lswR;
+  g.wpe = g.offC + (W + 2 * g.ring) * g.lswC;
   return g;
+}
+// index in the grid arena (in words) of word w of environment env
+MG_HD size_t grid_word(const Geom &g, int env, int w) {
+  return g.layout == LAYOUT_TILED ? ((size_t)(env >> 5) * g.wpe + w) * 32 + (env & 31) : (size_t)env * g.wpe + w;
 }
 
 struct RngRec {  // 48 bytes, 16-byte aligned
@@ -113,7 +130,7 @@ struct Params {
   int n_envs, n_tiles;
   int max_steps, see_through, mode, kind;
   int kp[8];                // generator parameters (see include/minigrid_b200.h)
-  uint32_t *grid;           // [n_tiles][wpe][32]
+  uint32_t *grid;           // n_tiles * 32 * wpe words, see grid_word()
   uint4 *agent;             // [n_tiles * 32]
   RngRec *rng;              // [n_tiles * 32]
   const double *reward_lut; // [max_steps + 1], 1 - 0.9 * (k / max_steps) computed on the host in IEEE double
@@ -124,13 +141,16 @@ struct Params {
 };
 
 struct StepPlan {  // launch shape of K1, chosen once per handle (mg_step.cu: configure_step)
-  int warps, vis, nbuf, ctas_per_sm, grid;
+  int warps, vis, nbuf, mode, ctas_per_sm, grid;
   size_t smem;
 };
 
 // word index of byte (line, pos) and helpers for the interleaved tile
-MG_HD int r_word(const Geom &g, int x, int y) { return (y + 1) * g.lswR + (x >> 2); }
-MG_HD int c_word(const Geom &g, int x, int y) { return g.offC + (x + 1) * g.lswC + (y >> 2); }
+MG_HD int r_word(const Geom &g, int x, int y) { return (y + g.ring) * g.lswR + (x >> 2); }
+MG_HD int c_word(const Geom &g, int x, int y) { return g.offC + (x + g.ring) * g.lswC + (y >> 2); }
+// byte offsets in the grid arena of cell (x, y) in the two arrays
+MG_HD size_t cell_byte_R(const Geom &g, int env, int x, int y) { return grid_word(g, env, r_word(g, x, y)) * 4 + (x & 3); }
+MG_HD size_t cell_byte_C(const Geom &g, int env, int x, int y) { return grid_word(g, env, c_word(g, x, y)) * 4 + (y & 3); }
 
 // PTX prmt.b32 (generic mode): selector nibble bits 0-2 pick one of the 8 source bytes, bit 3 replicates that
 // byte's sign bit instead. CUDA's __byte_perm() only honours the low 3 bits, hence the inline PTX.

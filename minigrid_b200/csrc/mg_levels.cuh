@@ -213,7 +213,7 @@ MG_D uint32_t level_word(const Params &p, const Level &L, int w) {
   const bool inC = w >= g.offC;
   const int lw = inC ? g.lswC : g.lswR;
   const int rel = inC ? w - g.offC : w;
-  const int line = rel / lw - 1, wi = rel - (line + 1) * lw;
+  const int line = rel / lw - g.ring, wi = rel - (line + g.ring) * lw;
   const int nlines = inC ? g.W : g.H, plen = inC ? g.H : g.W;
   uint32_t word = 0;
 #pragma unroll
@@ -225,10 +225,10 @@ MG_D uint32_t level_word(const Params &p, const Level &L, int w) {
   }
   return word;
 }
-// both arrays of one env; col points at the env's lane column of its tile (word w at col[w * 32])
+// both arrays of one env
 template <int KIND>
-MG_D void fill_level(const Params &p, const Level &L, uint32_t *col) {
-  for (int w = 0; w < p.g.wpe; ++w) col[w * 32] = level_word<KIND>(p, L, w);
+MG_D void fill_level(const Params &p, const Level &L, int env) {
+  for (int w = 0; w < p.g.wpe; ++w) p.grid[grid_word(p.g, env, w)] = level_word<KIND>(p, L, w);
 }
 
 // ---- template + patch form of the fill (the in-step autoreset of K1) ----

@@ -18,17 +18,30 @@
 
 namespace mg {
 
-// one word of the lane's tile. base already points at this lane's column: word w is base[w * 32].
+// Word accessors: gen_obs_words asks for word w of the environment (w as in r_word / c_word).
+struct AccTiled {   // LAYOUT_TILED, lane column of a tile in shared (K1) or global (K2) memory: word w at base[w * 32]
+  const uint32_t *base;
+  bool smem;
+  MG_D uint32_t operator()(int w) const {
+#ifdef __CUDA_ARCH__
+    if (smem) {
+      uint32_t v;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(base) + (uint32_t)(w << 7)));
+      return v;
+    }
+#endif
+    return base[w << 5];
+  }
+};
+struct AccFlat {    // LAYOUT_WINDOW: env-major words; `base` is shifted so that base[w] is word w (global memory in
+  const uint32_t *base;  // K2; in K1 the lane's 7-line window in shared memory, shifted by its first word index)
+  MG_D uint32_t operator()(int w) const { return base[w]; }
+};
+// kept for the transition's single front-cell read out of a staged tile
 template <bool SMEM>
 MG_D uint32_t tile_word(const uint32_t *base, int w) {
-#ifdef __CUDA_ARCH__
-  if (SMEM) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(base) + (uint32_t)(w << 7)));
-    return v;
-  }
-#endif
-  return base[w << 5];
+  AccTiled a = {base, SMEM};
+  return a(w);
 }
 
 // One row of Grid.process_vis (grid.py:291-328) on 7-bit masks (bit i = view column i): m = cells of this row
@@ -95,11 +108,11 @@ MG_D void process_vis_tbl(const uint16_t *tbl, uint32_t oplo, uint32_t ophi, uin
 }
 
 // Produces the 147-byte image of one env as 37 little-endian words S (byte 147 is zero).
-//   base   lane's tile column (shared or global), lut: 256-entry decode table (shared or global)
+//   acc    word accessor (AccTiled / AccFlat), lut: 256-entry decode table (shared or global)
 //   VIS    VIS_NONE: see_through_walls (minigrid_env.py:616-621); VIS_ALU: bit tricks; VIS_TBL: vis_tbl lookups
 constexpr int VIS_NONE = 0, VIS_ALU = 1, VIS_TBL = 2;
-template <int VIS, bool SMEM>
-MG_D void gen_obs_words(const Geom &g, const uint32_t *base, const uint32_t *lut, const uint16_t *vis_tbl,
+template <int VIS, class Acc>
+MG_D void gen_obs_words(const Geom &g, const Acc &acc, const uint32_t *lut, const uint16_t *vis_tbl,
                         int ax, int ay, int dir, uint32_t carry, uint32_t (&S)[OBS_WORDS]) {
   const bool useC = dir & 1;
   const bool rev = dir < 2;
@@ -126,11 +139,11 @@ MG_D void gen_obs_words(const Geom &g, const uint32_t *base, const uint32_t *lut
   uint32_t oplo = 0, ophi = 0;
 #pragma unroll
   for (int vx = 0; vx < VIEW; ++vx) {
-    const int l = clampi(lc + lstep * (vx - 3), -1, nlines) + 1;
+    const int l = clampi(lc + lstep * (vx - 3), -g.ring, nlines + g.ring - 1) + g.ring;
     const int rw = abase + l * lsw;
-    const uint32_t w0 = tile_word<SMEM>(base, rw + k0);
-    const uint32_t w1 = tile_word<SMEM>(base, rw + k1);
-    const uint32_t w2 = tile_word<SMEM>(base, rw + k2);
+    const uint32_t w0 = acc(rw + k0);
+    const uint32_t w1 = acc(rw + k1);
+    const uint32_t w2 = acc(rw + k2);
     const uint32_t a = __funnelshift_r(w0, w1, sh);
     const uint32_t b = __funnelshift_r(w1, w2, sh);
     uint32_t lo = prmt(a, b, selLo);

@@ -9,17 +9,29 @@
 
 namespace mg {
 
+// gen_obs straight out of HBM (rare paths), either layout
+__device__ void gen_obs_global(const Params &p, int env, int ax, int ay, int dir, uint32_t carry, uint32_t (&S)[OBS_WORDS]) {
+  const uint32_t *base = p.grid + grid_word(p.g, env, 0);
+  if (p.g.layout == LAYOUT_TILED) {
+    const AccTiled acc = {base, false};
+    if (p.see_through) gen_obs_words<VIS_NONE>(p.g, acc, p.cell_lut, p.vis_tbl, ax, ay, dir, carry, S);
+    else gen_obs_words<VIS_ALU>(p.g, acc, p.cell_lut, p.vis_tbl, ax, ay, dir, carry, S);
+  } else {
+    const AccFlat acc = {base};
+    if (p.see_through) gen_obs_words<VIS_NONE>(p.g, acc, p.cell_lut, p.vis_tbl, ax, ay, dir, carry, S);
+    else gen_obs_words<VIS_ALU>(p.g, acc, p.cell_lut, p.vis_tbl, ax, ay, dir, carry, S);
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(128)
 k_reset(Params p, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out) {
-  const Geom &g = p.g;
   for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < p.n_envs; env += gridDim.x * blockDim.x) {
     Pcg r = load_rng(p.rng + env);
     Level L;
     draw_level<KIND>(p, r, L);
     store_rng(p.rng + env, r);
-    uint32_t *col = p.grid + (size_t)(env >> 5) * g.wpe * 32 + (env & 31);
-    fill_level<KIND>(p, L, col);
+    fill_level<KIND>(p, L, env);
     uint4 rec;
     rec.x = (uint32_t)L.ax | ((uint32_t)L.ay << 8);
     rec.y = (uint32_t)L.adir;  // flags cleared: SyncVectorEnv.reset() clears _autoreset_envs
@@ -29,8 +41,7 @@ k_reset(Params p, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out) {
     if (dir_out) dir_out[env] = L.adir;
     if (obs) {
       uint32_t S[OBS_WORDS];
-      if (p.see_through) gen_obs_words<VIS_NONE, false>(g, col, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
-      else gen_obs_words<VIS_ALU, false>(g, col, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
+      gen_obs_global(p, env, L.ax, L.ay, L.adir, 0u, S);
       emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
     }
   }

@@ -5,8 +5,7 @@
 namespace mg {
 
 __device__ __forceinline__ uint32_t load_code(const Params &p, int env, int x, int y) {
-  const uint32_t *col = p.grid + (size_t)(env >> 5) * p.g.wpe * 32 + (env & 31);
-  return (col[c_word(p.g, x, y) * 32] >> (8 * (y & 3))) & 0xFFu;
+  return reinterpret_cast<const uint8_t *>(p.grid)[cell_byte_C(p.g, env, x, y)];
 }
 
 // out[n][W][H][3] = grid.encode(), agent cell = (OBJECT_TO_IDX["agent"], COLOR_TO_IDX["red"], agent_dir).
@@ -52,9 +51,9 @@ __global__ void k_set_grid(Params p, const uint8_t *__restrict__ grid) {
   const int x = c / p.g.H, y = c % p.g.H;
   const uint8_t *in = grid + gid * 3;
   const uint8_t code = (uint8_t)encode_cell(in[0], in[1], in[2]);
-  uint8_t *col = reinterpret_cast<uint8_t *>(p.grid + (size_t)(env >> 5) * p.g.wpe * 32 + (env & 31));
-  col[(size_t)r_word(p.g, x, y) * 128 + (x & 3)] = code;
-  col[(size_t)c_word(p.g, x, y) * 128 + (y & 3)] = code;
+  uint8_t *gb = reinterpret_cast<uint8_t *>(p.grid);
+  gb[cell_byte_R(p.g, env, x, y)] = code;
+  gb[cell_byte_C(p.g, env, x, y)] = code;
 }
 
 __global__ void k_set_agent(Params p, const int32_t *__restrict__ agent, const uint64_t *__restrict__ rng,

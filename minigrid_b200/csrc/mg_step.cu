@@ -14,6 +14,8 @@
 //   4. observation in registers (mg_obs.cuh), staged into the consumed tile buffer in output layout, then one
 //      TMA bulk store of the warp's 32 x 147 = 4704 contiguous bytes.
 //   5. coalesced stores of direction / reward / terminated / truncated and the agent record.
+// Large grids (LAYOUT_WINDOW) skip step 1: the transition reads its one front byte straight from HBM and each lane
+// then copies only the 7 lines its view needs (224 B, cp.async) into shared memory.
 #include <cstdio>
 #include <cstdlib>
 
@@ -25,14 +27,16 @@
 
 namespace mg {
 
-// per-warp buffer: holds the staged tile, then (once the gather has consumed it) the warp's 4704-byte
-// observation block in output layout.
+enum : int { MODE_TILED1 = 0, MODE_TILED2 = 1, MODE_WINDOW = 2 };  // buffers per warp / layout of K1
+
+// per-warp buffer: holds the staged tile (or the 32 lanes' view windows), then, once the gather has consumed it,
+// the warp's 4704-byte observation block in output layout.
 __host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
-  uint32_t b = (uint32_t)g.wpe * 128u;
+  uint32_t b = g.layout == LAYOUT_TILED ? (uint32_t)g.wpe * 128u : (uint32_t)(TILE * WIN_LANE_BYTES);
   if (b < (uint32_t)OBS_TILE_BYTES) b = OBS_TILE_BYTES;
   return (b + 127u) & ~127u;
 }
-// [cell table 1 KB][visibility table 32 KB, VIS_TBL only][warps x buffer][mbarriers: one per warp + table][tile counter]
+// [cell table 1 KB][visibility table 32 KB, VIS_TBL only][warps x nbuf x buffer][mbarriers][tile counter]
 __host__ __device__ inline size_t step_smem_bytes(const Geom &g, int vis, int warps, int nbuf) {
   return 1024 + (vis == VIS_TBL ? VIS_TBL_BYTES : 0) + (size_t)warps * nbuf * step_buf_bytes(g) + 16 * (size_t)warps + 16;
 }
@@ -84,17 +88,20 @@ __device__ __forceinline__ int load_action(const void *actions, int dtype, int e
   return v;
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
 // MiniGridEnv.reset() for the lanes in `pend`. Phase 1: every pending lane replays the numpy-exact draws of ITS
 // environment (lane per env; only the rejection loops diverge). Phase 2, one environment at a time with the whole
-// warp: the owner's drawn integers are broadcast, lane L copies words L, L+32, ... of the level template into the
-// staged tile and HBM, then the few cells that depend on the draw are re-evaluated and written as bytes.
-// Out of line: it is the rare path and must not cost the hot loop registers.
+// warp: the owner's drawn integers are broadcast, lane L copies words L, L+32, ... of the level template into HBM
+// (and into the staged tile when there is one), then the few cells that depend on the draw are re-evaluated and
+// written as bytes. Out of line: it is the rare path and must not cost the hot loop registers.
 struct ResetOut { int ax, ay, dir; };
 
 template <int KIND>
 __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int tile, uint32_t *gtile, int lane) {
   const Geom &g = p.g;
-  uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
   Level L = blank_level();
   if ((pend >> lane) & 1u) {
     RngRec *rr = p.rng + (size_t)tile * TILE + lane;
@@ -104,9 +111,11 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
   }
   const ResetOut out = {L.ax, L.ay, L.adir};
   __syncwarp();
+  uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(p.grid);
   while (pend) {
     const int src = __ffs(pend) - 1;
     pend &= pend - 1;
+    const int env = tile * TILE + src;
     Level B;  // the owner's draw, broadcast
     B.ax = B.ay = B.adir = 0;
     B.a = __shfl_sync(0xFFFFFFFFu, L.a, src); B.b = __shfl_sync(0xFFFFFFFFu, L.b, src);
@@ -116,29 +125,31 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
     B.ov = __shfl_sync(0xFFFFFFFFu, L.ov, src); B.oh = __shfl_sync(0xFFFFFFFFu, L.oh, src);
     for (int w = lane; w < g.wpe; w += 32) {
       const uint32_t word = __ldg(p.tmpl + w);
-      gtile[w * 32 + src] = word;
-      gsrc[w * 32 + src] = word;
+      if (gtile) gtile[w * 32 + src] = word;
+      p.grid[grid_word(g, env, w)] = word;
     }
     __syncwarp();  // template words land before the byte patches other lanes write into them
-    uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(gsrc);
     patch_level<KIND>(p, B, lane, [&](int x, int y) {
       const uint8_t code = (uint8_t)cell_of<KIND>(p, B, x, y);
-      const size_t ro = ((size_t)r_word(g, x, y) * 32 + src) * 4 + (x & 3), co = ((size_t)c_word(g, x, y) * 32 + src) * 4 + (y & 3);
-      sb[ro] = code; sb[co] = code;
-      gb[ro] = code; gb[co] = code;
+      const int rw = r_word(g, x, y), cw = c_word(g, x, y);
+      if (gtile) { sb[((size_t)rw * 32 + src) * 4 + (x & 3)] = code; sb[((size_t)cw * 32 + src) * 4 + (y & 3)] = code; }
+      gb[grid_word(g, env, rw) * 4 + (x & 3)] = code;
+      gb[grid_word(g, env, cw) * 4 + (y & 3)] = code;
     });
   }
   __syncwarp();
   return out;
 }
 
-// NBUF == 2: each warp owns two buffers and prefetches its next tile (TMA + agent records + actions) before it
+// MODE_TILED2: each warp owns two buffers and prefetches its next tile (TMA + agent records + actions) before it
 // processes the current one, so HBM transfers overlap compute instead of alternating with it in GPU-wide bursts.
-template <int KIND, int VIS, int NBUF>
-__global__ void __launch_bounds__(NBUF == 2 ? 640 : 1024, 1)  // one CTA per SM: <= 20 warps (96 regs) or <= 32 (64 regs)
+template <int KIND, int VIS, int MODE>
+__global__ void __launch_bounds__(MODE == MODE_TILED2 ? 640 : 1024, 1)  // one CTA per SM: <= 20 warps (96 regs) or <= 32 (64 regs)
 k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
        int32_t *__restrict__ dir_out, double *__restrict__ reward_out, uint8_t *__restrict__ term_out,
        uint8_t *__restrict__ trunc_out, int obs_tma_ok) {
+  constexpr int NBUF = (MODE == MODE_TILED2) ? 2 : 1;
+  constexpr bool WIN = (MODE == MODE_WINDOW);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const Geom g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -197,6 +208,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     if (stepping && env0 < p.n_envs) action = load_action(actions, act_dtype, env0);
   }
 
+  uint8_t *gb = reinterpret_cast<uint8_t *>(p.grid);
   uint32_t phase = 0;  // bit b = parity to wait for on buffer b
   int b = 0;
   while (tile < p.n_tiles) {
@@ -219,8 +231,10 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     } else {
       if (lane == 0) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left the buffer
-        mbar_expect_tx(bar0, tile_bytes);
-        tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
+        if (!WIN) {
+          mbar_expect_tx(bar0, tile_bytes);
+          tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
+        }
         nn = atomicAdd(s_next, 1);  // consumed at the end of this tile
         if (nn >= t_hi) nn = p.n_tiles;
       }
@@ -229,7 +243,6 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       action = (stepping && env0 < p.n_envs) ? load_action(actions, act_dtype, env0) : A_DONE;
     }
     uint32_t *gtile = reinterpret_cast<uint32_t *>(bufs + (size_t)b * buf_bytes);
-    uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
     const int env = tile * TILE + lane;
     const bool active = env < p.n_envs;
     int ax = rec.x & 0xFF, ay = (rec.x >> 8) & 0xFF;
@@ -238,8 +251,12 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     uint32_t carry = rec.z;
     int steps = (int)rec.w;
 
-    mbar_wait(bar0 + 8u * (uint32_t)b, (phase >> b) & 1u);
-    phase ^= 1u << b;
+    if (!WIN) {
+      mbar_wait(bar0 + 8u * (uint32_t)b, (phase >> b) & 1u);
+      phase ^= 1u << b;
+    } else {
+      __syncwarp();  // lane 0 has waited for the bulk store that was still reading this buffer
+    }
 
     const uint32_t *base = gtile + lane;
     double reward = 0.0;
@@ -251,7 +268,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       fresh = active && (flags & FLAG_PENDING);
       const unsigned pend = __ballot_sync(0xFFFFFFFFu, fresh);
       if (pend) {
-        const ResetOut ro = warp_reset<KIND>(p, pend, tile, gtile, lane);
+        const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
         if (fresh) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; flags &= ~FLAG_PENDING; }
       }
     }
@@ -261,7 +278,9 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       int fx, fy;
       front_pos(g, ax, ay, dir, fx, fy);
       const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
-      const uint32_t fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
+      uint32_t fc;
+      if (WIN) fc = gb[grid_word(g, env, rw) * 4 + (fx & 3)];  // one byte straight from HBM / L2
+      else fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
       const StepOut so = transition(action, fc, fx, fy, ax, ay, dir, carry);
       const uint32_t newc = so.newc;
       terminated = so.terminated;
@@ -270,11 +289,13 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
                                       : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
       if (so.bad_action) atomicOr(p.err, 1);  // ValueError("Unknown action"), minigrid_env.py:584-585
       if (newc != fc && active) {
-        uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
-        uint8_t *gb = reinterpret_cast<uint8_t *>(gsrc);
-        const size_t ro = ((size_t)rw * 32 + lane) * 4 + (fx & 3), co = ((size_t)cw * 32 + lane) * 4 + (fy & 3);
-        sb[ro] = (uint8_t)newc; sb[co] = (uint8_t)newc;
-        gb[ro] = (uint8_t)newc; gb[co] = (uint8_t)newc;
+        if (!WIN) {
+          uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
+          sb[((size_t)rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)newc;
+          sb[((size_t)cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)newc;
+        }
+        gb[grid_word(g, env, rw) * 4 + (fx & 3)] = (uint8_t)newc;
+        gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)newc;
       }
       truncated = steps >= p.max_steps;
       const bool done = (terminated | truncated) != 0;
@@ -285,7 +306,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       const bool again = active && ((terminated | truncated) != 0);
       const unsigned pend = __ballot_sync(0xFFFFFFFFu, again);
       if (pend) {
-        const ResetOut ro = warp_reset<KIND>(p, pend, tile, gtile, lane);
+        const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
         if (again) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; }
       }
     }
@@ -293,11 +314,27 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     // ---- gen_obs ----
     if (obs != nullptr) {
       uint32_t S[OBS_WORDS];
-      gen_obs_words<VIS, true>(g, base, lut, vis_tbl, ax, ay, dir, carry, S);
+      if (WIN) {
+        // the 7 lines of the view (after the transition): 224 contiguous bytes of array R (facing +-x) or C (+-y)
+        const bool useC = dir & 1;
+        const int w0 = (useC ? g.offC : 0) + ((useC ? ax : ay) - 3 + g.ring) * WIN_LINE_WORDS;
+        const uint32_t *src = p.grid + grid_word(g, env, w0);
+        uint32_t *win = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(gtile) + lane * WIN_LANE_BYTES);
+        const uint32_t dst = smem_u32(win);
+#pragma unroll
+        for (int j = 0; j < WIN_BYTES / 16; ++j) cp_async16(dst + 16u * j, src + 4 * j);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const AccFlat acc = {win - w0};
+        gen_obs_words<VIS>(g, acc, lut, vis_tbl, ax, ay, dir, carry, S);
+      } else {
+        const AccTiled acc = {base, true};
+        gen_obs_words<VIS>(g, acc, lut, vis_tbl, ax, ay, dir, carry, S);
+      }
       const bool full = (tile + 1) * TILE <= p.n_envs;
       if (full && obs_tma_ok) {
-        const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);  // also: every lane is past its tile reads
-        emit_obs_staged(gtile, lane, S, n0);                         // the consumed tile buffer becomes the stage
+        const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);  // also: every lane is past its tile / window reads
+        emit_obs_staged(gtile, lane, S, n0);                         // the consumed buffer becomes the stage
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
@@ -337,33 +374,34 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
 
 typedef void (*StepKernel)(Params, const void *, int, uint8_t *, int32_t *, double *, uint8_t *, uint8_t *, int);
 
-template <int VIS, int NBUF>
+template <int VIS, int MODE>
 static StepKernel pick_kind(int kind) {
   switch (kind) {
-    case KIND_EMPTY: return (StepKernel)k_step<KIND_EMPTY, VIS, NBUF>;
-    case KIND_DOORKEY: return (StepKernel)k_step<KIND_DOORKEY, VIS, NBUF>;
-    case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS, NBUF>;
-    case KIND_LAVAGAP: return (StepKernel)k_step<KIND_LAVAGAP, VIS, NBUF>;
-    case KIND_DISTSHIFT: return (StepKernel)k_step<KIND_DISTSHIFT, VIS, NBUF>;
-    default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, NBUF>;
+    case KIND_EMPTY: return (StepKernel)k_step<KIND_EMPTY, VIS, MODE>;
+    case KIND_DOORKEY: return (StepKernel)k_step<KIND_DOORKEY, VIS, MODE>;
+    case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS, MODE>;
+    case KIND_LAVAGAP: return (StepKernel)k_step<KIND_LAVAGAP, VIS, MODE>;
+    case KIND_DISTSHIFT: return (StepKernel)k_step<KIND_DISTSHIFT, VIS, MODE>;
+    default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, MODE>;
   }
 }
-template <int NBUF>
+template <int MODE>
 static StepKernel pick_vis(int kind, int vis) {
-  if (vis == VIS_NONE) return pick_kind<VIS_NONE, NBUF>(kind);
-  if (vis == VIS_ALU) return pick_kind<VIS_ALU, NBUF>(kind);
-  return pick_kind<VIS_TBL, NBUF>(kind);
+  if (vis == VIS_NONE) return pick_kind<VIS_NONE, MODE>(kind);
+  if (vis == VIS_ALU) return pick_kind<VIS_ALU, MODE>(kind);
+  return pick_kind<VIS_TBL, MODE>(kind);
 }
-static StepKernel step_kernel(int kind, int vis, int nbuf) {
-  return nbuf == 2 ? pick_vis<2>(kind, vis) : pick_vis<1>(kind, vis);
+static StepKernel step_kernel(int kind, int vis, int mode) {
+  if (mode == MODE_WINDOW) return pick_vis<MODE_WINDOW>(kind, vis);
+  return mode == MODE_TILED2 ? pick_vis<MODE_TILED2>(kind, vis) : pick_vis<MODE_TILED1>(kind, vis);
 }
 
-// Choose the CTA shape once per handle. One persistent CTA of W <= 32 warps per SM (a second CTA per SM when
-// the tiles are small enough that both fit); W is taken from the upper half of what shared memory allows so
-// that tiles_per_SM / W lands just below an integer (the last round of tiles is then full: 8192 tiles on
-// 148 SMs is 55.35 per SM, and 28 warps finish in 1.98 rounds where 32 would need 2 with the second 73 % full).
-// The table-driven process_vis costs 32 KB per CTA and is preferred unless it costs more than a quarter of the
-// resident warps. MINIGRID_B200_CFG="warps,vis" (vis: 1 ALU, 2 table) overrides the choice (tuning knob).
+// Choose the CTA shape once per handle. One persistent CTA of W <= 32 warps per SM; W is taken from the upper half
+// of what shared memory allows so that tiles_per_SM / W lands just below an integer (the last round of tiles is
+// then full: 8192 tiles on 148 SMs is 55.35 per SM, and 19 warps finish in 2.91 rounds). Measured preferences
+// (profiles/r01_sweep_*): the table-driven process_vis (32 KB of shared memory) beats the ALU form, prefetching
+// (two buffers per warp) beats occupancy, and beyond ~20 resident warps nothing is gained.
+// MINIGRID_B200_CFG="warps,vis,nbuf" (vis: 1 ALU, 2 table) overrides the choice (tuning knob).
 cudaError_t configure_step(const Params &p, StepPlan *plan) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -371,16 +409,18 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
   int want_warps = 0, want_vis = 0, want_nbuf = 0;
   if (const char *cfg = getenv("MINIGRID_B200_CFG")) sscanf(cfg, "%d,%d,%d", &want_warps, &want_vis, &want_nbuf);
   const double tiles_per_sm = (double)p.n_tiles / sms;
+  const bool win = p.g.layout == LAYOUT_WINDOW;
   double best_score = -1.0;
   plan->warps = 0;
   const int vis_opts[2] = {VIS_TBL, VIS_ALU};
   for (int vi = 0; vi < (p.see_through ? 1 : 2); ++vi) {
     const int vis = p.see_through ? VIS_NONE : vis_opts[vi];
     if (!p.see_through && want_vis && vis != want_vis) continue;
-    for (int nbuf = 2; nbuf >= 1; --nbuf) {
-      if (want_nbuf && nbuf != want_nbuf) continue;
-      StepKernel k = step_kernel(p.kind, vis, nbuf);
-      const int wcap = nbuf == 2 ? 20 : 32;  // __launch_bounds__ of the two variants
+    for (int nbuf = win ? 1 : 2; nbuf >= 1; --nbuf) {
+      if (!win && want_nbuf && nbuf != want_nbuf) continue;
+      const int mode = win ? MODE_WINDOW : (nbuf == 2 ? MODE_TILED2 : MODE_TILED1);
+      StepKernel k = step_kernel(p.kind, vis, mode);
+      const int wcap = nbuf == 2 ? 20 : 32;  // __launch_bounds__ of the variants
       int wmax = 0;
       for (int w = wcap; w >= 1; --w)
         if (step_smem_bytes(p.g, vis, w, nbuf) <= 227 * 1024 - 1024) { wmax = w; break; }
@@ -400,11 +440,11 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
         const int resident = ctas * w;
         const double rounds = tiles_per_sm / resident;
         const double fill = rounds <= 1.0 ? 1.0 : rounds / (double)(long long)(rounds + 0.999999);  // last-round efficiency
-        // measured on DoorKey-8x8 x 262144 (profiles/r01_sweep_*): prefetching beats occupancy, table beats ALU
-        const double score = (resident < 20 ? resident : 20) * fill * (vis == VIS_TBL ? 1.3 : 1.0) * (nbuf == 2 ? 1.25 : 1.0);
+        const int cap = win ? 32 : 20;  // the window layout has two dependent HBM latencies per tile to hide
+        const double score = (resident < cap ? resident : cap) * fill * (vis == VIS_TBL ? 1.3 : 1.0) * (nbuf == 2 ? 1.25 : 1.0);
         if (score > best_score + 1e-9) {
           best_score = score;
-          plan->warps = w; plan->vis = vis; plan->nbuf = nbuf; plan->ctas_per_sm = ctas; plan->smem = smem;
+          plan->warps = w; plan->vis = vis; plan->nbuf = nbuf; plan->mode = mode; plan->ctas_per_sm = ctas; plan->smem = smem;
         }
       }
     }
@@ -420,7 +460,7 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
 cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
                         int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream) {
   const int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
-  StepKernel k = step_kernel(p.kind, plan.vis, plan.nbuf);
+  StepKernel k = step_kernel(p.kind, plan.vis, plan.mode);
   static const bool use_pdl = []() { const char *e = getenv("MINIGRID_B200_PDL"); return !e || atoi(e) != 0; }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)plan.grid);

@@ -27,7 +27,7 @@ def lib():
         L = C.CDLL(_LIB)
         p = C.c_void_p
         L.emu_create.restype = p
-        L.emu_create.argtypes = [C.c_int] * 5 + [p, C.c_int, C.c_int, C.c_int]
+        L.emu_create.argtypes = [C.c_int] * 5 + [p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.emu_destroy.argtypes = [p]
         L.emu_seed.argtypes = [p, p]
         L.emu_reset.argtypes = [p, p, p]
@@ -45,12 +45,12 @@ def _ptr(a):
 
 
 class EmuVecEnv:
-    def __init__(self, spec, num_envs, autoreset="next_step"):
+    def __init__(self, spec, num_envs, autoreset="next_step", layout=-1):
         kind, W, H, max_steps, see_through, params = spec
         self.width, self.height, self.num_envs = W, H, int(num_envs)
         prm = np.asarray(list(params), dtype=np.int32)
         self._h = lib().emu_create(KIND[kind], W, H, max_steps, int(see_through), _ptr(prm), len(prm), self.num_envs,
-                                   AUTORESET[autoreset])
+                                   AUTORESET[autoreset], layout)
         n = self.num_envs
         self.obs = np.zeros((n, 7, 7, 3), np.uint8)
         self.dir = np.zeros(n, np.int32)

@@ -16,7 +16,10 @@
 
 using namespace mg;
 
-static size_t step_words(const Geom &g) { size_t w = (size_t)g.wpe * 32; return w < 1184 ? 1184 : w; }
+static size_t step_words(const Geom &g) {
+  size_t w = g.layout == LAYOUT_TILED ? (size_t)g.wpe * 32 : (size_t)32 * WIN_LANE_BYTES / 4;
+  return w < 1184 ? 1184 : w;
+}
 
 struct Emu {
   Params p;
@@ -38,8 +41,7 @@ static void reset_env(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {  // k_r
   Level L;
   draw_level<KIND>(p, r, L);
   store_rng(&e->rng[env], r);
-  uint32_t *col = p.grid + (size_t)(env >> 5) * p.g.wpe * 32 + (env & 31);
-  fill_level<KIND>(p, L, col);
+  fill_level<KIND>(p, L, env);
   uint4 rec;
   rec.x = (uint32_t)L.ax | ((uint32_t)L.ay << 8);
   rec.y = (uint32_t)L.adir;
@@ -48,8 +50,16 @@ static void reset_env(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {  // k_r
   if (dir_out) dir_out[env] = L.adir;
   if (obs) {
     uint32_t S[OBS_WORDS];
-    if (p.see_through) gen_obs_words<VIS_NONE, false>(p.g, col, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
-    else gen_obs_words<VIS_ALU, false>(p.g, col, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
+    const uint32_t *base = p.grid + grid_word(p.g, env, 0);  // gen_obs_global body
+    if (p.g.layout == LAYOUT_TILED) {
+      const AccTiled acc = {base, false};
+      if (p.see_through) gen_obs_words<VIS_NONE>(p.g, acc, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
+      else gen_obs_words<VIS_ALU>(p.g, acc, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
+    } else {
+      const AccFlat acc = {base};
+      if (p.see_through) gen_obs_words<VIS_NONE>(p.g, acc, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
+      else gen_obs_words<VIS_ALU>(p.g, acc, p.cell_lut, p.vis_tbl, L.ax, L.ay, L.adir, 0u, S);
+    }
     emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
   }
 }
@@ -69,7 +79,6 @@ template <int KIND>
 static void warp_reset_k(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOut out[32]) {
   Params &p = e->p;
   const Geom &g = p.g;
-  uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
   std::vector<Level> Ls(32, blank_level());
   for (int lane = 0; lane < 32; ++lane)
     if ((pend >> lane) & 1u) {
@@ -83,14 +92,19 @@ static void warp_reset_k(Emu *e, unsigned pend, int tile, uint32_t *gtile, Reset
     const int src = __ffs(pend) - 1;
     pend &= pend - 1;
     const Level &B = Ls[src];
-    for (int w = 0; w < g.wpe; ++w) { gtile[w * 32 + src] = e->tmpl[w]; gsrc[w * 32 + src] = e->tmpl[w]; }
-    uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(gsrc);
+    const int env = tile * TILE + src;
+    for (int w = 0; w < g.wpe; ++w) {
+      if (gtile) gtile[w * 32 + src] = e->tmpl[w];
+      p.grid[grid_word(g, env, w)] = e->tmpl[w];
+    }
+    uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(p.grid);
     for (int lane = 0; lane < 32; ++lane)
       patch_level<KIND>(p, B, lane, [&](int x, int y) {
         const uint8_t code = (uint8_t)cell_of<KIND>(p, B, x, y);
-        const size_t ro = ((size_t)r_word(g, x, y) * 32 + src) * 4 + (x & 3), co = ((size_t)c_word(g, x, y) * 32 + src) * 4 + (y & 3);
-        sb[ro] = code; sb[co] = code;
-        gb[ro] = code; gb[co] = code;
+        const int rw = r_word(g, x, y), cw = c_word(g, x, y);
+        if (gtile) { sb[((size_t)rw * 32 + src) * 4 + (x & 3)] = code; sb[((size_t)cw * 32 + src) * 4 + (y & 3)] = code; }
+        gb[grid_word(g, env, rw) * 4 + (x & 3)] = code;
+        gb[grid_word(g, env, cw) * 4 + (y & 3)] = code;
       });
   }
 }
@@ -111,10 +125,11 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
   Params &p = e->p;
   const Geom g = p.g;
   const bool stepping = actions != nullptr;
+  const bool WIN = g.layout == LAYOUT_WINDOW;
   std::vector<uint32_t> gtile((size_t)step_words(g)), S_all(32 * OBS_WORDS);
+  uint8_t *gb = reinterpret_cast<uint8_t *>(p.grid);
   for (int tile = 0; tile < p.n_tiles; ++tile) {
-    uint32_t *gsrc = p.grid + (size_t)tile * g.wpe * 32;
-    memcpy(gtile.data(), gsrc, (size_t)g.wpe * 128);  // the TMA bulk load
+    if (!WIN) memcpy(gtile.data(), p.grid + (size_t)tile * g.wpe * 32, (size_t)g.wpe * 128);  // the TMA bulk load
     const bool full = (tile + 1) * TILE <= p.n_envs;
     int ax[32], ay[32], dir[32], steps[32];
     uint32_t flags[32], carry[32], terminated[32] = {0}, truncated[32] = {0};
@@ -133,7 +148,7 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
       for (int lane = 0; lane < 32; ++lane) { fresh[lane] = active[lane] && (flags[lane] & FLAG_PENDING); if (fresh[lane]) pend |= 1u << lane; }
       if (pend) {
         ResetOut ro[32];
-        warp_reset(e, pend, tile, gtile.data(), ro);
+        warp_reset(e, pend, tile, WIN ? nullptr : gtile.data(), ro);
         for (int lane = 0; lane < 32; ++lane)
           if (fresh[lane]) { ax[lane] = ro[lane].ax; ay[lane] = ro[lane].ay; dir[lane] = ro[lane].dir; carry[lane] = 0; steps[lane] = 0; flags[lane] &= ~FLAG_PENDING; }
       }
@@ -147,7 +162,9 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
       int fx, fy;
       front_pos(g, ax[lane], ay[lane], dir[lane], fx, fy);
       const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
-      const uint32_t fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
+      uint32_t fc;
+      if (WIN) fc = gb[grid_word(g, env, rw) * 4 + (fx & 3)];
+      else fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
       const StepOut so = transition(action, fc, fx, fy, ax[lane], ay[lane], dir[lane], carry[lane]);
       terminated[lane] = so.terminated;
       if (so.goal) {
@@ -156,11 +173,13 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
       }
       if (so.bad_action) e->err |= 1;
       if (so.newc != fc && active[lane]) {
-        uint8_t *sb = reinterpret_cast<uint8_t *>(gtile.data());
-        uint8_t *gb = reinterpret_cast<uint8_t *>(gsrc);
-        const size_t ro = ((size_t)rw * 32 + lane) * 4 + (fx & 3), co = ((size_t)cw * 32 + lane) * 4 + (fy & 3);
-        sb[ro] = (uint8_t)so.newc; sb[co] = (uint8_t)so.newc;
-        gb[ro] = (uint8_t)so.newc; gb[co] = (uint8_t)so.newc;
+        if (!WIN) {
+          uint8_t *sb = reinterpret_cast<uint8_t *>(gtile.data());
+          sb[((size_t)rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)so.newc;
+          sb[((size_t)cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)so.newc;
+        }
+        gb[grid_word(g, env, rw) * 4 + (fx & 3)] = (uint8_t)so.newc;
+        gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)so.newc;
       }
       truncated[lane] = steps[lane] >= p.max_steps;
       const bool done = (terminated[lane] | truncated[lane]) != 0;
@@ -172,7 +191,7 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
       for (int lane = 0; lane < 32; ++lane) { again[lane] = active[lane] && ((terminated[lane] | truncated[lane]) != 0); if (again[lane]) pend |= 1u << lane; }
       if (pend) {
         ResetOut ro[32];
-        warp_reset(e, pend, tile, gtile.data(), ro);
+        warp_reset(e, pend, tile, WIN ? nullptr : gtile.data(), ro);
         for (int lane = 0; lane < 32; ++lane)
           if (again[lane]) { ax[lane] = ro[lane].ax; ay[lane] = ro[lane].ay; dir[lane] = ro[lane].dir; carry[lane] = 0; steps[lane] = 0; }
       }
@@ -180,7 +199,18 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
     if (obs) {
       for (int lane = 0; lane < 32; ++lane) {
         uint32_t(&S)[OBS_WORDS] = *reinterpret_cast<uint32_t(*)[OBS_WORDS]>(&S_all[lane * OBS_WORDS]);
-        gen_obs_words<VIS, true>(g, gtile.data() + lane, p.cell_lut, p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], S);
+        if (WIN) {  // the lane's 7-line window, copied as the cp.async loop does
+          const int env = tile * TILE + lane;
+          const bool useC = dir[lane] & 1;
+          const int w0 = (useC ? g.offC : 0) + ((useC ? ax[lane] : ay[lane]) - 3 + g.ring) * WIN_LINE_WORDS;
+          uint32_t *win = gtile.data() + lane * (WIN_LANE_BYTES / 4);
+          memcpy(win, p.grid + grid_word(g, env, w0), WIN_BYTES);
+          const AccFlat acc = {win - w0};
+          gen_obs_words<VIS>(g, acc, p.cell_lut, p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], S);
+        } else {
+          const AccTiled acc = {gtile.data() + lane, true};
+          gen_obs_words<VIS>(g, acc, p.cell_lut, p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], S);
+        }
         if (!full && active[lane]) emit_obs_bytes(obs + (size_t)(tile * TILE + lane) * OBS_BYTES, S);
       }
       if (full) {  // the consumed tile buffer becomes the stage
@@ -212,16 +242,17 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
 extern "C" {
 
 void *emu_create(int kind, int W, int H, int max_steps, int see_through, const int32_t *params, int n_params,
-                 int n_envs, int mode) {
+                 int n_envs, int mode, int layout) {
   Emu *e = new Emu();
   Params &p = e->p;
   memset(&p, 0, sizeof(p));
-  p.g = make_geom(W, H);
+  if (layout < 0) layout = make_geom(W, H, LAYOUT_TILED).wpe * 4 > 512 ? LAYOUT_WINDOW : LAYOUT_TILED;  // mg_create rule
+  p.g = make_geom(W, H, layout);
   p.n_envs = n_envs; p.n_tiles = (n_envs + 31) / 32;
   p.max_steps = max_steps; p.see_through = see_through; p.mode = mode; p.kind = kind;
   for (int i = 0; i < 8; ++i) p.kp[i] = (params && i < n_params) ? params[i] : 0;
   const size_t n_pad = (size_t)p.n_tiles * 32;
-  e->grid.assign((size_t)p.n_tiles * p.g.wpe * 32, CODE_WALL4);
+  e->grid.assign((size_t)p.n_tiles * p.g.wpe * 32 + 64, CODE_WALL4);
   e->agent.assign(n_pad, make_uint4(1u | (1u << 8), 0, 0, 0));
   e->rng.resize(n_pad);
   memset(e->rng.data(), 0, n_pad * sizeof(RngRec));
@@ -275,8 +306,7 @@ void emu_full_obs(void *h, uint8_t *out, int with_agent) {  // k_full_obs body
   for (int env = 0; env < p.n_envs; ++env)
     for (int x = 0; x < p.g.W; ++x)
       for (int y = 0; y < p.g.H; ++y) {
-        const uint32_t *col = p.grid + (size_t)(env >> 5) * p.g.wpe * 32 + (env & 31);
-        const uint32_t code = (col[c_word(p.g, x, y) * 32] >> (8 * (y & 3))) & 0xFFu;
+        const uint32_t code = reinterpret_cast<const uint8_t *>(p.grid)[cell_byte_C(p.g, env, x, y)];
         uint32_t t = p.cell_lut[code];
         const uint4 rec = p.agent[env];
         if (with_agent && (int)(rec.x & 0xFF) == x && (int)((rec.x >> 8) & 0xFF) == y) t = T_AGENT | (C_RED << 8) | ((rec.y & 3u) << 16);
@@ -306,9 +336,9 @@ void emu_set_state(void *h, const uint8_t *grid, const int32_t *agent) {  // k_s
         for (int y = 0; y < p.g.H; ++y) {
           const uint8_t *in = grid + (((size_t)env * p.g.W + x) * p.g.H + y) * 3;
           const uint8_t code = (uint8_t)encode_cell(in[0], in[1], in[2]);
-          uint8_t *col = reinterpret_cast<uint8_t *>(p.grid + (size_t)(env >> 5) * p.g.wpe * 32 + (env & 31));
-          col[(size_t)r_word(p.g, x, y) * 128 + (x & 3)] = code;
-          col[(size_t)c_word(p.g, x, y) * 128 + (y & 3)] = code;
+          uint8_t *gbp = reinterpret_cast<uint8_t *>(p.grid);
+          gbp[cell_byte_R(p.g, env, x, y)] = code;
+          gbp[cell_byte_C(p.g, env, x, y)] = code;
         }
     if (agent) {
       const int32_t *a = agent + (size_t)env * 6;

@@ -14,8 +14,8 @@ from emu import EmuVecEnv  # noqa: E402
 from oracle.oracle import ENV_SPECS, OracleVecEnv  # noqa: E402
 
 
-def make_emu(env_id, n, mode):
-    return EmuVecEnv(ENV_SPECS[env_id], n, autoreset=mode)
+def make_emu(env_id, n, mode, layout=-1):
+    return EmuVecEnv(ENV_SPECS[env_id], n, autoreset=mode, layout=layout)
 
 
 @pytest.mark.parametrize("path", golden_files("rollout") + golden_files("rollout_samestep"), ids=os.path.basename)
@@ -35,3 +35,15 @@ def test_emu_lockstep_vs_oracle(env_id, mode, n):
     emu = make_emu(env_id, n, mode)
     orc = OracleVecEnv(env_id, n, autoreset=mode)
     parity.check_lockstep_vs_oracle(emu, orc, 300, seed=4242, check_state_every=100)
+
+
+@pytest.mark.parametrize("layout", [0, 1], ids=["tiled", "window"])
+@pytest.mark.parametrize("path", golden_files("rollout")[:6] + golden_files("inject"), ids=os.path.basename)
+def test_emu_fixture_in_both_layouts(path, layout):
+    """Every grid size through both HBM layouts (mg_create picks one by size; the other must agree)."""
+    g = load_golden(path)
+    mk = lambda env_id, n, mode: make_emu(env_id, n, mode, layout)  # noqa: E731
+    if "rng0" in g:
+        parity.check_rollout_fixture(mk, g)
+    else:
+        parity.check_inject_fixture(mk, g)
