@@ -264,10 +264,12 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     // NEXT_STEP autoreset (gymnasium >= 1.0 SyncVectorEnv): an env that ended last step ignores its action,
     // is reset now, and returns the reset obs with reward 0 / False / False
     bool fresh = false;
+    bool wrote = false;  // this warp wrote grid bytes through the generic proxy during this tile
     if (stepping && p.mode == AUTORESET_NEXT_STEP) {
       fresh = active && (flags & FLAG_PENDING);
       const unsigned pend = __ballot_sync(0xFFFFFFFFu, fresh);
       if (pend) {
+        wrote = true;
         const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
         if (fresh) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; flags &= ~FLAG_PENDING; }
       }
@@ -289,6 +291,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
                                       : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
       if (so.bad_action) atomicOr(p.err, 1);  // ValueError("Unknown action"), minigrid_env.py:584-585
       if (newc != fc && active) {
+        wrote = true;
         if (!WIN) {
           uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
           sb[((size_t)rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)newc;
@@ -306,6 +309,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       const bool again = active && ((terminated | truncated) != 0);
       const unsigned pend = __ballot_sync(0xFFFFFFFFu, again);
       if (pend) {
+        wrote = true;
         const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
         if (again) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; }
       }
@@ -320,11 +324,13 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
         const int w0 = (useC ? g.offC : 0) + ((useC ? ax : ay) - 3 + g.ring) * WIN_LINE_WORDS;
         const uint32_t *src = p.grid + grid_word(g, env, w0);
         uint32_t *win = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(gtile) + lane * WIN_LANE_BYTES);
-        const uint32_t dst = smem_u32(win);
-#pragma unroll
-        for (int j = 0; j < WIN_BYTES / 16; ++j) cp_async16(dst + 16u * j, src + 4 * j);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // generic-proxy writes of this step (autoreset fill, a mutated cell) must be visible to the bulk copy
+        if (__ballot_sync(0xFFFFFFFFu, wrote)) asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(bar0, TILE * WIN_BYTES);
+        tma_load_1d(smem_u32(win), src, WIN_BYTES, bar0);  // one 224-byte bulk copy per lane, one mbarrier per warp
+        mbar_wait(bar0, phase & 1u);
+        phase ^= 1u;
         const AccFlat acc = {win - w0};
         gen_obs_words<VIS>(g, acc, lut, vis_tbl, ax, ay, dir, carry, S);
       } else {
