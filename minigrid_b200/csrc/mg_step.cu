@@ -14,8 +14,8 @@
 //   4. observation in registers (mg_obs.cuh), staged into the consumed tile buffer in output layout, then one
 //      TMA bulk store of the warp's 32 x 147 = 4704 contiguous bytes.
 //   5. coalesced stores of direction / reward / terminated / truncated and the agent record.
-// Large grids (LAYOUT_WINDOW) skip step 1: the transition reads its one front byte straight from HBM and each lane
-// then copies only the 7 lines its view needs (224 B, cp.async) into shared memory.
+// Large grids (LAYOUT_WINDOW) skip step 1: each lane copies only the 7 lines its view needs (224 B, one bulk copy per
+// lane) into shared memory, in flight together with the one front-cell byte the transition reads from HBM.
 #include <cstdio>
 #include <cstdlib>
 
@@ -150,6 +150,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
        uint8_t *__restrict__ trunc_out, int obs_tma_ok) {
   constexpr int NBUF = (MODE == MODE_TILED2) ? 2 : 1;
   constexpr bool WIN = (MODE == MODE_WINDOW);
+  constexpr bool PREF = (MODE != MODE_TILED1);  // agent records / actions / tile index are fetched one tile ahead
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const Geom g = p.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -173,7 +174,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
   const int t_lo = (int)(((long long)p.n_tiles * blockIdx.x) / gridDim.x);
   const int t_hi = (int)(((long long)p.n_tiles * (blockIdx.x + 1)) / gridDim.x);
   if (threadIdx.x == 0) {
-    *s_next = t_lo + NBUF * WARPS;
+    *s_next = t_lo + (PREF ? 2 : 1) * WARPS;
     if (VIS == VIS_TBL) {  // the table is immutable after mg_create: its copy may run ahead of griddepcontrol.wait
       mbar_init(tbl_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,7 +183,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     }
   }
   int tile = t_lo + warp;
-  int next = (NBUF == 2) ? t_lo + WARPS + warp : p.n_tiles;
+  int next = PREF ? t_lo + WARPS + warp : p.n_tiles;
   if (tile >= t_hi) tile = p.n_tiles;
   if (next >= t_hi) next = p.n_tiles;
   if (lane == 0) {
@@ -198,8 +199,8 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
 
   uint4 rec = make_uint4(0, 0, 0, 0);
   int action = A_DONE;
-  if (NBUF == 2 && tile < p.n_tiles) {
-    if (lane == 0) {
+  if (PREF && tile < p.n_tiles) {
+    if (NBUF == 2 && lane == 0) {
       mbar_expect_tx(bar0, tile_bytes);
       tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
     }
@@ -214,13 +215,16 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
   while (tile < p.n_tiles) {
     uint4 rec_n = make_uint4(0, 0, 0, 0);
     int action_n = A_DONE, nn = p.n_tiles;
-    if (NBUF == 2) {
-      if (next < p.n_tiles) {  // prefetch the next tile into the other buffer, and the index of the one after it
+    if (PREF) {
+      if (WIN && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left
+      if (next < p.n_tiles) {  // prefetch the next tile (into the other buffer), and the index of the one after it
         if (lane == 0) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the obs block staged there two tiles ago
-          const uint32_t nb = bar0 + 8u * (uint32_t)(b ^ 1);
-          mbar_expect_tx(nb, tile_bytes);
-          tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
+          if (NBUF == 2) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the obs block staged there two tiles ago
+            const uint32_t nb = bar0 + 8u * (uint32_t)(b ^ 1);
+            mbar_expect_tx(nb, tile_bytes);
+            tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
+          }
           nn = atomicAdd(s_next, 1);  // shared-memory atomic, consumed one tile later
           if (nn >= t_hi) nn = p.n_tiles;
         }
@@ -231,10 +235,8 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     } else {
       if (lane == 0) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left the buffer
-        if (!WIN) {
-          mbar_expect_tx(bar0, tile_bytes);
-          tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
-        }
+        mbar_expect_tx(bar0, tile_bytes);
+        tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
         nn = atomicAdd(s_next, 1);  // consumed at the end of this tile
         if (nn >= t_hi) nn = p.n_tiles;
       }
@@ -274,6 +276,34 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
         if (fresh) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; flags &= ~FLAG_PENDING; }
       }
     }
+    // LAYOUT_WINDOW: the 7 lines of the view are 224 contiguous bytes of array R (facing +-x) or C (+-y), one bulk
+    // copy per lane. Which lines is known before the transition: a turn depends on the action alone and a
+    // forward move never changes the line coordinate of the array it faces along, so the window and the
+    // front-cell byte are requested together (one HBM round trip per tile).
+    uint32_t *win = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(gtile) + lane * WIN_LANE_BYTES);
+    auto load_window = [&](int d, bool wrote_any) {
+      const bool useC = d & 1;
+      const int w0 = (useC ? g.offC : 0) + ((useC ? ax : ay) - 3 + g.ring) * WIN_LINE_WORDS;
+      // generic-proxy writes of this step (autoreset fill, a mutated cell) must be visible to the bulk copy
+      if (__ballot_sync(0xFFFFFFFFu, wrote_any)) asm volatile("fence.proxy.async;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_expect_tx(bar0, TILE * WIN_BYTES);
+      tma_load_1d(smem_u32(win), p.grid + grid_word(g, env, w0), WIN_BYTES, bar0);  // one mbarrier per warp
+    };
+    auto wait_window = [&]() {
+      mbar_wait(bar0, phase & 1u);
+      phase ^= 1u;
+    };
+    uint32_t fc_win = CODE_WALL;
+    if (WIN) {
+      int dirn = dir, fx0, fy0;
+      if (stepping && !fresh) dirn = (dir + (action == A_LEFT ? 3 : 0) + (action == A_RIGHT ? 1 : 0)) & 3;
+      front_pos(g, ax, ay, dir, fx0, fy0);
+      const uint8_t *fcp = gb + grid_word(g, env, r_word(g, fx0, fy0)) * 4 + (fx0 & 3);
+      asm volatile("ld.global.u8 %0, [%1];" : "=r"(fc_win) : "l"(fcp));  // in flight together with the window
+      load_window(dirn, wrote);
+      wait_window();
+    }
     if (stepping && !fresh) {
       // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
       steps += 1;
@@ -281,7 +311,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       front_pos(g, ax, ay, dir, fx, fy);
       const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
       uint32_t fc;
-      if (WIN) fc = gb[grid_word(g, env, rw) * 4 + (fx & 3)];  // one byte straight from HBM / L2
+      if (WIN) fc = fc_win;
       else fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
       const StepOut so = transition(action, fc, fx, fy, ax, ay, dir, carry);
       const uint32_t newc = so.newc;
@@ -296,6 +326,8 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
           uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
           sb[((size_t)rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)newc;
           sb[((size_t)cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)newc;
+        } else {  // pickup / drop / toggle do not turn: the front cell is on the window's centre line
+          reinterpret_cast<uint8_t *>(win)[3 * 32 + ((dir & 1) ? fy : fx)] = (uint8_t)newc;
         }
         gb[grid_word(g, env, rw) * 4 + (fx & 3)] = (uint8_t)newc;
         gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)newc;
@@ -312,6 +344,10 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
         wrote = true;
         const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
         if (again) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; }
+        if (WIN) {  // the regenerated levels invalidate the staged windows
+          load_window(dir, true);
+          wait_window();
+        }
       }
     }
 
@@ -319,18 +355,8 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     if (obs != nullptr) {
       uint32_t S[OBS_WORDS];
       if (WIN) {
-        // the 7 lines of the view (after the transition): 224 contiguous bytes of array R (facing +-x) or C (+-y)
         const bool useC = dir & 1;
         const int w0 = (useC ? g.offC : 0) + ((useC ? ax : ay) - 3 + g.ring) * WIN_LINE_WORDS;
-        const uint32_t *src = p.grid + grid_word(g, env, w0);
-        uint32_t *win = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(gtile) + lane * WIN_LANE_BYTES);
-        // generic-proxy writes of this step (autoreset fill, a mutated cell) must be visible to the bulk copy
-        if (__ballot_sync(0xFFFFFFFFu, wrote)) asm volatile("fence.proxy.async;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_expect_tx(bar0, TILE * WIN_BYTES);
-        tma_load_1d(smem_u32(win), src, WIN_BYTES, bar0);  // one 224-byte bulk copy per lane, one mbarrier per warp
-        mbar_wait(bar0, phase & 1u);
-        phase ^= 1u;
         const AccFlat acc = {win - w0};
         gen_obs_words<VIS>(g, acc, lut, vis_tbl, ax, ay, dir, carry, S);
       } else {
@@ -365,12 +391,12 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       if (trunc_out) trunc_out[env] = (uint8_t)truncated;
     }
     __syncwarp();  // lanes may still be reading this buffer (partial-tile path) before it is refilled
-    if (NBUF == 2) {
+    if (PREF) {
       tile = next;
       next = __shfl_sync(0xFFFFFFFFu, nn, 0);
       rec = rec_n;
       action = action_n;
-      b ^= 1;
+      if (NBUF == 2) b ^= 1;
     } else {
       tile = __shfl_sync(0xFFFFFFFFu, nn, 0);
     }
