@@ -107,22 +107,6 @@ MG_D void process_vis_tbl(const uint16_t *tbl, uint32_t oplo, uint32_t ophi, uin
   }
 }
 
-// (type, colour, state) of the cell code in byte k of `word`. On the device: one byte permute (ALU pipe), one
-// multiply-add for the table address (FMA pipe, which this kernel leaves mostly idle) and the shared load, instead
-// of shift + mask on the busy ALU pipe.
-MG_D uint32_t lut_triple(const uint32_t *lut, uint32_t word, int k) {
-#ifdef __CUDA_ARCH__
-  if (__isShared(lut)) {
-    uint32_t code, addr, v;
-    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(code) : "r"(word), "r"(0x4440u + (uint32_t)k));
-    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(code), "r"(smem_u32(lut)));
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-  }
-#endif
-  return lut[(word >> (8 * k)) & 0xFFu];
-}
-
 // Produces the 147-byte image of one env as 37 little-endian words S (byte 147 is zero).
 //   acc    word accessor (AccTiled / AccFlat), lut: 256-entry decode table (shared or global)
 //   VIS    VIS_NONE: see_through_walls (minigrid_env.py:616-621); VIS_ALU: bit tricks; VIS_TBL: vis_tbl lookups
@@ -193,7 +177,8 @@ MG_D void gen_obs_words(const Geom &g, const Acc &acc, const uint32_t *lut, cons
 #pragma unroll
     for (int vy = 0; vy < VIEW; ++vy) {
       const uint32_t word = (vy < 4) ? clo[vx] : chi[vx];
-      T[vx * VIEW + vy] = lut_triple(lut, word, vy & 3);
+      const uint32_t code = (word >> (8 * (vy & 3))) & 0xFFu;
+      T[vx * VIEW + vy] = lut[code];
     }
   }
   T[VIEW * VIEW] = 0;
