@@ -88,10 +88,6 @@ __device__ __forceinline__ int load_action(const void *actions, int dtype, int e
   return v;
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-
 // MiniGridEnv.reset() for the lanes in `pend`. Phase 1: every pending lane replays the numpy-exact draws of ITS
 // environment (lane per env; only the rejection loops diverge). Phase 2, one environment at a time with the whole
 // warp: the owner's drawn integers are broadcast, lane L copies words L, L+32, ... of the level template into HBM
