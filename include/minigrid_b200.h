@@ -40,6 +40,7 @@ extern "C" {
 #define MG_KIND_FOURROOMS 3
 #define MG_KIND_LAVAGAP 4   /* envs/lavagap.py */
 #define MG_KIND_DISTSHIFT 5 /* envs/distshift.py */
+#define MG_KIND_MULTIROOM 6 /* envs/multiroom.py (up to 6 rooms) */
 
 /* gymnasium.vector.AutoresetMode */
 #define MG_AUTORESET_NEXT_STEP 0
@@ -59,7 +60,8 @@ typedef struct mg_env mg_env;
 /* Replaces: constructing n_envs MiniGridEnv objects (minigrid_env.py:34-117) of one registered id
  * (minigrid/__init__.py). kind/width/height/max_steps/see_through_walls are the constructor arguments;
  * params: EMPTY {random_start, start_x, start_y, start_dir}; CROSSING {num_crossings, obstacle_type
- * (9 lava | 2 wall)}; LAVAGAP {obstacle_type}; DISTSHIFT {strip2_row, start_x, start_y, start_dir}; others none.
+ * (9 lava | 2 wall)}; LAVAGAP {obstacle_type}; DISTSHIFT {strip2_row, start_x, start_y, start_dir};
+ * MULTIROOM {minNumRooms, maxNumRooms, maxRoomSize}; others none.
  * device < 0 selects the current CUDA device. */
 int mg_create(int kind, int width, int height, int max_steps, int see_through_walls,
               const int32_t *params, int n_params, int64_t n_envs, int autoreset_mode, int device,

@@ -98,6 +98,13 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   if (kind == MG_KIND_EMPTY && !p.kp[0] && n_params < 4) { p.kp[1] = 1; p.kp[2] = 1; p.kp[3] = 0; }
   if (kind == MG_KIND_CROSSING && n_params < 2) { p.kp[0] = 1; p.kp[1] = (int)T_LAVA; }
   if (kind == MG_KIND_LAVAGAP && n_params < 1) p.kp[0] = (int)T_LAVA;
+  if (kind == MG_KIND_MULTIROOM) {
+    if (n_params < 3) p.kp[2] = 10;
+    if (p.kp[0] < 1 || p.kp[1] < p.kp[0] || p.kp[1] > 6 || p.kp[2] < 4 || p.kp[2] > 10) {
+      delete h;
+      return fail(MG_ERR_INVALID_ARG, "multiroom: need 1 <= minNumRooms <= maxNumRooms <= 6 and 4 <= maxRoomSize <= 10");
+    }
+  }
   if (kind == MG_KIND_DISTSHIFT && n_params < 4) { if (n_params < 1) p.kp[0] = 2; p.kp[1] = 1; p.kp[2] = 1; p.kp[3] = 0; }
   h->device = device;
 

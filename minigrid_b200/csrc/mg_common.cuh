@@ -59,7 +59,7 @@ constexpr uint32_t CODE_LAVA = T_LAVA | (C_RED << 4);
 constexpr uint32_t FLAG_PENDING = 2u;  // episode ended last step (SyncVectorEnv._autoreset_envs[i], NEXT_STEP)
 
 enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS = 3, KIND_LAVAGAP = 4, KIND_DISTSHIFT = 5,
-             KIND_COUNT = 6 };
+             KIND_MULTIROOM = 6, KIND_COUNT = 7 };
 enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
 
 // (type, colour, state) -> cell code. None/unseen/agent all mean "no object" (WorldObj.decode,

@@ -18,7 +18,31 @@ struct Level {
   // crossing: every river is crossed exactly once (crossing.py:170-188). 5-bit fields, one per river in
   // ascending position order: the open row y of each vertical river / the open column x of each horizontal river.
   unsigned long long ov, oh;
+  // multiroom: up to 6 rooms in creation order, 32 bits each (rooms 0-3 in rm03, 4-5 in rm45):
+  // top_x:5 top_y:5 size_x:4 size_y:4 entry_door_x:5 entry_door_y:5 door_colour:3; (e, f) = goal
+  u128 rm03;
+  unsigned long long rm45;
+  int nrooms;
 };
+
+MG_D uint32_t room_get(const Level &L, int i) {
+  return i < 4 ? (uint32_t)(L.rm03 >> (32 * i)) : (uint32_t)(L.rm45 >> (32 * (i - 4)));
+}
+MG_D void room_set(Level &L, int i, uint32_t v) {
+  if (i < 4) L.rm03 = (L.rm03 & ~((u128)0xFFFFFFFFu << (32 * i))) | ((u128)v << (32 * i));
+  else L.rm45 = (L.rm45 & ~(0xFFFFFFFFull << (32 * (i - 4)))) | ((unsigned long long)v << (32 * (i - 4)));
+}
+struct Room { int tx, ty, sx, sy, dx, dy, col; };
+MG_D Room room_unpack(uint32_t v) {
+  Room r;
+  r.tx = v & 31; r.ty = (v >> 5) & 31; r.sx = (v >> 10) & 15; r.sy = (v >> 14) & 15;
+  r.dx = (v >> 18) & 31; r.dy = (v >> 23) & 31; r.col = (v >> 28) & 7;
+  return r;
+}
+MG_D uint32_t room_pack(int tx, int ty, int sx, int sy, int dx, int dy, int col) {
+  return (uint32_t)tx | ((uint32_t)ty << 5) | ((uint32_t)sx << 10) | ((uint32_t)sy << 14) | ((uint32_t)dx << 18) |
+         ((uint32_t)dy << 23) | ((uint32_t)col << 28);
+}
 
 // ---- cell functions: the finished grid of each generator ----
 MG_D bool on_border(const Geom &g, int x, int y) { return x == 0 || y == 0 || x == g.W - 1 || y == g.H - 1; }
@@ -75,8 +99,26 @@ MG_D uint32_t cell_distshift(const Geom &g, int strip2_row, int x, int y) {
   return CODE_EMPTY;
 }
 
+// envs/multiroom.py:149-193: rooms are drawn in creation order (walls, then the room's entry door), the goal last;
+// everything outside the rooms stays None
+MG_D uint32_t cell_multiroom(const Level &L, int x, int y) {
+  uint32_t code = CODE_EMPTY;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    if (i < L.nrooms) {
+      const Room r = room_unpack(room_get(L, i));
+      const bool inside = x >= r.tx && x < r.tx + r.sx && y >= r.ty && y < r.ty + r.sy;
+      if (inside && (x == r.tx || x == r.tx + r.sx - 1 || y == r.ty || y == r.ty + r.sy - 1)) code = CODE_WALL;
+      if (i > 0 && x == r.dx && y == r.dy) code = T4_DOOR_CLOSED | ((uint32_t)r.col << 4) | OPAQUE_BIT;  // Door(color): closed
+    }
+  }
+  if (x == L.e && y == L.f) code = CODE_GOAL;
+  return code;
+}
+
 template <int KIND>
 MG_D uint32_t cell_of(const Params &p, const Level &L, int x, int y) {
+  if (KIND == KIND_MULTIROOM) return cell_multiroom(L, x, y);
   if (KIND == KIND_LAVAGAP) return cell_lavagap(p.g, L, x, y, (p.kp[0] == (int)T_WALL) ? CODE_WALL : CODE_LAVA);
   if (KIND == KIND_DISTSHIFT) return cell_distshift(p.g, p.kp[0], x, y);
   if (KIND == KIND_EMPTY) return cell_empty(p.g, L, x, y);
@@ -96,7 +138,85 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
   L.a = L.b = L.c = L.d = L.e = L.f = -1;
   L.rv = L.rh = 0;
   L.ov = L.oh = 0;
-  if (KIND == KIND_EMPTY) {
+  L.rm03 = 0; L.rm45 = 0; L.nrooms = 0;
+  if (KIND == KIND_MULTIROOM) {
+    // MultiRoomEnv._gen_grid / _placeRoom (multiroom.py:117-284). _placeRoom returns True as soon as ONE next room
+    // has been placed (or after 8 failed tries), so the recursion is a chain without backtracking: room k+1 is
+    // tried up to 8 times against room k, and the list only grows.
+    const int num_rooms = rng_integers(r, p.kp[0], p.kp[1] + 1);
+    const int max_sz = p.kp[2];
+    while (L.nrooms < num_rooms) {
+      Level cur;
+      cur.rm03 = 0; cur.rm45 = 0; cur.nrooms = 0;
+      int ex = rng_integers(r, 0, W - 2);
+      int ey = rng_integers(r, 0, W - 2);
+      int entry_wall = 2;
+      auto try_place = [&](int wall, int dx, int dy) -> bool {
+        const int sx = rng_integers(r, 4, max_sz + 1), sy = rng_integers(r, 4, max_sz + 1);
+        int tx, ty;
+        if (cur.nrooms == 0) { tx = dx; ty = dy; }
+        else if (wall == 0) { tx = dx - sx + 1; ty = rng_integers(r, dy - sy + 2, dy); }
+        else if (wall == 1) { tx = rng_integers(r, dx - sx + 2, dx); ty = dy - sy + 1; }
+        else if (wall == 2) { tx = dx; ty = rng_integers(r, dy - sy + 2, dy); }
+        else { tx = rng_integers(r, dx - sx + 2, dx); ty = dy; }
+        if (tx < 0 || ty < 0) return false;
+        if (tx + sx > W || ty + sy >= H) return false;
+        for (int k = 0; k < cur.nrooms - 1; ++k) {  // roomList[:-1]
+          const Room o = room_unpack(room_get(cur, k));
+          const bool non_overlap = tx + sx < o.tx || o.tx + o.sx <= tx || ty + sy < o.ty || o.ty + o.sy <= ty;
+          if (!non_overlap) return false;
+        }
+        room_set(cur, cur.nrooms, room_pack(tx, ty, sx, sy, dx, dy, 0));
+        cur.nrooms += 1;
+        return true;
+      };
+      bool placed = try_place(entry_wall, ex, ey);
+      while (placed && cur.nrooms < num_rooms) {
+        placed = false;
+        const Room last = room_unpack(room_get(cur, cur.nrooms - 1));
+        for (int i = 0; i < 8; ++i) {
+          int exit_wall = rng_integers(r, 0, 3);  // _rand_elem(sorted({0,1,2,3} - {entryDoorWall}))
+          if (exit_wall >= entry_wall) exit_wall += 1;
+          const int next_entry = (exit_wall + 2) & 3;
+          int px, py;
+          if (exit_wall == 0) { px = last.tx + last.sx - 1; py = last.ty + rng_integers(r, 1, last.sy - 1); }
+          else if (exit_wall == 1) { px = last.tx + rng_integers(r, 1, last.sx - 1); py = last.ty + last.sy - 1; }
+          else if (exit_wall == 2) { px = last.tx; py = last.ty + rng_integers(r, 1, last.sy - 1); }
+          else { px = last.tx + rng_integers(r, 1, last.sx - 1); py = last.ty; }
+          if (try_place(next_entry, px, py)) { placed = true; entry_wall = next_entry; break; }
+        }
+      }
+      if (cur.nrooms > L.nrooms) { L.rm03 = cur.rm03; L.rm45 = cur.rm45; L.nrooms = cur.nrooms; }
+    }
+    // door colours: _rand_elem(sorted(COLOR_NAMES minus the previous door's colour)); sorted names are
+    // blue green grey purple red yellow
+    int prev = -1;
+    for (int idx = 1; idx < L.nrooms; ++idx) {
+      int pick = rng_integers(r, 0, prev < 0 ? 6 : 5), col = 0;
+      for (int c = 0; c < 6; ++c) {
+        const int cidx = (int)((0x403512u >> (4 * c)) & 15u);  // C_BLUE, C_GREEN, C_GREY, C_PURPLE, C_RED, C_YELLOW
+        if (cidx == prev) continue;
+        if (pick-- == 0) { col = cidx; break; }
+      }
+      room_set(L, idx, (room_get(L, idx) & 0x0FFFFFFFu) | ((uint32_t)col << 28));
+      prev = col;
+    }
+    const Room first = room_unpack(room_get(L, 0)), lastr = room_unpack(room_get(L, L.nrooms - 1));
+    for (;;) {  // place_agent(roomList[0].top, roomList[0].size)
+      const int x = rng_integers(r, first.tx, min(first.tx + first.sx, W)), y = rng_integers(r, first.ty, min(first.ty + first.sy, H));
+      if (cell_multiroom(L, x, y) != CODE_EMPTY) continue;
+      L.ax = x; L.ay = y;
+      break;
+    }
+    L.adir = rng_integers(r, 0, 4);
+    for (;;) {  // place_obj(Goal(), roomList[-1].top, roomList[-1].size)
+      const int x = rng_integers(r, lastr.tx, min(lastr.tx + lastr.sx, W)), y = rng_integers(r, lastr.ty, min(lastr.ty + lastr.sy, H));
+      if (cell_multiroom(L, x, y) != CODE_EMPTY) continue;
+      if (x == L.ax && y == L.ay) continue;
+      L.e = x; L.f = y;
+      break;
+    }
+  } else if (KIND == KIND_EMPTY) {
     if (!p.kp[0]) { L.ax = p.kp[1]; L.ay = p.kp[2]; L.adir = p.kp[3]; }
     else {  // place_agent(): minigrid_env.py:383-397 over the whole grid
       for (;;) {
@@ -241,13 +361,25 @@ MG_D Level blank_level() {
   L.a = L.b = L.c = L.d = L.e = L.f = -1;
   L.rv = L.rh = 0;
   L.ov = L.oh = 0;
+  L.rm03 = 0; L.rm45 = 0; L.nrooms = 0;
   return L;
 }
 // calls put(x, y) for this lane's share of the cells that may differ from the template
 template <int KIND, class Put>
 MG_D void patch_level(const Params &p, const Level &L, int lane, Put &&put) {
   const Geom &g = p.g;
-  if (KIND == KIND_LAVAGAP) {
+  if (KIND == KIND_MULTIROOM) {
+    for (int i = 0; i < L.nrooms; ++i) {  // every room's perimeter (doors are on perimeters), then the goal
+      const Room r = room_unpack(room_get(L, i));
+      for (int k = lane; k < 2 * (r.sx + r.sy); k += 32) {
+        if (k < r.sx) put(r.tx + k, r.ty);
+        else if (k < 2 * r.sx) put(r.tx + k - r.sx, r.ty + r.sy - 1);
+        else if (k < 2 * r.sx + r.sy) put(r.tx, r.ty + k - 2 * r.sx);
+        else put(r.tx + r.sx - 1, r.ty + k - 2 * r.sx - r.sy);
+      }
+    }
+    if (lane == 0) put(L.e, L.f);
+  } else if (KIND == KIND_LAVAGAP) {
     if (lane >= 1 && lane <= g.H - 2) put(L.a, lane);  // the obstacle column (gap included)
   } else if (KIND == KIND_DOORKEY) {
     if (lane >= 1 && lane <= g.H - 2) put(L.a, lane);  // the split column (door included)

@@ -56,6 +56,7 @@ cudaError_t launch_reset(const Params &p, uint8_t *obs, int32_t *dir, cudaStream
     case KIND_CROSSING: k_reset<KIND_CROSSING><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
     case KIND_LAVAGAP: k_reset<KIND_LAVAGAP><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
     case KIND_DISTSHIFT: k_reset<KIND_DISTSHIFT><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_MULTIROOM: k_reset<KIND_MULTIROOM><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
     default: k_reset<KIND_FOURROOMS><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
   }
   return cudaGetLastError();
@@ -77,6 +78,7 @@ cudaError_t launch_template(const Params &p, uint32_t *tmpl, cudaStream_t stream
     case KIND_CROSSING: k_template<KIND_CROSSING><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     case KIND_LAVAGAP: k_template<KIND_LAVAGAP><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     case KIND_DISTSHIFT: k_template<KIND_DISTSHIFT><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_MULTIROOM: k_template<KIND_MULTIROOM><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     default: k_template<KIND_FOURROOMS><<<blocks, 64, 0, stream>>>(p, tmpl); break;
   }
   return cudaGetLastError();

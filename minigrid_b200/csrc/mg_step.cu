@@ -119,6 +119,13 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
     B.e = __shfl_sync(0xFFFFFFFFu, L.e, src); B.f = __shfl_sync(0xFFFFFFFFu, L.f, src);
     B.rv = __shfl_sync(0xFFFFFFFFu, L.rv, src); B.rh = __shfl_sync(0xFFFFFFFFu, L.rh, src);
     B.ov = __shfl_sync(0xFFFFFFFFu, L.ov, src); B.oh = __shfl_sync(0xFFFFFFFFu, L.oh, src);
+    if (KIND == KIND_MULTIROOM) {
+      const unsigned long long lo = __shfl_sync(0xFFFFFFFFu, (unsigned long long)L.rm03, src);
+      const unsigned long long hi = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(L.rm03 >> 64), src);
+      B.rm03 = ((u128)hi << 64) | lo;
+      B.rm45 = __shfl_sync(0xFFFFFFFFu, L.rm45, src);
+      B.nrooms = __shfl_sync(0xFFFFFFFFu, L.nrooms, src);
+    } else { B.rm03 = 0; B.rm45 = 0; B.nrooms = 0; }
     for (int w = lane; w < g.wpe; w += 32) {
       const uint32_t word = __ldg(p.tmpl + w);
       if (gtile) gtile[w * 32 + src] = word;
@@ -410,6 +417,7 @@ static StepKernel pick_kind(int kind) {
     case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS, MODE>;
     case KIND_LAVAGAP: return (StepKernel)k_step<KIND_LAVAGAP, VIS, MODE>;
     case KIND_DISTSHIFT: return (StepKernel)k_step<KIND_DISTSHIFT, VIS, MODE>;
+    case KIND_MULTIROOM: return (StepKernel)k_step<KIND_MULTIROOM, VIS, MODE>;
     default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, MODE>;
   }
 }

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
-KIND_EMPTY, KIND_DOORKEY, KIND_CROSSING, KIND_FOURROOMS, KIND_LAVAGAP, KIND_DISTSHIFT = 0, 1, 2, 3, 4, 5
+KIND_EMPTY, KIND_DOORKEY, KIND_CROSSING, KIND_FOURROOMS, KIND_LAVAGAP, KIND_DISTSHIFT, KIND_MULTIROOM = 0, 1, 2, 3, 4, 5, 6
 T_WALL, T_LAVA = 2, 9
 
 
@@ -63,6 +63,12 @@ def distshift(width=9, height=7, strip2_row=2, agent_start_pos=(1, 1), agent_sta
                    (strip2_row, agent_start_pos[0], agent_start_pos[1], agent_start_dir), "get to the green goal square")
 
 
+def multiroom(minNumRooms, maxNumRooms, maxRoomSize=10, max_steps=None):
+    """envs/multiroom.py:77-115 (25 x 25, max_steps = maxNumRooms * 20)."""
+    return EnvSpec(KIND_MULTIROOM, 25, 25, max_steps or maxNumRooms * 20, False, (minNumRooms, maxNumRooms, maxRoomSize),
+                   "traverse the rooms to get to the goal")
+
+
 REGISTRY = {
     # BASELINE.json configs
     "MiniGrid-Empty-5x5-v0": empty(size=5),
@@ -91,6 +97,11 @@ REGISTRY = {
     "MiniGrid-LavaGapS7-v0": lavagap(7),
     "MiniGrid-DistShift1-v0": distshift(strip2_row=2),
     "MiniGrid-DistShift2-v0": distshift(strip2_row=5),
+    # __init__.py:363-385 (N4-S5-v0 is registered with 6 rooms: "legacy, misconfigured")
+    "MiniGrid-MultiRoom-N2-S4-v0": multiroom(2, 2, 4),
+    "MiniGrid-MultiRoom-N4-S5-v0": multiroom(6, 6, 5),
+    "MiniGrid-MultiRoom-N4-S5-v1": multiroom(4, 4, 5),
+    "MiniGrid-MultiRoom-N6-v0": multiroom(6, 6),
 }
 
 

@@ -38,6 +38,8 @@ ROLLOUTS = {  # id -> (N, T, seed)
     "MiniGrid-LavaGapS7-v0": (4, 300, 17),
     "MiniGrid-DistShift1-v0": (4, 300, 19),
     "MiniGrid-DistShift2-v0": (4, 300, 23),
+    "MiniGrid-MultiRoom-N2-S4-v0": (6, 130, 29),
+    "MiniGrid-MultiRoom-N6-v0": (4, 260, 37),
 }
 INJECTS = {  # id (host env whose size/see_through/max_steps are used) -> (N, T)
     "MiniGrid-DoorKey-8x8-v0": (16, 120),

@@ -410,6 +410,82 @@ static void gen_distshift(const mgo_vec *v, env_t *e) {
   e->agent_x = v->params[1]; e->agent_y = v->params[2]; e->agent_dir = v->params[3];
 }
 
+/* envs/multiroom.py:117-284 */
+typedef struct { int top_x, top_y, size_x, size_y, door_x, door_y; } mroom_t;
+typedef struct { mroom_t r[16]; int n; } mroom_list_t;
+
+/* MultiRoomEnv._placeRoom (multiroom.py:196-284), recursion kept as in the reference */
+static int mr_place_room(const mgo_vec *v, env_t *e, int num_left, mroom_list_t *list, int min_sz, int max_sz,
+                         int entry_wall, int ex, int ey) {
+  int size_x = (int)rand_int(e, min_sz, max_sz + 1);
+  int size_y = (int)rand_int(e, min_sz, max_sz + 1);
+  int top_x, top_y;
+  if (list->n == 0) { top_x = ex; top_y = ey; }
+  else if (entry_wall == 0) { top_x = ex - size_x + 1; top_y = (int)rand_int(e, ey - size_y + 2, ey); }
+  else if (entry_wall == 1) { top_x = (int)rand_int(e, ex - size_x + 2, ex); top_y = ey - size_y + 1; }
+  else if (entry_wall == 2) { top_x = ex; top_y = (int)rand_int(e, ey - size_y + 2, ey); }
+  else { top_x = (int)rand_int(e, ex - size_x + 2, ex); top_y = ey; }
+  if (top_x < 0 || top_y < 0) return 0;
+  if (top_x + size_x > v->width || top_y + size_y >= v->height) return 0;
+  for (int k = 0; k < list->n - 1; k++) { /* roomList[:-1] */
+    const mroom_t *r = &list->r[k];
+    int non_overlap = top_x + size_x < r->top_x || r->top_x + r->size_x <= top_x || top_y + size_y < r->top_y ||
+                      r->top_y + r->size_y <= top_y;
+    if (!non_overlap) return 0;
+  }
+  mroom_t *nr = &list->r[list->n++];
+  nr->top_x = top_x; nr->top_y = top_y; nr->size_x = size_x; nr->size_y = size_y; nr->door_x = ex; nr->door_y = ey;
+  if (num_left == 1) return 1;
+  for (int i = 0; i < 8; i++) {
+    /* wallSet = {0,1,2,3} - {entryDoorWall}; exitDoorWall = _rand_elem(sorted(wallSet)) */
+    int walls[3], nw = 0;
+    for (int w = 0; w < 4; w++) if (w != entry_wall) walls[nw++] = w;
+    int exit_wall = walls[rand_int(e, 0, 3)];
+    int next_entry = (exit_wall + 2) % 4;
+    int px, py;
+    if (exit_wall == 0) { px = top_x + size_x - 1; py = top_y + (int)rand_int(e, 1, size_y - 1); }
+    else if (exit_wall == 1) { px = top_x + (int)rand_int(e, 1, size_x - 1); py = top_y + size_y - 1; }
+    else if (exit_wall == 2) { px = top_x; py = top_y + (int)rand_int(e, 1, size_y - 1); }
+    else { px = top_x + (int)rand_int(e, 1, size_x - 1); py = top_y; }
+    if (mr_place_room(v, e, num_left - 1, list, min_sz, max_sz, next_entry, px, py)) break;
+  }
+  return 1;
+}
+static void gen_multiroom(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  int min_rooms = v->params[0], max_rooms = v->params[1], max_size = v->params[2];
+  mroom_list_t best; best.n = 0;
+  int num_rooms = (int)rand_int(e, min_rooms, max_rooms + 1);
+  while (best.n < num_rooms) {
+    mroom_list_t cur; cur.n = 0;
+    int ex = (int)rand_int(e, 0, W - 2), ey = (int)rand_int(e, 0, W - 2);
+    mr_place_room(v, e, num_rooms, &cur, 4, max_size, 2, ex, ey);
+    if (cur.n > best.n) best = cur;
+  }
+  grid_clear(&e->grid);
+  /* COLOR_NAMES sorted: blue green grey purple red yellow -> COLOR_TO_IDX */
+  static const int SORTED_COLORS[6] = {C_BLUE, C_GREEN, C_GREY, C_PURPLE, C_RED, C_YELLOW};
+  int prev_color = -1;
+  for (int idx = 0; idx < best.n; idx++) {
+    const mroom_t *r = &best.r[idx];
+    for (int i = 0; i < r->size_x; i++) { grid_set(&e->grid, r->top_x + i, r->top_y, WALL_GREY); grid_set(&e->grid, r->top_x + i, r->top_y + r->size_y - 1, WALL_GREY); }
+    for (int j = 0; j < r->size_y; j++) { grid_set(&e->grid, r->top_x, r->top_y + j, WALL_GREY); grid_set(&e->grid, r->top_x + r->size_x - 1, r->top_y + j, WALL_GREY); }
+    if (idx > 0) {
+      int colors[6], nc = 0;
+      for (int c = 0; c < 6; c++) if (SORTED_COLORS[c] != prev_color) colors[nc++] = SORTED_COLORS[c];
+      int color = colors[rand_int(e, 0, nc)];
+      cell_t door = {T_DOOR, (uint8_t)color, S_CLOSED};
+      grid_set(&e->grid, r->door_x, r->door_y, door);
+      prev_color = color;
+    }
+  }
+  place_agent(e, best.r[0].top_x, best.r[0].top_y, best.r[0].size_x, best.r[0].size_y);
+  cell_t goal = {T_GOAL, C_GREEN, 0};
+  int gx, gy;
+  const mroom_t *last = &best.r[best.n - 1];
+  place_obj(e, &goal, last->top_x, last->top_y, last->size_x, last->size_y, &gx, &gy);
+}
+
 /* minigrid_env.py:119-157 (without the gen_obs at the end) */
 static void env_reset(const mgo_vec *v, env_t *e) {
   e->agent_x = -1; e->agent_y = -1; e->agent_dir = -1;
@@ -419,6 +495,7 @@ static void env_reset(const mgo_vec *v, env_t *e) {
     case MGO_CROSSING: gen_crossing(v, e); break;
     case MGO_LAVAGAP: gen_lavagap(v, e); break;
     case MGO_DISTSHIFT: gen_distshift(v, e); break;
+    case MGO_MULTIROOM: gen_multiroom(v, e); break;
     default: gen_fourrooms(v, e); break;
   }
   e->carrying = 0;

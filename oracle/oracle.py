@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmg_oracle.so")
 
-KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5}
+KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 
 # id -> (kind, width, height, max_steps, see_through_walls, params); restated from
@@ -39,6 +39,10 @@ ENV_SPECS = {
     "MiniGrid-LavaGapS7-v0": ("lavagap", 7, 7, 196, False, [9]),
     "MiniGrid-DistShift1-v0": ("distshift", 9, 7, 252, True, [2, 1, 1, 0]),
     "MiniGrid-DistShift2-v0": ("distshift", 9, 7, 252, True, [5, 1, 1, 0]),
+    # multiroom.py:77-115 (25x25, max_steps = maxNumRooms * 20), __init__.py:363-385
+    "MiniGrid-MultiRoom-N2-S4-v0": ("multiroom", 25, 25, 40, False, [2, 2, 4]),
+    "MiniGrid-MultiRoom-N4-S5-v0": ("multiroom", 25, 25, 120, False, [6, 6, 5]),
+    "MiniGrid-MultiRoom-N6-v0": ("multiroom", 25, 25, 120, False, [6, 6, 10]),
 }
 
 

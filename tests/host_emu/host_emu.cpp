@@ -70,6 +70,7 @@ static void reset_one(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {
     case KIND_CROSSING: reset_env<KIND_CROSSING>(e, env, obs, dir_out); break;
     case KIND_LAVAGAP: reset_env<KIND_LAVAGAP>(e, env, obs, dir_out); break;
     case KIND_DISTSHIFT: reset_env<KIND_DISTSHIFT>(e, env, obs, dir_out); break;
+    case KIND_MULTIROOM: reset_env<KIND_MULTIROOM>(e, env, obs, dir_out); break;
     default: reset_env<KIND_FOURROOMS>(e, env, obs, dir_out); break;
   }
 }
@@ -115,6 +116,7 @@ static void warp_reset(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOu
     case KIND_CROSSING: warp_reset_k<KIND_CROSSING>(e, pend, tile, gtile, out); break;
     case KIND_LAVAGAP: warp_reset_k<KIND_LAVAGAP>(e, pend, tile, gtile, out); break;
     case KIND_DISTSHIFT: warp_reset_k<KIND_DISTSHIFT>(e, pend, tile, gtile, out); break;
+    case KIND_MULTIROOM: warp_reset_k<KIND_MULTIROOM>(e, pend, tile, gtile, out); break;
     default: warp_reset_k<KIND_FOURROOMS>(e, pend, tile, gtile, out); break;
   }
 }
@@ -274,6 +276,7 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
         case KIND_CROSSING: e->tmpl[w] = level_word<KIND_CROSSING>(p, L, w); break;
         case KIND_LAVAGAP: e->tmpl[w] = level_word<KIND_LAVAGAP>(p, L, w); break;
         case KIND_DISTSHIFT: e->tmpl[w] = level_word<KIND_DISTSHIFT>(p, L, w); break;
+        case KIND_MULTIROOM: e->tmpl[w] = level_word<KIND_MULTIROOM>(p, L, w); break;
         default: e->tmpl[w] = level_word<KIND_FOURROOMS>(p, L, w); break;
       }
     p.tmpl = e->tmpl.data();
