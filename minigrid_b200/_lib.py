@@ -27,7 +27,7 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("MINIGRID_B200_LIB") or _build.LIB_PATH  # override: A/B runs of two builds on one box
     if not os.path.exists(path):
         if not build_if_missing:
             raise MinigridB200Error(f"{path} is missing: run `python -m minigrid_b200._build` (needs nvcc)")
