@@ -155,7 +155,9 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
   constexpr bool WIN = (MODE == MODE_WINDOW);
   constexpr bool PREF = (MODE != MODE_TILED1);  // agent records / actions / tile index are fetched one tile ahead
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const Geom g = p.g;
+  Geom g = p.g;
+  g.layout = WIN ? LAYOUT_WINDOW : LAYOUT_TILED;  // both are implied by MODE: let the compiler fold them
+  g.ring = WIN ? 3 : 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int WARPS = blockDim.x >> 5;
   const uint32_t tile_bytes = (uint32_t)g.wpe * 128u;
