@@ -368,18 +368,24 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
         const AccTiled acc = {base, true};
         gen_obs_words<VIS>(g, acc, lut, vis_tbl, ax, ay, dir, carry, S);
       }
-      const bool full = (tile + 1) * TILE <= p.n_envs;
-      if (full && obs_tma_ok) {
-        const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);  // also: every lane is past its tile / window reads
-        emit_obs_staged(gtile, lane, S, n0);                         // the consumed buffer becomes the stage
+      // stage the 32 images in output layout in the consumed buffer, then ONE bulk store of the 4704-byte block.
+      // (The ragged last tile / an unaligned obs pointer copy the valid bytes out of the stage instead: keeping the
+      // stream words out of any byte-store path stops the compiler from spilling S to local memory on every tile.)
+      const int nvalid = min(TILE, p.n_envs - tile * TILE);
+      const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);  // also: every lane is past its tile / window reads
+      emit_obs_staged(gtile, lane, S, n0);
+      if (nvalid == TILE && obs_tma_ok) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
           tma_store_1d(obs + (size_t)tile * OBS_TILE_BYTES, smem_u32(gtile), OBS_TILE_BYTES);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-      } else if (active) {
-        emit_obs_bytes(obs + (size_t)env * OBS_BYTES, S);
+      } else {
+        __syncwarp();
+        const uint8_t *sbytes = reinterpret_cast<const uint8_t *>(gtile);
+        uint8_t *dst = obs + (size_t)tile * OBS_TILE_BYTES;
+        for (int i = lane; i < nvalid * OBS_BYTES; i += 32) dst[i] = sbytes[i];
       }
     }
     if (active) {

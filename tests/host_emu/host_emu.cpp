@@ -213,14 +213,15 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
           const AccTiled acc = {gtile.data() + lane, true};
           gen_obs_words<VIS>(g, acc, p.cell_lut, p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], S);
         }
-        if (!full && active[lane]) emit_obs_bytes(obs + (size_t)(tile * TILE + lane) * OBS_BYTES, S);
       }
-      if (full) {  // the consumed tile buffer becomes the stage
+      const int nvalid = p.n_envs - tile * TILE < TILE ? p.n_envs - tile * TILE : TILE;
+      (void)full;
+      {  // the consumed tile buffer becomes the stage; full tiles leave by bulk store, the ragged tail byte by byte
         for (int lane = 0; lane < 32; ++lane) {
           uint32_t(&S)[OBS_WORDS] = *reinterpret_cast<uint32_t(*)[OBS_WORDS]>(&S_all[lane * OBS_WORDS]);
           emit_obs_staged(gtile.data(), lane, S, S_all[(lane < 31 ? lane + 1 : lane) * OBS_WORDS]);
         }
-        memcpy(obs + (size_t)tile * OBS_TILE_BYTES, gtile.data(), OBS_TILE_BYTES);  // the TMA bulk store
+        memcpy(obs + (size_t)tile * OBS_TILE_BYTES, gtile.data(), (size_t)nvalid * OBS_BYTES);
       }
     }
     for (int lane = 0; lane < 32; ++lane) {
