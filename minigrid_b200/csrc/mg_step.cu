@@ -329,13 +329,19 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
         wrote = true;
         if (!WIN) {
           uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
-          sb[((size_t)rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)newc;
-          sb[((size_t)cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)newc;
+          sb[(rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)newc;
+          sb[(cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)newc;
         } else {  // pickup / drop / toggle do not turn: the front cell is on the window's centre line
           reinterpret_cast<uint8_t *>(win)[3 * 32 + ((dir & 1) ? fy : fx)] = (uint8_t)newc;
         }
-        gb[grid_word(g, env, rw) * 4 + (fx & 3)] = (uint8_t)newc;
-        gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)newc;
+        if (!WIN) {  // tile-relative addressing: 32-bit index math on the common path
+          uint8_t *tb = reinterpret_cast<uint8_t *>(p.grid + (size_t)tile * g.wpe * 32);
+          tb[(rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)newc;
+          tb[(cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)newc;
+        } else {
+          gb[grid_word(g, env, rw) * 4 + (fx & 3)] = (uint8_t)newc;
+          gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)newc;
+        }
       }
       truncated = steps >= p.max_steps;
       const bool done = (terminated | truncated) != 0;
