@@ -1,0 +1,478 @@
+// mg_step_kernel.cuh — K1, the step kernel template (see mg_step.cu for the overview). It is instantiated in three
+// translation units, mg_step.cu (tiled layout, two buffers per warp), mg_step_tiled1.cu (one buffer) and
+// mg_step_window.cu (window layout): ptxas's code for the tiled
+// kernels measurably depends on what else it compiles alongside them (profiles/README.md, r01 A/B runs).
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+
+#include "mg_common.cuh"
+#include "mg_levels.cuh"
+#include "mg_obs.cuh"
+#include "mg_pcg64.cuh"
+#include "mg_transition.cuh"
+
+namespace mg {
+
+enum : int { MODE_TILED1 = 0, MODE_TILED2 = 1, MODE_WINDOW = 2 };  // buffers per warp / layout of K1
+
+#ifdef MG_TIMELINE  // debug build only (scripts/timeline.py): per-CTA %globaltimer stamps of the last two launches
+static __device__ unsigned long long g_tl[2][160][8];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define MG_TL(slot) do { if (threadIdx.x == 0) g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][slot] = gtime(); } while (0)
+#define MG_TL_EXIT() do { if ((threadIdx.x & 31) == 0) { const unsigned long long t_ = gtime(); \
+    atomicMax(&g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][6], t_); atomicMin(&g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][7], t_); } } while (0)
+#else
+#define MG_TL(slot) do { } while (0)
+#define MG_TL_EXIT() do { } while (0)
+#endif
+
+// per-warp buffer: holds the staged tile (or the 32 lanes' view windows), then, once the gather has consumed it,
+// the warp's 4704-byte observation block in output layout.
+__host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
+  uint32_t b = g.layout == LAYOUT_TILED ? (uint32_t)g.wpe * 128u : (uint32_t)(TILE * WIN_LANE_BYTES);
+  if (b < (uint32_t)OBS_TILE_BYTES) b = OBS_TILE_BYTES;
+  return (b + 127u) & ~127u;
+}
+// [cell table 1 KB][visibility table 32 KB, VIS_TBL only][warps x nbuf x buffer][mbarriers][tile counter]
+__host__ __device__ inline size_t step_smem_bytes(const Geom &g, int vis, int warps, int nbuf) {
+  return 1024 + (vis == VIS_TBL ? VIS_TBL_BYTES : 0) + (size_t)warps * nbuf * step_buf_bytes(g) + 16 * (size_t)warps + 16;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// volatile asm loads: they stay where they are written (ahead of the mbarrier wait), so a prefetch really is one
+__device__ __forceinline__ uint4 ldg_rec(const uint4 *ptr) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ int load_action(const void *actions, int dtype, int env) {
+  int v;
+  if (dtype == 1) {
+    long long w;
+    asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(w) : "l"(reinterpret_cast<const long long *>(actions) + env));
+    return (int)w;
+  }
+  if (dtype == 2) {
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const uint8_t *>(actions) + env));
+    return v;
+  }
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const int *>(actions) + env));
+  return v;
+}
+
+// MiniGridEnv.reset() for the lanes in `pend`. Phase 1: every pending lane replays the numpy-exact draws of ITS
+// environment (lane per env; only the rejection loops diverge). Phase 2, one environment at a time with the whole
+// warp: the owner's drawn integers are broadcast, lane L copies words L, L+32, ... of the level template into HBM
+// (and into the staged tile when there is one), then the few cells that depend on the draw are re-evaluated and
+// written as bytes. Out of line: it is the rare path and must not cost the hot loop registers.
+struct ResetOut { int ax, ay, dir; };
+
+template <int KIND>
+__device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int tile, uint32_t *gtile, int lane) {
+  const Geom &g = p.g;
+  Level L = blank_level();
+  if ((pend >> lane) & 1u) {
+    RngRec *rr = p.rng + (size_t)tile * TILE + lane;
+    Pcg r = load_rng(rr);
+    draw_level<KIND>(p, r, L);
+    store_rng(rr, r);
+  }
+  const ResetOut out = {L.ax, L.ay, L.adir};
+  __syncwarp();
+  uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(p.grid);
+  while (pend) {
+    const int src = __ffs(pend) - 1;
+    pend &= pend - 1;
+    const int env = tile * TILE + src;
+    Level B;  // the owner's draw, broadcast
+    B.ax = B.ay = B.adir = 0;
+    B.a = __shfl_sync(0xFFFFFFFFu, L.a, src); B.b = __shfl_sync(0xFFFFFFFFu, L.b, src);
+    B.c = __shfl_sync(0xFFFFFFFFu, L.c, src); B.d = __shfl_sync(0xFFFFFFFFu, L.d, src);
+    B.e = __shfl_sync(0xFFFFFFFFu, L.e, src); B.f = __shfl_sync(0xFFFFFFFFu, L.f, src);
+    B.rv = __shfl_sync(0xFFFFFFFFu, L.rv, src); B.rh = __shfl_sync(0xFFFFFFFFu, L.rh, src);
+    B.ov = __shfl_sync(0xFFFFFFFFu, L.ov, src); B.oh = __shfl_sync(0xFFFFFFFFu, L.oh, src);
+    if (KIND == KIND_MULTIROOM) {
+      const unsigned long long lo = __shfl_sync(0xFFFFFFFFu, (unsigned long long)L.rm03, src);
+      const unsigned long long hi = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(L.rm03 >> 64), src);
+      B.rm03 = ((u128)hi << 64) | lo;
+      B.rm45 = __shfl_sync(0xFFFFFFFFu, L.rm45, src);
+      B.nrooms = __shfl_sync(0xFFFFFFFFu, L.nrooms, src);
+    } else { B.rm03 = 0; B.rm45 = 0; B.nrooms = 0; }
+    for (int w = lane; w < g.wpe; w += 32) {
+      const uint32_t word = __ldg(p.tmpl + w);
+      if (gtile) gtile[w * 32 + src] = word;
+      p.grid[grid_word(g, env, w)] = word;
+    }
+    __syncwarp();  // template words land before the byte patches other lanes write into them
+    patch_level<KIND>(p, B, lane, [&](int x, int y) {
+      const uint8_t code = (uint8_t)cell_of<KIND>(p, B, x, y);
+      const int rw = r_word(g, x, y), cw = c_word(g, x, y);
+      if (gtile) { sb[((size_t)rw * 32 + src) * 4 + (x & 3)] = code; sb[((size_t)cw * 32 + src) * 4 + (y & 3)] = code; }
+      gb[grid_word(g, env, rw) * 4 + (x & 3)] = code;
+      gb[grid_word(g, env, cw) * 4 + (y & 3)] = code;
+    });
+  }
+  __syncwarp();
+  return out;
+}
+
+// MODE_TILED2: each warp owns two buffers and prefetches its next tile (TMA + agent records + actions) before it
+// processes the current one, so HBM transfers overlap compute instead of alternating with it in GPU-wide bursts.
+template <int KIND, int VIS, int MODE>
+__global__ void __launch_bounds__(MODE == MODE_TILED2 ? 640 : 1024, 1)  // one CTA per SM: <= 20 warps (96 regs) or <= 32 (64 regs)
+k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
+       int32_t *__restrict__ dir_out, double *__restrict__ reward_out, uint8_t *__restrict__ term_out,
+       uint8_t *__restrict__ trunc_out, int obs_tma_ok) {
+  constexpr int NBUF = (MODE == MODE_TILED2) ? 2 : 1;
+  constexpr bool WIN = (MODE == MODE_WINDOW);
+  constexpr bool PREF = (MODE != MODE_TILED1);  // agent records / actions / tile index are fetched one tile ahead
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  Geom g = p.g;
+  g.layout = WIN ? LAYOUT_WINDOW : LAYOUT_TILED;  // both are implied by MODE: let the compiler fold them
+  g.ring = WIN ? 3 : 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int WARPS = blockDim.x >> 5;
+  const uint32_t tile_bytes = (uint32_t)g.wpe * 128u;
+  const uint32_t buf_bytes = step_buf_bytes(g);
+  constexpr uint32_t TBL = (VIS == VIS_TBL) ? (uint32_t)VIS_TBL_BYTES : 0u;
+
+  uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);
+  const uint16_t *vis_tbl = reinterpret_cast<const uint16_t *>(smem_raw + 1024);
+  uint8_t *bufs = smem_raw + 1024 + TBL + (size_t)warp * NBUF * buf_bytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + TBL + (size_t)WARPS * NBUF * buf_bytes);
+  const uint32_t bar0 = smem_u32(bars + 2 * warp), tbl_bar = smem_u32(bars + 2 * WARPS);
+  int *s_next = reinterpret_cast<int *>(bars + 2 * WARPS + 1);
+
+  // Programmatic dependent launch: let the next kernel in the stream start its prologue while this grid drains,
+  // and do our own prologue (nothing the previous step wrote is touched) before waiting for it to complete.
+  asm volatile("griddepcontrol.launch_dependents;");
+#ifdef MG_TIMELINE
+  if (threadIdx.x == 0) { g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][6] = 0ull; g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][7] = ~0ull; }
+#endif
+  MG_TL(0);
+  const bool stepping = actions != nullptr;  // nullptr: observation-only pass (MiniGridEnv.gen_obs), state untouched
+  // one wave of persistent CTAs; CTA c owns tiles [c T/G, (c+1) T/G), its warps pull from a shared counter
+  // (the first n_tiles % gridDim CTAs own one tile more; 32-bit arithmetic: no division subroutine in the prologue)
+  const unsigned tq = (unsigned)p.n_tiles / gridDim.x, tr = (unsigned)p.n_tiles % gridDim.x;
+  const int t_lo = (int)(blockIdx.x * tq + min(blockIdx.x, tr));
+  const int t_hi = t_lo + (int)tq + (blockIdx.x < tr ? 1 : 0);
+  if (threadIdx.x == 0) {
+    *s_next = t_lo + (PREF ? 2 : 1) * WARPS;
+    if (VIS == VIS_TBL) {  // the table is immutable after mg_create: its copy may run ahead of griddepcontrol.wait
+      mbar_init(tbl_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(tbl_bar, TBL);
+      tma_load_1d(smem_u32(vis_tbl), p.vis_tbl, TBL, tbl_bar);
+    }
+  }
+  int tile = t_lo + warp;
+  int next = PREF ? t_lo + WARPS + warp : p.n_tiles;
+  if (tile >= t_hi) tile = p.n_tiles;
+  if (next >= t_hi) next = p.n_tiles;
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the 256-entry (type, colour, state) table is pure arithmetic: no global load anywhere near the critical path
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = decode_cell((uint32_t)i);
+  __syncthreads();
+  MG_TL(1);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads state the previous step wrote
+  MG_TL(2);
+  bool first = true;  // first tile of this warp
+
+  uint4 rec = make_uint4(0, 0, 0, 0);
+  int action = A_DONE;
+  if (PREF && tile < p.n_tiles) {
+    if (NBUF == 2 && lane == 0) {
+      mbar_expect_tx(bar0, tile_bytes);
+      tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
+    }
+    const int env0 = tile * TILE + lane;
+    rec = ldg_rec(p.agent + env0);
+    if (stepping && env0 < p.n_envs) action = load_action(actions, act_dtype, env0);
+  }
+
+  uint8_t *gb = reinterpret_cast<uint8_t *>(p.grid);
+  uint32_t phase = 0;  // bit b = parity to wait for on buffer b
+  int b = 0;
+  while (tile < p.n_tiles) {
+    uint4 rec_n = make_uint4(0, 0, 0, 0);
+    int action_n = A_DONE, nn = p.n_tiles;
+    // prefetch the next tile (into the other buffer), its agent records and actions, and the index of the tile after it
+    auto prefetch = [&]() {
+      if (next < p.n_tiles) {
+        if (lane == 0) {
+          if (NBUF == 2) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the obs block staged there two tiles ago
+            const uint32_t nb = bar0 + 8u * (uint32_t)(b ^ 1);
+            mbar_expect_tx(nb, tile_bytes);
+            tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
+          }
+          nn = atomicAdd(s_next, 1);  // shared-memory atomic, consumed one tile later
+          if (nn >= t_hi) nn = p.n_tiles;
+        }
+        const int env_n = next * TILE + lane;
+        rec_n = ldg_rec(p.agent + env_n);
+        if (stepping && env_n < p.n_envs) action_n = load_action(actions, act_dtype, env_n);
+      }
+    };
+    // A warp's first tile: every warp of the GPU is fetching its first tile at this moment, and nothing can be
+    // computed anywhere until those arrive, so the second tile is requested only once the first is here (its fetch
+    // then overlaps the first tile's compute like every later one) instead of doubling the opening burst.
+    const bool defer = (NBUF == 2) && first;
+    if (PREF) {
+      if (WIN && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left
+      if (!defer) prefetch();
+    } else {
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left the buffer
+        mbar_expect_tx(bar0, tile_bytes);
+        tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
+        nn = atomicAdd(s_next, 1);  // consumed at the end of this tile
+        if (nn >= t_hi) nn = p.n_tiles;
+      }
+      const int env0 = tile * TILE + lane;
+      rec = ldg_rec(p.agent + env0);
+      action = (stepping && env0 < p.n_envs) ? load_action(actions, act_dtype, env0) : A_DONE;
+    }
+    uint32_t *gtile = reinterpret_cast<uint32_t *>(bufs + (size_t)b * buf_bytes);
+    const int env = tile * TILE + lane;
+    const bool active = env < p.n_envs;
+    int ax = rec.x & 0xFF, ay = (rec.x >> 8) & 0xFF;
+    int dir = rec.y & 3;
+    uint32_t flags = rec.y >> 8;
+    uint32_t carry = rec.z;
+    int steps = (int)rec.w;
+
+    if (!WIN) {
+      mbar_wait(bar0 + 8u * (uint32_t)b, (phase >> b) & 1u);
+      phase ^= 1u << b;
+#ifdef MG_TIMELINE
+      if (first) MG_TL(3);
+#endif
+      if (defer) prefetch();
+    } else {
+      __syncwarp();  // lane 0 has waited for the bulk store that was still reading this buffer
+    }
+
+    const uint32_t *base = gtile + lane;
+    double reward = 0.0;
+    uint32_t terminated = 0, truncated = 0;
+    // NEXT_STEP autoreset (gymnasium >= 1.0 SyncVectorEnv): an env that ended last step ignores its action,
+    // is reset now, and returns the reset obs with reward 0 / False / False
+    bool fresh = false;
+    bool wrote = false;  // this warp wrote grid bytes through the generic proxy during this tile
+    if (stepping && p.mode == AUTORESET_NEXT_STEP) {
+      fresh = active && (flags & FLAG_PENDING);
+      const unsigned pend = __ballot_sync(0xFFFFFFFFu, fresh);
+      if (pend) {
+        wrote = true;
+        const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
+        if (fresh) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; flags &= ~FLAG_PENDING; }
+      }
+    }
+    // LAYOUT_WINDOW: the 7 lines of the view are 224 contiguous bytes of array R (facing +-x) or C (+-y), one bulk
+    // copy per lane. Which lines is known before the transition: a turn depends on the action alone and a
+    // forward move never changes the line coordinate of the array it faces along, so the window and the
+    // front-cell byte are requested together (one HBM round trip per tile).
+    uint32_t *win = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(gtile) + lane * WIN_LANE_BYTES);
+    auto load_window = [&](int d, bool wrote_any) {
+      const bool useC = d & 1;
+      const int w0 = (useC ? g.offC : 0) + ((useC ? ax : ay) - 3 + g.ring) * WIN_LINE_WORDS;
+      // generic-proxy writes of this step (autoreset fill, a mutated cell) must be visible to the bulk copy
+      if (__ballot_sync(0xFFFFFFFFu, wrote_any)) asm volatile("fence.proxy.async;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_expect_tx(bar0, TILE * WIN_BYTES);
+      tma_load_1d(smem_u32(win), p.grid + grid_word(g, env, w0), WIN_BYTES, bar0);  // one mbarrier per warp
+    };
+    auto wait_window = [&]() {
+      mbar_wait(bar0, phase & 1u);
+      phase ^= 1u;
+    };
+    uint32_t fc_win = CODE_WALL;
+    if (WIN) {
+      int dirn = dir, fx0, fy0;
+      if (stepping && !fresh) dirn = (dir + (action == A_LEFT ? 3 : 0) + (action == A_RIGHT ? 1 : 0)) & 3;
+      front_pos(g, ax, ay, dir, fx0, fy0);
+      const uint8_t *fcp = gb + grid_word(g, env, r_word(g, fx0, fy0)) * 4 + (fx0 & 3);
+      asm volatile("ld.global.u8 %0, [%1];" : "=r"(fc_win) : "l"(fcp));  // in flight together with the window
+      load_window(dirn, wrote);
+      wait_window();
+    }
+    if (stepping && !fresh) {
+      // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
+      steps += 1;
+      int fx, fy;
+      front_pos(g, ax, ay, dir, fx, fy);
+      const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
+      uint32_t fc;
+      if (WIN) fc = fc_win;
+      else fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
+      const StepOut so = transition(action, fc, fx, fy, ax, ay, dir, carry);
+      const uint32_t newc = so.newc;
+      terminated = so.terminated;
+      if (so.goal)  // _reward(), minigrid_env.py:240-245: host-computed table, never an FMA
+        reward = steps <= p.max_steps ? p.reward_lut[steps]
+                                      : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
+      if (so.bad_action) atomicOr(p.err, 1);  // ValueError("Unknown action"), minigrid_env.py:584-585
+      if (newc != fc && active) {
+        wrote = true;
+        if (!WIN) {
+          uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
+          sb[(rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)newc;
+          sb[(cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)newc;
+        } else {  // pickup / drop / toggle do not turn: the front cell is on the window's centre line
+          reinterpret_cast<uint8_t *>(win)[3 * 32 + ((dir & 1) ? fy : fx)] = (uint8_t)newc;
+        }
+        if (!WIN) {  // tile-relative addressing: 32-bit index math on the common path
+          uint8_t *tb = reinterpret_cast<uint8_t *>(p.grid + (size_t)tile * g.wpe * 32);
+          tb[(rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)newc;
+          tb[(cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)newc;
+        } else {
+          gb[grid_word(g, env, rw) * 4 + (fx & 3)] = (uint8_t)newc;
+          gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)newc;
+        }
+      }
+      truncated = steps >= p.max_steps;
+      const bool done = (terminated | truncated) != 0;
+      if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
+    }
+    // SAME_STEP autoreset: the env is reset inside the step that ended it and the reset obs is returned
+    if (stepping && p.mode == AUTORESET_SAME_STEP) {
+      const bool again = active && ((terminated | truncated) != 0);
+      const unsigned pend = __ballot_sync(0xFFFFFFFFu, again);
+      if (pend) {
+        wrote = true;
+        const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
+        if (again) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; }
+        if (WIN) {  // the regenerated levels invalidate the staged windows
+          load_window(dir, true);
+          wait_window();
+        }
+      }
+    }
+
+    // ---- gen_obs ----
+    if (obs != nullptr) {
+      uint32_t S[OBS_WORDS];
+      if (VIS == VIS_TBL && first) mbar_wait(tbl_bar, 0);  // the visibility table, requested in the prologue
+      if (WIN) {
+        const bool useC = dir & 1;
+        const int w0 = (useC ? g.offC : 0) + ((useC ? ax : ay) - 3 + g.ring) * WIN_LINE_WORDS;
+        const AccFlat acc = {win - w0};
+        gen_obs_words<VIS>(g, acc, lut, vis_tbl, ax, ay, dir, carry, S);
+      } else {
+        const AccTiled acc = {base, true};
+        gen_obs_words<VIS>(g, acc, lut, vis_tbl, ax, ay, dir, carry, S);
+      }
+      // stage the 32 images in output layout in the consumed buffer, then ONE bulk store of the 4704-byte block.
+      // (The ragged last tile / an unaligned obs pointer copy the valid bytes out of the stage instead: keeping the
+      // stream words out of any byte-store path stops the compiler from spilling S to local memory on every tile.)
+      const int nvalid = min(TILE, p.n_envs - tile * TILE);
+      const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);  // also: every lane is past its tile / window reads
+      emit_obs_staged(gtile, lane, S, n0);
+      if (nvalid == TILE && (obs_tma_ok & 1)) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_1d(obs + (size_t)tile * OBS_TILE_BYTES, smem_u32(gtile), OBS_TILE_BYTES);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        __syncwarp();
+        const uint8_t *sbytes = reinterpret_cast<const uint8_t *>(gtile);
+        uint8_t *dst = obs + (size_t)tile * OBS_TILE_BYTES;
+        for (int i = lane; i < nvalid * OBS_BYTES; i += 32) dst[i] = sbytes[i];
+      }
+    }
+    if (active) {
+      if (stepping) {
+        rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
+        rec.y = (uint32_t)dir | (flags << 8);
+        rec.z = carry;
+        rec.w = (uint32_t)steps;
+        p.agent[env] = rec;
+      }
+      if (dir_out) dir_out[env] = dir;
+      if (reward_out) reward_out[env] = reward;
+      if (term_out) term_out[env] = (uint8_t)terminated;
+      if (trunc_out) trunc_out[env] = (uint8_t)truncated;
+    }
+    __syncwarp();  // lanes may still be reading this buffer (partial-tile path) before it is refilled
+#ifdef MG_TIMELINE
+    if (first) MG_TL(4);
+#endif
+    first = false;
+    if (PREF) {
+      tile = next;
+      next = __shfl_sync(0xFFFFFFFFu, nn, 0);
+      rec = rec_n;
+      action = action_n;
+      if (NBUF == 2) b ^= 1;
+    } else {
+      tile = __shfl_sync(0xFFFFFFFFu, nn, 0);
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  MG_TL(5);
+  MG_TL_EXIT();
+}
+
+
+typedef void (*StepKernel)(Params, const void *, int, uint8_t *, int32_t *, double *, uint8_t *, uint8_t *, int);
+
+template <int VIS, int MODE>
+static StepKernel pick_kind(int kind) {
+  switch (kind) {
+    case KIND_EMPTY: return (StepKernel)k_step<KIND_EMPTY, VIS, MODE>;
+    case KIND_DOORKEY: return (StepKernel)k_step<KIND_DOORKEY, VIS, MODE>;
+    case KIND_CROSSING: return (StepKernel)k_step<KIND_CROSSING, VIS, MODE>;
+    case KIND_LAVAGAP: return (StepKernel)k_step<KIND_LAVAGAP, VIS, MODE>;
+    case KIND_DISTSHIFT: return (StepKernel)k_step<KIND_DISTSHIFT, VIS, MODE>;
+    case KIND_MULTIROOM: return (StepKernel)k_step<KIND_MULTIROOM, VIS, MODE>;
+    default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, MODE>;
+  }
+}
+template <int MODE>
+static StepKernel pick_vis(int kind, int vis) {
+  if (vis == VIS_NONE) return pick_kind<VIS_NONE, MODE>(kind);
+  if (vis == VIS_ALU) return pick_kind<VIS_ALU, MODE>(kind);
+  return pick_kind<VIS_TBL, MODE>(kind);
+}
+
+StepKernel step_kernel_window(int kind, int vis);  // mg_step_window.cu
+StepKernel step_kernel_tiled1(int kind, int vis);  // mg_step_tiled1.cu
+
+}  // namespace mg

@@ -1,0 +1,8 @@
+// mg_step_tiled1.cu — the MODE_TILED1 instantiations of K1 (tiled layout, one buffer per warp), see mg_step_kernel.cuh.
+#include "mg_step_kernel.cuh"
+
+namespace mg {
+
+StepKernel step_kernel_tiled1(int kind, int vis) { return pick_vis<MODE_TILED1>(kind, vis); }
+
+}  // namespace mg
