@@ -4,8 +4,8 @@
 // One warp = one tile of 32 environments, one lane per environment.
 //   1. lane 0 issues a TMA bulk copy (cp.async.bulk -> SASS UBLKCP) of the tile's interleaved grid words
 //      into shared memory and arms an mbarrier with the byte count; meanwhile every lane loads its
-//      action and 16-byte agent record with coalesced loads. Warps are persistent (one wave of CTAs); other
-//      resident warps cover the copy's latency (double-buffering per warp measured slower: it halves occupancy).
+//      action and 16-byte agent record with coalesced loads. Warps are persistent (one CTA per SM, one wave); each
+//      warp owns two buffers and requests its next tile (copy + records + actions) while it works on the current one.
 //   2. autoreset (NEXT_STEP: envs flagged last step, before the transition; SAME_STEP: envs that just ended,
 //      after it): rare, so the whole warp regenerates one environment at a time — every lane replays the
 //      numpy-exact RNG draws (uniform control flow) and fills a 1/32 share of the level's words.

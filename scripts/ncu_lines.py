@@ -9,8 +9,12 @@ n_tiles = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "minigrid_b200", "libminigrid_b200.so")], cwd=tmp, capture_output=True)
-cub = [f for f in os.listdir(tmp) if f.startswith("mg_step")][0]
-sass = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.split("\n")
+sass = []
+for cub in sorted(f for f in os.listdir(tmp) if f.startswith("mg_step")):  # K1 is instantiated in several translation units
+    out = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+    if ".text." + mangled in out:
+        sass = out.split("\n")
+        break
 start = next(i for i, l in enumerate(sass) if l.startswith(".text." + mangled))
 end = next(i for i in range(start + 1, len(sass)) if sass[i].startswith(".text.") or sass[i].startswith(".section"))
 lines = []

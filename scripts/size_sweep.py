@@ -9,7 +9,7 @@ env_id = sys.argv[1] if len(sys.argv) > 1 else "MiniGrid-DoorKey-8x8-v0"
 sizes = [int(s) for s in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4736, 32768, 131072, 262144, 524288, 1048576]
 out = []
 for n in sizes:
-    e = MinigridVecEnv(env_id, n); e.reset(seed=0)
+    e = MinigridVecEnv(env_id, n, autoreset_mode=os.environ.get("SWEEP_AUTORESET", "next_step")); e.reset(seed=0)
     acts = torch.randint(0, 7, (64, n), device="cuda", dtype=torch.int32)
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):

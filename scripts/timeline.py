@@ -39,6 +39,8 @@ for n in sizes:
             print(f"  {tag} {nm:28s} {stat(tl[k, :, i] - t0)}")
     print(f"  period (B entry min - A entry min): {(tl[b,:,0].min() - tl[a,:,0].min())/1e3:.2f} us;  "
           f"A last exit -> B first 'after wait': {(tl[b,:,2].min() - tl[a,:,6].max())/1e3:.2f} us")
+    if os.environ.get("TIMELINE_DUMP"):
+        np.save(os.environ["TIMELINE_DUMP"] + f"_{n}.npy", np.stack([tl[a] - t0, tl[b] - t0]))
     res = np.unique(np.diff(np.sort(tl[a].ravel())))
     print("  timer granularity (smallest nonzero delta, ns):", res[res > 0][:3])
     del e, g
