@@ -26,9 +26,9 @@ sys.path.insert(0, ROOT)
 ALGO_BYTES_PER_STEP = 348  # action 4 + patch 147 + obs 147 + reward 8 + flags 2 + agent 20 r + 20 w
 L2_BYTES = 126e6
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch from the committed ncu --set full capture
-# (profiles/r01_kstep_v10_summary.txt: 47.27 MB read + 12.3-13.8 MB written; obs writes mostly stay in L2)
-TRAFFIC_BYTES_PER_LAUNCH = 60.3e6
-TRAFFIC_SOURCE = "ncu --set full, profiles/r01_kstep_v10 (DoorKey-8x8 x 262144; applies to the default workload only)"
+# (profiles/r01_final_kstep_summary.txt: 47.27 MB read + 13.2-13.3 MB written; obs writes mostly stay in L2)
+TRAFFIC_BYTES_PER_LAUNCH = 60.5e6
+TRAFFIC_SOURCE = "ncu --set full, profiles/r01_final_kstep_summary.txt (DoorKey-8x8 x 262144; applies to the default workload only)"
 
 
 def parse_args():
@@ -344,11 +344,13 @@ def main():
     d2h = n * (147 + 4 + 8 + 1 + 1)
 
     peak, peak_src = load_peaks()
+    default_workload = args.env == "MiniGrid-DoorKey-8x8-v0" and n == 262144  # what the committed ncu capture measured
     roof = None
     if kstep_ms:
         achieved = ALGO_BYTES_PER_STEP * n / (kstep_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "k_step (K1: transition + gen_obs)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH, "traffic_source": TRAFFIC_SOURCE,
+                "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH if default_workload else None,
+                "traffic_source": TRAFFIC_SOURCE if default_workload else None,
                 "peak_source": peak_src, "kernel_ms": kstep_ms, "kernel_ms_per_launch_events": kstep_ms_events,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * n}
 
