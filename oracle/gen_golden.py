@@ -2,6 +2,8 @@
 
 Run:  python -m oracle.gen_golden          (needs /root/reference; see oracle/ref_loader.py)
 
+Run:  python -m oracle.gen_golden next     (only the next_rollout_* fixtures of generators that have no device kernel yet)
+
 Two families of fixtures, both produced by the reference's own MiniGridEnv objects:
   rollout_<id>.npz   seeded reset + T lockstep steps of N envs with SyncVectorEnv NEXT_STEP
                      autoreset, uniform-random actions (np.random.default_rng(1234)); records every
@@ -40,6 +42,10 @@ ROLLOUTS = {  # id -> (N, T, seed)
     "MiniGrid-DistShift2-v0": (4, 300, 23),
     "MiniGrid-MultiRoom-N2-S4-v0": (6, 130, 29),
     "MiniGrid-MultiRoom-N6-v0": (4, 260, 37),
+}
+NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist yet: next_rollout_<id>.npz (oracle only)
+    "MiniGrid-LockedRoom-v0": (4, 420, 41),
+    "MiniGrid-Playground-v0": (4, 330, 43),
 }
 INJECTS = {  # id (host env whose size/see_through/max_steps are used) -> (N, T)
     "MiniGrid-DoorKey-8x8-v0": (16, 120),
@@ -149,6 +155,14 @@ def gen_inject(env_id, n, t_steps, seed=99):
                 width=W, height=H, max_steps=e0.max_steps, see_through=e0.see_through_walls)
 
 
+def main_next():
+    os.makedirs(OUT, exist_ok=True)
+    for env_id, (n, t, seed) in NEXT_ROLLOUTS.items():
+        d = gen_rollout(env_id, n, t, seed)
+        np.savez_compressed(os.path.join(OUT, f"next_rollout_{env_id}.npz"), **d)
+        print("next_rollout", env_id, "episodes ended:", int((d["terminated"] | d["truncated"]).sum()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     for env_id, (n, t, seed) in ROLLOUTS.items():
@@ -172,4 +186,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["next"]:   # python -m oracle.gen_golden next: only the next_rollout_* fixtures
+        main_next()
+    else:
+        main()
+        main_next()

@@ -452,7 +452,7 @@ static int mr_place_room(const mgo_vec *v, env_t *e, int num_left, mroom_list_t 
   return 1;
 }
 static void gen_multiroom(const mgo_vec *v, env_t *e) {
-  int W = v->width, H = v->height;
+  int W = v->width;
   int min_rooms = v->params[0], max_rooms = v->params[1], max_size = v->params[2];
   mroom_list_t best; best.n = 0;
   int num_rooms = (int)rand_int(e, min_rooms, max_rooms + 1);
@@ -486,6 +486,98 @@ static void gen_multiroom(const mgo_vec *v, env_t *e) {
   place_obj(e, &goal, last->top_x, last->top_y, last->size_x, last->size_y, &gx, &gy);
 }
 
+/* COLOR_NAMES = sorted(COLORS) (constants.py:17): blue green grey purple red yellow, as COLOR_TO_IDX values */
+static const int COLOR_NAMES_IDX[6] = {C_BLUE, C_GREEN, C_GREY, C_PURPLE, C_RED, C_YELLOW};
+
+/* envs/lockedroom.py:108-173. _rand_elem(lst) = lst[_rand_int(0, len(lst))] (minigrid_env.py:268-275);
+ * LockedRoom.rand_pos = _rand_pos(topX + 1, topX + sizeX - 1, topY + 1, topY + sizeY - 1) (lockedroom.py:18-23) */
+static void gen_lockedroom(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  grid_clear(&e->grid);
+  for (int i = 0; i < W; i++) { grid_set(&e->grid, i, 0, WALL_GREY); grid_set(&e->grid, i, H - 1, WALL_GREY); }
+  for (int j = 0; j < H; j++) { grid_set(&e->grid, 0, j, WALL_GREY); grid_set(&e->grid, W - 1, j, WALL_GREY); }
+  int lwall = W / 2 - 2, rwall = W / 2 + 2;
+  for (int j = 0; j < H; j++) { grid_set(&e->grid, lwall, j, WALL_GREY); grid_set(&e->grid, rwall, j, WALL_GREY); }
+  struct { int top_x, top_y, size_x, size_y, door_x, door_y, color, locked; } rooms[6];
+  int nr = 0;
+  for (int n = 0; n < 3; n++) {
+    int j = n * (H / 3);
+    for (int i = 0; i < lwall; i++) grid_set(&e->grid, i, j, WALL_GREY);
+    for (int i = rwall; i < W; i++) grid_set(&e->grid, i, j, WALL_GREY);
+    int room_w = lwall + 1, room_h = H / 3 + 1;
+    rooms[nr].top_x = 0; rooms[nr].top_y = j; rooms[nr].size_x = room_w; rooms[nr].size_y = room_h;
+    rooms[nr].door_x = lwall; rooms[nr].door_y = j + 3; rooms[nr].color = -1; rooms[nr].locked = 0; nr++;
+    rooms[nr].top_x = rwall; rooms[nr].top_y = j; rooms[nr].size_x = room_w; rooms[nr].size_y = room_h;
+    rooms[nr].door_x = rwall; rooms[nr].door_y = j + 3; rooms[nr].color = -1; rooms[nr].locked = 0; nr++;
+  }
+  int locked = (int)rand_int(e, 0, nr);
+  rooms[locked].locked = 1;
+  {
+    int gx = (int)rand_int(e, rooms[locked].top_x + 1, rooms[locked].top_x + rooms[locked].size_x - 1);
+    int gy = (int)rand_int(e, rooms[locked].top_y + 1, rooms[locked].top_y + rooms[locked].size_y - 1);
+    cell_t goal = {T_GOAL, C_GREEN, 0};
+    grid_set(&e->grid, gx, gy, goal);
+  }
+  int left[6], nleft = 6;  /* sorted(colors): the remaining names keep their sorted order */
+  for (int c = 0; c < 6; c++) left[c] = COLOR_NAMES_IDX[c];
+  for (int k = 0; k < nr; k++) {
+    int pick = (int)rand_int(e, 0, nleft);
+    rooms[k].color = left[pick];
+    for (int c = pick; c + 1 < nleft; c++) left[c] = left[c + 1];
+    nleft--;
+    cell_t door = {T_DOOR, (uint8_t)rooms[k].color, (uint8_t)(rooms[k].locked ? S_LOCKED : S_CLOSED)};
+    grid_set(&e->grid, rooms[k].door_x, rooms[k].door_y, door);
+  }
+  int key_room;
+  do { key_room = (int)rand_int(e, 0, nr); } while (key_room == locked);
+  {
+    int kx = (int)rand_int(e, rooms[key_room].top_x + 1, rooms[key_room].top_x + rooms[key_room].size_x - 1);
+    int ky = (int)rand_int(e, rooms[key_room].top_y + 1, rooms[key_room].top_y + rooms[key_room].size_y - 1);
+    cell_t key = {T_KEY, (uint8_t)rooms[locked].color, 0};
+    grid_set(&e->grid, kx, ky, key);
+  }
+  place_agent(e, lwall, 0, rwall - lwall, H);
+}
+
+/* envs/playground.py:33-90 */
+static void gen_playground(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  grid_clear(&e->grid);
+  grid_horz_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_horz_wall(&e->grid, 0, H - 1, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, W - 1, 0, -1, WALL_GREY);
+  int room_w = W / 3, room_h = H / 3;
+  for (int j = 0; j < 3; j++) {
+    for (int i = 0; i < 3; i++) {
+      int xl = i * room_w, yt = j * room_h, xr = xl + room_w, yb = yt + room_h;
+      if (i + 1 < 3) {
+        grid_vert_wall(&e->grid, xr, yt, room_h, WALL_GREY);
+        int py = (int)rand_int(e, yt + 1, yb - 1);
+        int color = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+        cell_t door = {T_DOOR, (uint8_t)color, S_CLOSED};
+        grid_set(&e->grid, xr, py, door);
+      }
+      if (j + 1 < 3) {
+        grid_horz_wall(&e->grid, xl, yb, room_w, WALL_GREY);
+        int px = (int)rand_int(e, xl + 1, xr - 1);
+        int color = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+        cell_t door = {T_DOOR, (uint8_t)color, S_CLOSED};
+        grid_set(&e->grid, px, yb, door);
+      }
+    }
+  }
+  place_agent(e, 0, 0, W, H);
+  static const int TYPES[3] = {T_KEY, T_BALL, T_BOX};
+  for (int k = 0; k < 12; k++) {
+    int type = TYPES[rand_int(e, 0, 3)];
+    int color = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+    cell_t obj = {(uint8_t)type, (uint8_t)color, 0};
+    int ox, oy;
+    place_obj(e, &obj, 0, 0, W, H, &ox, &oy);
+  }
+}
+
 /* minigrid_env.py:119-157 (without the gen_obs at the end) */
 static void env_reset(const mgo_vec *v, env_t *e) {
   e->agent_x = -1; e->agent_y = -1; e->agent_dir = -1;
@@ -496,6 +588,8 @@ static void env_reset(const mgo_vec *v, env_t *e) {
     case MGO_LAVAGAP: gen_lavagap(v, e); break;
     case MGO_DISTSHIFT: gen_distshift(v, e); break;
     case MGO_MULTIROOM: gen_multiroom(v, e); break;
+    case MGO_LOCKEDROOM: gen_lockedroom(v, e); break;
+    case MGO_PLAYGROUND: gen_playground(v, e); break;
     default: gen_fourrooms(v, e); break;
   }
   e->carrying = 0;

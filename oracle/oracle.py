@@ -14,7 +14,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmg_oracle.so")
 
-KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6}
+KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6,
+        "lockedroom": 7, "playground": 8}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 
 # id -> (kind, width, height, max_steps, see_through_walls, params); restated from
@@ -43,6 +44,13 @@ ENV_SPECS = {
     "MiniGrid-MultiRoom-N2-S4-v0": ("multiroom", 25, 25, 40, False, [2, 2, 4]),
     "MiniGrid-MultiRoom-N4-S5-v0": ("multiroom", 25, 25, 120, False, [6, 6, 5]),
     "MiniGrid-MultiRoom-N6-v0": ("multiroom", 25, 25, 120, False, [6, 6, 10]),
+}
+
+# SURVEY 8(f-1) generators restated ahead of their device kernels: the oracle and its fixtures exist, the product does
+# not register these ids yet (lockedroom.py:74-90 / __init__.py:312-318, playground.py:16-25 / __init__.py:516-522)
+NEXT_SPECS = {
+    "MiniGrid-LockedRoom-v0": ("lockedroom", 19, 19, 190, False, []),
+    "MiniGrid-Playground-v0": ("playground", 19, 19, 100, False, []),
 }
 
 
@@ -91,7 +99,7 @@ def _ptr(a):
 
 class OracleVecEnv:
     def __init__(self, env_id=None, num_envs=1, *, spec=None, autoreset="next_step", n_threads=1):
-        kind, W, H, max_steps, see_through, params = spec if spec is not None else ENV_SPECS[env_id]
+        kind, W, H, max_steps, see_through, params = spec if spec is not None else {**ENV_SPECS, **NEXT_SPECS}[env_id]
         self.kind, self.width, self.height = kind, W, H
         self.max_steps, self.see_through, self.params = max_steps, see_through, list(params)
         self.num_envs = int(num_envs)

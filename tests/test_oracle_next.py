@@ -1,0 +1,50 @@
+"""SURVEY 8(f-1) generators restated in the oracle ahead of their device kernels (LockedRoom, Playground): the oracle
+against fixtures produced by the Python reference (travels to any box) and, where /root/reference exists, against
+the live reference. The product does not register these ids yet, so there is no GPU counterpart of this file."""
+import os
+
+import numpy as np
+import pytest
+from conftest import golden_files
+from test_oracle_golden import test_rollout_matches_reference_fixture as check_rollout_fixture
+
+from oracle import ref_loader
+from oracle.oracle import ENV_SPECS, NEXT_SPECS, OracleVecEnv
+
+
+@pytest.mark.parametrize("path", golden_files("next_rollout"), ids=os.path.basename)
+def test_next_rollout_matches_reference_fixture(path):
+    check_rollout_fixture(path)
+
+
+def test_next_ids_are_not_product_ids_yet():
+    from minigrid_b200 import specs
+
+    assert not (set(NEXT_SPECS) & set(ENV_SPECS))
+    for env_id in NEXT_SPECS:
+        with pytest.raises(Exception):
+            specs.get(env_id)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("env_id", list(NEXT_SPECS))
+@pytest.mark.parametrize("mode", ["next_step", "same_step"])
+def test_next_lockstep_rollout_against_live_reference(env_id, mode):
+    n, t_steps = 5, 420
+    ref = ref_loader.ReferenceVecEnv(env_id, n, autoreset=mode)
+    orc = OracleVecEnv(env_id, n, autoreset=mode)
+    e0 = ref.envs[0]
+    assert (orc.width, orc.height, orc.max_steps, orc.see_through) == (e0.width, e0.height, e0.max_steps, e0.see_through_walls)
+    ro, rd = ref.reset(seed=2024)
+    oo, od = orc.reset(seed=2024)
+    np.testing.assert_array_equal(ro, oo)
+    np.testing.assert_array_equal(rd, od)
+    rng = np.random.default_rng(78)
+    for t in range(t_steps):
+        a = rng.integers(0, 7, n)
+        for x, y, name in zip(ref.step(a), orc.step(a), ["obs", "dir", "reward", "terminated", "truncated"]):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=f"{name} t={t}")
+    rs, os_ = ref.get_state(), orc.get_state()
+    for k in rs:
+        np.testing.assert_array_equal(rs[k], os_[k], err_msg=k)
+    np.testing.assert_array_equal(ref.full_obs(), orc.full_obs())
