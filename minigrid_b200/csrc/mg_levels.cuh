@@ -1,5 +1,7 @@
-// mg_levels.cuh — the four level generators (_gen_grid) as "draw the integers, then evaluate a cell function".
+// mg_levels.cuh — the level generators (_gen_grid) as "draw the integers, then evaluate a cell function".
 //   envs/empty.py:97-114, envs/doorkey.py:74-99, envs/crossing.py:131-188, envs/fourrooms.py:78-126,
+//   envs/lavagap.py:100-135, envs/distshift.py:98-120, envs/multiroom.py:117-284; next (not instantiated in the
+//   kernels yet): envs/lockedroom.py:108-173, envs/playground.py:33-90,
 //   place_obj / place_agent rejection sampling: minigrid_env.py:313-397.
 // A finished level is a pure function of a handful of drawn integers, so generation is two phases:
 //   draw   the RNG calls in exactly the reference's order (rejection loops test the closed-form cell
@@ -20,6 +22,8 @@ struct Level {
   unsigned long long ov, oh;
   // multiroom: up to 6 rooms in creation order, 32 bits each (rooms 0-3 in rm03, 4-5 in rm45):
   // top_x:5 top_y:5 size_x:4 size_y:4 entry_door_x:5 entry_door_y:5 door_colour:3; (e, f) = goal
+  // playground: 12 objects in placement order, 15 bits each (objects 0-7 in rm03, 8-11 in rm45):
+  // x:5 y:5 kind:2 (0 key, 1 ball, 2 box) colour:3; nrooms = objects placed so far
   u128 rm03;
   unsigned long long rm45;
   int nrooms;
@@ -116,8 +120,64 @@ MG_D uint32_t cell_multiroom(const Level &L, int x, int y) {
   return code;
 }
 
+// COLOR_NAMES = sorted(COLORS) (constants.py:17): blue green grey purple red yellow -> COLOR_TO_IDX, 3 bits each
+MG_D uint32_t color_name_idx(int i) { return (0403512u >> (3 * i)) & 7u; }  // octal digits, last = blue: yellow 4, red 0, purple 3, grey 5, green 1, blue 2
+
+// envs/lockedroom.py:108-173. Six rooms: room k is on the left (k even) or right of the corridor, in row band k / 2;
+// a = locked room, (b, c) = goal, d = the rooms' colours (3 bits each), e = key room (not needed by the cells),
+// (rv, rh) = key position. Doors sit at fixed cells: (lWall | rWall, band * (H / 3) + 3).
+MG_D uint32_t cell_lockedroom(const Geom &g, const Level &L, int x, int y) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  const int lw = g.W / 2 - 2, rw = g.W / 2 + 2, h3 = g.H / 3;
+  if (x == lw || x == rw) {
+    const int band = y / h3;
+    if (band < 3 && y - band * h3 == 3) {
+      const int k = 2 * band + (x == rw);
+      const uint32_t col = ((uint32_t)L.d >> (3 * k)) & 7u;
+      return (k == L.a ? T4_DOOR_LOCKED : T4_DOOR_CLOSED) | (col << 4) | OPAQUE_BIT;
+    }
+    return CODE_WALL;
+  }
+  if ((x < lw || x > rw) && y % h3 == 0 && y / h3 < 3) return CODE_WALL;
+  if (x == L.b && y == L.c) return CODE_GOAL;
+  if (x == (int)L.rv && y == (int)L.rh) return T_KEY | ((((uint32_t)L.d >> (3 * L.a)) & 7u) << 4);
+  return CODE_EMPTY;
+}
+
+// envs/playground.py:33-90 (19 x 19: a 3 x 3 arrangement of 6 x 6 rooms). a = the 6 doors in the vertical walls
+// (index 2 j + i for the wall right of room (i, j)), b = the 6 doors in the horizontal walls (index 3 j + i for the
+// wall below room (i, j)); 5 bits each: offset:2 (door cell = first interior cell + offset) colour:3, colour 7 = no
+// door (the blank template). Objects: see Level.
+MG_D uint32_t play_obj(const Level &L, int k) {
+  return k < 8 ? (uint32_t)(L.rm03 >> (15 * k)) & 0x7FFFu : (uint32_t)(L.rm45 >> (15 * (k - 8))) & 0x7FFFu;
+}
+MG_D uint32_t cell_playground(const Geom &g, const Level &L, int x, int y) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  const int rw = g.W / 3, rh = g.H / 3;
+  const int i = x / rw, j = y / rh, lx = x - i * rw, ly = y - j * rh;
+  if (ly == 0 && j >= 1 && j <= 2 && i < 3) {  // the wall below room (i, j - 1): x = i rw .. i rw + rw - 1
+    const uint32_t dsc = ((uint32_t)L.b >> (5 * (3 * (j - 1) + i))) & 31u;
+    if (lx >= 1 && (dsc >> 2) != 7u && lx - 1 == (int)(dsc & 3u)) return T4_DOOR_CLOSED | ((dsc >> 2) << 4) | OPAQUE_BIT;
+    return CODE_WALL;
+  }
+  if (lx == 0 && i >= 1 && i <= 2 && j < 3) {  // the wall right of room (i - 1, j): y = j rh .. j rh + rh - 1
+    const uint32_t dsc = ((uint32_t)L.a >> (5 * (2 * j + (i - 1)))) & 31u;
+    if (ly >= 1 && (dsc >> 2) != 7u && ly - 1 == (int)(dsc & 3u)) return T4_DOOR_CLOSED | ((dsc >> 2) << 4) | OPAQUE_BIT;
+    return CODE_WALL;
+  }
+  for (int k = 0; k < 12; ++k) {
+    if (k < L.nrooms) {
+      const uint32_t o = play_obj(L, k);
+      if ((int)(o & 31u) == x && (int)((o >> 5) & 31u) == y) return (T_KEY + ((o >> 10) & 3u)) | (((o >> 12) & 7u) << 4);
+    }
+  }
+  return CODE_EMPTY;
+}
+
 template <int KIND>
 MG_D uint32_t cell_of(const Params &p, const Level &L, int x, int y) {
+  if (KIND == KIND_LOCKEDROOM) return cell_lockedroom(p.g, L, x, y);
+  if (KIND == KIND_PLAYGROUND) return cell_playground(p.g, L, x, y);
   if (KIND == KIND_MULTIROOM) return cell_multiroom(L, x, y);
   if (KIND == KIND_LAVAGAP) return cell_lavagap(p.g, L, x, y, (p.kp[0] == (int)T_WALL) ? CODE_WALL : CODE_LAVA);
   if (KIND == KIND_DISTSHIFT) return cell_distshift(p.g, p.kp[0], x, y);
@@ -215,6 +275,69 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
       if (x == L.ax && y == L.ay) continue;
       L.e = x; L.f = y;
       break;
+    }
+  } else if (KIND == KIND_LOCKEDROOM) {
+    const int lw = W / 2 - 2, rw = W / 2 + 2, h3 = H / 3;
+    auto room_x = [&](int k) { return (k & 1) ? rw : 0; };   // LockedRoom.top; size = (lw + 1, h3 + 1)
+    auto room_y = [&](int k) { return (k >> 1) * h3; };
+    L.a = rng_integers(r, 0, 6);                              // lockedRoom = _rand_elem(self.rooms)
+    L.b = rng_integers(r, room_x(L.a) + 1, room_x(L.a) + lw); // goalPos = lockedRoom.rand_pos(): x in [topX + 1, topX + sizeX - 1)
+    L.c = rng_integers(r, room_y(L.a) + 1, room_y(L.a) + h3);
+    uint32_t left = 0403512u, cols = 0;                       // sorted(colors) as 3-bit entries, room colours
+    for (int k = 0; k < 6; ++k) {                             // color = _rand_elem(sorted(colors)); colors.remove(color)
+      const int pick = rng_integers(r, 0, 6 - k);             // (the sixth pick has one candidate: numpy draws nothing)
+      cols |= ((left >> (3 * pick)) & 7u) << (3 * k);
+      left = (left & ((1u << (3 * pick)) - 1u)) | ((left >> (3 * (pick + 1))) << (3 * pick));
+    }
+    L.d = (int)cols;
+    do { L.e = rng_integers(r, 0, 6); } while (L.e == L.a);   // keyRoom
+    L.rv = (uint32_t)rng_integers(r, room_x(L.e) + 1, room_x(L.e) + lw);
+    L.rh = (uint32_t)rng_integers(r, room_y(L.e) + 1, room_y(L.e) + h3);
+    for (;;) {  // place_agent(top=(lWallIdx, 0), size=(rWallIdx - lWallIdx, height))
+      const int x = rng_integers(r, lw, rw), y = rng_integers(r, 0, H);
+      if (cell_lockedroom(g, L, x, y) != CODE_EMPTY) continue;
+      L.ax = x; L.ay = y;
+      break;
+    }
+    L.adir = rng_integers(r, 0, 4);
+  } else if (KIND == KIND_PLAYGROUND) {
+    const int rw = W / 3, rh = H / 3;
+    uint32_t vd = 0, hd = 0;
+    for (int j = 0; j < 3; ++j)
+      for (int i = 0; i < 3; ++i) {
+        if (i + 1 < 3) {  // pos = (xR, _rand_int(yT + 1, yB - 1)); color = _rand_elem(COLOR_NAMES)
+          const uint32_t off = (uint32_t)rng_integers(r, 0, rh - 2);
+          const uint32_t col = color_name_idx(rng_integers(r, 0, 6));
+          vd |= (off | (col << 2)) << (5 * (2 * j + i));
+        }
+        if (j + 1 < 3) {
+          const uint32_t off = (uint32_t)rng_integers(r, 0, rw - 2);
+          const uint32_t col = color_name_idx(rng_integers(r, 0, 6));
+          hd |= (off | (col << 2)) << (5 * (3 * j + i));
+        }
+      }
+    // doors that do not exist keep colour 7 in the blank template; here all 12 exist
+    L.a = (int)vd; L.b = (int)hd;
+    L.nrooms = 0;
+    for (;;) {  // place_agent()
+      const int x = rng_integers(r, 0, W), y = rng_integers(r, 0, H);
+      if (cell_playground(g, L, x, y) != CODE_EMPTY) continue;
+      L.ax = x; L.ay = y;
+      break;
+    }
+    L.adir = rng_integers(r, 0, 4);
+    for (int k = 0; k < 12; ++k) {  // objType = _rand_elem(types); objColor = _rand_elem(COLOR_NAMES); place_obj(obj)
+      const uint32_t kind = (uint32_t)rng_integers(r, 0, 3);
+      const uint32_t col = color_name_idx(rng_integers(r, 0, 6));
+      for (;;) {
+        const int x = rng_integers(r, 0, W), y = rng_integers(r, 0, H);
+        if (cell_playground(g, L, x, y) != CODE_EMPTY) continue;
+        if (x == L.ax && y == L.ay) continue;
+        const uint32_t o = (uint32_t)x | ((uint32_t)y << 5) | (kind << 10) | (col << 12);
+        if (k < 8) L.rm03 |= (u128)o << (15 * k); else L.rm45 |= (unsigned long long)o << (15 * (k - 8));
+        L.nrooms = k + 1;
+        break;
+      }
     }
   } else if (KIND == KIND_EMPTY) {
     if (!p.kp[0]) { L.ax = p.kp[1]; L.ay = p.kp[2]; L.adir = p.kp[3]; }
@@ -379,6 +502,16 @@ MG_D void patch_level(const Params &p, const Level &L, int lane, Put &&put) {
       }
     }
     if (lane == 0) put(L.e, L.f);
+  } else if (KIND == KIND_LOCKEDROOM) {
+    const int lw = g.W / 2 - 2, rw = g.W / 2 + 2, h3 = g.H / 3;
+    if (lane < 6) put((lane & 1) ? rw : lw, (lane >> 1) * h3 + 3);  // the six doors (colours and the lock are drawn)
+    if (lane == 6) put(L.b, L.c);                                    // goal
+    if (lane == 7) put((int)L.rv, (int)L.rh);                        // key
+  } else if (KIND == KIND_PLAYGROUND) {
+    const int rw = g.W / 3, rh = g.H / 3;
+    if (lane < 6) put((lane % 2 + 1) * rw, (lane / 2) * rh + 1 + (int)(((uint32_t)L.a >> (5 * lane)) & 3u));
+    else if (lane < 12) put(((lane - 6) % 3) * rw + 1 + (int)(((uint32_t)L.b >> (5 * (lane - 6))) & 3u), ((lane - 6) / 3 + 1) * rh);
+    else if (lane < 24) { const uint32_t o = play_obj(L, lane - 12); put((int)(o & 31u), (int)((o >> 5) & 31u)); }
   } else if (KIND == KIND_LAVAGAP) {
     if (lane >= 1 && lane <= g.H - 2) put(L.a, lane);  // the obstacle column (gap included)
   } else if (KIND == KIND_DOORKEY) {

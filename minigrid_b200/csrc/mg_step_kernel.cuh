@@ -121,7 +121,7 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
     B.e = __shfl_sync(0xFFFFFFFFu, L.e, src); B.f = __shfl_sync(0xFFFFFFFFu, L.f, src);
     B.rv = __shfl_sync(0xFFFFFFFFu, L.rv, src); B.rh = __shfl_sync(0xFFFFFFFFu, L.rh, src);
     B.ov = __shfl_sync(0xFFFFFFFFu, L.ov, src); B.oh = __shfl_sync(0xFFFFFFFFu, L.oh, src);
-    if (KIND == KIND_MULTIROOM) {
+    if (KIND == KIND_MULTIROOM || KIND == KIND_PLAYGROUND) {
       const unsigned long long lo = __shfl_sync(0xFFFFFFFFu, (unsigned long long)L.rm03, src);
       const unsigned long long hi = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(L.rm03 >> 64), src);
       B.rm03 = ((u128)hi << 64) | lo;

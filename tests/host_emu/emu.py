@@ -11,7 +11,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "libmg_host_emu.so")
-KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6}
+KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6,
+        "lockedroom": 7, "playground": 8}  # 7, 8: device generators checked here before the kernels are instantiated
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 _lib = None
 

@@ -71,6 +71,8 @@ static void reset_one(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {
     case KIND_LAVAGAP: reset_env<KIND_LAVAGAP>(e, env, obs, dir_out); break;
     case KIND_DISTSHIFT: reset_env<KIND_DISTSHIFT>(e, env, obs, dir_out); break;
     case KIND_MULTIROOM: reset_env<KIND_MULTIROOM>(e, env, obs, dir_out); break;
+    case KIND_LOCKEDROOM: reset_env<KIND_LOCKEDROOM>(e, env, obs, dir_out); break;
+    case KIND_PLAYGROUND: reset_env<KIND_PLAYGROUND>(e, env, obs, dir_out); break;
     default: reset_env<KIND_FOURROOMS>(e, env, obs, dir_out); break;
   }
 }
@@ -117,6 +119,8 @@ static void warp_reset(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOu
     case KIND_LAVAGAP: warp_reset_k<KIND_LAVAGAP>(e, pend, tile, gtile, out); break;
     case KIND_DISTSHIFT: warp_reset_k<KIND_DISTSHIFT>(e, pend, tile, gtile, out); break;
     case KIND_MULTIROOM: warp_reset_k<KIND_MULTIROOM>(e, pend, tile, gtile, out); break;
+    case KIND_LOCKEDROOM: warp_reset_k<KIND_LOCKEDROOM>(e, pend, tile, gtile, out); break;
+    case KIND_PLAYGROUND: warp_reset_k<KIND_PLAYGROUND>(e, pend, tile, gtile, out); break;
     default: warp_reset_k<KIND_FOURROOMS>(e, pend, tile, gtile, out); break;
   }
 }
@@ -278,6 +282,8 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
         case KIND_LAVAGAP: e->tmpl[w] = level_word<KIND_LAVAGAP>(p, L, w); break;
         case KIND_DISTSHIFT: e->tmpl[w] = level_word<KIND_DISTSHIFT>(p, L, w); break;
         case KIND_MULTIROOM: e->tmpl[w] = level_word<KIND_MULTIROOM>(p, L, w); break;
+        case KIND_LOCKEDROOM: e->tmpl[w] = level_word<KIND_LOCKEDROOM>(p, L, w); break;
+        case KIND_PLAYGROUND: e->tmpl[w] = level_word<KIND_PLAYGROUND>(p, L, w); break;
         default: e->tmpl[w] = level_word<KIND_FOURROOMS>(p, L, w); break;
       }
     p.tmpl = e->tmpl.data();

@@ -48,3 +48,32 @@ def test_next_lockstep_rollout_against_live_reference(env_id, mode):
     for k in rs:
         np.testing.assert_array_equal(rs[k], os_[k], err_msg=k)
     np.testing.assert_array_equal(ref.full_obs(), orc.full_obs())
+
+
+# ---- the device generators of these kinds (mg_levels.cuh), compiled for the CPU by tests/host_emu ----
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
+import parity  # noqa: E402
+from conftest import load_golden  # noqa: E402
+from emu import EmuVecEnv  # noqa: E402
+
+
+def make_next_emu(env_id, n, mode, layout=-1):
+    return EmuVecEnv(NEXT_SPECS[env_id], n, autoreset=mode, layout=layout)
+
+
+@pytest.mark.parametrize("layout", [0, 1], ids=["tiled", "window"])
+@pytest.mark.parametrize("path", golden_files("next_rollout"), ids=os.path.basename)
+def test_next_device_generators_replay_reference_fixture(path, layout):
+    """draw_level / cell_of / level_word / patch_level of the next kinds, through K2's fill and K1's template + patch
+    autoreset as replayed by the host emulation, against what the Python reference produced."""
+    parity.check_rollout_fixture(lambda env_id, n, mode: make_next_emu(env_id, n, mode, layout), load_golden(path))
+
+
+@pytest.mark.parametrize("env_id", list(NEXT_SPECS))
+@pytest.mark.parametrize("mode,n", [("next_step", 70), ("same_step", 45)])
+def test_next_device_generators_lockstep_vs_oracle(env_id, mode, n):
+    emu = make_next_emu(env_id, n, mode)
+    orc = OracleVecEnv(env_id, n, autoreset=mode)
+    parity.check_lockstep_vs_oracle(emu, orc, 450, seed=99, check_state_every=150)
