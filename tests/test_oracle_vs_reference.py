@@ -39,3 +39,32 @@ def test_spec_table_matches_registry():
     for env_id, (kind, w, h, ms, st, prm) in ENV_SPECS.items():
         e = gym.make(env_id).unwrapped
         assert (e.width, e.height, e.max_steps, e.see_through_walls) == (w, h, ms, st), env_id
+
+
+@pytest.mark.parametrize("base_id,kind,size,max_steps,see_through,params", [
+    ("MiniGrid-Empty-5x5-v0", "empty", 26, 4 * 26 * 26, True, [1, 0, 0, 0]),  # agent_start_pos=None: random start
+    ("MiniGrid-DoorKey-5x5-v0", "doorkey", 26, 10 * 26 * 26, False, []),
+    ("MiniGrid-DoorKey-5x5-v0", "doorkey", 6, 10 * 6 * 6, False, []),
+])
+def test_lockstep_rollout_at_unregistered_sizes(base_id, kind, size, max_steps, see_through, params):
+    """The engine's size limit (26) and a small DoorKey that no id registers: the reference classes take `size`."""
+    n, t_steps = 4, 200
+    kwargs = {"size": size}
+    if kind == "empty":
+        kwargs["agent_start_pos"] = None
+    ref = ref_loader.ReferenceVecEnv(base_id, n, **kwargs)
+    orc = OracleVecEnv(None, n, spec=(kind, size, size, max_steps, see_through, params))
+    e0 = ref.envs[0]
+    assert (e0.width, e0.height, e0.max_steps, e0.see_through_walls) == (size, size, max_steps, see_through)
+    ro, rd = ref.reset(seed=5)
+    oo, od = orc.reset(seed=5)
+    np.testing.assert_array_equal(ro, oo)
+    np.testing.assert_array_equal(rd, od)
+    rng = np.random.default_rng(6)
+    for t in range(t_steps):
+        a = rng.integers(0, 7, n)
+        for x, y, name in zip(ref.step(a), orc.step(a), ["obs", "dir", "reward", "terminated", "truncated"]):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=f"{name} t={t}")
+    rs, os_ = ref.get_state(), orc.get_state()
+    for k in rs:
+        np.testing.assert_array_equal(rs[k], os_[k], err_msg=k)
