@@ -161,7 +161,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"{args.env}, {n} envs, uniform random actions, NEXT_STEP autoreset", "env": args.env,
                    "envs": n, "host_threads": cores},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "per_core": value / cores, "kind": "port",
                          "sample": f"{n} envs x {steps} lockstep steps, C port of the reference algorithm (oracle/mg_oracle.c), {cores} threads"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -180,7 +180,7 @@ def cpu_baseline(args):
     secs, _ = env.rollout(rng.integers(0, 7, (2, n)).astype(np.int32), n_threads=cores)
     steps = int(max(4, min(2000, args.cpu_seconds / max(secs / 2, 1e-6))))
     secs, _ = env.rollout(rng.integers(0, 7, (steps, n)).astype(np.int32), n_threads=cores)
-    return {"value": n * steps / secs, "unit": "env-steps/s", "cores": cores, "kind": "port",
+    return {"value": n * steps / secs, "unit": "env-steps/s", "cores": cores, "per_core": n * steps / secs / cores, "kind": "port",
             "sample": f"{n} envs x {steps} lockstep steps of {args.env} ({secs:.1f} s), oracle C port on {cores} host threads "
                       f"(os.cpu_count()={os.cpu_count()}, cgroup CPU quota respected)"}
 
