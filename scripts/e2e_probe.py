@@ -24,4 +24,4 @@ with torch.cuda.stream(s):
         dt = (time.perf_counter() - t0) / 20
         print(name, "sync copy ms", dt * 1e3, "GB/s", host.numel() / dt / 1e9)
 print("numa/affinity", os.sched_getaffinity(0).__len__())
-os.system("numactl --show 2>/dev/null | head -3; cat /proc/self/status | grep -i 'Mems_allowed_list\|Cpus_allowed_list'")
+os.system(r"numactl --show 2>/dev/null | head -3; cat /proc/self/status | grep -i 'Mems_allowed_list\|Cpus_allowed_list'")
