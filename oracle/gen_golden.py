@@ -46,6 +46,8 @@ ROLLOUTS = {  # id -> (N, T, seed)
 NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist yet: next_rollout_<id>.npz (oracle only)
     "MiniGrid-LockedRoom-v0": (4, 420, 41),
     "MiniGrid-Playground-v0": (4, 330, 43),
+    "MiniGrid-GoToDoor-5x5-v0": (6, 260, 47),
+    "MiniGrid-GoToDoor-8x8-v0": (6, 400, 53),
 }
 INJECTS = {  # id (host env whose size/see_through/max_steps are used) -> (N, T)
     "MiniGrid-DoorKey-8x8-v0": (16, 120),

@@ -228,6 +228,7 @@ typedef struct {
   int step_count;
   pcg64_t rng;
   uint8_t pending_reset; /* SyncVectorEnv._autoreset_envs[i] */
+  int target_x, target_y; /* kinds with a step post-filter (GoToDoor: target_pos) */
 } env_t;
 
 struct mgo_vec {
@@ -578,6 +579,33 @@ static void gen_playground(const mgo_vec *v, env_t *e) {
   }
 }
 
+/* envs/gotodoor.py:88-128: a room of random size in the top-left corner, one door per wall, distinct colours */
+static void gen_gotodoor(const mgo_vec *v, env_t *e) {
+  grid_clear(&e->grid);
+  int width = (int)rand_int(e, 5, v->width + 1);
+  int height = (int)rand_int(e, 5, v->height + 1);
+  grid_wall_rect(&e->grid, 0, 0, width, height);
+  int door_x[4], door_y[4], door_color[4], n_colors = 0;
+  door_x[0] = (int)rand_int(e, 2, width - 2); door_y[0] = 0;
+  door_x[1] = (int)rand_int(e, 2, width - 2); door_y[1] = height - 1;
+  door_x[2] = 0; door_y[2] = (int)rand_int(e, 2, height - 2);
+  door_x[3] = width - 1; door_y[3] = (int)rand_int(e, 2, height - 2);
+  while (n_colors < 4) {
+    int color = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+    int dup = 0;
+    for (int k = 0; k < n_colors; k++) dup |= door_color[k] == color;
+    if (dup) continue;
+    door_color[n_colors++] = color;
+  }
+  for (int k = 0; k < 4; k++) {
+    cell_t door = {T_DOOR, (uint8_t)door_color[k], S_CLOSED};
+    grid_set(&e->grid, door_x[k], door_y[k], door);
+  }
+  place_agent(e, 0, 0, width, height);
+  int idx = (int)rand_int(e, 0, 4);
+  e->target_x = door_x[idx]; e->target_y = door_y[idx];
+}
+
 /* minigrid_env.py:119-157 (without the gen_obs at the end) */
 static void env_reset(const mgo_vec *v, env_t *e) {
   e->agent_x = -1; e->agent_y = -1; e->agent_dir = -1;
@@ -590,6 +618,7 @@ static void env_reset(const mgo_vec *v, env_t *e) {
     case MGO_MULTIROOM: gen_multiroom(v, e); break;
     case MGO_LOCKEDROOM: gen_lockedroom(v, e); break;
     case MGO_PLAYGROUND: gen_playground(v, e); break;
+    case MGO_GOTODOOR: gen_gotodoor(v, e); break;
     default: gen_fourrooms(v, e); break;
   }
   e->carrying = 0;
@@ -669,6 +698,14 @@ static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint
     default: e->step_count -= 1; return -1;
   }
   if (e->step_count >= v->max_steps) *truncated = 1;
+  if (v->kind == MGO_GOTODOOR) { /* GoToDoorEnv.step after super().step, gotodoor.py:130-149 */
+    if (action == A_TOGGLE) *terminated = 1;
+    if (action == A_DONE) {
+      int dx = e->agent_x - e->target_x, dy = e->agent_y - e->target_y;
+      if ((dx == 0 && (dy == 1 || dy == -1)) || (dy == 0 && (dx == 1 || dx == -1))) *reward = env_reward(v, e);
+      *terminated = 1;
+    }
+  }
   return 0;
 }
 

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmg_oracle.so")
 
 KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6,
-        "lockedroom": 7, "playground": 8}
+        "lockedroom": 7, "playground": 8, "gotodoor": 9}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 
 # id -> (kind, width, height, max_steps, see_through_walls, params); restated from
@@ -51,6 +51,10 @@ ENV_SPECS = {
 NEXT_SPECS = {
     "MiniGrid-LockedRoom-v0": ("lockedroom", 19, 19, 190, False, []),
     "MiniGrid-Playground-v0": ("playground", 19, 19, 100, False, []),
+    # SURVEY 8(f-2), first of the step post-filters: gotodoor.py:65-86 (4 * size^2 steps, see_through_walls=True), __init__.py:218-236
+    "MiniGrid-GoToDoor-5x5-v0": ("gotodoor", 5, 5, 100, True, []),
+    "MiniGrid-GoToDoor-6x6-v0": ("gotodoor", 6, 6, 144, True, []),
+    "MiniGrid-GoToDoor-8x8-v0": ("gotodoor", 8, 8, 256, True, []),
 }
 
 

@@ -1,4 +1,5 @@
-"""SURVEY 8(f-1) generators restated in the oracle ahead of their device kernels (LockedRoom, Playground): the oracle
+"""SURVEY 8(f) rows restated in the oracle ahead of their device kernels (f-1: LockedRoom, Playground; f-2, the first
+step post-filter: GoToDoor): the oracle
 against fixtures produced by the Python reference (travels to any box) and, where /root/reference exists, against
 the live reference. The product does not register these ids yet, so there is no GPU counterpart of this file."""
 import os
@@ -59,19 +60,23 @@ from conftest import load_golden  # noqa: E402
 from emu import EmuVecEnv  # noqa: E402
 
 
+# ids whose device generators exist in mg_levels.cuh (the step post-filter kinds are oracle-only so far)
+DEVICE_NEXT = ["MiniGrid-LockedRoom-v0", "MiniGrid-Playground-v0"]
+
+
 def make_next_emu(env_id, n, mode, layout=-1):
     return EmuVecEnv(NEXT_SPECS[env_id], n, autoreset=mode, layout=layout)
 
 
 @pytest.mark.parametrize("layout", [0, 1], ids=["tiled", "window"])
-@pytest.mark.parametrize("path", golden_files("next_rollout"), ids=os.path.basename)
+@pytest.mark.parametrize("path", [p for p in golden_files("next_rollout") if any(i in p for i in DEVICE_NEXT)], ids=os.path.basename)
 def test_next_device_generators_replay_reference_fixture(path, layout):
     """draw_level / cell_of / level_word / patch_level of the next kinds, through K2's fill and K1's template + patch
     autoreset as replayed by the host emulation, against what the Python reference produced."""
     parity.check_rollout_fixture(lambda env_id, n, mode: make_next_emu(env_id, n, mode, layout), load_golden(path))
 
 
-@pytest.mark.parametrize("env_id", list(NEXT_SPECS))
+@pytest.mark.parametrize("env_id", DEVICE_NEXT)
 @pytest.mark.parametrize("mode,n", [("next_step", 70), ("same_step", 45)])
 def test_next_device_generators_lockstep_vs_oracle(env_id, mode, n):
     emu = make_next_emu(env_id, n, mode)
