@@ -48,6 +48,9 @@ NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist 
     "MiniGrid-Playground-v0": (4, 330, 43),
     "MiniGrid-GoToDoor-5x5-v0": (6, 260, 47),
     "MiniGrid-GoToDoor-8x8-v0": (6, 400, 53),
+    "MiniGrid-Fetch-5x5-N2-v0": (6, 260, 59),
+    "MiniGrid-Fetch-8x8-N3-v0": (6, 500, 61),
+    "MiniGrid-RedBlueDoors-6x6-v0": (8, 900, 67),
 }
 INJECTS = {  # id (host env whose size/see_through/max_steps are used) -> (N, T)
     "MiniGrid-DoorKey-8x8-v0": (16, 120),

@@ -228,7 +228,7 @@ typedef struct {
   int step_count;
   pcg64_t rng;
   uint8_t pending_reset; /* SyncVectorEnv._autoreset_envs[i] */
-  int target_x, target_y; /* kinds with a step post-filter (GoToDoor: target_pos) */
+  int target_x, target_y; /* kinds with a step post-filter (GoToDoor: target_pos; Fetch: targetType, targetColor) */
 } env_t;
 
 struct mgo_vec {
@@ -606,6 +606,47 @@ static void gen_gotodoor(const mgo_vec *v, env_t *e) {
   e->target_x = door_x[idx]; e->target_y = door_y[idx];
 }
 
+/* envs/fetch.py:118-160: numObjs random keys / balls, then the agent, a target among the objects, and one draw for
+ * the wording of the mission (consumed, the string itself is not modelled) */
+static void gen_fetch(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height, num_objs = v->params[0];
+  grid_clear(&e->grid);
+  grid_horz_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_horz_wall(&e->grid, 0, H - 1, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, W - 1, 0, -1, WALL_GREY);
+  cell_t objs[16];
+  for (int k = 0; k < num_objs; k++) {
+    int type = rand_int(e, 0, 2) == 0 ? T_KEY : T_BALL;
+    int color = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+    cell_t obj = {(uint8_t)type, (uint8_t)color, 0};
+    int ox, oy;
+    place_obj(e, &obj, 0, 0, W, H, &ox, &oy);
+    objs[k] = obj;
+  }
+  place_agent(e, 0, 0, W, H);
+  cell_t target = objs[rand_int(e, 0, num_objs)];
+  e->target_x = target.type; e->target_y = target.color;
+  (void)rand_int(e, 0, 5);
+}
+
+/* envs/redbluedoors.py:78-103: size = height, the grid is 2 * size wide; the agent is placed before the doors exist */
+static void gen_redbluedoors(const mgo_vec *v, env_t *e) {
+  int size = v->height;
+  grid_clear(&e->grid);
+  grid_wall_rect(&e->grid, 0, 0, 2 * size, size);
+  grid_wall_rect(&e->grid, size / 2, 0, size, size);
+  place_agent(e, size / 2, 0, size, size);
+  int pos = (int)rand_int(e, 1, size - 1);
+  cell_t red = {T_DOOR, C_RED, S_CLOSED};
+  grid_set(&e->grid, size / 2, pos, red);
+  e->target_x = pos;
+  pos = (int)rand_int(e, 1, size - 1);
+  cell_t blue = {T_DOOR, C_BLUE, S_CLOSED};
+  grid_set(&e->grid, size / 2 + size - 1, pos, blue);
+  e->target_y = pos;
+}
+
 /* minigrid_env.py:119-157 (without the gen_obs at the end) */
 static void env_reset(const mgo_vec *v, env_t *e) {
   e->agent_x = -1; e->agent_y = -1; e->agent_dir = -1;
@@ -619,6 +660,8 @@ static void env_reset(const mgo_vec *v, env_t *e) {
     case MGO_LOCKEDROOM: gen_lockedroom(v, e); break;
     case MGO_PLAYGROUND: gen_playground(v, e); break;
     case MGO_GOTODOOR: gen_gotodoor(v, e); break;
+    case MGO_FETCH: gen_fetch(v, e); break;
+    case MGO_REDBLUEDOORS: gen_redbluedoors(v, e); break;
     default: gen_fourrooms(v, e); break;
   }
   e->carrying = 0;
@@ -661,6 +704,11 @@ static double env_reward(const mgo_vec *v, const env_t *e) {
 
 /* minigrid_env.py:525-595 (transition only; the caller generates the obs). returns -1 on bad action */
 static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint8_t *terminated, uint8_t *truncated) {
+  int red_before = 0, blue_before = 0; /* RedBlueDoorEnv.step, redbluedoors.py:105-108 */
+  if (v->kind == MGO_REDBLUEDOORS) {
+    red_before = grid_get(&e->grid, v->height / 2, e->target_x).state == S_OPEN;
+    blue_before = grid_get(&e->grid, v->height / 2 + v->height - 1, e->target_y).state == S_OPEN;
+  }
   e->step_count += 1;
   *reward = 0; *terminated = 0; *truncated = 0;
   int fx = e->agent_x + DIR_X[e->agent_dir], fy = e->agent_y + DIR_Y[e->agent_dir];
@@ -705,6 +753,21 @@ static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint
       if ((dx == 0 && (dy == 1 || dy == -1)) || (dy == 0 && (dx == 1 || dx == -1))) *reward = env_reward(v, e);
       *terminated = 1;
     }
+  }
+  if (v->kind == MGO_REDBLUEDOORS) { /* redbluedoors.py:110-126 */
+    int red_after = grid_get(&e->grid, v->height / 2, e->target_x).state == S_OPEN;
+    int blue_after = grid_get(&e->grid, v->height / 2 + v->height - 1, e->target_y).state == S_OPEN;
+    if (blue_after) {
+      *reward = red_before ? env_reward(v, e) : 0.0;
+      *terminated = 1;
+    } else if (red_after && blue_before) {
+      *reward = 0.0;
+      *terminated = 1;
+    }
+  }
+  if (v->kind == MGO_FETCH && e->carrying) { /* FetchEnv.step after super().step, fetch.py:162-175 */
+    *reward = (e->carry.type == e->target_x && e->carry.color == e->target_y) ? env_reward(v, e) : 0.0;
+    *terminated = 1;
   }
   return 0;
 }

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmg_oracle.so")
 
 KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6,
-        "lockedroom": 7, "playground": 8, "gotodoor": 9}
+        "lockedroom": 7, "playground": 8, "gotodoor": 9, "fetch": 10, "redbluedoors": 11}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 
 # id -> (kind, width, height, max_steps, see_through_walls, params); restated from
@@ -55,6 +55,13 @@ NEXT_SPECS = {
     "MiniGrid-GoToDoor-5x5-v0": ("gotodoor", 5, 5, 100, True, []),
     "MiniGrid-GoToDoor-6x6-v0": ("gotodoor", 6, 6, 144, True, []),
     "MiniGrid-GoToDoor-8x8-v0": ("gotodoor", 8, 8, 256, True, []),
+    # fetch.py:72-103 (5 * size^2 steps, see_through_walls=True), __init__.py:196-208; params {numObjs}
+    "MiniGrid-Fetch-5x5-N2-v0": ("fetch", 5, 5, 125, True, [2]),
+    "MiniGrid-Fetch-6x6-N2-v0": ("fetch", 6, 6, 180, True, [2]),
+    "MiniGrid-Fetch-8x8-N3-v0": ("fetch", 8, 8, 320, True, [3]),
+    # redbluedoors.py:60-72 (2 size x size, 20 * size^2 steps), __init__.py:541-551
+    "MiniGrid-RedBlueDoors-6x6-v0": ("redbluedoors", 12, 6, 720, False, []),
+    "MiniGrid-RedBlueDoors-8x8-v0": ("redbluedoors", 16, 8, 1280, False, []),
 }
 
 
