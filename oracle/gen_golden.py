@@ -51,6 +51,10 @@ NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist 
     "MiniGrid-Fetch-5x5-N2-v0": (6, 260, 59),
     "MiniGrid-Fetch-8x8-N3-v0": (6, 500, 61),
     "MiniGrid-RedBlueDoors-6x6-v0": (8, 900, 67),
+    "MiniGrid-GoToObject-8x8-N2-v0": (6, 400, 71),
+    "MiniGrid-PutNear-8x8-N3-v0": (8, 300, 73),
+    "MiniGrid-MemoryS13Random-v0": (6, 600, 79),
+    "MiniGrid-MemoryS7-v0": (6, 400, 83),
 }
 INJECTS = {  # id (host env whose size/see_through/max_steps are used) -> (N, T)
     "MiniGrid-DoorKey-8x8-v0": (16, 120),

@@ -229,6 +229,7 @@ typedef struct {
   pcg64_t rng;
   uint8_t pending_reset; /* SyncVectorEnv._autoreset_envs[i] */
   int target_x, target_y; /* kinds with a step post-filter (GoToDoor: target_pos; Fetch: targetType, targetColor) */
+  int aux[4];             /* PutNear: move_type, moveColor; Memory: failure_pos (target = success_pos) */
 } env_t;
 
 struct mgo_vec {
@@ -630,6 +631,97 @@ static void gen_fetch(const mgo_vec *v, env_t *e) {
   (void)rand_int(e, 0, 5);
 }
 
+/* envs/putnear.py:99-166: like GoToObject, but no object within one cell of an earlier one (reject_fn), and a second,
+ * different object as the target. place_obj order of tests: cell empty, not the agent, then reject_fn (:348-361). */
+static void gen_putnear(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height, num_objs = v->params[0];
+  grid_clear(&e->grid);
+  grid_horz_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_horz_wall(&e->grid, 0, H - 1, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, W - 1, 0, -1, WALL_GREY);
+  static const int TYPES[3] = {T_KEY, T_BALL, T_BOX};
+  int type[16], color[16], px[16], py[16], n = 0;
+  while (n < num_objs) {
+    int t = TYPES[rand_int(e, 0, 3)];
+    int c = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+    int dup = 0;
+    for (int k = 0; k < n; k++) dup |= type[k] == t && color[k] == c;
+    if (dup) continue;
+    for (;;) { /* place_obj(obj, reject_fn=near_obj) over the whole grid */
+      int x = (int)rand_int(e, 0, W), y = (int)rand_int(e, 0, H);
+      if (!cell_is_none(grid_get(&e->grid, x, y))) continue;
+      if (x == e->agent_x && y == e->agent_y) continue;
+      int near = 0;
+      for (int k = 0; k < n; k++) near |= abs(x - px[k]) <= 1 && abs(y - py[k]) <= 1;
+      if (near) continue;
+      px[n] = x; py[n] = y;
+      break;
+    }
+    cell_t obj = {(uint8_t)t, (uint8_t)c, 0};
+    grid_set(&e->grid, px[n], py[n], obj);
+    type[n] = t; color[n] = c; n++;
+  }
+  place_agent(e, 0, 0, W, H);
+  int move = (int)rand_int(e, 0, n), target;
+  do { target = (int)rand_int(e, 0, n); } while (target == move);
+  e->aux[0] = type[move]; e->aux[1] = color[move];
+  e->target_x = px[target]; e->target_y = py[target];
+}
+
+/* envs/memory.py:90-150 */
+static void gen_memory(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  grid_clear(&e->grid);
+  grid_horz_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_horz_wall(&e->grid, 0, H - 1, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, 0, 0, -1, WALL_GREY);
+  grid_vert_wall(&e->grid, W - 1, 0, -1, WALL_GREY);
+  int upper = H / 2 - 2, lower = H / 2 + 2;
+  int hallway_end = v->params[0] ? (int)rand_int(e, 4, W - 2) : W - 3;
+  for (int i = 1; i < 5; i++) { grid_set(&e->grid, i, upper, WALL_GREY); grid_set(&e->grid, i, lower, WALL_GREY); }
+  grid_set(&e->grid, 4, upper + 1, WALL_GREY);
+  grid_set(&e->grid, 4, lower - 1, WALL_GREY);
+  for (int i = 5; i < hallway_end; i++) { grid_set(&e->grid, i, upper + 1, WALL_GREY); grid_set(&e->grid, i, lower - 1, WALL_GREY); }
+  for (int j = 0; j < H; j++) {
+    if (j != H / 2) grid_set(&e->grid, hallway_end, j, WALL_GREY);
+    grid_set(&e->grid, hallway_end + 2, j, WALL_GREY);
+  }
+  e->agent_x = (int)rand_int(e, 1, hallway_end + 1); e->agent_y = H / 2; e->agent_dir = 0;
+  int start_type = rand_int(e, 0, 2) == 0 ? T_KEY : T_BALL;            /* _rand_elem([Key, Ball]) */
+  cell_t start_obj = {(uint8_t)start_type, C_GREEN, 0};
+  grid_set(&e->grid, 1, H / 2 - 1, start_obj);
+  int first_type = rand_int(e, 0, 2) == 0 ? T_BALL : T_KEY;            /* _rand_elem([[Ball, Key], [Key, Ball]]) */
+  cell_t o0 = {(uint8_t)first_type, C_GREEN, 0}, o1 = {(uint8_t)(first_type == T_BALL ? T_KEY : T_BALL), C_GREEN, 0};
+  int x = hallway_end + 1, y0 = H / 2 - 2, y1 = H / 2 + 2;
+  grid_set(&e->grid, x, y0, o0);
+  grid_set(&e->grid, x, y1, o1);
+  if (start_type == first_type) { e->target_x = x; e->target_y = y0 + 1; e->aux[0] = x; e->aux[1] = y1 - 1; }
+  else { e->target_x = x; e->target_y = y1 - 1; e->aux[0] = x; e->aux[1] = y0 + 1; }
+}
+
+/* envs/gotoobject.py:92-139: numObjs distinct (type, colour) objects, then the agent, then the target */
+static void gen_gotoobject(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height, num_objs = v->params[0];
+  grid_clear(&e->grid);
+  grid_wall_rect(&e->grid, 0, 0, W, H);
+  static const int TYPES[3] = {T_KEY, T_BALL, T_BOX};
+  int type[16], color[16], px[16], py[16], n = 0;
+  while (n < num_objs) {
+    int t = TYPES[rand_int(e, 0, 3)];
+    int c = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+    int dup = 0;
+    for (int k = 0; k < n; k++) dup |= type[k] == t && color[k] == c;
+    if (dup) continue;
+    cell_t obj = {(uint8_t)t, (uint8_t)c, 0};
+    place_obj(e, &obj, 0, 0, W, H, &px[n], &py[n]);
+    type[n] = t; color[n] = c; n++;
+  }
+  place_agent(e, 0, 0, W, H);
+  int idx = (int)rand_int(e, 0, n);
+  e->target_x = px[idx]; e->target_y = py[idx];
+}
+
 /* envs/redbluedoors.py:78-103: size = height, the grid is 2 * size wide; the agent is placed before the doors exist */
 static void gen_redbluedoors(const mgo_vec *v, env_t *e) {
   int size = v->height;
@@ -662,6 +754,9 @@ static void env_reset(const mgo_vec *v, env_t *e) {
     case MGO_GOTODOOR: gen_gotodoor(v, e); break;
     case MGO_FETCH: gen_fetch(v, e); break;
     case MGO_REDBLUEDOORS: gen_redbluedoors(v, e); break;
+    case MGO_GOTOOBJECT: gen_gotoobject(v, e); break;
+    case MGO_PUTNEAR: gen_putnear(v, e); break;
+    case MGO_MEMORY: gen_memory(v, e); break;
     default: gen_fourrooms(v, e); break;
   }
   e->carrying = 0;
@@ -709,6 +804,8 @@ static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint
     red_before = grid_get(&e->grid, v->height / 2, e->target_x).state == S_OPEN;
     blue_before = grid_get(&e->grid, v->height / 2 + v->height - 1, e->target_y).state == S_OPEN;
   }
+  const int pre_carrying = e->carrying; /* PutNearEnv.step, putnear.py:168-169 */
+  if (v->kind == MGO_MEMORY && action == A_PICKUP) action = A_TOGGLE; /* memory.py:152-154 */
   e->step_count += 1;
   *reward = 0; *terminated = 0; *truncated = 0;
   int fx = e->agent_x + DIR_X[e->agent_dir], fy = e->agent_y + DIR_Y[e->agent_dir];
@@ -746,13 +843,26 @@ static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint
     default: e->step_count -= 1; return -1;
   }
   if (e->step_count >= v->max_steps) *truncated = 1;
-  if (v->kind == MGO_GOTODOOR) { /* GoToDoorEnv.step after super().step, gotodoor.py:130-149 */
+  if (v->kind == MGO_GOTODOOR || v->kind == MGO_GOTOOBJECT) { /* gotodoor.py:130-149, gotoobject.py:141-160 (same filter) */
     if (action == A_TOGGLE) *terminated = 1;
     if (action == A_DONE) {
       int dx = e->agent_x - e->target_x, dy = e->agent_y - e->target_y;
       if ((dx == 0 && (dy == 1 || dy == -1)) || (dy == 0 && (dx == 1 || dx == -1))) *reward = env_reward(v, e);
       *terminated = 1;
     }
+  }
+  if (v->kind == MGO_PUTNEAR) { /* putnear.py:171-199 */
+    int ox = e->agent_x + DIR_X[e->agent_dir], oy = e->agent_y + DIR_Y[e->agent_dir];
+    if (action == A_PICKUP && e->carrying && (e->carry.type != e->aux[0] || e->carry.color != e->aux[1])) *terminated = 1;
+    if (action == A_DROP && pre_carrying) {
+      /* "self.grid.get(ox, oy) is preCarrying": the drop happened, i.e. nothing is carried any more */
+      if (!e->carrying && abs(ox - e->target_x) <= 1 && abs(oy - e->target_y) <= 1) *reward = env_reward(v, e);
+      *terminated = 1;
+    }
+  }
+  if (v->kind == MGO_MEMORY) { /* memory.py:156-164 */
+    if (e->agent_x == e->target_x && e->agent_y == e->target_y) { *reward = env_reward(v, e); *terminated = 1; }
+    if (e->agent_x == e->aux[0] && e->agent_y == e->aux[1]) { *reward = 0.0; *terminated = 1; }
   }
   if (v->kind == MGO_REDBLUEDOORS) { /* redbluedoors.py:110-126 */
     int red_after = grid_get(&e->grid, v->height / 2, e->target_x).state == S_OPEN;

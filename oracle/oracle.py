@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmg_oracle.so")
 
 KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6,
-        "lockedroom": 7, "playground": 8, "gotodoor": 9, "fetch": 10, "redbluedoors": 11}
+        "lockedroom": 7, "playground": 8, "gotodoor": 9, "fetch": 10, "redbluedoors": 11, "gotoobject": 12, "putnear": 13,
+        "memory": 14}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 
 # id -> (kind, width, height, max_steps, see_through_walls, params); restated from
@@ -62,6 +63,19 @@ NEXT_SPECS = {
     # redbluedoors.py:60-72 (2 size x size, 20 * size^2 steps), __init__.py:541-551
     "MiniGrid-RedBlueDoors-6x6-v0": ("redbluedoors", 12, 6, 720, False, []),
     "MiniGrid-RedBlueDoors-8x8-v0": ("redbluedoors", 16, 8, 1280, False, []),
+    # gotoobject.py:66-90 (size 6, numObjs 2, 5 * size^2 steps, see_through_walls=True), __init__.py:241-250; params {numObjs}
+    "MiniGrid-GoToObject-6x6-N2-v0": ("gotoobject", 6, 6, 180, True, [2]),
+    "MiniGrid-GoToObject-8x8-N2-v0": ("gotoobject", 8, 8, 320, True, [2]),
+    # putnear.py:66-92 (size 6, numObjs 2, 5 * size steps, see_through_walls=True), __init__.py:527-537; params {numObjs}
+    "MiniGrid-PutNear-6x6-N2-v0": ("putnear", 6, 6, 30, True, [2]),
+    "MiniGrid-PutNear-8x8-N3-v0": ("putnear", 8, 8, 40, True, [3]),
+    # memory.py:67-88 (5 * size^2 steps, see_through_walls=False), __init__.py:323-357; params {random_length}
+    "MiniGrid-MemoryS17Random-v0": ("memory", 17, 17, 1445, False, [1]),
+    "MiniGrid-MemoryS13Random-v0": ("memory", 13, 13, 845, False, [1]),
+    "MiniGrid-MemoryS13-v0": ("memory", 13, 13, 845, False, [0]),
+    "MiniGrid-MemoryS11-v0": ("memory", 11, 11, 605, False, [0]),
+    "MiniGrid-MemoryS9-v0": ("memory", 9, 9, 405, False, [0]),
+    "MiniGrid-MemoryS7-v0": ("memory", 7, 7, 245, False, [0]),
 }
 
 

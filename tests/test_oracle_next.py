@@ -82,3 +82,26 @@ def test_next_device_generators_lockstep_vs_oracle(env_id, mode, n):
     emu = make_next_emu(env_id, n, mode)
     orc = OracleVecEnv(env_id, n, autoreset=mode)
     parity.check_lockstep_vs_oracle(emu, orc, 450, seed=99, check_state_every=150)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("env_id", ["MiniGrid-MemoryS7-v0", "MiniGrid-MemoryS13Random-v0"])
+def test_memory_success_and_failure_cells_against_live_reference(env_id):
+    """Random actions almost never walk the hallway: drive every env to its end, half of them up and half down, so that
+    both post-filter branches (memory.py:156-164) fire in the reference and in the oracle."""
+    n = 24
+    ref = ref_loader.ReferenceVecEnv(env_id, n)
+    orc = OracleVecEnv(env_id, n)
+    np.testing.assert_array_equal(ref.reset(seed=300)[0], orc.reset(seed=300)[0])
+    size = ref.envs[0].width
+    turn = np.where(np.arange(n) % 2 == 0, 0, 1)  # left = up, right = down
+    script = [np.full(n, 2)] * size + [turn] + [np.full(n, 2)] * 2 + [np.full(n, 3)] * 2
+    rewards, ended = [], 0
+    for a in script * 2:  # the second pass runs on the autoreset episodes
+        r, q = ref.step(a), orc.step(a)
+        for x, y, name in zip(r, q, ["obs", "dir", "reward", "terminated", "truncated"]):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=name)
+        rewards.append(np.asarray(r[2]))
+        ended += int(np.asarray(r[3]).sum())
+    rewards = np.concatenate(rewards)
+    assert ended >= n and (rewards > 0).any() and ended > int((rewards > 0).sum())  # successes and failures both seen
