@@ -230,6 +230,7 @@ typedef struct {
   uint8_t pending_reset; /* SyncVectorEnv._autoreset_envs[i] */
   int target_x, target_y; /* kinds with a step post-filter (GoToDoor: target_pos; Fetch: targetType, targetColor) */
   int aux[4];             /* PutNear: move_type, moveColor; Memory: failure_pos (target = success_pos) */
+  int n_obst, obst_x[8], obst_y[8]; /* Dynamic-Obstacles: self.obstacles[i].cur_pos, in list order */
 } env_t;
 
 struct mgo_vec {
@@ -631,6 +632,40 @@ static void gen_fetch(const mgo_vec *v, env_t *e) {
   (void)rand_int(e, 0, 5);
 }
 
+/* place_obj with max_tries (minigrid_env.py:340-343: `if num_tries > max_tries: raise`, i.e. max_tries + 1 attempts).
+ * Returns 0 when the reference would raise RecursionError. */
+static int place_obj_tries(env_t *e, const cell_t *obj, int top_x, int top_y, int size_w, int size_h, int max_tries, int *px, int *py) {
+  if (top_x < 0) top_x = 0;
+  if (top_y < 0) top_y = 0;
+  int hi_x = top_x + size_w < e->grid.width ? top_x + size_w : e->grid.width;
+  int hi_y = top_y + size_h < e->grid.height ? top_y + size_h : e->grid.height;
+  for (int tries = 0; tries <= max_tries; tries++) {
+    int x = (int)rand_int(e, top_x, hi_x);
+    int y = (int)rand_int(e, top_y, hi_y);
+    if (!cell_is_none(grid_get(&e->grid, x, y))) continue;
+    if (x == e->agent_x && y == e->agent_y) continue;
+    grid_set(&e->grid, x, y, *obj);
+    *px = x; *py = y;
+    return 1;
+  }
+  return 0;
+}
+static const cell_t BALL_BLUE = {T_BALL, C_BLUE, 0}; /* Ball() defaults to blue, world_object.py:254 */
+
+/* envs/dynamicobstacles.py:107-133 */
+static void gen_dynobstacles(const mgo_vec *v, env_t *e) {
+  int W = v->width, H = v->height;
+  grid_clear(&e->grid);
+  grid_wall_rect(&e->grid, 0, 0, W, H);
+  cell_t goal = {T_GOAL, C_GREEN, 0};
+  grid_set(&e->grid, W - 2, H - 2, goal);
+  if (!v->params[1]) { e->agent_x = v->params[2]; e->agent_y = v->params[3]; e->agent_dir = v->params[4]; }
+  else place_agent(e, 0, 0, W, H);
+  e->n_obst = v->params[0];
+  for (int i = 0; i < e->n_obst; i++)
+    place_obj_tries(e, &BALL_BLUE, 0, 0, W, H, 100, &e->obst_x[i], &e->obst_y[i]);
+}
+
 /* envs/putnear.py:99-166: like GoToObject, but no object within one cell of an earlier one (reject_fn), and a second,
  * different object as the target. place_obj order of tests: cell empty, not the agent, then reject_fn (:348-361). */
 static void gen_putnear(const mgo_vec *v, env_t *e) {
@@ -757,6 +792,7 @@ static void env_reset(const mgo_vec *v, env_t *e) {
     case MGO_GOTOOBJECT: gen_gotoobject(v, e); break;
     case MGO_PUTNEAR: gen_putnear(v, e); break;
     case MGO_MEMORY: gen_memory(v, e); break;
+    case MGO_DYNOBSTACLES: gen_dynobstacles(v, e); break;
     default: gen_fourrooms(v, e); break;
   }
   e->carrying = 0;
@@ -803,6 +839,19 @@ static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint
   if (v->kind == MGO_REDBLUEDOORS) {
     red_before = grid_get(&e->grid, v->height / 2, e->target_x).state == S_OPEN;
     blue_before = grid_get(&e->grid, v->height / 2 + v->height - 1, e->target_y).state == S_OPEN;
+  }
+  int not_clear = 0;
+  if (v->kind == MGO_DYNOBSTACLES) { /* DynamicObstaclesEnv.step before super().step, dynamicobstacles.py:135-158 */
+    if (action >= 3) action = 0; /* action_space = Discrete(forward + 1); the unknown-action error cannot occur */
+    cell_t front = grid_get(&e->grid, e->agent_x + DIR_X[e->agent_dir], e->agent_y + DIR_Y[e->agent_dir]);
+    not_clear = !cell_is_none(front) && front.type != T_GOAL;
+    for (int i = 0; i < e->n_obst; i++) {
+      int ox = e->obst_x[i], oy = e->obst_y[i], nx, ny;
+      if (place_obj_tries(e, &BALL_BLUE, ox - 1, oy - 1, 3, 3, 100, &nx, &ny)) {
+        grid_set(&e->grid, ox, oy, CELL_NONE);
+        e->obst_x[i] = nx; e->obst_y[i] = ny;
+      }
+    }
   }
   const int pre_carrying = e->carrying; /* PutNearEnv.step, putnear.py:168-169 */
   if (v->kind == MGO_MEMORY && action == A_PICKUP) action = A_TOGGLE; /* memory.py:152-154 */
@@ -851,6 +900,7 @@ static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint
       *terminated = 1;
     }
   }
+  if (v->kind == MGO_DYNOBSTACLES && action == A_FORWARD && not_clear) { *reward = -1.0; *terminated = 1; } /* :162-165 */
   if (v->kind == MGO_PUTNEAR) { /* putnear.py:171-199 */
     int ox = e->agent_x + DIR_X[e->agent_dir], oy = e->agent_y + DIR_Y[e->agent_dir];
     if (action == A_PICKUP && e->carrying && (e->carry.type != e->aux[0] || e->carry.color != e->aux[1])) *terminated = 1;

@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(_HERE, "libmg_oracle.so")
 
 KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6,
         "lockedroom": 7, "playground": 8, "gotodoor": 9, "fetch": 10, "redbluedoors": 11, "gotoobject": 12, "putnear": 13,
-        "memory": 14}
+        "memory": 14, "dynobstacles": 15}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 
 # id -> (kind, width, height, max_steps, see_through_walls, params); restated from
@@ -76,6 +76,14 @@ NEXT_SPECS = {
     "MiniGrid-MemoryS11-v0": ("memory", 11, 11, 605, False, [0]),
     "MiniGrid-MemoryS9-v0": ("memory", 9, 9, 405, False, [0]),
     "MiniGrid-MemoryS7-v0": ("memory", 7, 7, 245, False, [0]),
+    # dynamicobstacles.py:72-105 (4 * size^2 steps, see_through_walls=True), __init__.py:117-153;
+    # params {n_obstacles, random_start, start_x, start_y, start_dir}
+    "MiniGrid-Dynamic-Obstacles-5x5-v0": ("dynobstacles", 5, 5, 100, True, [2, 0, 1, 1, 0]),
+    "MiniGrid-Dynamic-Obstacles-Random-5x5-v0": ("dynobstacles", 5, 5, 100, True, [2, 1, 0, 0, 0]),
+    "MiniGrid-Dynamic-Obstacles-6x6-v0": ("dynobstacles", 6, 6, 144, True, [3, 0, 1, 1, 0]),
+    "MiniGrid-Dynamic-Obstacles-Random-6x6-v0": ("dynobstacles", 6, 6, 144, True, [3, 1, 0, 0, 0]),
+    "MiniGrid-Dynamic-Obstacles-8x8-v0": ("dynobstacles", 8, 8, 256, True, [4, 0, 1, 1, 0]),
+    "MiniGrid-Dynamic-Obstacles-16x16-v0": ("dynobstacles", 16, 16, 1024, True, [8, 0, 1, 1, 0]),
 }
 
 
