@@ -62,7 +62,10 @@ enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS
              KIND_MULTIROOM = 6, KIND_COUNT = 7,  // kinds mg_create accepts (the kernels are instantiated for these)
              // the generators below exist in mg_levels.cuh and are checked against the oracle on the
              // CPU (tests/test_host_emu.py); K1 / K2 are not instantiated for them yet and mg_create rejects them
-             KIND_LOCKEDROOM = 7, KIND_PLAYGROUND = 8 };
+             KIND_LOCKEDROOM = 7, KIND_PLAYGROUND = 8,
+             // generator + step post-filter (mg_postfilter.cuh); same status as the two above
+             KIND_GOTODOOR = 9, KIND_FETCH = 10, KIND_REDBLUEDOORS = 11, KIND_GOTOOBJECT = 12, KIND_PUTNEAR = 13,
+             KIND_MEMORY = 14 };
 enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
 
 // (type, colour, state) -> cell code. None/unseen/agent all mean "no object" (WorldObj.decode,

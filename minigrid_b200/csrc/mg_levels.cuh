@@ -24,10 +24,21 @@ struct Level {
   // top_x:5 top_y:5 size_x:4 size_y:4 entry_door_x:5 entry_door_y:5 door_colour:3; (e, f) = goal
   // playground: 12 objects in placement order, 15 bits each (objects 0-7 in rm03, 8-11 in rm45):
   // x:5 y:5 kind:2 (0 key, 1 ball, 2 box) colour:3; nrooms = objects placed so far
+  // goto-object / fetch / put-near: the objects in placement order, same 15-bit records, nrooms = their number
   u128 rm03;
   unsigned long long rm45;
   int nrooms;
+  // kinds with a step post-filter (mg_postfilter.cuh): what the filter compares against is packed into `ov`
+  // (tx | ty << 8 | aux << 16, see level_target) and from there into the spare bits of the agent record
+  // (x | y << 8 | tx << 16 | ty << 24, dir | flags << 8 | aux << 16). The struct itself is unchanged: MultiRoom keeps
+  // it in local memory and its code must not move while these kinds are CPU-checked only.
 };
+MG_D void level_target(Level &L, int tx, int ty, uint32_t aux) {
+  L.ov = (unsigned long long)(uint32_t)tx | ((unsigned long long)(uint32_t)ty << 8) | ((unsigned long long)aux << 16);
+}
+MG_D int level_tx(const Level &L) { return (int)(L.ov & 0xFFull); }
+MG_D int level_ty(const Level &L) { return (int)((L.ov >> 8) & 0xFFull); }
+MG_D uint32_t level_aux(const Level &L) { return (uint32_t)((L.ov >> 16) & 0xFFFFull); }
 
 MG_D uint32_t room_get(const Level &L, int i) {
   return i < 4 ? (uint32_t)(L.rm03 >> (32 * i)) : (uint32_t)(L.rm45 >> (32 * (i - 4)));
@@ -174,8 +185,61 @@ MG_D uint32_t cell_playground(const Geom &g, const Level &L, int x, int y) {
   return CODE_EMPTY;
 }
 
+// envs/gotoobject.py:92-139, fetch.py:118-160, putnear.py:99-166: border walls and the objects
+MG_D uint32_t cell_objroom(const Geom &g, const Level &L, int x, int y) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  for (int k = 0; k < 8; ++k) {
+    if (k < L.nrooms) {
+      const uint32_t o = play_obj(L, k);
+      if ((int)(o & 31u) == x && (int)((o >> 5) & 31u) == y) return (T_KEY + ((o >> 10) & 3u)) | (((o >> 12) & 7u) << 4);
+    }
+  }
+  return CODE_EMPTY;
+}
+// envs/gotodoor.py:88-128: a = room width | height << 8 (the room is the top-left corner of the grid, the rest stays
+// None), b = door coordinates (5 bits each: x on the top wall, x on the bottom wall, y on the left, y on the right),
+// c = their colours (3 bits each)
+MG_D uint32_t cell_gotodoor(const Geom &, const Level &L, int x, int y) {
+  const int rw = L.a & 255, rh = (L.a >> 8) & 255;
+  if (x >= rw || y >= rh) return CODE_EMPTY;
+  const uint32_t b = (uint32_t)L.b, c = (uint32_t)L.c;
+  if (y == 0 && x == (int)(b & 31u)) return T4_DOOR_CLOSED | ((c & 7u) << 4) | OPAQUE_BIT;
+  if (y == rh - 1 && x == (int)((b >> 5) & 31u)) return T4_DOOR_CLOSED | (((c >> 3) & 7u) << 4) | OPAQUE_BIT;
+  if (x == 0 && y == (int)((b >> 10) & 31u)) return T4_DOOR_CLOSED | (((c >> 6) & 7u) << 4) | OPAQUE_BIT;
+  if (x == rw - 1 && y == (int)((b >> 15) & 31u)) return T4_DOOR_CLOSED | (((c >> 9) & 7u) << 4) | OPAQUE_BIT;
+  if (x == 0 || y == 0 || x == rw - 1 || y == rh - 1) return CODE_WALL;
+  return CODE_EMPTY;
+}
+// envs/redbluedoors.py:78-103 (W = 2 H): a = row of the red door in column H / 2, b = row of the blue door in
+// column H / 2 + H - 1; -1 = no door (the blank template)
+MG_D uint32_t cell_redbluedoors(const Geom &g, const Level &L, int x, int y) {
+  const int s = g.H, xl = s / 2, xr = s / 2 + s - 1;
+  if (x == xl && y == L.a) return T4_DOOR_CLOSED | (C_RED << 4) | OPAQUE_BIT;
+  if (x == xr && y == L.b) return T4_DOOR_CLOSED | (C_BLUE << 4) | OPAQUE_BIT;
+  if (on_border(g, x, y) || x == xl || x == xr) return CODE_WALL;
+  return CODE_EMPTY;
+}
+// envs/memory.py:90-150: a = hallway_end, b = type of the object in the start room, c = type of the upper object at
+// the end of the hallway (the lower one is the other type); all three are green
+MG_D uint32_t cell_memory(const Geom &g, const Level &L, int x, int y) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  const int mid = g.H / 2, upper = mid - 2, lower = mid + 2, he = L.a;
+  if (x >= 1 && x <= 4 && (y == upper || y == lower)) return CODE_WALL;
+  if (x == 4 && (y == upper + 1 || y == lower - 1)) return CODE_WALL;
+  if (x >= 5 && x < he && (y == upper + 1 || y == lower - 1)) return CODE_WALL;
+  if ((x == he && y != mid) || x == he + 2) return CODE_WALL;
+  if (x == 1 && y == mid - 1) return (uint32_t)L.b | (C_GREEN << 4);
+  if (x == he + 1 && y == mid - 2) return (uint32_t)L.c | (C_GREEN << 4);
+  if (x == he + 1 && y == mid + 2) return (uint32_t)(L.c == (int)T_BALL ? T_KEY : T_BALL) | (C_GREEN << 4);
+  return CODE_EMPTY;
+}
+
 template <int KIND>
 MG_D uint32_t cell_of(const Params &p, const Level &L, int x, int y) {
+  if (KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR) return cell_objroom(p.g, L, x, y);
+  if (KIND == KIND_GOTODOOR) return cell_gotodoor(p.g, L, x, y);
+  if (KIND == KIND_REDBLUEDOORS) return cell_redbluedoors(p.g, L, x, y);
+  if (KIND == KIND_MEMORY) return cell_memory(p.g, L, x, y);
   if (KIND == KIND_LOCKEDROOM) return cell_lockedroom(p.g, L, x, y);
   if (KIND == KIND_PLAYGROUND) return cell_playground(p.g, L, x, y);
   if (KIND == KIND_MULTIROOM) return cell_multiroom(L, x, y);
@@ -276,6 +340,105 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
       L.e = x; L.f = y;
       break;
     }
+  } else if (KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR) {
+    // gotoobject.py:100-139, fetch.py:127-160, putnear.py:108-166. kp[0] = numObjs.
+    const int n_objs = p.kp[0];
+    while (L.nrooms < n_objs) {
+      const uint32_t kind = (uint32_t)rng_integers(r, 0, KIND == KIND_FETCH ? 2 : 3);  // fetch: key | ball only
+      const uint32_t col = color_name_idx(rng_integers(r, 0, 6));
+      if (KIND != KIND_FETCH) {  // `if (objType, objColor) in objs: continue`
+        bool dup = false;
+        for (int k = 0; k < 8; ++k)
+          if (k < L.nrooms) dup |= ((play_obj(L, k) >> 10) & 31u) == (kind | (col << 2));
+        if (dup) continue;
+      }
+      for (;;) {  // place_obj(obj[, reject_fn=near_obj]) over the whole grid; the agent is not placed yet
+        const int x = rng_integers(r, 0, W), y = rng_integers(r, 0, H);
+        if (cell_objroom(g, L, x, y) != CODE_EMPTY) continue;
+        if (KIND == KIND_PUTNEAR) {
+          bool near = false;
+          for (int k = 0; k < 8; ++k)
+            if (k < L.nrooms) {
+              const uint32_t o = play_obj(L, k);
+              const int dx = x - (int)(o & 31u), dy = y - (int)((o >> 5) & 31u);
+              near |= dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1;
+            }
+          if (near) continue;
+        }
+        L.rm03 |= (u128)((uint32_t)x | ((uint32_t)y << 5) | (kind << 10) | (col << 12)) << (15 * L.nrooms);
+        L.nrooms += 1;
+        break;
+      }
+    }
+    for (;;) {  // place_agent()
+      const int x = rng_integers(r, 0, W), y = rng_integers(r, 0, H);
+      if (cell_objroom(g, L, x, y) != CODE_EMPTY) continue;
+      L.ax = x; L.ay = y;
+      break;
+    }
+    L.adir = rng_integers(r, 0, 4);
+    const uint32_t first = play_obj(L, rng_integers(r, 0, n_objs));  // target (fetch, gotoobject) / object to move (putnear)
+    if (KIND == KIND_FETCH) {
+      level_target(L, (int)(T_KEY + ((first >> 10) & 3u)), (int)((first >> 12) & 7u), 0u);  // targetType, targetColor
+      (void)rng_integers(r, 0, 5);  // the wording of the mission: drawn, not modelled
+    } else if (KIND == KIND_GOTOOBJECT) {
+      level_target(L, (int)(first & 31u), (int)((first >> 5) & 31u), 0u);  // target_pos
+    } else {
+      uint32_t target;
+      do { target = play_obj(L, rng_integers(r, 0, n_objs)); } while (target == first);  // objects are distinct
+      // target_pos; move_type, moveColor as a cell code
+      level_target(L, (int)(target & 31u), (int)((target >> 5) & 31u), (T_KEY + ((first >> 10) & 3u)) | (((first >> 12) & 7u) << 4));
+    }
+  } else if (KIND == KIND_GOTODOOR) {
+    const int rw = rng_integers(r, 5, W + 1), rh = rng_integers(r, 5, H + 1);
+    L.a = rw | (rh << 8);
+    const uint32_t d0 = (uint32_t)rng_integers(r, 2, rw - 2), d1 = (uint32_t)rng_integers(r, 2, rw - 2);
+    const uint32_t d2 = (uint32_t)rng_integers(r, 2, rh - 2), d3 = (uint32_t)rng_integers(r, 2, rh - 2);
+    L.b = (int)(d0 | (d1 << 5) | (d2 << 10) | (d3 << 15));
+    uint32_t cols = 0;
+    for (int n = 0; n < 4;) {  // distinct colours, redrawn on a repeat
+      const uint32_t col = color_name_idx(rng_integers(r, 0, 6));
+      bool dup = false;
+      for (int k = 0; k < 4; ++k)
+        if (k < n) dup |= ((cols >> (3 * k)) & 7u) == col;
+      if (dup) continue;
+      cols |= col << (3 * n);
+      ++n;
+    }
+    L.c = (int)cols;
+    for (;;) {  // place_agent(size=(width, height))
+      const int x = rng_integers(r, 0, rw), y = rng_integers(r, 0, rh);
+      if (cell_gotodoor(g, L, x, y) != CODE_EMPTY) continue;
+      L.ax = x; L.ay = y;
+      break;
+    }
+    L.adir = rng_integers(r, 0, 4);
+    const int idx = rng_integers(r, 0, 4);
+    level_target(L, idx == 0 ? (int)d0 : idx == 1 ? (int)d1 : idx == 2 ? 0 : rw - 1,
+                 idx == 0 ? 0 : idx == 1 ? rh - 1 : idx == 2 ? (int)d2 : (int)d3, 0u);
+  } else if (KIND == KIND_REDBLUEDOORS) {
+    const int s = H;
+    L.a = L.b = -1;  // the agent is placed before the doors exist
+    for (;;) {  // place_agent(top=(size // 2, 0), size=(size, size))
+      const int x = rng_integers(r, s / 2, s / 2 + s), y = rng_integers(r, 0, s);
+      if (cell_redbluedoors(g, L, x, y) != CODE_EMPTY) continue;
+      L.ax = x; L.ay = y;
+      break;
+    }
+    L.adir = rng_integers(r, 0, 4);
+    L.a = rng_integers(r, 1, s - 1);
+    L.b = rng_integers(r, 1, s - 1);
+    level_target(L, L.a, L.b, 0u);
+  } else if (KIND == KIND_MEMORY) {
+    const int mid = H / 2;
+    L.a = p.kp[0] ? rng_integers(r, 4, W - 2) : W - 3;  // hallway_end
+    L.ax = rng_integers(r, 1, L.a + 1); L.ay = mid; L.adir = 0;
+    L.b = rng_integers(r, 0, 2) == 0 ? (int)T_KEY : (int)T_BALL;  // _rand_elem([Key, Ball])
+    L.c = rng_integers(r, 0, 2) == 0 ? (int)T_BALL : (int)T_KEY;  // _rand_elem([[Ball, Key], [Key, Ball]])[0]
+    const int x = L.a + 1;
+    const bool upper_matches = L.b == L.c;
+    level_target(L, x, upper_matches ? mid - 1 : mid + 1,                               // success_pos
+                 (uint32_t)x | ((uint32_t)(upper_matches ? mid + 1 : mid - 1) << 8));  // failure_pos
   } else if (KIND == KIND_LOCKEDROOM) {
     const int lw = W / 2 - 2, rw = W / 2 + 2, h3 = H / 3;
     auto room_x = [&](int k) { return (k & 1) ? rw : 0; };   // LockedRoom.top; size = (lw + 1, h3 + 1)
@@ -502,6 +665,14 @@ MG_D void patch_level(const Params &p, const Level &L, int lane, Put &&put) {
       }
     }
     if (lane == 0) put(L.e, L.f);
+  } else if (KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR) {
+    if (lane < L.nrooms) { const uint32_t o = play_obj(L, lane); put((int)(o & 31u), (int)((o >> 5) & 31u)); }
+  } else if (KIND == KIND_REDBLUEDOORS) {
+    if (lane == 0) put(g.H / 2, L.a);
+    if (lane == 1) put(g.H / 2 + g.H - 1, L.b);
+  } else if (KIND == KIND_GOTODOOR || KIND == KIND_MEMORY) {
+    // the walls themselves are drawn (room size / hallway length): every cell may differ from the template
+    for (int c = lane; c < g.W * g.H; c += 32) put(c % g.W, c / g.W);
   } else if (KIND == KIND_LOCKEDROOM) {
     const int lw = g.W / 2 - 2, rw = g.W / 2 + 2, h3 = g.H / 3;
     if (lane < 6) put((lane & 1) ? rw : lw, (lane >> 1) * h3 + 3);  // the six doors (colours and the lock are drawn)

@@ -13,6 +13,7 @@
 #include "../../minigrid_b200/csrc/mg_obs.cuh"
 #include "../../minigrid_b200/csrc/mg_pcg64.cuh"
 #include "../../minigrid_b200/csrc/mg_transition.cuh"
+#include "../../minigrid_b200/csrc/mg_postfilter.cuh"
 
 using namespace mg;
 
@@ -45,6 +46,10 @@ static void reset_env(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {  // k_r
   uint4 rec;
   rec.x = (uint32_t)L.ax | ((uint32_t)L.ay << 8);
   rec.y = (uint32_t)L.adir;
+  if (KIND >= KIND_GOTODOOR) {  // post-filter targets
+    rec.x |= ((uint32_t)level_tx(L) << 16) | ((uint32_t)level_ty(L) << 24);
+    rec.y |= level_aux(L) << 16;
+  }
   rec.z = 0; rec.w = 0;
   p.agent[env] = rec;
   if (dir_out) dir_out[env] = L.adir;
@@ -73,11 +78,17 @@ static void reset_one(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {
     case KIND_MULTIROOM: reset_env<KIND_MULTIROOM>(e, env, obs, dir_out); break;
     case KIND_LOCKEDROOM: reset_env<KIND_LOCKEDROOM>(e, env, obs, dir_out); break;
     case KIND_PLAYGROUND: reset_env<KIND_PLAYGROUND>(e, env, obs, dir_out); break;
+    case KIND_GOTODOOR: reset_env<KIND_GOTODOOR>(e, env, obs, dir_out); break;
+    case KIND_FETCH: reset_env<KIND_FETCH>(e, env, obs, dir_out); break;
+    case KIND_REDBLUEDOORS: reset_env<KIND_REDBLUEDOORS>(e, env, obs, dir_out); break;
+    case KIND_GOTOOBJECT: reset_env<KIND_GOTOOBJECT>(e, env, obs, dir_out); break;
+    case KIND_PUTNEAR: reset_env<KIND_PUTNEAR>(e, env, obs, dir_out); break;
+    case KIND_MEMORY: reset_env<KIND_MEMORY>(e, env, obs, dir_out); break;
     default: reset_env<KIND_FOURROOMS>(e, env, obs, dir_out); break;
   }
 }
 // warp_reset body: phase 1 lane-per-env draws, phase 2 template copy + byte patches per environment
-struct ResetOut { int ax, ay, dir; };
+struct ResetOut { int ax, ay, dir, tx, ty; uint32_t aux; };
 template <int KIND>
 static void warp_reset_k(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOut out[32]) {
   Params &p = e->p;
@@ -90,7 +101,11 @@ static void warp_reset_k(Emu *e, unsigned pend, int tile, uint32_t *gtile, Reset
       draw_level<KIND>(p, r, Ls[lane]);
       store_rng(&e->rng[env], r);
     }
-  for (int lane = 0; lane < 32; ++lane) { out[lane].ax = Ls[lane].ax; out[lane].ay = Ls[lane].ay; out[lane].dir = Ls[lane].adir; }
+  for (int lane = 0; lane < 32; ++lane) {
+    out[lane].ax = Ls[lane].ax; out[lane].ay = Ls[lane].ay; out[lane].dir = Ls[lane].adir;
+    const bool pf = KIND >= KIND_GOTODOOR;  // kinds with a post-filter: their targets ride in Level::ov
+    out[lane].tx = pf ? level_tx(Ls[lane]) : 0; out[lane].ty = pf ? level_ty(Ls[lane]) : 0; out[lane].aux = pf ? level_aux(Ls[lane]) : 0u;
+  }
   while (pend) {
     const int src = __ffs(pend) - 1;
     pend &= pend - 1;
@@ -121,7 +136,27 @@ static void warp_reset(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOu
     case KIND_MULTIROOM: warp_reset_k<KIND_MULTIROOM>(e, pend, tile, gtile, out); break;
     case KIND_LOCKEDROOM: warp_reset_k<KIND_LOCKEDROOM>(e, pend, tile, gtile, out); break;
     case KIND_PLAYGROUND: warp_reset_k<KIND_PLAYGROUND>(e, pend, tile, gtile, out); break;
+    case KIND_GOTODOOR: warp_reset_k<KIND_GOTODOOR>(e, pend, tile, gtile, out); break;
+    case KIND_FETCH: warp_reset_k<KIND_FETCH>(e, pend, tile, gtile, out); break;
+    case KIND_REDBLUEDOORS: warp_reset_k<KIND_REDBLUEDOORS>(e, pend, tile, gtile, out); break;
+    case KIND_GOTOOBJECT: warp_reset_k<KIND_GOTOOBJECT>(e, pend, tile, gtile, out); break;
+    case KIND_PUTNEAR: warp_reset_k<KIND_PUTNEAR>(e, pend, tile, gtile, out); break;
+    case KIND_MEMORY: warp_reset_k<KIND_MEMORY>(e, pend, tile, gtile, out); break;
     default: warp_reset_k<KIND_FOURROOMS>(e, pend, tile, gtile, out); break;
+  }
+}
+
+// the step post-filters (mg_postfilter.cuh) of the kinds that have one
+static int emu_pre_filter(int kind, int action) { return kind == KIND_MEMORY ? pre_filter<KIND_MEMORY>(action) : action; }
+static PostOut emu_post_filter(int kind, const PostIn &in, uint32_t terminated) {
+  switch (kind) {
+    case KIND_GOTODOOR: return post_filter<KIND_GOTODOOR>(in, terminated);
+    case KIND_GOTOOBJECT: return post_filter<KIND_GOTOOBJECT>(in, terminated);
+    case KIND_FETCH: return post_filter<KIND_FETCH>(in, terminated);
+    case KIND_PUTNEAR: return post_filter<KIND_PUTNEAR>(in, terminated);
+    case KIND_MEMORY: return post_filter<KIND_MEMORY>(in, terminated);
+    case KIND_REDBLUEDOORS: return post_filter<KIND_REDBLUEDOORS>(in, terminated);
+    default: { PostOut o = {terminated, POST_KEEP}; return o; }
   }
 }
 
@@ -137,7 +172,7 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
   for (int tile = 0; tile < p.n_tiles; ++tile) {
     if (!WIN) memcpy(gtile.data(), p.grid + (size_t)tile * g.wpe * 32, (size_t)g.wpe * 128);  // the TMA bulk load
     const bool full = (tile + 1) * TILE <= p.n_envs;
-    int ax[32], ay[32], dir[32], steps[32];
+    int ax[32], ay[32], dir[32], steps[32], tx[32], ty[32];
     uint32_t flags[32], carry[32], terminated[32] = {0}, truncated[32] = {0};
     double reward[32] = {0};
     bool active[32], fresh[32] = {false};
@@ -147,6 +182,7 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
       active[lane] = env < p.n_envs;
       rec[lane] = p.agent[env];
       ax[lane] = rec[lane].x & 0xFF; ay[lane] = (rec[lane].x >> 8) & 0xFF; dir[lane] = rec[lane].y & 3;
+      tx[lane] = (rec[lane].x >> 16) & 0xFF; ty[lane] = rec[lane].x >> 24;  // post-filter targets; aux rides in flags >> 8
       flags[lane] = rec[lane].y >> 8; carry[lane] = rec[lane].z; steps[lane] = (int)rec[lane].w;
     }
     if (stepping && p.mode == AUTORESET_NEXT_STEP) {
@@ -156,13 +192,17 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
         ResetOut ro[32];
         warp_reset(e, pend, tile, WIN ? nullptr : gtile.data(), ro);
         for (int lane = 0; lane < 32; ++lane)
-          if (fresh[lane]) { ax[lane] = ro[lane].ax; ay[lane] = ro[lane].ay; dir[lane] = ro[lane].dir; carry[lane] = 0; steps[lane] = 0; flags[lane] &= ~FLAG_PENDING; }
+          if (fresh[lane]) {
+            ax[lane] = ro[lane].ax; ay[lane] = ro[lane].ay; dir[lane] = ro[lane].dir; carry[lane] = 0; steps[lane] = 0; flags[lane] &= ~FLAG_PENDING;
+            tx[lane] = ro[lane].tx; ty[lane] = ro[lane].ty; flags[lane] = (flags[lane] & 0xFFu) | (ro[lane].aux << 8);
+          }
       }
     }
     for (int lane = 0; lane < 32; ++lane) {
       if (!(stepping && !fresh[lane])) continue;
       const int env = tile * TILE + lane;
-      const int action = active[lane] ? actions[env] : A_DONE;
+      const int action = emu_pre_filter(p.kind, active[lane] ? actions[env] : A_DONE);
+      const uint32_t carry_before = carry[lane];
       const uint32_t *base = gtile.data() + lane;
       steps[lane] += 1;
       int fx, fy;
@@ -187,6 +227,27 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
         gb[grid_word(g, env, rw) * 4 + (fx & 3)] = (uint8_t)so.newc;
         gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)so.newc;
       }
+      if (p.kind >= KIND_GOTODOOR) {  // step post-filter
+        PostIn in;
+        in.action = action; in.ax = ax[lane]; in.ay = ay[lane]; in.dir = dir[lane];
+        in.carry_before = carry_before; in.carry = carry[lane];
+        in.tx = tx[lane]; in.ty = ty[lane]; in.aux = flags[lane] >> 8;
+        in.red_before = in.blue_before = in.red_after = in.blue_after = false;
+        if (p.kind == KIND_REDBLUEDOORS) {  // a door changes only as the front cell of a toggle
+          const int xl = g.H / 2, xr = g.H / 2 + g.H - 1;
+          in.red_after = (gb[cell_byte_R(g, env, xl, tx[lane])] & 15u) == T_DOOR;
+          in.blue_after = (gb[cell_byte_R(g, env, xr, ty[lane])] & 15u) == T_DOOR;
+          in.red_before = (fx == xl && fy == tx[lane]) ? (fc & 15u) == T_DOOR : in.red_after;
+          in.blue_before = (fx == xr && fy == ty[lane]) ? (fc & 15u) == T_DOOR : in.blue_after;
+        }
+        const PostOut po = emu_post_filter(p.kind, in, terminated[lane]);
+        terminated[lane] = po.terminated;
+        if (po.reward == POST_ZERO) reward[lane] = 0.0;
+        if (po.reward == POST_REWARD) {
+          if (steps[lane] <= p.max_steps) reward[lane] = p.reward_lut[steps[lane]];
+          else { volatile double q = (double)steps[lane] / (double)p.max_steps; volatile double m = 0.9 * q; reward[lane] = 1.0 - m; }
+        }
+      }
       truncated[lane] = steps[lane] >= p.max_steps;
       const bool done = (terminated[lane] | truncated[lane]) != 0;
       if (p.mode == AUTORESET_NEXT_STEP) flags[lane] = done ? (flags[lane] | FLAG_PENDING) : (flags[lane] & ~FLAG_PENDING);
@@ -199,7 +260,10 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
         ResetOut ro[32];
         warp_reset(e, pend, tile, WIN ? nullptr : gtile.data(), ro);
         for (int lane = 0; lane < 32; ++lane)
-          if (again[lane]) { ax[lane] = ro[lane].ax; ay[lane] = ro[lane].ay; dir[lane] = ro[lane].dir; carry[lane] = 0; steps[lane] = 0; }
+          if (again[lane]) {
+            ax[lane] = ro[lane].ax; ay[lane] = ro[lane].ay; dir[lane] = ro[lane].dir; carry[lane] = 0; steps[lane] = 0;
+            tx[lane] = ro[lane].tx; ty[lane] = ro[lane].ty; flags[lane] = (flags[lane] & 0xFFu) | (ro[lane].aux << 8);
+          }
       }
     }
     if (obs) {
@@ -233,7 +297,7 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
       const int env = tile * TILE + lane;
       if (stepping) {
         uint4 r = rec[lane];
-        r.x = (uint32_t)ax[lane] | ((uint32_t)ay[lane] << 8);
+        r.x = (uint32_t)ax[lane] | ((uint32_t)ay[lane] << 8) | ((uint32_t)tx[lane] << 16) | ((uint32_t)ty[lane] << 24);
         r.y = (uint32_t)dir[lane] | (flags[lane] << 8);
         r.z = carry[lane]; r.w = (uint32_t)steps[lane];
         p.agent[env] = r;
@@ -284,6 +348,12 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
         case KIND_MULTIROOM: e->tmpl[w] = level_word<KIND_MULTIROOM>(p, L, w); break;
         case KIND_LOCKEDROOM: e->tmpl[w] = level_word<KIND_LOCKEDROOM>(p, L, w); break;
         case KIND_PLAYGROUND: e->tmpl[w] = level_word<KIND_PLAYGROUND>(p, L, w); break;
+        case KIND_GOTODOOR: e->tmpl[w] = level_word<KIND_GOTODOOR>(p, L, w); break;
+        case KIND_FETCH: e->tmpl[w] = level_word<KIND_FETCH>(p, L, w); break;
+        case KIND_REDBLUEDOORS: e->tmpl[w] = level_word<KIND_REDBLUEDOORS>(p, L, w); break;
+        case KIND_GOTOOBJECT: e->tmpl[w] = level_word<KIND_GOTOOBJECT>(p, L, w); break;
+        case KIND_PUTNEAR: e->tmpl[w] = level_word<KIND_PUTNEAR>(p, L, w); break;
+        case KIND_MEMORY: e->tmpl[w] = level_word<KIND_MEMORY>(p, L, w); break;
         default: e->tmpl[w] = level_word<KIND_FOURROOMS>(p, L, w); break;
       }
     p.tmpl = e->tmpl.data();
