@@ -59,13 +59,14 @@ constexpr uint32_t CODE_LAVA = T_LAVA | (C_RED << 4);
 constexpr uint32_t FLAG_PENDING = 2u;  // episode ended last step (SyncVectorEnv._autoreset_envs[i], NEXT_STEP)
 
 enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS = 3, KIND_LAVAGAP = 4, KIND_DISTSHIFT = 5,
-             KIND_MULTIROOM = 6, KIND_COUNT = 7,  // kinds mg_create accepts (the kernels are instantiated for these)
-             // the generators below exist in mg_levels.cuh and are checked against the oracle on the
-             // CPU (tests/test_host_emu.py); K1 / K2 are not instantiated for them yet and mg_create rejects them
+             KIND_MULTIROOM = 6,
+             // the generators (mg_levels.cuh) and step post-filters (mg_postfilter.cuh) of
+             // the kinds below exist and are checked against the oracle on the CPU (tests/test_oracle_next.py); K1 / K2
+             // are not instantiated for them yet and mg_create rejects them (KIND_COUNT)
              KIND_LOCKEDROOM = 7, KIND_PLAYGROUND = 8,
-             // generator + step post-filter (mg_postfilter.cuh); same status as the two above
              KIND_GOTODOOR = 9, KIND_FETCH = 10, KIND_REDBLUEDOORS = 11, KIND_GOTOOBJECT = 12, KIND_PUTNEAR = 13,
              KIND_MEMORY = 14 };
+constexpr int KIND_COUNT = 7;  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
 enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
 
 // (type, colour, state) -> cell code. None/unseen/agent all mean "no object" (WorldObj.decode,
