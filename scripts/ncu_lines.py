@@ -56,7 +56,7 @@ print("matched", matched)
 files = {}
 tot = sum(agg.values())
 print("total per tile", tot / n_tiles)
-for (f, l), c in agg.most_common(45):
+for (f, l), c in agg.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 45):
     if f not in files:
         pth = os.path.join(root, "minigrid_b200", "csrc", f)
         files[f] = open(pth).read().split("\n") if os.path.exists(pth) else None
