@@ -41,6 +41,15 @@ extern "C" {
 #define MG_KIND_LAVAGAP 4   /* envs/lavagap.py */
 #define MG_KIND_DISTSHIFT 5 /* envs/distshift.py */
 #define MG_KIND_MULTIROOM 6 /* envs/multiroom.py (up to 6 rooms) */
+#define MG_KIND_LOCKEDROOM 7 /* envs/lockedroom.py (square, 13 <= size <= 26) */
+#define MG_KIND_PLAYGROUND 8 /* envs/playground.py (19 x 19) */
+/* generator + step post-filter */
+#define MG_KIND_GOTODOOR 9      /* envs/gotodoor.py */
+#define MG_KIND_FETCH 10        /* envs/fetch.py: params {numObjs} */
+#define MG_KIND_REDBLUEDOORS 11 /* envs/redbluedoors.py: width = 2 * height */
+#define MG_KIND_GOTOOBJECT 12   /* envs/gotoobject.py: params {numObjs} */
+#define MG_KIND_PUTNEAR 13      /* envs/putnear.py: params {numObjs} */
+#define MG_KIND_MEMORY 14       /* envs/memory.py: params {random_length}; odd height */
 
 /* gymnasium.vector.AutoresetMode */
 #define MG_AUTORESET_NEXT_STEP 0
@@ -61,7 +70,7 @@ typedef struct mg_env mg_env;
  * (minigrid/__init__.py). kind/width/height/max_steps/see_through_walls are the constructor arguments;
  * params: EMPTY {random_start, start_x, start_y, start_dir}; CROSSING {num_crossings, obstacle_type
  * (9 lava | 2 wall)}; LAVAGAP {obstacle_type}; DISTSHIFT {strip2_row, start_x, start_y, start_dir};
- * MULTIROOM {minNumRooms, maxNumRooms, maxRoomSize}; others none.
+ * MULTIROOM {minNumRooms, maxNumRooms, maxRoomSize}; others (DOORKEY, FOURROOMS, LOCKEDROOM, PLAYGROUND) none.
  * device < 0 selects the current CUDA device. */
 int mg_create(int kind, int width, int height, int max_steps, int see_through_walls,
               const int32_t *params, int n_params, int64_t n_envs, int autoreset_mode, int device,

@@ -69,6 +69,19 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   if (max_steps < 1) return fail(MG_ERR_INVALID_ARG, "max_steps must be >= 1");
   if (n_envs < 1 || n_envs > (int64_t)1 << 30) return fail(MG_ERR_INVALID_ARG, "n_envs out of range");
   if (autoreset_mode < 0 || autoreset_mode > 2) return fail(MG_ERR_INVALID_ARG, "unknown autoreset mode");
+  if ((kind == MG_KIND_FETCH || kind == MG_KIND_GOTOOBJECT || kind == MG_KIND_PUTNEAR) &&
+      (n_params < 1 || params[0] < 1 || params[0] > 8))
+    return fail(MG_ERR_INVALID_ARG, "fetch / gotoobject / putnear need params {numObjs}, 1 <= numObjs <= 8");
+  if (kind == MG_KIND_GOTODOOR && (width < 5 || height < 5))
+    return fail(MG_ERR_INVALID_ARG, "gotodoor needs at least 5 x 5 (gotodoor.py:66)");
+  if (kind == MG_KIND_REDBLUEDOORS && (width != 2 * height || height < 4))
+    return fail(MG_ERR_INVALID_ARG, "redbluedoors is 2 size x size (redbluedoors.py:60-72)");
+  if (kind == MG_KIND_MEMORY && (height % 2 == 0 || height < 7 || width < 7))
+    return fail(MG_ERR_INVALID_ARG, "memory needs an odd height and at least 7 x 7 (memory.py:98)");
+  if (kind == MG_KIND_LOCKEDROOM && (width != height || width < 13))
+    return fail(MG_ERR_INVALID_ARG, "lockedroom needs a square grid of at least 13 x 13 (lockedroom.py:108-173)");
+  if (kind == MG_KIND_PLAYGROUND && (width != 19 || height != 19))
+    return fail(MG_ERR_INVALID_ARG, "playground is 19 x 19 (playground.py:16-25)");
   if (kind == MG_KIND_CROSSING && (width % 2 == 0 || height % 2 == 0))
     return fail(MG_ERR_INVALID_ARG, "crossing needs odd sizes (crossing.py:132)");
   int ndev = 0;

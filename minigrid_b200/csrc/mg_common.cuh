@@ -66,7 +66,7 @@ enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS
              KIND_LOCKEDROOM = 7, KIND_PLAYGROUND = 8,
              KIND_GOTODOOR = 9, KIND_FETCH = 10, KIND_REDBLUEDOORS = 11, KIND_GOTOOBJECT = 12, KIND_PUTNEAR = 13,
              KIND_MEMORY = 14 };
-constexpr int KIND_COUNT = 7;  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
+constexpr int KIND_COUNT = 15;  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
 enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
 
 // (type, colour, state) -> cell code. None/unseen/agent all mean "no object" (WorldObj.decode,

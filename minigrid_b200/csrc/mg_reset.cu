@@ -35,6 +35,10 @@ k_reset(Params p, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out) {
     uint4 rec;
     rec.x = (uint32_t)L.ax | ((uint32_t)L.ay << 8);
     rec.y = (uint32_t)L.adir;  // flags cleared: SyncVectorEnv.reset() clears _autoreset_envs
+    if (KIND >= KIND_GOTODOOR) {  // post-filter targets in the spare bits (mg_postfilter.cuh)
+      rec.x |= ((uint32_t)level_tx(L) << 16) | ((uint32_t)level_ty(L) << 24);
+      rec.y |= level_aux(L) << 16;
+    }
     rec.z = 0;  // carrying = None
     rec.w = 0;  // step_count = 0
     p.agent[env] = rec;
@@ -57,6 +61,14 @@ cudaError_t launch_reset(const Params &p, uint8_t *obs, int32_t *dir, cudaStream
     case KIND_LAVAGAP: k_reset<KIND_LAVAGAP><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
     case KIND_DISTSHIFT: k_reset<KIND_DISTSHIFT><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
     case KIND_MULTIROOM: k_reset<KIND_MULTIROOM><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_LOCKEDROOM: k_reset<KIND_LOCKEDROOM><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_PLAYGROUND: k_reset<KIND_PLAYGROUND><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_GOTODOOR: k_reset<KIND_GOTODOOR><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_FETCH: k_reset<KIND_FETCH><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_REDBLUEDOORS: k_reset<KIND_REDBLUEDOORS><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_GOTOOBJECT: k_reset<KIND_GOTOOBJECT><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_PUTNEAR: k_reset<KIND_PUTNEAR><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_MEMORY: k_reset<KIND_MEMORY><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
     default: k_reset<KIND_FOURROOMS><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
   }
   return cudaGetLastError();
@@ -79,6 +91,14 @@ cudaError_t launch_template(const Params &p, uint32_t *tmpl, cudaStream_t stream
     case KIND_LAVAGAP: k_template<KIND_LAVAGAP><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     case KIND_DISTSHIFT: k_template<KIND_DISTSHIFT><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     case KIND_MULTIROOM: k_template<KIND_MULTIROOM><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_LOCKEDROOM: k_template<KIND_LOCKEDROOM><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_PLAYGROUND: k_template<KIND_PLAYGROUND><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_GOTODOOR: k_template<KIND_GOTODOOR><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_FETCH: k_template<KIND_FETCH><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_REDBLUEDOORS: k_template<KIND_REDBLUEDOORS><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_GOTOOBJECT: k_template<KIND_GOTOOBJECT><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_PUTNEAR: k_template<KIND_PUTNEAR><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_MEMORY: k_template<KIND_MEMORY><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     default: k_template<KIND_FOURROOMS><<<blocks, 64, 0, stream>>>(p, tmpl); break;
   }
   return cudaGetLastError();

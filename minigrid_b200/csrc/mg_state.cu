@@ -63,7 +63,7 @@ __global__ void k_set_agent(Params p, const int32_t *__restrict__ agent, const u
   uint4 rec = p.agent[env];
   if (agent) {
     const int32_t *a = agent + (size_t)env * 6;
-    rec.x = (uint32_t)(a[0] & 0xFF) | ((uint32_t)(a[1] & 0xFF) << 8);
+    rec.x = (rec.x & 0xFFFF0000u) | (uint32_t)(a[0] & 0xFF) | ((uint32_t)(a[1] & 0xFF) << 8);  // keeps the post-filter targets
     rec.y = (rec.y & ~3u) | (uint32_t)(a[2] & 3);
     rec.z = a[3] >= 0 ? ((uint32_t)(a[3] & 15) | ((uint32_t)(a[4] & 7) << 4)) : 0u;
     rec.w = (uint32_t)a[5];

@@ -11,6 +11,7 @@
 #include "mg_obs.cuh"
 #include "mg_pcg64.cuh"
 #include "mg_transition.cuh"
+#include "mg_postfilter.cuh"
 
 namespace mg {
 
@@ -95,7 +96,7 @@ __device__ __forceinline__ int load_action(const void *actions, int dtype, int e
 // warp: the owner's drawn integers are broadcast, lane L copies words L, L+32, ... of the level template into HBM
 // (and into the staged tile when there is one), then the few cells that depend on the draw are re-evaluated and
 // written as bytes. Out of line: it is the rare path and must not cost the hot loop registers.
-struct ResetOut { int ax, ay, dir; };
+struct ResetOut { int ax, ay, dir, tx, ty; uint32_t aux; };  // tx, ty, aux: post-filter targets (0 for the other kinds)
 
 template <int KIND>
 __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int tile, uint32_t *gtile, int lane) {
@@ -107,9 +108,35 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
     draw_level<KIND>(p, r, L);
     store_rng(rr, r);
   }
-  const ResetOut out = {L.ax, L.ay, L.adir};
+  constexpr bool PF = has_post_filter<KIND>();
+  const ResetOut out = {L.ax, L.ay, L.adir, PF ? level_tx(L) : 0, PF ? level_ty(L) : 0, PF ? level_aux(L) : 0u};
   __syncwarp();
   uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(p.grid);
+  // Dense case (a synchronised truncation wave: under random actions nearly every env of a batch truncates in the
+  // same step): every pending lane fills ITS OWN env — template words (one broadcast load per word; in the tiled
+  // layout the 32 lanes' stores of a word index are one 128-byte line), then all patch cells of its own level —
+  // instead of the warp going through the environments one at a time.
+  constexpr int DENSE_RESET_MIN = 4;  // pending envs per tile from which the lane-parallel fill is used
+  if (__popc(pend) >= DENSE_RESET_MIN) {
+    if ((pend >> lane) & 1u) {
+      const int env = tile * TILE + lane;
+      for (int w = 0; w < g.wpe; ++w) {
+        const uint32_t word = __ldg(p.tmpl + w);
+        if (gtile) gtile[w * 32 + lane] = word;
+        p.grid[grid_word(g, env, w)] = word;
+      }
+      for (int share = 0; share < 32; ++share)  // patch_level hands out the cells in 32 shares: take them all
+        patch_level<KIND>(p, L, share, [&](int x, int y) {
+          const uint8_t code = (uint8_t)cell_of<KIND>(p, L, x, y);
+          const int rw = r_word(g, x, y), cw = c_word(g, x, y);
+          if (gtile) { sb[((size_t)rw * 32 + lane) * 4 + (x & 3)] = code; sb[((size_t)cw * 32 + lane) * 4 + (y & 3)] = code; }
+          gb[grid_word(g, env, rw) * 4 + (x & 3)] = code;
+          gb[grid_word(g, env, cw) * 4 + (y & 3)] = code;
+        });
+    }
+    __syncwarp();
+    return out;
+  }
   while (pend) {
     const int src = __ffs(pend) - 1;
     pend &= pend - 1;
@@ -121,7 +148,7 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
     B.e = __shfl_sync(0xFFFFFFFFu, L.e, src); B.f = __shfl_sync(0xFFFFFFFFu, L.f, src);
     B.rv = __shfl_sync(0xFFFFFFFFu, L.rv, src); B.rh = __shfl_sync(0xFFFFFFFFu, L.rh, src);
     B.ov = __shfl_sync(0xFFFFFFFFu, L.ov, src); B.oh = __shfl_sync(0xFFFFFFFFu, L.oh, src);
-    if (KIND == KIND_MULTIROOM || KIND == KIND_PLAYGROUND) {
+    if (KIND == KIND_MULTIROOM || KIND == KIND_PLAYGROUND || KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR) {
       const unsigned long long lo = __shfl_sync(0xFFFFFFFFu, (unsigned long long)L.rm03, src);
       const unsigned long long hi = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(L.rm03 >> 64), src);
       B.rm03 = ((u128)hi << 64) | lo;
@@ -150,7 +177,7 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
 // processes the current one, so HBM transfers overlap compute instead of alternating with it in GPU-wide bursts.
 template <int KIND, int VIS, int MODE>
 __global__ void __launch_bounds__(MODE == MODE_TILED2 ? 640 : 1024, 1)  // one CTA per SM: <= 20 warps (96 regs) or <= 32 (64 regs)
-k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
+k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
        int32_t *__restrict__ dir_out, double *__restrict__ reward_out, uint8_t *__restrict__ term_out,
        uint8_t *__restrict__ trunc_out, int obs_tma_ok) {
   constexpr int NBUF = (MODE == MODE_TILED2) ? 2 : 1;
@@ -275,6 +302,8 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     uint32_t flags = rec.y >> 8;
     uint32_t carry = rec.z;
     int steps = (int)rec.w;
+    constexpr bool PF = has_post_filter<KIND>();  // the record's spare bits hold the filter's targets
+    int tx = PF ? (int)((rec.x >> 16) & 0xFFu) : 0, ty = PF ? (int)(rec.x >> 24) : 0;
 
     if (!WIN) {
       mbar_wait(bar0 + 8u * (uint32_t)b, (phase >> b) & 1u);
@@ -300,7 +329,10 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       if (pend) {
         wrote = true;
         const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
-        if (fresh) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; flags &= ~FLAG_PENDING; }
+        if (fresh) {
+          ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; flags &= ~FLAG_PENDING;
+          if (PF) { tx = ro.tx; ty = ro.ty; flags = (flags & 0xFFu) | (ro.aux << 8); }
+        }
       }
     }
     // LAYOUT_WINDOW: the 7 lines of the view are 224 contiguous bytes of array R (facing +-x) or C (+-y), one bulk
@@ -340,7 +372,9 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       uint32_t fc;
       if (WIN) fc = fc_win;
       else fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
-      const StepOut so = transition(action, fc, fx, fy, ax, ay, dir, carry);
+      const uint32_t carry_before = carry;
+      const int act = pre_filter<KIND>(action);
+      const StepOut so = transition(act, fc, fx, fy, ax, ay, dir, carry);
       const uint32_t newc = so.newc;
       terminated = so.terminated;
       if (so.goal)  // _reward(), minigrid_env.py:240-245: host-computed table, never an FMA
@@ -365,6 +399,34 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
           gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)newc;
         }
       }
+      if (PF) {  // the env's own step(): a few predicates on top of MiniGridEnv.step (mg_postfilter.cuh)
+        PostIn in;
+        in.action = act; in.ax = ax; in.ay = ay; in.dir = dir;
+        in.carry_before = carry_before; in.carry = carry;
+        in.tx = tx; in.ty = ty; in.aux = flags >> 8;
+        in.red_before = in.blue_before = in.red_after = in.blue_after = false;
+        if (KIND == KIND_REDBLUEDOORS) {  // a door changes only as the front cell of a toggle
+          const int xl = g.H / 2, xr = g.H / 2 + g.H - 1;
+          uint32_t cr, cb;
+          if (!WIN) {
+            cr = (tile_word<true>(base, r_word(g, xl, tx)) >> (8 * (xl & 3))) & 0xFFu;
+            cb = (tile_word<true>(base, r_word(g, xr, ty)) >> (8 * (xr & 3))) & 0xFFu;
+          } else {
+            cr = gb[grid_word(g, env, r_word(g, xl, tx)) * 4 + (xl & 3)];
+            cb = gb[grid_word(g, env, r_word(g, xr, ty)) * 4 + (xr & 3)];
+          }
+          in.red_after = (cr & 15u) == T_DOOR;
+          in.blue_after = (cb & 15u) == T_DOOR;
+          in.red_before = (fx == xl && fy == tx) ? (fc & 15u) == T_DOOR : in.red_after;
+          in.blue_before = (fx == xr && fy == ty) ? (fc & 15u) == T_DOOR : in.blue_after;
+        }
+        const PostOut po = post_filter<KIND>(in, terminated);
+        terminated = po.terminated;
+        if (po.reward == POST_ZERO) reward = 0.0;
+        if (po.reward == POST_REWARD)
+          reward = steps <= p.max_steps ? p.reward_lut[steps]
+                                        : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
+      }
       truncated = steps >= p.max_steps;
       const bool done = (terminated | truncated) != 0;
       if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
@@ -376,7 +438,10 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
       if (pend) {
         wrote = true;
         const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
-        if (again) { ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; }
+        if (again) {
+          ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0;
+          if (PF) { tx = ro.tx; ty = ro.ty; flags = (flags & 0xFFu) | (ro.aux << 8); }
+        }
         if (WIN) {  // the regenerated levels invalidate the staged windows
           load_window(dir, true);
           wait_window();
@@ -420,6 +485,7 @@ k_step(Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__res
     if (active) {
       if (stepping) {
         rec.x = (uint32_t)ax | ((uint32_t)ay << 8);
+        if (PF) rec.x |= ((uint32_t)tx << 16) | ((uint32_t)ty << 24);
         rec.y = (uint32_t)dir | (flags << 8);
         rec.z = carry;
         rec.w = (uint32_t)steps;
@@ -462,6 +528,14 @@ static StepKernel pick_kind(int kind) {
     case KIND_LAVAGAP: return (StepKernel)k_step<KIND_LAVAGAP, VIS, MODE>;
     case KIND_DISTSHIFT: return (StepKernel)k_step<KIND_DISTSHIFT, VIS, MODE>;
     case KIND_MULTIROOM: return (StepKernel)k_step<KIND_MULTIROOM, VIS, MODE>;
+    case KIND_LOCKEDROOM: return (StepKernel)k_step<KIND_LOCKEDROOM, VIS, MODE>;
+    case KIND_PLAYGROUND: return (StepKernel)k_step<KIND_PLAYGROUND, VIS, MODE>;
+    case KIND_GOTODOOR: return (StepKernel)k_step<KIND_GOTODOOR, VIS, MODE>;
+    case KIND_FETCH: return (StepKernel)k_step<KIND_FETCH, VIS, MODE>;
+    case KIND_REDBLUEDOORS: return (StepKernel)k_step<KIND_REDBLUEDOORS, VIS, MODE>;
+    case KIND_GOTOOBJECT: return (StepKernel)k_step<KIND_GOTOOBJECT, VIS, MODE>;
+    case KIND_PUTNEAR: return (StepKernel)k_step<KIND_PUTNEAR, VIS, MODE>;
+    case KIND_MEMORY: return (StepKernel)k_step<KIND_MEMORY, VIS, MODE>;
     default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, MODE>;
   }
 }

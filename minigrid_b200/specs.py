@@ -11,6 +11,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 
 KIND_EMPTY, KIND_DOORKEY, KIND_CROSSING, KIND_FOURROOMS, KIND_LAVAGAP, KIND_DISTSHIFT, KIND_MULTIROOM = 0, 1, 2, 3, 4, 5, 6
+KIND_LOCKEDROOM, KIND_PLAYGROUND = 7, 8
+KIND_GOTODOOR, KIND_FETCH, KIND_REDBLUEDOORS, KIND_GOTOOBJECT, KIND_PUTNEAR, KIND_MEMORY = 9, 10, 11, 12, 13, 14
 T_WALL, T_LAVA = 2, 9
 
 
@@ -69,6 +71,50 @@ def multiroom(minNumRooms, maxNumRooms, maxRoomSize=10, max_steps=None):
                    "traverse the rooms to get to the goal")
 
 
+def lockedroom(size=19, max_steps=None):
+    """envs/lockedroom.py:74-90 (max_steps = 10 * size). The mission names the drawn colours; it is not produced here."""
+    return EnvSpec(KIND_LOCKEDROOM, size, size, max_steps or 10 * size, False, (),
+                   "get the {lockedroom_color} key from the {keyroom_color} room, unlock the {door_color} door and go to the goal")
+
+
+def playground(max_steps=100):
+    """envs/playground.py:16-31 (19 x 19, max_steps 100, empty mission)."""
+    return EnvSpec(KIND_PLAYGROUND, 19, 19, max_steps, False, (), "")
+
+
+def gotodoor(size=5, max_steps=None):
+    """envs/gotodoor.py:65-86. The mission names the target door's colour; it is not produced here."""
+    return EnvSpec(KIND_GOTODOOR, size, size, max_steps or 4 * size * size, True, (), "go to the {color} door")
+
+
+def fetch(size=8, numObjs=3, max_steps=None):
+    """envs/fetch.py:72-103."""
+    return EnvSpec(KIND_FETCH, size, size, max_steps or 5 * size * size, True, (numObjs,), "{syntax} {color} {type}")
+
+
+def redbluedoors(size=8, max_steps=None):
+    """envs/redbluedoors.py:60-72: the grid is 2 * size wide."""
+    return EnvSpec(KIND_REDBLUEDOORS, 2 * size, size, max_steps or 20 * size * size, False, (),
+                   "open the red door then the blue door")
+
+
+def gotoobject(size=6, numObjs=2, max_steps=None):
+    """envs/gotoobject.py:66-90."""
+    return EnvSpec(KIND_GOTOOBJECT, size, size, max_steps or 5 * size * size, True, (numObjs,), "go to the {color} {type}")
+
+
+def putnear(size=6, numObjs=2, max_steps=None):
+    """envs/putnear.py:66-92 (max_steps = 5 * size)."""
+    return EnvSpec(KIND_PUTNEAR, size, size, max_steps or 5 * size, True, (numObjs,),
+                   "put the {move_color} {move_type} near the {target_color} {target_type}")
+
+
+def memory(size=8, random_length=False, max_steps=None):
+    """envs/memory.py:67-88."""
+    return EnvSpec(KIND_MEMORY, size, size, max_steps or 5 * size * size, False, (int(random_length),),
+                   "go to the matching object at the end of the hallway")
+
+
 REGISTRY = {
     # BASELINE.json configs
     "MiniGrid-Empty-5x5-v0": empty(size=5),
@@ -102,6 +148,28 @@ REGISTRY = {
     "MiniGrid-MultiRoom-N4-S5-v0": multiroom(6, 6, 5),
     "MiniGrid-MultiRoom-N4-S5-v1": multiroom(4, 4, 5),
     "MiniGrid-MultiRoom-N6-v0": multiroom(6, 6),
+    # __init__.py:312-318, :516-522
+    "MiniGrid-LockedRoom-v0": lockedroom(),
+    "MiniGrid-Playground-v0": playground(),
+    # generator + step post-filter: __init__.py:218-236, 241-250, 196-208, 527-537, 541-551, 323-357
+    "MiniGrid-GoToDoor-5x5-v0": gotodoor(5),
+    "MiniGrid-GoToDoor-6x6-v0": gotodoor(6),
+    "MiniGrid-GoToDoor-8x8-v0": gotodoor(8),
+    "MiniGrid-GoToObject-6x6-N2-v0": gotoobject(6, 2),
+    "MiniGrid-GoToObject-8x8-N2-v0": gotoobject(8, 2),
+    "MiniGrid-Fetch-5x5-N2-v0": fetch(5, 2),
+    "MiniGrid-Fetch-6x6-N2-v0": fetch(6, 2),
+    "MiniGrid-Fetch-8x8-N3-v0": fetch(8, 3),
+    "MiniGrid-PutNear-6x6-N2-v0": putnear(6, 2),
+    "MiniGrid-PutNear-8x8-N3-v0": putnear(8, 3),
+    "MiniGrid-RedBlueDoors-6x6-v0": redbluedoors(6),
+    "MiniGrid-RedBlueDoors-8x8-v0": redbluedoors(8),
+    "MiniGrid-MemoryS17Random-v0": memory(17, True),
+    "MiniGrid-MemoryS13Random-v0": memory(13, True),
+    "MiniGrid-MemoryS13-v0": memory(13),
+    "MiniGrid-MemoryS11-v0": memory(11),
+    "MiniGrid-MemoryS9-v0": memory(9),
+    "MiniGrid-MemoryS7-v0": memory(7),
 }
 
 

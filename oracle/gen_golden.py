@@ -42,8 +42,6 @@ ROLLOUTS = {  # id -> (N, T, seed)
     "MiniGrid-DistShift2-v0": (4, 300, 23),
     "MiniGrid-MultiRoom-N2-S4-v0": (6, 130, 29),
     "MiniGrid-MultiRoom-N6-v0": (4, 260, 37),
-}
-NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist yet: next_rollout_<id>.npz (oracle only)
     "MiniGrid-LockedRoom-v0": (4, 420, 41),
     "MiniGrid-Playground-v0": (4, 330, 43),
     "MiniGrid-GoToDoor-5x5-v0": (6, 260, 47),
@@ -55,6 +53,8 @@ NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist 
     "MiniGrid-PutNear-8x8-N3-v0": (8, 300, 73),
     "MiniGrid-MemoryS13Random-v0": (6, 600, 79),
     "MiniGrid-MemoryS7-v0": (6, 400, 83),
+}
+NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist yet: next_rollout_<id>.npz (oracle only)
     "MiniGrid-Dynamic-Obstacles-Random-6x6-v0": (8, 400, 89),
     "MiniGrid-Dynamic-Obstacles-8x8-v0": (8, 500, 97),
 }

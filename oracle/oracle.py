@@ -45,37 +45,37 @@ ENV_SPECS = {
     "MiniGrid-MultiRoom-N2-S4-v0": ("multiroom", 25, 25, 40, False, [2, 2, 4]),
     "MiniGrid-MultiRoom-N4-S5-v0": ("multiroom", 25, 25, 120, False, [6, 6, 5]),
     "MiniGrid-MultiRoom-N6-v0": ("multiroom", 25, 25, 120, False, [6, 6, 10]),
-}
-
-# SURVEY 8(f-1) generators restated ahead of their device kernels: the oracle and its fixtures exist, the product does
-# not register these ids yet (lockedroom.py:74-90 / __init__.py:312-318, playground.py:16-25 / __init__.py:516-522)
-NEXT_SPECS = {
     "MiniGrid-LockedRoom-v0": ("lockedroom", 19, 19, 190, False, []),
     "MiniGrid-Playground-v0": ("playground", 19, 19, 100, False, []),
-    # SURVEY 8(f-2), first of the step post-filters: gotodoor.py:65-86 (4 * size^2 steps, see_through_walls=True), __init__.py:218-236
     "MiniGrid-GoToDoor-5x5-v0": ("gotodoor", 5, 5, 100, True, []),
     "MiniGrid-GoToDoor-6x6-v0": ("gotodoor", 6, 6, 144, True, []),
     "MiniGrid-GoToDoor-8x8-v0": ("gotodoor", 8, 8, 256, True, []),
-    # fetch.py:72-103 (5 * size^2 steps, see_through_walls=True), __init__.py:196-208; params {numObjs}
     "MiniGrid-Fetch-5x5-N2-v0": ("fetch", 5, 5, 125, True, [2]),
     "MiniGrid-Fetch-6x6-N2-v0": ("fetch", 6, 6, 180, True, [2]),
     "MiniGrid-Fetch-8x8-N3-v0": ("fetch", 8, 8, 320, True, [3]),
-    # redbluedoors.py:60-72 (2 size x size, 20 * size^2 steps), __init__.py:541-551
     "MiniGrid-RedBlueDoors-6x6-v0": ("redbluedoors", 12, 6, 720, False, []),
     "MiniGrid-RedBlueDoors-8x8-v0": ("redbluedoors", 16, 8, 1280, False, []),
-    # gotoobject.py:66-90 (size 6, numObjs 2, 5 * size^2 steps, see_through_walls=True), __init__.py:241-250; params {numObjs}
     "MiniGrid-GoToObject-6x6-N2-v0": ("gotoobject", 6, 6, 180, True, [2]),
     "MiniGrid-GoToObject-8x8-N2-v0": ("gotoobject", 8, 8, 320, True, [2]),
-    # putnear.py:66-92 (size 6, numObjs 2, 5 * size steps, see_through_walls=True), __init__.py:527-537; params {numObjs}
     "MiniGrid-PutNear-6x6-N2-v0": ("putnear", 6, 6, 30, True, [2]),
     "MiniGrid-PutNear-8x8-N3-v0": ("putnear", 8, 8, 40, True, [3]),
-    # memory.py:67-88 (5 * size^2 steps, see_through_walls=False), __init__.py:323-357; params {random_length}
     "MiniGrid-MemoryS17Random-v0": ("memory", 17, 17, 1445, False, [1]),
     "MiniGrid-MemoryS13Random-v0": ("memory", 13, 13, 845, False, [1]),
     "MiniGrid-MemoryS13-v0": ("memory", 13, 13, 845, False, [0]),
     "MiniGrid-MemoryS11-v0": ("memory", 11, 11, 605, False, [0]),
     "MiniGrid-MemoryS9-v0": ("memory", 9, 9, 405, False, [0]),
     "MiniGrid-MemoryS7-v0": ("memory", 7, 7, 245, False, [0]),
+}
+
+# SURVEY 8(f-1) generators restated ahead of their device kernels: the oracle and its fixtures exist, the product does
+# not register these ids yet (lockedroom.py:74-90 / __init__.py:312-318, playground.py:16-25 / __init__.py:516-522)
+NEXT_SPECS = {
+    # SURVEY 8(f-2), first of the step post-filters: gotodoor.py:65-86 (4 * size^2 steps, see_through_walls=True), __init__.py:218-236
+    # fetch.py:72-103 (5 * size^2 steps, see_through_walls=True), __init__.py:196-208; params {numObjs}
+    # redbluedoors.py:60-72 (2 size x size, 20 * size^2 steps), __init__.py:541-551
+    # gotoobject.py:66-90 (size 6, numObjs 2, 5 * size^2 steps, see_through_walls=True), __init__.py:241-250; params {numObjs}
+    # putnear.py:66-92 (size 6, numObjs 2, 5 * size steps, see_through_walls=True), __init__.py:527-537; params {numObjs}
+    # memory.py:67-88 (5 * size^2 steps, see_through_walls=False), __init__.py:323-357; params {random_length}
     # dynamicobstacles.py:72-105 (4 * size^2 steps, see_through_walls=True), __init__.py:117-153;
     # params {n_obstacles, random_start, start_x, start_y, start_dir}
     "MiniGrid-Dynamic-Obstacles-5x5-v0": ("dynobstacles", 5, 5, 100, True, [2, 0, 1, 1, 0]),

@@ -106,6 +106,27 @@ static void warp_reset_k(Emu *e, unsigned pend, int tile, uint32_t *gtile, Reset
     const bool pf = KIND >= KIND_GOTODOOR;  // kinds with a post-filter: their targets ride in Level::ov
     out[lane].tx = pf ? level_tx(Ls[lane]) : 0; out[lane].ty = pf ? level_ty(Ls[lane]) : 0; out[lane].aux = pf ? level_aux(Ls[lane]) : 0u;
   }
+  if (__builtin_popcount(pend) >= 4) {  // DENSE_RESET_MIN: every pending lane fills its own env
+    uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(p.grid);
+    for (int lane = 0; lane < 32; ++lane) {
+      if (!((pend >> lane) & 1u)) continue;
+      const Level &L = Ls[lane];
+      const int env = tile * TILE + lane;
+      for (int w = 0; w < g.wpe; ++w) {
+        if (gtile) gtile[w * 32 + lane] = e->tmpl[w];
+        p.grid[grid_word(g, env, w)] = e->tmpl[w];
+      }
+      for (int share = 0; share < 32; ++share)
+        patch_level<KIND>(p, L, share, [&](int x, int y) {
+          const uint8_t code = (uint8_t)cell_of<KIND>(p, L, x, y);
+          const int rw = r_word(g, x, y), cw = c_word(g, x, y);
+          if (gtile) { sb[((size_t)rw * 32 + lane) * 4 + (x & 3)] = code; sb[((size_t)cw * 32 + lane) * 4 + (y & 3)] = code; }
+          gb[grid_word(g, env, rw) * 4 + (x & 3)] = code;
+          gb[grid_word(g, env, cw) * 4 + (y & 3)] = code;
+        });
+    }
+    return;
+  }
   while (pend) {
     const int src = __ffs(pend) - 1;
     pend &= pend - 1;

@@ -31,7 +31,7 @@ def test_create_rejects_bad_arguments_without_device_work():
 
     L = _lib.load()
     h = C.c_void_p()
-    assert L.mg_create(9, 8, 8, 100, 0, None, 0, 4, 0, 0, C.byref(h)) == -1
+    assert L.mg_create(99, 8, 8, 100, 0, None, 0, 4, 0, 0, C.byref(h)) == -1
     assert b"kind" in L.mg_last_error()
     assert L.mg_create(0, 40, 8, 100, 0, None, 0, 4, 0, 0, C.byref(h)) == -1
     assert L.mg_create(2, 8, 8, 100, 0, None, 0, 4, 0, 0, C.byref(h)) == -1  # crossing needs odd sizes
@@ -67,7 +67,7 @@ def test_spec_tables_agree():
     from minigrid_b200 import specs
     from oracle.oracle import ENV_SPECS
 
-    kinds = ["empty", "doorkey", "crossing", "fourrooms", "lavagap", "distshift", "multiroom"]
+    kinds = ["empty", "doorkey", "crossing", "fourrooms", "lavagap", "distshift", "multiroom", "lockedroom", "playground", "gotodoor", "fetch", "redbluedoors", "gotoobject", "putnear", "memory"]
     for env_id, (kind, w, h, ms, st, prm) in ENV_SPECS.items():
         s = specs.get(env_id)
         assert (kinds[s.kind], s.width, s.height, s.max_steps, s.see_through_walls) == (kind, w, h, ms, st), env_id

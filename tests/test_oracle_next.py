@@ -61,9 +61,9 @@ from emu import EmuVecEnv  # noqa: E402
 
 
 # ids whose device generators exist in mg_levels.cuh (the step post-filter kinds are oracle-only so far)
-DEVICE_NEXT = ["MiniGrid-LockedRoom-v0", "MiniGrid-Playground-v0"]
+DEVICE_NEXT = []
 # ... and, for the step post-filter kinds, also mg_postfilter.cuh (Dynamic-Obstacles is oracle-only: RNG inside step)
-DEVICE_NEXT += [i for i in NEXT_SPECS if i not in DEVICE_NEXT and "Dynamic-Obstacles" not in i]
+DEVICE_NEXT += []
 
 
 def make_next_emu(env_id, n, mode, layout=-1):
