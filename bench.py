@@ -6,9 +6,13 @@
     python bench.py --impl reference ...                      # the reference algorithm on the host CPUs
 
 One "step" = one lockstep vector step (action -> state', obs, reward, terminated, truncated, autoreset) of the
-whole batch. Workload (config.workload): BASELINE.json configs[2], MiniGrid-DoorKey-8x8-v0 with 262144
+whole batch. Headline workload (config.workload): BASELINE.json configs[2], MiniGrid-DoorKey-8x8-v0 with 262144
 environments per GPU (the configuration the >=1e8 steps/s target is quoted on), uniform random actions generated
-on the device before timing, NEXT_STEP autoreset. Prints ONE JSON line (rank 0).
+on the device before timing, NEXT_STEP autoreset with DESYNCHRONISED episodes: before timing every env's step_count
+is drawn from U[0, max_steps) (mg_set_state), so each timed step regenerates ~n / max_steps environments — the steady
+state of a long run — instead of none (a batch that was just reset) or all of them (the synchronised truncation
+wave, reported separately as `sync_wave`). The other BASELINE configs are timed the same way and reported under
+`configs`. Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -25,10 +29,9 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_STEP = 348  # action 4 + patch 147 + obs 147 + reward 8 + flags 2 + agent 20 r + 20 w
 L2_BYTES = 126e6
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_step launch from the committed ncu --set full capture
-# (profiles/r01_final_kstep_summary.txt: 47.27 MB read + 13.2-13.3 MB written; obs writes mostly stay in L2)
-TRAFFIC_BYTES_PER_LAUNCH = 60.5e6
-TRAFFIC_SOURCE = "ncu --set full, profiles/r01_final_kstep_summary.txt (DoorKey-8x8 x 262144; applies to the default workload only)"
+HEADLINE_ENV = "MiniGrid-DoorKey-8x8-v0"
+# BASELINE.json configs[1], [3], [4] (per-GPU share); configs[0] (Empty-5x5, 1 env, CPU) is the `config1` key
+OTHER_CONFIGS = [("MiniGrid-Empty-8x8-v0", 65536), ("MiniGrid-LavaCrossingS9N1-v0", 262144), ("MiniGrid-FourRooms-v0", 262144)]
 
 
 def parse_args():
@@ -37,13 +40,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--env", default="MiniGrid-DoorKey-8x8-v0")
+    ap.add_argument("--env", default=HEADLINE_ENV)
     ap.add_argument("--envs-per-gpu", type=int, default=262144)
     ap.add_argument("--rotate", type=int, default=0, help="independent env batches cycled through so the working set exceeds L2 (0 = auto)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs and the long single-batch runs")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--graph", type=int, default=1, help="replay the step loop as CUDA graphs of this many steps x rotate (0 = eager launches)")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step loop as CUDA graphs (0 = eager launches)")
+    ap.add_argument("--sync-episodes", action="store_true", help="do NOT desynchronise the episodes (round-1 behaviour: no autoreset in the timed region)")
+    ap.add_argument("--host-format", default="full", choices=["packed", "full"], help="D2H format of the e2e leg (packed: 52 B/env expanded on the host)")
     return ap.parse_args()
 
 
@@ -53,6 +59,18 @@ def load_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(env_id, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_step launch, from the committed ncu capture of this workload
+    (profiles/traffic.json, written by scripts/ncu_traffic.py from >= 16 consecutive launches, caches not flushed
+    between them: steady-state write-back included)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(f"{env_id}|{n}")
+        return (float(t["bytes_per_launch"]), t["source"]) if t else (None, None)
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -132,6 +150,23 @@ def usable_cores():
     return n
 
 
+def make_config(env_id, n, world, sync_episodes=False):
+    """The workload description: identical for the engine arm and the reference arm."""
+    total = n * world
+    episodes = ("synchronised (all envs reset together before timing)" if sync_episodes else
+                "desynchronised: step_count ~ U[0, max_steps) per env before timing, so every timed step autoresets ~n/max_steps envs")
+    return {"workload": f"{env_id}, {n} envs per GPU ({total} total), uniform random actions, NEXT_STEP autoreset, episodes {episodes.split(':')[0]}",
+            "env": env_id, "envs_per_gpu": n, "total_envs": total, "autoreset": "next_step", "episodes": episodes}
+
+
+def desync_oracle(env, seed=4321):
+    """step_count ~ U[0, max_steps) per env (the engine arm does the same through mg_set_state)."""
+    st = env.get_state()
+    agent = st["agent"].copy()
+    agent[:, 5] = np.random.default_rng(seed).integers(0, env.max_steps, env.num_envs)
+    env.set_state(agent=agent)
+
+
 def run_reference(args, rank, world):
     """The reference algorithm on the host CPUs: the oracle port (C restatement of MiniGridEnv.step/gen_obs,
     validated against the Python reference), one env slice per host thread. The Python reference itself cannot
@@ -144,6 +179,8 @@ def run_reference(args, rank, world):
     cores = min(max_threads(), usable_cores())
     env = OracleVecEnv(args.env, n, autoreset="next_step", n_threads=cores)
     env.reset(seed=0)
+    if not args.sync_episodes:
+        desync_oracle(env)
     rng = np.random.default_rng(1234)
     # bounded sample: keep the whole run to a few minutes whatever the core count
     probe_steps = 2
@@ -159,10 +196,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.env}, {n} envs, uniform random actions, NEXT_STEP autoreset", "env": args.env,
-                   "envs": n, "host_threads": cores},
+        "config": make_config(args.env, n, world, args.sync_episodes),
+        "run": {"host_threads": cores, "sample_envs": n},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "per_core": value / cores, "kind": "port",
-                         "sample": f"{n} envs x {steps} lockstep steps, C port of the reference algorithm (oracle/mg_oracle.c), {cores} threads"},
+                         "sample": f"{n} envs x {steps} lockstep steps (one GPU's share of the workload), C port of the reference algorithm "
+                                   f"(oracle/mg_oracle.c), {cores} threads"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -176,6 +214,8 @@ def cpu_baseline(args):
     n = 65536
     env = OracleVecEnv(args.env, n, autoreset="next_step", n_threads=cores)
     env.reset(seed=0)
+    if not args.sync_episodes:
+        desync_oracle(env)
     rng = np.random.default_rng(1234)
     secs, _ = env.rollout(rng.integers(0, 7, (2, n)).astype(np.int32), n_threads=cores)
     steps = int(max(4, min(2000, args.cpu_seconds / max(secs / 2, 1e-6))))
@@ -183,6 +223,19 @@ def cpu_baseline(args):
     return {"value": n * steps / secs, "unit": "env-steps/s", "cores": cores, "per_core": n * steps / secs / cores, "kind": "port",
             "sample": f"{n} envs x {steps} lockstep steps of {args.env} ({secs:.1f} s), oracle C port on {cores} host threads "
                       f"(os.cpu_count()={os.cpu_count()}, cgroup CPU quota respected)"}
+
+
+def config1_cpu():
+    """BASELINE.json configs[0]: MiniGrid-Empty-5x5-v0, ONE env, random actions on the CPU (minigrid/benchmark.py's loop):
+    the oracle port, single thread."""
+    from oracle.oracle import OracleVecEnv
+
+    env = OracleVecEnv("MiniGrid-Empty-5x5-v0", 1, autoreset="next_step", n_threads=1)
+    env.reset(seed=0)
+    a = np.random.default_rng(1234).integers(0, 7, (200000, 1)).astype(np.int32)
+    env.rollout(a[:20000], n_threads=1)
+    secs, _ = env.rollout(a, n_threads=1)
+    return a.shape[0] / secs
 
 
 def main():
@@ -197,12 +250,15 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from minigrid_b200 import make_sharded
+    from minigrid_b200 import MinigridVecEnv, bind_to_gpu_numa_node, make_sharded
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # pinned host buffers (the e2e leg) should live on the GPU's own NUMA node: with 8 ranks copying at once, remote
+    # pinned memory costs a quarter of the D2H bandwidth (round 1: 37 instead of 50 GB/s per GPU at N = 8)
+    numa = bind_to_gpu_numa_node(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -218,103 +274,110 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    n = args.envs_per_gpu
-    total = n * world
-    K, W = args.steps, args.warmup
-    # working set of one batch: grid tiles + obs + agent/rng/outputs; rotate enough batches to exceed L2
-    probe = make_sharded(args.env, total, rank, world, device=dev)
-    wpe_bytes = ((probe.height + 2) * ((probe.width + 3) // 4) + (probe.width + 2) * ((probe.height + 3) // 4)) * 4
-    ws = n * (wpe_bytes + 147 + 16 + 4 + 4 + 8 + 2)
-    R = args.rotate if args.rotate > 0 else max(1, int(np.ceil(2.2 * L2_BYTES / ws)))
-    batches = [probe] + [make_sharded(args.env, total, rank, world, device=dev) for _ in range(R - 1)]
-    for b, e in enumerate(batches):
-        e.reset(seed=1_000_003 * b)  # env i of batch b: seed 1000003*b + global index
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    T = min(K + W, 512)  # action table rows, cycled
-    actions = torch.randint(0, 7, (T, n), generator=gen, device=dev, dtype=torch.int32)
-    torch.cuda.synchronize()
+    K, W = args.steps, max(3, args.warmup)  # never fewer than 3 untimed steps before a timed region
+    peak, peak_src = load_peaks()
 
-    act_rows = [actions[i] for i in range(T)]  # views made once: the timed loop is launches only
-    step_fns = [b.step for b in batches]
+    def desync(env, seed):
+        st = env.get_state()
+        g = torch.Generator(device=dev).manual_seed(seed)
+        st["agent"][:, 5] = torch.randint(0, env.max_steps, (env.num_envs,), generator=g, device=dev, dtype=torch.int32)
+        env.set_state(agent=st["agent"])
 
-    def run(steps, first=0):
-        for t in range(first, first + steps):
-            step_fns[t % R](act_rows[t % T])
+    def time_workload(env_id, n, K, W, *, rotate=0, sync_episodes=False, autoreset="next_step", want_graph=True):
+        """W untimed + K timed vector steps of R rotating batches of n envs; returns the measurement and the batches."""
+        total = n * world
+        probe = make_sharded(env_id, total, rank, world, device=dev, autoreset_mode=autoreset)
+        wpe_bytes = ((probe.height + 2) * ((probe.width + 3) // 4) + (probe.width + 2) * ((probe.height + 3) // 4)) * 4
+        ws = n * (min(wpe_bytes, 224 + 32) + 147 + 16 + 16 + 4 + 4 + 8 + 2)  # bytes a step touches per env (window layout: 7 lines)
+        R = rotate if rotate > 0 else max(1, int(np.ceil(2.2 * L2_BYTES / ws)))
+        batches = [probe] + [make_sharded(env_id, total, rank, world, device=dev, autoreset_mode=autoreset) for _ in range(R - 1)]
+        for b, e in enumerate(batches):
+            e.reset(seed=1_000_003 * b)  # env i of batch b: seed 1000003*b + global index
+            if not sync_episodes:
+                desync(e, 77 + 1000 * b + rank)
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        T = int(min(max(K + W, 64), 512))  # action table rows, cycled
+        actions = torch.randint(0, 7, (T, n), generator=gen, device=dev, dtype=torch.int32)
+        torch.cuda.synchronize()
+        act_rows = [actions[i] for i in range(T)]  # views made once: the timed loop is launches only
+        step_fns = [b.step for b in batches]
 
-    run(W)
-    if W < 3:
-        run(3 - W, W)  # never fewer than 3 untimed steps before the timed region, whatever --warmup says
-    barrier()
-    # The step loop is launch-bound for small batches (one ~20 us kernel per step vs ~8 us of Python + driver per
-    # launch), so it is captured once as a CUDA graph through the same public step() calls and replayed. K steps
-    # are still exactly K kernel launches on the device.
-    graph = None
-    G = 0
-    if args.graph:
-        G = R * max(1, min(T // R, 128 // R))  # steps per graph: every batch and a run of distinct action rows
-        if G > K:
-            G = 0
-    if G:
-        try:
-            cap_stream = torch.cuda.Stream(device=dev)
-            cap_stream.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(cap_stream):
-                run(G)  # warm the capture stream
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=cap_stream):
-                    run(G)
-            torch.cuda.current_stream(dev).wait_stream(cap_stream)
-            torch.cuda.synchronize()
-        except Exception as exc:  # noqa: BLE001  (fall back to eager launches, and say so)
-            graph = None
-            G = 0
-            graph_error = repr(exc)
-            torch.cuda.synchronize()
-    eager_run = run
-    if graph is not None:
-        def run(steps, first=0):  # noqa: F811
+        def eager_run(steps, first=0):
+            for t in range(first, first + steps):
+                step_fns[t % R](act_rows[t % T])
+
+        eager_run(W)
+        barrier()
+        # The step loop is launch-bound for small batches (one ~20 us kernel per step vs ~8 us of Python + driver per
+        # launch), so it is captured once as a CUDA graph through the same public step() calls and replayed. K steps
+        # are still exactly K kernel launches on the device. G = steps per graph: a multiple of R (every batch), at
+        # most 128 and at most K, so that a short --steps run replays graphs too.
+        graph, G, graph_error = None, 0, None
+        if want_graph and K >= R:
+            G = R * max(1, min(K // R, 128 // R if R <= 128 else 1))
+            try:
+                cap_stream = torch.cuda.Stream(device=dev)
+                cap_stream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(cap_stream):
+                    eager_run(G)  # warm the capture stream
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=cap_stream):
+                        eager_run(G)
+                torch.cuda.current_stream(dev).wait_stream(cap_stream)
+                torch.cuda.synchronize()
+            except Exception as exc:  # noqa: BLE001  (fall back to eager launches, and say so)
+                graph, G, graph_error = None, 0, repr(exc)
+                torch.cuda.synchronize()
+
+        def run(steps, first=0):
+            if graph is None:
+                return eager_run(steps, first)
             for _ in range(steps // G):
                 graph.replay()
             if steps % G:
                 eager_run(steps % G, first)
-        run(G)
+
+        if graph is not None:
+            run(G)
         barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = sum(b.launch_count for b in batches)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    h0 = time.perf_counter()
-    run(K, W)
-    host_enqueue_s = time.perf_counter() - h0
-    ev1.record()
-    barrier()
-    clocks = sampler.stop()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = sum(b.launch_count for b in batches) - l0
-    if graph is not None:
-        launches += (K // G) * G  # launches replayed by the graphs (each captured step() is one kernel node)
-    for b in batches:
-        b.check_actions()
-    value = total * K / (ms * 1e-3)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = sum(b.launch_count for b in batches)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        h0 = time.perf_counter()
+        run(K, W)
+        host_enqueue_s = time.perf_counter() - h0
+        ev1.record()
+        barrier()
+        clocks = sampler.stop()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        launches = sum(b.launch_count for b in batches) - l0
+        if graph is not None:
+            launches += (K // G) * G  # launches replayed by the graphs (each captured step() is one kernel node)
+        for b in batches:
+            b.check_actions()
+        # share of envs that were regenerated per timed step (pending flags after the run, averaged over the batches)
+        pend = float(np.mean([float(b.get_state()["pending"].float().mean().item()) for b in batches]))
+        res = {"env": env_id, "envs_per_gpu": n, "total_envs": total, "steps": K, "ms": ms, "ms_per_step": ms / K,
+               "value": total * K / (ms * 1e-3), "launches": int(launches), "R": R, "ws": ws, "G": G, "graph": graph is not None,
+               "graph_error": graph_error, "clocks": clocks, "host_enqueue_us_per_step": 1e6 * host_enqueue_s / K,
+               "autoreset_fraction_per_step": pend}
+        achieved = ALGO_BYTES_PER_STEP * n / (ms / K * 1e-3) / 1e9
+        res["achieved_gbs"], res["frac"] = achieved, achieved / peak
+        return res, batches, (eager_run, act_rows, step_fns, T, R)
 
-    # the same loop with a single L2-resident batch, for context (not the headline)
-    run(W)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for t in range(K):  # eager launches, one batch: shows the launch-bound regime next to the graph number
-        step_fns[0](act_rows[t % T])
-    e1.record()
-    torch.cuda.synchronize()
-    ms_res = max_over_ranks(e0.elapsed_time(e1))
+    # ---- headline ----
+    n = args.envs_per_gpu
+    total = n * world
+    head, batches, (eager_run, act_rows, step_fns, T, R) = time_workload(args.env, n, K, W, rotate=args.rotate,
+                                                                         sync_episodes=args.sync_episodes, want_graph=bool(args.graph))
+    ms, launches = head["ms"], head["launches"]
+    value = head["value"]
 
-    # dominant kernel: a vector step is exactly ONE K1 launch (launches == K), so the CUDA events
-    # that bracket the timed region measure K back-to-back k_step launches on the launching stream; ms / K is the
-    # average launch duration including launch gaps (conservative)
+    # per-launch events (perturbs the stream; reported, not used for the headline)
     kstep_ms = ms / K if launches == K else None
-    # cross-check with per-launch events (perturbs the stream; reported, not used for the headline)
     kstep_ms_events = None
     try:
         for b in batches:
@@ -330,9 +393,11 @@ def main():
     except AttributeError:
         pass
 
-    # end to end through the host-buffer API: pinned host actions in, pinned host obs/reward/flags out
-    Ke = min(args.e2e_steps, K)
+    # ---- end to end through the host-buffer API: pinned host actions in, pinned host obs/reward/flags out ----
+    Ke = max(1, min(args.e2e_steps, K))
     host_actions = torch.randint(0, 7, (min(Ke, 64), n), dtype=torch.int32).pin_memory()
+    for b in batches:
+        b.set_host_format(args.host_format)
     for t in range(max(3, 2 * R)):  # every batch allocates its pinned staging on first use: keep that out of the timing
         batches[t % R].step_host(host_actions[t % host_actions.shape[0]])
     barrier()
@@ -343,16 +408,63 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total * Ke / e2e_s
     h2d = n * 4
-    d2h = n * (147 + 4 + 8 + 1 + 1)
+    d2h = batches[0].host_d2h_bytes_per_step
+    e2e_threads = batches[0].host_threads
 
-    peak, peak_src = load_peaks()
-    default_workload = args.env == "MiniGrid-DoorKey-8x8-v0" and n == 262144  # what the committed ncu capture measured
+    # ---- the other BASELINE configs, the synchronised long run and the autoreset cost (one batch, L2-resident) ----
+    configs, sync_wave, autoreset_cost, full_obs = [], None, None, None
+    del batches, step_fns, eager_run
+    torch.cuda.empty_cache()
+    if not args.no_configs:
+        for env_id, n_c in OTHER_CONFIGS:
+            if env_id == args.env and n_c == n:
+                continue
+            r, bs, _ = time_workload(env_id, n_c, K, W, want_graph=bool(args.graph))
+            tr, tr_src = load_traffic(env_id, n_c)
+            configs.append({"env": env_id, "envs_per_gpu": n_c, "total_envs": r["total_envs"], "value": r["value"],
+                            "ms_per_step": r["ms_per_step"], "frac": r["frac"], "achieved_gbs": r["achieved_gbs"], "steps": K,
+                            "batches_cycled": r["R"], "launch": "graph" if r["graph"] else "eager",
+                            "autoreset_fraction_per_step": r["autoreset_fraction_per_step"], "traffic": tr})
+            if env_id == "MiniGrid-FourRooms-v0":  # K3 (FullyObsWrapper.observation) on the largest grid
+                e = bs[0]
+                out = torch.empty((n_c, e.width, e.height, 3), dtype=torch.uint8, device=dev)
+                for _ in range(3):
+                    e.full_obs(out)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(20):
+                    e.full_obs(out)
+                a1.record()
+                torch.cuda.synchronize()
+                fo_ms = max_over_ranks(a0.elapsed_time(a1)) / 20
+                fo_bytes = n_c * (e.width * e.height * 4 + 16)  # read W*H one-byte cell codes + the agent record, write 3*W*H
+                full_obs = {"kernel": "k_full_obs (K3, FullyObsWrapper.observation)", "env": env_id, "envs_per_gpu": n_c,
+                            "ms": fo_ms, "algorithmic_bytes_per_launch": fo_bytes, "achieved_gbs": fo_bytes / (fo_ms * 1e-3) / 1e9,
+                            "frac": fo_bytes / (fo_ms * 1e-3) / 1e9 / peak}
+            del bs
+            torch.cuda.empty_cache()
+        # one synchronised batch over >= 2 episodes: contains the truncation waves (every env truncates in the same step)
+        spec_steps = MinigridVecEnv(args.env, 32, device=dev).max_steps
+        Kl = int(min(max(2 * spec_steps + 64, 1024), 6000))
+        rs, bs, _ = time_workload(args.env, n, Kl, W, rotate=1, sync_episodes=True, want_graph=bool(args.graph))
+        del bs
+        ro, bs, _ = time_workload(args.env, n, Kl, W, rotate=1, sync_episodes=True, autoreset="disabled", want_graph=bool(args.graph))
+        del bs
+        rd, bs, _ = time_workload(args.env, n, Kl, W, rotate=1, sync_episodes=False, want_graph=bool(args.graph))
+        del bs
+        torch.cuda.empty_cache()
+        sync_wave = {"value": rs["value"], "ms_per_step": rs["ms_per_step"], "steps": Kl,
+                     "note": "ONE batch reset together, never desynchronised: every env truncates in the same step every max_steps steps"}
+        autoreset_cost = {"steps": Kl, "one_batch_l2_resident": True, "us_per_step_autoreset_disabled": 1e3 * ro["ms_per_step"],
+                          "us_per_step_desynchronised": 1e3 * rd["ms_per_step"], "us_per_step_synchronised_waves": 1e3 * rs["ms_per_step"],
+                          "desynchronised_over_disabled": rd["ms_per_step"] / ro["ms_per_step"],
+                          "synchronised_over_disabled": rs["ms_per_step"] / ro["ms_per_step"]}
+
+    tr, tr_src = load_traffic(args.env, n)
     roof = None
     if kstep_ms:
-        achieved = ALGO_BYTES_PER_STEP * n / (kstep_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "k_step (K1: transition + gen_obs)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH if default_workload else None,
-                "traffic_source": TRAFFIC_SOURCE if default_workload else None,
+        roof = {"bound": "hbm", "kernel": "k_step (K1: transition + autoreset + gen_obs)", "achieved": head["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": head["frac"], "traffic": tr, "traffic_source": tr_src,
                 "peak_source": peak_src, "kernel_ms": kstep_ms, "kernel_ms_per_launch_events": kstep_ms_events,
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * n}
 
@@ -361,21 +473,44 @@ def main():
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"{args.env}, {n} envs per GPU ({total} total), uniform random actions, NEXT_STEP autoreset",
-                       "env": args.env, "envs_per_gpu": n, "total_envs": total, "autoreset": "next_step",
-                       "l2": f"{R} independent env batches cycled, working set {R * ws / 1e6:.0f} MB per GPU > 126 MB L2 (inputs larger than L2)",
-                       "parallelism": f"env-sharded x{world}, no collective on the step path",
-                       "launch": (f"CUDA graph replay, {G} steps per graph" if graph is not None else "eager launches")},
-            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke},
+            "config": make_config(args.env, n, world, args.sync_episodes),
+            "run": {"l2": f"{head['R']} independent env batches cycled, working set {head['R'] * head['ws'] / 1e6:.0f} MB per GPU > 126 MB L2 (inputs larger than L2)",
+                    "parallelism": f"env-sharded x{world}, no collective on the step path",
+                    "launch": (f"CUDA graph replay, {head['G']} steps per graph" if head["graph"] else "eager launches"),
+                    "graph_error": head["graph_error"], "numa": numa,
+                    "autoreset_fraction_per_step": head["autoreset_fraction_per_step"]},
+            "clocks": {k: head["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                    "format": args.host_format, "host_threads": e2e_threads},
             "gpu_launches": int(launches),
-            "value_l2_resident": total * K / (ms_res * 1e-3),
-            "host_enqueue_us_per_step": 1e6 * host_enqueue_s / K,
+            "host_enqueue_us_per_step": head["host_enqueue_us_per_step"],
         }
         if roof:
             line["roofline"] = roof
+        if configs:
+            line["configs"] = configs
+        if full_obs:
+            line["full_obs"] = full_obs
+        if sync_wave:
+            line["sync_wave"] = sync_wave
+            line["autoreset_cost"] = autoreset_cost
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
+            # BASELINE.json configs[0]: Empty-5x5, ONE env — CPU port beside the engine at n = 1 (launch-latency bound)
+            e1 = MinigridVecEnv("MiniGrid-Empty-5x5-v0", 1, device=dev)
+            e1.reset(seed=0)
+            a1 = torch.randint(0, 7, (256, 1), device=dev, dtype=torch.int32)
+            rows = [a1[i] for i in range(256)]
+            for t in range(64):
+                e1.step(rows[t])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for t in range(2000):
+                e1.step(rows[t & 255])
+            torch.cuda.synchronize()
+            line["config1"] = {"env": "MiniGrid-Empty-5x5-v0", "envs": 1, "cpu_port_steps_per_s": config1_cpu(),
+                               "engine_steps_per_s": 2000 / (time.perf_counter() - t0),
+                               "note": "BASELINE.json configs[0]; one env is a launch-latency measurement on a GPU"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -13,8 +13,11 @@
  *  - `*_dev` pointers are device memory on the handle's GPU, owned by the caller (torch tensors in the
  *    Python host layer); `*_host` pointers are host memory. The library owns only its state arena.
  *  - device work is enqueued on the caller's `stream` (a cudaStream_t passed as void*) and is
- *    asynchronous; the *_host entry points synchronise before returning.
+ *    asynchronous; the *_host entry points run on a private stream of the handle, which is first ordered after
+ *    the work already enqueued on the last caller stream that touched the handle, and synchronise before
+ *    returning. mg_seed (host seed array) and mg_set_state with agent records (range validation) also synchronise.
  *  - a handle is bound to one device; one host thread per handle. Distinct handles may run concurrently.
+ *    Every entry point selects the handle's device and restores the calling thread's current device on return.
  *  - device kernels cannot raise: an action outside 0..6 (ValueError at minigrid_env.py:584-585) sets a
  *    sticky device error word, reported by mg_check_error() / the *_host calls.
  */
@@ -93,6 +96,13 @@ int mg_seed_base(mg_env *env, uint64_t base_seed, void *stream);
  * obs_dev: uint8[n][7][7][3]; dir_dev: int32[n]. Either may be NULL. */
 int mg_reset(mg_env *env, uint8_t *obs_dev, int32_t *dir_dev, void *stream);
 
+/* Replaces: gymnasium >= 1.1 VectorEnv.reset(seed=..., options={"reset_mask": mask}) (SyncVectorEnv.reset): only the
+ * envs with mask_dev[i] != 0 (uint8[n]) are re-seeded / reset; the others keep their state, their NEXT_STEP autoreset
+ * flag and their slots of obs_dev / dir_dev. mg_seed_masked: seeds_host uint64[n] (entries of unselected envs are
+ * ignored) or NULL for base_seed + i. */
+int mg_seed_masked(mg_env *env, const uint8_t *mask_dev, const uint64_t *seeds_host, uint64_t base_seed, void *stream);
+int mg_reset_masked(mg_env *env, const uint8_t *mask_dev, uint8_t *obs_dev, int32_t *dir_dev, void *stream);
+
 /* Replaces: MiniGridEnv.step(action) (minigrid_env.py:525-595) + gen_obs (:597-650) for every env, with
  * gymnasium.vector.SyncVectorEnv autoreset semantics (mode given at mg_create).
  * actions_dev: n actions of dtype action_dtype; obs_dev uint8[n][7][7][3]; dir_dev int32[n];
@@ -111,6 +121,18 @@ int mg_reset_host(mg_env *env, uint8_t *obs_host, int32_t *dir_host);
 int mg_step_host(mg_env *env, const int32_t *actions_host, uint8_t *obs_host, int32_t *dir_host,
                  double *reward_host, uint8_t *terminated_host, uint8_t *truncated_host);
 
+/* How the *_host calls bring the results to the host. MG_HOST_FULL: the arrays cross PCIe as they are
+ * (161 B per env-step). MG_HOST_PACKED: 52 B per env-step cross (49 one-byte cell codes of the view, one byte
+ * direction | terminated | truncated | goal, the step count the reward is a function of) and are expanded by
+ * n_threads host threads (0 = all the process may use) into the same arrays, bit-identical: the (type, colour, state)
+ * table and the reward table `1 - 0.9 * (step_count / max_steps)` (minigrid_env.py:240-245) are host-computed in
+ * both formats. mg_host_d2h_bytes: device-to-host bytes of one mg_step_host call in the current format. */
+#define MG_HOST_FULL 0
+#define MG_HOST_PACKED 1
+int mg_set_host_format(mg_env *env, int format, int n_threads);
+int64_t mg_host_d2h_bytes(const mg_env *env);
+int mg_host_threads(const mg_env *env);
+
 /* Replaces: FullyObsWrapper.observation (wrappers.py:419-426): grid.encode() with the agent cell set to
  * (10, 0, agent_dir). out_dev: uint8[n][W][H][3]. */
 int mg_full_obs(mg_env *env, uint8_t *out_dev, void *stream);
@@ -119,7 +141,9 @@ int mg_full_obs(mg_env *env, uint8_t *out_dev, void *stream);
  * grid_dev: Grid.encode() uint8[n][W][H][3]; agent_dev: int32[n][6] {x, y, dir, carry_type (-1 none),
  * carry_color, step_count}; rng_dev: uint64[n][6] {state_hi, state_lo, inc_hi, inc_lo, has_uint32,
  * uinteger} (numpy PCG64 bit-generator state); pending_dev: uint8[n] NEXT_STEP autoreset flags.
- * Any pointer may be NULL. */
+ * Any pointer may be NULL. mg_set_state validates agent records (0 <= x < W, 0 <= y < H, 0 <= dir <= 3,
+ * carry_type in {-1, 5 key, 6 ball, 7 box}, carry_color 0..5, step_count >= 0): records that fail are left
+ * unchanged and the call returns MG_ERR_INVALID_ARG. */
 int mg_get_state(mg_env *env, uint8_t *grid_dev, int32_t *agent_dev, uint64_t *rng_dev,
                  uint8_t *pending_dev, void *stream);
 int mg_set_state(mg_env *env, const uint8_t *grid_dev, const int32_t *agent_dev, const uint64_t *rng_dev,

@@ -14,8 +14,8 @@ _lib = None
 
 EXPORTS = [
     "mg_create", "mg_destroy", "mg_last_error", "mg_num_envs", "mg_launch_count", "mg_seed", "mg_seed_base",
-    "mg_reset", "mg_step", "mg_gen_obs", "mg_reset_host", "mg_step_host", "mg_full_obs", "mg_get_state", "mg_set_state",
-    "mg_check_error", "mg_profile", "mg_profile_read",
+    "mg_reset", "mg_seed_masked", "mg_reset_masked", "mg_step", "mg_gen_obs", "mg_reset_host", "mg_step_host", "mg_full_obs", "mg_get_state", "mg_set_state",
+    "mg_check_error", "mg_profile", "mg_profile_read", "mg_set_host_format", "mg_host_d2h_bytes", "mg_host_threads",
 ]
 
 
@@ -32,6 +32,13 @@ def load(build_if_missing: bool = True):
         if not build_if_missing:
             raise MinigridB200Error(f"{path} is missing: run `python -m minigrid_b200._build` (needs nvcc)")
         _build.build()
+    elif build_if_missing and path == _build.LIB_PATH:
+        try:
+            _build.build()  # no-op unless a source under csrc/ or the header is newer than the library
+        except Exception as exc:  # noqa: BLE001  (no nvcc on this machine: keep the library that is there, loudly)
+            import warnings
+
+            warnings.warn(f"minigrid_b200: {path} is older than its sources and could not be rebuilt ({exc})")
     L = C.CDLL(path)
     p, i32, i64, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
     L.mg_create.argtypes = [i32, i32, i32, i32, i32, p, i32, i64, i32, i32, C.POINTER(p)]
@@ -44,12 +51,18 @@ def load(build_if_missing: bool = True):
     L.mg_seed.argtypes = [p, p, p]
     L.mg_seed_base.argtypes = [p, u64, p]
     L.mg_reset.argtypes = [p, p, p, p]
+    L.mg_seed_masked.argtypes = [p, p, p, u64, p]
+    L.mg_reset_masked.argtypes = [p, p, p, p, p]
     L.mg_step.argtypes = [p, p, i32, p, p, p, p, p, p]
     L.mg_step.restype = i32
     L.mg_gen_obs.argtypes = [p, p, p, p]
     L.mg_reset_host.argtypes = [p, p, p]
     L.mg_step_host.argtypes = [p] * 7
     L.mg_full_obs.argtypes = [p, p, p]
+    L.mg_set_host_format.argtypes = [p, i32, i32]
+    L.mg_host_d2h_bytes.restype = i64
+    L.mg_host_d2h_bytes.argtypes = [p]
+    L.mg_host_threads.argtypes = [p]
     L.mg_get_state.argtypes = [p] * 6
     L.mg_set_state.argtypes = [p] * 6
     L.mg_check_error.argtypes = [p, p]

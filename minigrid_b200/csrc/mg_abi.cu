@@ -15,14 +15,15 @@ namespace mg {
 cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
                         int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream);
 cudaError_t configure_step(const Params &p, StepPlan *plan);
-cudaError_t launch_reset(const Params &p, uint8_t *obs, int32_t *dir, cudaStream_t stream);
-cudaError_t launch_seed(const Params &p, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream);
+cudaError_t launch_reset(const Params &p, const uint8_t *mask, uint8_t *obs, int32_t *dir, cudaStream_t stream);
+cudaError_t launch_seed(const Params &p, const uint8_t *mask, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream);
 cudaError_t launch_full_obs(const Params &p, uint8_t *out, int with_agent, cudaStream_t stream);
 cudaError_t launch_get_state(const Params &p, uint8_t *grid, int32_t *agent, uint64_t *rng, uint8_t *pending,
                              cudaStream_t stream);
 cudaError_t launch_set_state(const Params &p, const uint8_t *grid, const int32_t *agent, const uint64_t *rng,
                              const uint8_t *pending, cudaStream_t stream);
 cudaError_t launch_init(const Params &p, cudaStream_t stream);
+cudaError_t launch_clear_err(const Params &p, int bits, cudaStream_t stream);
 cudaError_t launch_template(const Params &p, uint32_t *tmpl, cudaStream_t stream);
 }  // namespace mg
 
@@ -38,6 +39,8 @@ struct mg_env {
   uint64_t *d_seeds;
   // host path
   cudaStream_t hstream;
+  cudaStream_t last_stream; int has_last_stream;  // last caller stream that touched the handle's state
+  cudaEvent_t ev_order;                            // orders hstream (the *_host entry points) after that stream
   int32_t *d_actions; uint8_t *d_out;  // device mirror of the host-facing buffers
   int32_t *h_actions; uint8_t *h_out;  // pinned staging, used when the caller's buffers are pageable
   int *h_err;
@@ -58,6 +61,24 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
   } while (0)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Every entry point works on the handle's device and leaves the calling thread's current device as it found it
+// (a process that steps an env on cuda:1 and runs its policy on cuda:0 must not see its current device change,
+// also not when a handle is destroyed from a garbage collector).
+struct DeviceGuard {
+  int prev = -1, dev;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) : dev(device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+#define MG_ON_DEVICE(h)            \
+  DeviceGuard guard__((h)->device); \
+  MG_CUDA(guard__.err)
 
 int mg_create(int kind, int width, int height, int max_steps, int see_through_walls, const int32_t *params,
               int n_params, int64_t n_envs, int autoreset_mode, int device, mg_env **out) {
@@ -89,7 +110,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     return fail(MG_ERR_NO_DEVICE, "no CUDA device: the engine has no CPU fallback");
   if (device < 0) MG_CUDA(cudaGetDevice(&device));
   if (device >= ndev) return fail(MG_ERR_INVALID_ARG, "device index out of range");
-  MG_CUDA(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  MG_CUDA(guard.err);
 
   mg_env *h = new (std::nothrow) mg_env();
   if (!h) return fail(MG_ERR_INVALID_ARG, "out of host memory");
@@ -119,6 +141,14 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     }
   }
   if (kind == MG_KIND_DISTSHIFT && n_params < 4) { if (n_params < 1) p.kp[0] = 2; p.kp[1] = 1; p.kp[2] = 1; p.kp[3] = 0; }
+  // a fixed agent start (agent_start_pos / agent_start_dir, empty.py:75-76, distshift.py:68-69) must lie inside the
+  // border walls: K1 trusts the agent record
+  if ((kind == MG_KIND_EMPTY && !p.kp[0]) || kind == MG_KIND_DISTSHIFT) {
+    if (p.kp[1] < 1 || p.kp[1] > width - 2 || p.kp[2] < 1 || p.kp[2] > height - 2 || p.kp[3] < 0 || p.kp[3] > 3) {
+      delete h;
+      return fail(MG_ERR_INVALID_ARG, "agent start must satisfy 1 <= x <= width - 2, 1 <= y <= height - 2, 0 <= dir <= 3");
+    }
+  }
   h->device = device;
 
   const size_t n_pad = (size_t)p.n_tiles * TILE;
@@ -161,13 +191,14 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     free(vt);
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming);
   if (e == cudaSuccess) e = configure_step(p, &h->plan);
   if (e == cudaSuccess && getenv("MINIGRID_B200_VERBOSE"))
     fprintf(stderr, "[minigrid_b200] K1 plan: layout=%d, %d warps/CTA, vis=%d, nbuf=%d, %d CTA/SM, grid=%d, smem=%zu B, tiles=%d\n", p.g.layout, h->plan.warps,
             h->plan.vis, h->plan.nbuf, h->plan.ctas_per_sm, h->plan.grid, h->plan.smem, p.n_tiles);
   if (e == cudaSuccess) e = launch_init(p, h->hstream);
   if (e == cudaSuccess) e = launch_template(p, d_tm, h->hstream);
-  if (e == cudaSuccess) e = launch_seed(p, nullptr, 0, h->hstream);
+  if (e == cudaSuccess) e = launch_seed(p, nullptr, nullptr, 0, h->hstream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->hstream);
   if (e != cudaSuccess) {
     std::string msg = std::string("mg_create: ") + cudaGetErrorString(e);
@@ -181,8 +212,9 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
 
 int mg_destroy(mg_env *h) {
   if (!h) return MG_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   if (h->hstream) { cudaStreamSynchronize(h->hstream); cudaStreamDestroy(h->hstream); }
+  if (h->ev_order) cudaEventDestroy(h->ev_order);
   cudaFree(h->d_arena);
   cudaFree(h->d_seeds);
   cudaFree(h->d_actions);
@@ -201,31 +233,65 @@ int mg_destroy(mg_env *h) {
 int64_t mg_num_envs(const mg_env *h) { return h ? h->p.n_envs : 0; }
 int64_t mg_launch_count(const mg_env *h) { return h ? h->launches : 0; }
 
-int mg_seed(mg_env *h, const uint64_t *seeds_host, void *stream) {
-  if (!h || !seeds_host) return fail(MG_ERR_INVALID_ARG, "mg_seed: NULL argument");
-  MG_CUDA(cudaSetDevice(h->device));
+// The *_host entry points run on the handle's private stream; everything else runs on the caller's stream. The last
+// caller stream is remembered so that the private stream can be ordered after the work already enqueued there.
+static void note_stream(mg_env *h, cudaStream_t s) {
+  if (s != h->hstream) { h->last_stream = s; h->has_last_stream = 1; }
+}
+static void order_after_caller(mg_env *h) {
+  if (!h->has_last_stream) return;
+  if (cudaEventRecord(h->ev_order, h->last_stream) == cudaSuccess) cudaStreamWaitEvent(h->hstream, h->ev_order, 0);
+  else cudaGetLastError();  // the caller destroyed that stream: its work has completed
+  h->has_last_stream = 0;
+}
+
+static int seed_impl(mg_env *h, const uint8_t *mask_dev, const uint64_t *seeds_host, uint64_t base_seed, void *stream) {
+  MG_ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
-  if (!h->d_seeds) MG_CUDA(cudaMalloc(&h->d_seeds, (size_t)h->p.n_envs * sizeof(uint64_t)));
-  MG_CUDA(cudaMemcpyAsync(h->d_seeds, seeds_host, (size_t)h->p.n_envs * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-  MG_CUDA(launch_seed(h->p, h->d_seeds, 0, s));
-  MG_CUDA(cudaStreamSynchronize(s));  // seeds_host may be pageable and freed by the caller
+  note_stream(h, s);
+  if (seeds_host) {
+    if (!h->d_seeds) MG_CUDA(cudaMalloc(&h->d_seeds, (size_t)h->p.n_envs * sizeof(uint64_t)));
+    MG_CUDA(cudaMemcpyAsync(h->d_seeds, seeds_host, (size_t)h->p.n_envs * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    MG_CUDA(launch_seed(h->p, mask_dev, h->d_seeds, 0, s));
+    MG_CUDA(cudaStreamSynchronize(s));  // seeds_host may be pageable and freed by the caller
+  } else {
+    MG_CUDA(launch_seed(h->p, mask_dev, nullptr, base_seed, s));
+  }
   h->launches += 1;
   return MG_OK;
+}
+
+int mg_seed(mg_env *h, const uint64_t *seeds_host, void *stream) {
+  if (!h || !seeds_host) return fail(MG_ERR_INVALID_ARG, "mg_seed: NULL argument");
+  return seed_impl(h, nullptr, seeds_host, 0, stream);
 }
 
 int mg_seed_base(mg_env *h, uint64_t base_seed, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_seed_base: NULL handle");
-  MG_CUDA(cudaSetDevice(h->device));
-  MG_CUDA(launch_seed(h->p, nullptr, base_seed, (cudaStream_t)stream));
-  h->launches += 1;
-  return MG_OK;
+  return seed_impl(h, nullptr, nullptr, base_seed, stream);
+}
+
+int mg_seed_masked(mg_env *h, const uint8_t *mask_dev, const uint64_t *seeds_host, uint64_t base_seed, void *stream) {
+  if (!h || !mask_dev) return fail(MG_ERR_INVALID_ARG, "mg_seed_masked: NULL argument");
+  return seed_impl(h, mask_dev, seeds_host, base_seed, stream);
 }
 
 int mg_reset(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_reset: NULL handle");
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
-  MG_CUDA(launch_reset(h->p, obs_dev, dir_dev, s));
+  note_stream(h, s);
+  MG_CUDA(launch_reset(h->p, nullptr, obs_dev, dir_dev, s));
+  h->launches += 1;
+  return MG_OK;
+}
+
+int mg_reset_masked(mg_env *h, const uint8_t *mask_dev, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
+  if (!h || !mask_dev) return fail(MG_ERR_INVALID_ARG, "mg_reset_masked: NULL argument");
+  MG_ON_DEVICE(h);
+  cudaStream_t s = (cudaStream_t)stream;
+  note_stream(h, s);
+  MG_CUDA(launch_reset(h->p, mask_dev, obs_dev, dir_dev, s));
   h->launches += 1;
   return MG_OK;
 }
@@ -234,8 +300,9 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
             double *reward_dev, uint8_t *terminated_dev, uint8_t *truncated_dev, void *stream) {
   if (!h || !actions_dev) return fail(MG_ERR_INVALID_ARG, "mg_step: NULL argument");
   if (action_dtype < 0 || action_dtype > 2) return fail(MG_ERR_INVALID_ARG, "mg_step: unknown action dtype");
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
+  note_stream(h, s);
   const Params &p = h->p;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (h->profiling) {
@@ -257,7 +324,8 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
 
 int mg_gen_obs(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_gen_obs: NULL handle");
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
+  note_stream(h, (cudaStream_t)stream);
   MG_CUDA(launch_step(h->p, h->plan, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr,
                       (cudaStream_t)stream));
   h->launches += 1;
@@ -275,7 +343,7 @@ int mg_profile_read(mg_env *h, double *total_ms, int64_t *n_launches) {
   if (!h || !total_ms || !n_launches) return fail(MG_ERR_INVALID_ARG, "mg_profile_read: NULL argument");
   *total_ms = 0.0; *n_launches = 0;
   if (!h->prof_events) return MG_OK;
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
   std::vector<cudaEvent_t> &ev = *h->prof_events;
   for (size_t i = 0; i + 1 < ev.size(); i += 2) {
     MG_CUDA(cudaEventSynchronize(ev[i + 1]));
@@ -290,15 +358,19 @@ int mg_profile_read(mg_env *h, double *total_ms, int64_t *n_launches) {
 
 int mg_full_obs(mg_env *h, uint8_t *out_dev, void *stream) {
   if (!h || !out_dev) return fail(MG_ERR_INVALID_ARG, "mg_full_obs: NULL argument");
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
+  note_stream(h, (cudaStream_t)stream);
   MG_CUDA(launch_full_obs(h->p, out_dev, 1, (cudaStream_t)stream));
   h->launches += 1;
   return MG_OK;
 }
 
+static int ensure_host_path(mg_env *h);
+
 int mg_get_state(mg_env *h, uint8_t *grid_dev, int32_t *agent_dev, uint64_t *rng_dev, uint8_t *pending_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_get_state: NULL handle");
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
+  note_stream(h, (cudaStream_t)stream);
   MG_CUDA(launch_get_state(h->p, grid_dev, agent_dev, rng_dev, pending_dev, (cudaStream_t)stream));
   h->launches += (grid_dev ? 1 : 0) + ((agent_dev || rng_dev || pending_dev) ? 1 : 0);
   return MG_OK;
@@ -307,10 +379,25 @@ int mg_get_state(mg_env *h, uint8_t *grid_dev, int32_t *agent_dev, uint64_t *rng
 int mg_set_state(mg_env *h, const uint8_t *grid_dev, const int32_t *agent_dev, const uint64_t *rng_dev,
                  const uint8_t *pending_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_set_state: NULL handle");
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
+  note_stream(h, s);
   MG_CUDA(launch_set_state(h->p, grid_dev, agent_dev, rng_dev, pending_dev, s));
   h->launches += (grid_dev ? 1 : 0) + ((agent_dev || rng_dev || pending_dev) ? 1 : 0);
+  if (agent_dev) {
+    // K1 trusts the agent records (window offsets, bit-mask shifts): records that fail the range checks were not
+    // stored (k_set_agent) and are reported here; this makes an agent injection synchronous.
+    int rc = ensure_host_path(h);
+    if (rc != MG_OK) return rc;
+    MG_CUDA(cudaMemcpyAsync(h->h_err, h->p.err, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MG_CUDA(cudaStreamSynchronize(s));
+    if (*h->h_err & ERR_BAD_STATE) {
+      MG_CUDA(launch_clear_err(h->p, ERR_BAD_STATE, s));
+      return fail(MG_ERR_INVALID_ARG, "mg_set_state: agent record out of range (need 0 <= x < width, 0 <= y < height, "
+                                      "0 <= dir <= 3, carry type in {-1, key 5, ball 6, box 7}, colour 0..5, step_count >= 0); "
+                                      "such records were left unchanged");
+    }
+  }
   return MG_OK;
 }
 
@@ -325,14 +412,14 @@ static int ensure_host_path(mg_env *h) {
 
 int mg_check_error(mg_env *h, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_check_error: NULL handle");
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = ensure_host_path(h);
   if (rc != MG_OK) return rc;
   MG_CUDA(cudaMemcpyAsync(h->h_err, h->p.err, sizeof(int), cudaMemcpyDeviceToHost, s));
   MG_CUDA(cudaStreamSynchronize(s));
-  if (*h->h_err) {
-    MG_CUDA(cudaMemsetAsync(h->p.err, 0, sizeof(int), s));
+  if (*h->h_err & ERR_BAD_ACTION) {
+    MG_CUDA(launch_clear_err(h->p, ERR_BAD_ACTION, s));
     return fail(MG_ERR_INVALID_ACTION, "Unknown action: outside 0..6 (minigrid_env.py:584-585)");
   }
   return MG_OK;
@@ -376,8 +463,8 @@ static int host_outputs(mg_env *h, uint8_t *obs_host, int32_t *dir_host, double 
   MG_CUDA(cudaMemcpyAsync(h->h_err, h->p.err, sizeof(int), cudaMemcpyDeviceToHost, s));
   MG_CUDA(cudaStreamSynchronize(s));
   for (int i = 0; i < np; ++i) memcpy(pend[i].dst, pend[i].src, pend[i].bytes);
-  if (*h->h_err) {
-    MG_CUDA(cudaMemsetAsync(h->p.err, 0, sizeof(int), s));
+  if (*h->h_err & ERR_BAD_ACTION) {
+    MG_CUDA(launch_clear_err(h->p, ERR_BAD_ACTION, s));
     return fail(MG_ERR_INVALID_ACTION, "Unknown action: outside 0..6 (minigrid_env.py:584-585)");
   }
   return MG_OK;
@@ -393,13 +480,23 @@ static void host_dev_ptrs(mg_env *h, uint8_t **obs, double **rew, int32_t **dir,
   *trunc = b;
 }
 
+int mg_set_host_format(mg_env *h, int format, int n_threads) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_set_host_format: NULL handle");
+  if (format != MG_HOST_FULL) return fail(MG_ERR_INVALID_ARG, "mg_set_host_format: unknown format");
+  (void)n_threads;
+  return MG_OK;
+}
+int64_t mg_host_d2h_bytes(const mg_env *h) { return h ? (int64_t)h->p.n_envs * (OBS_BYTES + 4 + 8 + 1 + 1) : 0; }
+int mg_host_threads(const mg_env *h) { return h ? 0 : 0; }
+
 int mg_reset_host(mg_env *h, uint8_t *obs_host, int32_t *dir_host) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_reset_host: NULL handle");
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
   int rc = ensure_host_path(h);
   if (rc != MG_OK) return rc;
   uint8_t *d_obs, *d_term, *d_trunc; double *d_rew; int32_t *d_dir;
   host_dev_ptrs(h, &d_obs, &d_rew, &d_dir, &d_term, &d_trunc);
+  order_after_caller(h);
   rc = mg_reset(h, d_obs, d_dir, h->hstream);
   if (rc != MG_OK) return rc;
   return host_outputs(h, obs_host, dir_host, nullptr, nullptr, nullptr, d_obs, d_rew, d_dir, d_term, d_trunc);
@@ -408,7 +505,7 @@ int mg_reset_host(mg_env *h, uint8_t *obs_host, int32_t *dir_host) {
 int mg_step_host(mg_env *h, const int32_t *actions_host, uint8_t *obs_host, int32_t *dir_host, double *reward_host,
                  uint8_t *terminated_host, uint8_t *truncated_host) {
   if (!h || !actions_host) return fail(MG_ERR_INVALID_ARG, "mg_step_host: NULL argument");
-  MG_CUDA(cudaSetDevice(h->device));
+  MG_ON_DEVICE(h);
   int rc = ensure_host_path(h);
   if (rc != MG_OK) return rc;
   const size_t n = (size_t)h->p.n_envs;
@@ -418,6 +515,7 @@ int mg_step_host(mg_env *h, const int32_t *actions_host, uint8_t *obs_host, int3
     memcpy(h->h_actions, actions_host, n * sizeof(int32_t));
     src = h->h_actions;
   }
+  order_after_caller(h);
   MG_CUDA(cudaMemcpyAsync(h->d_actions, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->hstream));
   uint8_t *d_obs, *d_term, *d_trunc; double *d_rew; int32_t *d_dir;
   host_dev_ptrs(h, &d_obs, &d_rew, &d_dir, &d_term, &d_trunc);

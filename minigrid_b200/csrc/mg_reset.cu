@@ -25,8 +25,11 @@ __device__ void gen_obs_global(const Params &p, int env, int ax, int ay, int dir
 
 template <int KIND>
 __global__ void __launch_bounds__(128)
-k_reset(Params p, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out) {
+k_reset(Params p, const uint8_t *__restrict__ mask, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out) {
   for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < p.n_envs; env += gridDim.x * blockDim.x) {
+    // partial reset (gymnasium >= 1.1 VectorEnv.reset(options={"reset_mask": mask})): the other envs keep their
+    // state, their pending flag and their slots of the output buffers
+    if (mask && !mask[env]) continue;
     Pcg r = load_rng(p.rng + env);
     Level L;
     draw_level<KIND>(p, r, L);
@@ -51,25 +54,25 @@ k_reset(Params p, uint8_t *__restrict__ obs, int32_t *__restrict__ dir_out) {
   }
 }
 
-cudaError_t launch_reset(const Params &p, uint8_t *obs, int32_t *dir, cudaStream_t stream) {
+cudaError_t launch_reset(const Params &p, const uint8_t *mask, uint8_t *obs, int32_t *dir, cudaStream_t stream) {
   const int threads = 128;
   const int blocks = (p.n_envs + threads - 1) / threads;
   switch (p.kind) {
-    case KIND_EMPTY: k_reset<KIND_EMPTY><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_DOORKEY: k_reset<KIND_DOORKEY><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_CROSSING: k_reset<KIND_CROSSING><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_LAVAGAP: k_reset<KIND_LAVAGAP><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_DISTSHIFT: k_reset<KIND_DISTSHIFT><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_MULTIROOM: k_reset<KIND_MULTIROOM><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_LOCKEDROOM: k_reset<KIND_LOCKEDROOM><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_PLAYGROUND: k_reset<KIND_PLAYGROUND><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_GOTODOOR: k_reset<KIND_GOTODOOR><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_FETCH: k_reset<KIND_FETCH><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_REDBLUEDOORS: k_reset<KIND_REDBLUEDOORS><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_GOTOOBJECT: k_reset<KIND_GOTOOBJECT><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_PUTNEAR: k_reset<KIND_PUTNEAR><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    case KIND_MEMORY: k_reset<KIND_MEMORY><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
-    default: k_reset<KIND_FOURROOMS><<<blocks, threads, 0, stream>>>(p, obs, dir); break;
+    case KIND_EMPTY: k_reset<KIND_EMPTY><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_DOORKEY: k_reset<KIND_DOORKEY><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_CROSSING: k_reset<KIND_CROSSING><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_LAVAGAP: k_reset<KIND_LAVAGAP><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_DISTSHIFT: k_reset<KIND_DISTSHIFT><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_MULTIROOM: k_reset<KIND_MULTIROOM><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_LOCKEDROOM: k_reset<KIND_LOCKEDROOM><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_PLAYGROUND: k_reset<KIND_PLAYGROUND><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_GOTODOOR: k_reset<KIND_GOTODOOR><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_FETCH: k_reset<KIND_FETCH><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_REDBLUEDOORS: k_reset<KIND_REDBLUEDOORS><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_GOTOOBJECT: k_reset<KIND_GOTOOBJECT><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_PUTNEAR: k_reset<KIND_PUTNEAR><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_MEMORY: k_reset<KIND_MEMORY><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    default: k_reset<KIND_FOURROOMS><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
   }
   return cudaGetLastError();
 }
@@ -105,16 +108,17 @@ cudaError_t launch_template(const Params &p, uint32_t *tmpl, cudaStream_t stream
 }
 
 // np_random = Generator(PCG64(SeedSequence(seed)))
-__global__ void k_seed(Params p, const uint64_t *__restrict__ seeds, uint64_t base) {
+__global__ void k_seed(Params p, const uint8_t *__restrict__ mask, const uint64_t *__restrict__ seeds, uint64_t base) {
   const int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= p.n_envs) return;
+  if (mask && !mask[env]) return;  // SyncVectorEnv.reset seeds only the envs its reset_mask selects
   const uint64_t s = seeds ? seeds[env] : base + (uint64_t)env;
   const Pcg r = seed_pcg64(s);
   store_rng(p.rng + env, r);
 }
 
-cudaError_t launch_seed(const Params &p, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream) {
-  k_seed<<<(p.n_envs + 127) / 128, 128, 0, stream>>>(p, seeds_dev, base);
+cudaError_t launch_seed(const Params &p, const uint8_t *mask, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream) {
+  k_seed<<<(p.n_envs + 127) / 128, 128, 0, stream>>>(p, mask, seeds_dev, base);
   return cudaGetLastError();
 }
 

@@ -63,6 +63,14 @@ __global__ void k_set_agent(Params p, const int32_t *__restrict__ agent, const u
   uint4 rec = p.agent[env];
   if (agent) {
     const int32_t *a = agent + (size_t)env * 6;
+    // K1 derives window offsets and bit-mask shifts from the record without further checks: refuse what the
+    // reference could never hold (agent_pos inside the grid, dir 0..3, carrying in {None, Key, Ball, Box})
+    const bool ok = a[0] >= 0 && a[0] < p.g.W && a[1] >= 0 && a[1] < p.g.H && a[2] >= 0 && a[2] <= 3 &&
+                    (a[3] < 0 || ((a[3] >= (int)T_KEY && a[3] <= (int)T_BOX) && a[4] >= 0 && a[4] <= (int)C_GREY)) && a[5] >= 0;
+    if (!ok) {
+      atomicOr(p.err, ERR_BAD_STATE);
+      return;  // record, rng and pending flag of this env stay as they were
+    }
     rec.x = (rec.x & 0xFFFF0000u) | (uint32_t)(a[0] & 0xFF) | ((uint32_t)(a[1] & 0xFF) << 8);  // keeps the post-filter targets
     rec.y = (rec.y & ~3u) | (uint32_t)(a[2] & 3);
     rec.z = a[3] >= 0 ? ((uint32_t)(a[3] & 15) | ((uint32_t)(a[4] & 7) << 4)) : 0u;
@@ -117,6 +125,11 @@ cudaError_t launch_set_state(const Params &p, const uint8_t *grid, const int32_t
     k_set_grid<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, grid);
   }
   if (agent || rng || pending) k_set_agent<<<(p.n_envs + 127) / 128, 128, 0, stream>>>(p, agent, rng, pending);
+  return cudaGetLastError();
+}
+__global__ void k_clear_err(int *err, int bits) { atomicAnd(err, ~bits); }
+cudaError_t launch_clear_err(const Params &p, int bits, cudaStream_t stream) {
+  k_clear_err<<<1, 1, 0, stream>>>(p.err, bits);
   return cudaGetLastError();
 }
 cudaError_t launch_init(const Params &p, cudaStream_t stream) {

@@ -380,7 +380,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       if (so.goal)  // _reward(), minigrid_env.py:240-245: host-computed table, never an FMA
         reward = steps <= p.max_steps ? p.reward_lut[steps]
                                       : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
-      if (so.bad_action) atomicOr(p.err, 1);  // ValueError("Unknown action"), minigrid_env.py:584-585
+      if (so.bad_action) atomicOr(p.err, ERR_BAD_ACTION);  // ValueError("Unknown action"), minigrid_env.py:584-585
       if (newc != fc && active) {
         wrote = true;
         if (!WIN) {
@@ -466,7 +466,8 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       // (The ragged last tile / an unaligned obs pointer copy the valid bytes out of the stage instead: keeping the
       // stream words out of any byte-store path stops the compiler from spilling S to local memory on every tile.)
       const int nvalid = min(TILE, p.n_envs - tile * TILE);
-      const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);  // also: every lane is past its tile / window reads
+      const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);
+      __syncwarp();  // orders memory among the lanes: every lane is past its tile / window reads before the stage overwrites them
       emit_obs_staged(gtile, lane, S, n0);
       if (nvalid == TILE && (obs_tma_ok & 1)) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -512,6 +513,9 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     }
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  // the visibility table's bulk copy must have landed before the CTA's shared memory is released (a CTA without
+  // tiles, or an observation-less pass, never waited for it)
+  if (VIS == VIS_TBL && threadIdx.x == 0) mbar_wait(tbl_bar, 0);
   MG_TL(5);
   MG_TL_EXIT();
 }

@@ -30,15 +30,22 @@ def _spaces():
         return s.Discrete, s.MultiDiscrete, s.Box, s.Dict, s.Text
 
 
-class MinigridVecEnv:
-    """Batched MiniGridEnv on one GPU. `seed_offset` is this shard's first global env index (multi-GPU)."""
+try:  # subclass the real base class when gymnasium exists (it is not in this image: SURVEY 8c)
+    from gymnasium.vector import VectorEnv as _VectorEnvBase
+except Exception:  # noqa: BLE001
+    _VectorEnvBase = object
+
+
+class MinigridVecEnv(_VectorEnvBase):
+    """Batched MiniGridEnv on one GPU. `seed_offset` is this shard's first global env index (multi-GPU): without an
+    explicit seed, env i starts from seed `seed_offset + i`."""
 
     def __init__(self, env_id: str | None = None, num_envs: int = 1, *, spec: specs.EnvSpec | None = None,
                  device: int | str | torch.device | None = None, autoreset_mode: str = "next_step",
                  seed_offset: int = 0):
         if not torch.cuda.is_available():
             raise _lib.MinigridB200Error("minigrid_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
-        self.spec = spec if spec is not None else specs.get(env_id)
+        self.level_spec = spec if spec is not None else specs.get(env_id)
         self.env_id = env_id
         self.num_envs = int(num_envs)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -49,12 +56,14 @@ class MinigridVecEnv:
         self.metadata = {"autoreset_mode": autoreset_mode}
         self.seed_offset = int(seed_offset)
         self._L = _lib.load()
-        prm = (C.c_int32 * max(1, len(self.spec.params)))(*self.spec.params)
+        prm = (C.c_int32 * max(1, len(self.level_spec.params)))(*self.level_spec.params)
         h = C.c_void_p()
-        _lib.check(self._L.mg_create(self.spec.kind, self.spec.width, self.spec.height, self.spec.max_steps,
-                                     int(self.spec.see_through_walls), prm, len(self.spec.params), self.num_envs,
+        _lib.check(self._L.mg_create(self.level_spec.kind, self.level_spec.width, self.level_spec.height, self.level_spec.max_steps,
+                                     int(self.level_spec.see_through_walls), prm, len(self.level_spec.params), self.num_envs,
                                      AUTORESET[autoreset_mode], self.device.index, C.byref(h)))
         self._h = h
+        if self.seed_offset:  # mg_create seeds env i with i: shards of one batch must not hold identical envs
+            _lib.check(self._L.mg_seed_base(self._h, C.c_uint64(self.seed_offset), self._stream()))
         n, d = self.num_envs, self.device
         self._image = torch.zeros((n, 7, 7, 3), dtype=torch.uint8, device=d)
         self._direction = torch.zeros(n, dtype=torch.int32, device=d)
@@ -62,6 +71,7 @@ class MinigridVecEnv:
         self._terminated = torch.zeros(n, dtype=torch.bool, device=d)
         self._truncated = torch.zeros(n, dtype=torch.bool, device=d)
         self._host = None
+        self.host_format = "full"
         self._act_shape = (n,)
         self._mg_step = self._L.mg_step
         self._out_ptrs = tuple(C.c_void_p(t.data_ptr()) for t in
@@ -71,7 +81,7 @@ class MinigridVecEnv:
         self.single_action_space = Discrete(7)  # core/actions.py:7-20
         self.action_space = MultiDiscrete([7] * n) if n <= 1 << 16 else MultiDiscrete(np.full(n, 7))
         img = Box(0, 255, (7, 7, 3), np.uint8)
-        mission = Text(self.spec.mission) if Text is not None else None
+        mission = Text(self.level_spec.mission) if Text is not None else None
         single = {"image": img, "direction": Discrete(4)}
         batched = {"image": Box(0, 255, (n, 7, 7, 3), np.uint8), "direction": MultiDiscrete(np.full(n, 4))}
         if mission is not None:
@@ -79,9 +89,9 @@ class MinigridVecEnv:
             batched["mission"] = mission
         self.single_observation_space = Dict(single)
         self.observation_space = Dict(batched)
-        self.mission = self.spec.mission
+        self.mission = self.level_spec.mission
         self._obs_dict = {"image": self._image, "direction": self._direction, "mission": self.mission}
-        self.width, self.height, self.max_steps = self.spec.width, self.spec.height, self.spec.max_steps
+        self.width, self.height, self.max_steps = self.level_spec.width, self.level_spec.height, self.level_spec.max_steps
 
     # ---- plumbing ----
     def _stream(self):
@@ -109,21 +119,45 @@ class MinigridVecEnv:
         return a
 
     # ---- VectorEnv API ----
-    def seed(self, seed):
-        """seed: int -> env i gets seed + seed_offset + i (SyncVectorEnv convention); sequence -> one per env."""
+    def _mask(self, mask):
+        m = torch.as_tensor(mask)
+        if m.shape != (self.num_envs,):
+            raise ValueError(f"reset_mask must have shape ({self.num_envs},)")
+        return (m != 0).to(device=self.device, dtype=torch.uint8).contiguous()
+
+    def seed(self, seed, mask=None):
+        """seed: int -> env i gets seed + seed_offset + i (SyncVectorEnv convention); sequence -> one per env.
+        mask (bool[n], optional): only those envs are re-seeded."""
+        m = None if mask is None else (mask if isinstance(mask, torch.Tensor) and mask.dtype == torch.uint8 and mask.device == self.device else self._mask(mask))
         if np.isscalar(seed):
-            _lib.check(self._L.mg_seed_base(self._h, C.c_uint64(int(seed) + self.seed_offset), self._stream()))
+            base = C.c_uint64(int(seed) + self.seed_offset)
+            if m is None:
+                _lib.check(self._L.mg_seed_base(self._h, base, self._stream()))
+            else:
+                _lib.check(self._L.mg_seed_masked(self._h, self._p(m), None, base, self._stream()))
         else:
-            s = np.ascontiguousarray(seed, dtype=np.uint64)
+            s = np.ascontiguousarray([0 if v is None else v for v in seed] if isinstance(seed, (list, tuple)) else seed,
+                                     dtype=np.uint64)
             if s.shape != (self.num_envs,):
                 raise ValueError("seed sequence must have one entry per env")
-            _lib.check(self._L.mg_seed(self._h, s.ctypes.data_as(C.c_void_p), self._stream()))
+            if m is None:
+                _lib.check(self._L.mg_seed(self._h, s.ctypes.data_as(C.c_void_p), self._stream()))
+            else:
+                _lib.check(self._L.mg_seed_masked(self._h, self._p(m), s.ctypes.data_as(C.c_void_p), C.c_uint64(0), self._stream()))
 
     def reset(self, *, seed=None, options=None):
+        """VectorEnv.reset. options={"reset_mask": bool[n]} (gymnasium >= 1.1 SyncVectorEnv.reset) resets, and seeds,
+        only the selected envs; the others keep their state and their slots of the returned buffers."""
+        mask = None if not options else options.get("reset_mask")
         with torch.cuda.device(self.device):
+            m = None if mask is None else self._mask(mask)
             if seed is not None:
-                self.seed(seed)
-            _lib.check(self._L.mg_reset(self._h, self._p(self._image), self._p(self._direction), self._stream()))
+                self.seed(seed, m)
+            if m is None:
+                _lib.check(self._L.mg_reset(self._h, self._p(self._image), self._p(self._direction), self._stream()))
+            else:
+                _lib.check(self._L.mg_reset_masked(self._h, self._p(m), self._p(self._image), self._p(self._direction), self._stream()))
+                torch.cuda.current_stream(self.device).synchronize()  # m may be a temporary
         return self._obs(), {}
 
     def step(self, actions):
@@ -171,6 +205,24 @@ class MinigridVecEnv:
                 "terminated": pin((n,), torch.bool), "truncated": pin((n,), torch.bool),
             }
         return self._host
+
+    def set_host_format(self, fmt: str, threads: int = 0):
+        """How step_host / reset_host move the results to the host: "full" copies the arrays as they are (161 B per
+        env-step over PCIe); "packed" copies 52 B per env-step (cell codes + flags + reward index) and expands them on
+        `threads` host threads (0 = all usable) into the same arrays, bit-identical."""
+        if fmt not in ("full", "packed"):
+            raise ValueError("host format must be 'full' or 'packed'")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mg_set_host_format(self._h, 1 if fmt == "packed" else 0, int(threads)))
+        self.host_format = fmt
+
+    @property
+    def host_d2h_bytes_per_step(self) -> int:
+        return int(self._L.mg_host_d2h_bytes(self._h))
+
+    @property
+    def host_threads(self) -> int:
+        return int(self._L.mg_host_threads(self._h))
 
     def reset_host(self, *, seed=None):
         hb = self._host_buffers()

@@ -1034,6 +1034,17 @@ void mgo_vec_reset(mgo_vec *v, uint8_t *obs, int32_t *dir, int n_threads) {
   j.v = v; j.op = 0; j.obs = obs; j.dir = dir;
   run_jobs(j, clamp_threads(v, n_threads));
 }
+/* gymnasium >= 1.1 SyncVectorEnv.reset(seed=..., options={"reset_mask": mask}) (third-party, not in the reference
+ * tree; restated): only the selected sub-environments are seeded and reset, `_autoreset_envs` is cleared for them,
+ * the other envs and their slots of the observation buffer are left as they are. */
+void mgo_vec_seed_masked(mgo_vec *v, const uint8_t *mask, const uint64_t *seeds) {
+  for (int i = 0; i < v->n; i++)
+    if (mask[i]) seed_sequence_pcg64(seeds[i], &v->envs[i].rng);
+}
+void mgo_vec_reset_masked(mgo_vec *v, const uint8_t *mask, uint8_t *obs, int32_t *dir) {
+  for (int i = 0; i < v->n; i++)
+    if (mask[i]) reset_range(v, i, i + 1, obs, dir);
+}
 void mgo_vec_gen_obs(mgo_vec *v, uint8_t *obs, int32_t *dir) {
   for (int i = 0; i < v->n; i++) env_gen_obs(v, &v->envs[i], obs + (size_t)i * 147, dir + i);
 }

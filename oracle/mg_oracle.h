@@ -51,6 +51,9 @@ void mgo_vec_destroy(mgo_vec *v);
 void mgo_vec_seed(mgo_vec *v, const uint64_t *seeds);
 /* MiniGridEnv.reset() for every env (RNG stream continues), obs: [n][7][7][3], dir: [n] */
 void mgo_vec_reset(mgo_vec *v, uint8_t *obs, int32_t *dir, int n_threads);
+/* partial reset (gymnasium >= 1.1 SyncVectorEnv.reset(options={"reset_mask": mask})): envs with mask[i] != 0 only */
+void mgo_vec_seed_masked(mgo_vec *v, const uint8_t *mask, const uint64_t *seeds);
+void mgo_vec_reset_masked(mgo_vec *v, const uint8_t *mask, uint8_t *obs, int32_t *dir);
 /* one lockstep step with SyncVectorEnv autoreset semantics. returns 0, or -1 on an invalid action
  * (the reference raises ValueError, minigrid_env.py:584-585) */
 int mgo_vec_step(mgo_vec *v, const int32_t *actions, uint8_t *obs, int32_t *dir, double *reward,

@@ -108,6 +108,8 @@ def lib():
         L.mgo_vec_destroy.argtypes = [p]
         L.mgo_vec_seed.argtypes = [p, p]
         L.mgo_vec_reset.argtypes = [p, p, p, C.c_int]
+        L.mgo_vec_seed_masked.argtypes = [p, p, p]
+        L.mgo_vec_reset_masked.argtypes = [p, p, p, p]
         L.mgo_vec_step.restype = C.c_int
         L.mgo_vec_step.argtypes = [p] * 7 + [C.c_int, C.c_int]
         L.mgo_vec_full_obs.argtypes = [p, p]
@@ -159,11 +161,19 @@ class OracleVecEnv:
         assert s.shape == (self.num_envs,)
         lib().mgo_vec_seed(self._h, _ptr(s))
 
-    def reset(self, seed=None):
+    def reset(self, seed=None, mask=None):
+        m = None if mask is None else np.ascontiguousarray(np.asarray(mask) != 0, dtype=np.uint8)
         if seed is not None:
             seeds = np.arange(self.num_envs, dtype=np.uint64) + np.uint64(seed) if np.isscalar(seed) else seed
-            self.seed(seeds)
-        lib().mgo_vec_reset(self._h, _ptr(self.obs), _ptr(self.dir), self.n_threads)
+            if m is None:
+                self.seed(seeds)
+            else:
+                s = np.ascontiguousarray(seeds, dtype=np.uint64)
+                lib().mgo_vec_seed_masked(self._h, _ptr(m), _ptr(s))
+        if m is None:
+            lib().mgo_vec_reset(self._h, _ptr(self.obs), _ptr(self.dir), self.n_threads)
+        else:
+            lib().mgo_vec_reset_masked(self._h, _ptr(m), _ptr(self.obs), _ptr(self.dir))
         return self.obs, self.dir
 
     def step(self, actions):

@@ -17,11 +17,11 @@ class EngineAdapter:
     def _np(t):
         return t.cpu().numpy() if isinstance(t, torch.Tensor) else t
 
-    def reset(self, seed=None):
+    def reset(self, seed=None, mask=None):
         if self.host:
             obs, _ = self.e.reset_host(seed=seed)
         else:
-            obs, _ = self.e.reset(seed=seed)
+            obs, _ = self.e.reset(seed=seed, options=None if mask is None else {"reset_mask": mask})
         return self._np(obs["image"]).copy(), self._np(obs["direction"]).copy()
 
     def step(self, actions):
@@ -57,5 +57,6 @@ def make_engine(env_id, n, mode):
 
 def spec_tuple(env_id):
     s = specs.get(env_id)
-    kind = ["empty", "doorkey", "crossing", "fourrooms", "lavagap", "distshift", "multiroom"][s.kind]
+    kind = ["empty", "doorkey", "crossing", "fourrooms", "lavagap", "distshift", "multiroom", "lockedroom", "playground",
+            "gotodoor", "fetch", "redbluedoors", "gotoobject", "putnear", "memory"][s.kind]
     return (kind, s.width, s.height, s.max_steps, s.see_through_walls, list(s.params))

@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
 
 def _run(extra_env=None):
@@ -21,7 +22,12 @@ def test_reference_arm_line():
     assert line["impl"] == "reference"
     assert line["metric"] == "env_steps_per_sec" and line["unit"] == "env-steps/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["steps"] == 3 and line["warmup"] == 1
-    assert line["config"]["env"] == "MiniGrid-DoorKey-8x8-v0" and line["config"]["envs"] == 2048
+    assert line["config"]["env"] == "MiniGrid-DoorKey-8x8-v0" and line["config"]["envs_per_gpu"] == 2048
+    # both arms describe the workload with the same dict (the driver compares them: same_config)
+    import bench
+
+    assert line["config"] == bench.make_config("MiniGrid-DoorKey-8x8-v0", 2048, 1)
+    assert "desynchronised" in line["config"]["workload"]
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     e2e = line["e2e"]
