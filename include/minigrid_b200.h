@@ -130,6 +130,11 @@ int mg_step_host(mg_env *env, const int32_t *actions_host, uint8_t *obs_host, in
 #define MG_HOST_FULL 0
 #define MG_HOST_PACKED 1
 int mg_set_host_format(mg_env *env, int format, int n_threads);
+/* The host-side expansion itself (host code, no device work), for callers that move the packed records themselves:
+ * packed uint8[n][52] -> obs uint8[n][7][7][3], dir int32[n], reward float64[n], terminated / truncated uint8[n]
+ * (any output may be NULL). Single-threaded: split n over threads by offsetting the pointers. */
+int mg_expand_packed(const uint8_t *packed, int64_t n_envs, int32_t max_steps, uint8_t *obs, int32_t *dir,
+                     double *reward, uint8_t *terminated, uint8_t *truncated);
 int64_t mg_host_d2h_bytes(const mg_env *env);
 int mg_host_threads(const mg_env *env);
 

@@ -10,10 +10,11 @@
 #include "../../include/minigrid_b200.h"
 #include "mg_common.cuh"
 #include "mg_obs.cuh"
+#include "mg_host_expand.h"
 
 namespace mg {
 cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
-                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream);
+                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, uint32_t *packed, cudaStream_t stream);
 cudaError_t configure_step(const Params &p, StepPlan *plan);
 cudaError_t launch_reset(const Params &p, const uint8_t *mask, uint8_t *obs, int32_t *dir, cudaStream_t stream);
 cudaError_t launch_seed(const Params &p, const uint8_t *mask, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream);
@@ -44,6 +45,13 @@ struct mg_env {
   int32_t *d_actions; uint8_t *d_out;  // device mirror of the host-facing buffers
   int32_t *h_actions; uint8_t *h_out;  // pinned staging, used when the caller's buffers are pageable
   int *h_err;
+  // MG_HOST_PACKED: 52-byte step records cross PCIe in chunks and are expanded by a pool of host threads
+  int host_format;
+  uint32_t *d_packed; uint8_t *h_packed;   // device records, pinned landing buffer
+  double *h_reward_lut;                    // host copy of the reward table
+  HostPool *pool;
+  cudaEvent_t chunk_ev[16];
+  int n_chunks;
   // optional per-launch timing of K1 (bench.py's roofline leg)
   int profiling;
   std::vector<cudaEvent_t> *prof_events;  // start/stop pairs
@@ -180,7 +188,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
       lut[k] = 1.0 - m;
     }
     e = cudaMemcpy(d_rl, lut, (size_t)(max_steps + 1) * sizeof(double), cudaMemcpyHostToDevice);
-    free(lut);
+    h->h_reward_lut = lut;  // also the table of the host-side expansion (MG_HOST_PACKED)
     uint32_t cl[256];
     for (uint32_t c = 0; c < 256; ++c) cl[c] = decode_cell(c);
     if (e == cudaSuccess) e = cudaMemcpy(d_cl, cl, sizeof(cl), cudaMemcpyHostToDevice);
@@ -222,6 +230,12 @@ int mg_destroy(mg_env *h) {
   cudaFreeHost(h->h_actions);
   cudaFreeHost(h->h_out);
   cudaFreeHost(h->h_err);
+  cudaFree(h->d_packed);
+  cudaFreeHost(h->h_packed);
+  free(h->h_reward_lut);
+  delete h->pool;
+  for (int c = 0; c < 16; ++c)
+    if (h->chunk_ev[c]) cudaEventDestroy(h->chunk_ev[c]);
   if (h->prof_events) {
     for (cudaEvent_t e : *h->prof_events) cudaEventDestroy(e);
     delete h->prof_events;
@@ -312,7 +326,7 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
   }
   // one launch: transition + autoreset (either mode) + observation
   MG_CUDA(launch_step(p, h->plan, actions_dev, action_dtype, obs_dev, dir_dev, reward_dev, terminated_dev,
-                      truncated_dev, s));
+                      truncated_dev, nullptr, s));
   h->launches += 1;
   if (h->profiling) {
     MG_CUDA(cudaEventRecord(ev1, s));
@@ -326,7 +340,7 @@ int mg_gen_obs(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_gen_obs: NULL handle");
   MG_ON_DEVICE(h);
   note_stream(h, (cudaStream_t)stream);
-  MG_CUDA(launch_step(h->p, h->plan, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr,
+  MG_CUDA(launch_step(h->p, h->plan, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr, nullptr,
                       (cudaStream_t)stream));
   h->launches += 1;
   return MG_OK;
@@ -482,12 +496,79 @@ static void host_dev_ptrs(mg_env *h, uint8_t **obs, double **rew, int32_t **dir,
 
 int mg_set_host_format(mg_env *h, int format, int n_threads) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_set_host_format: NULL handle");
-  if (format != MG_HOST_FULL) return fail(MG_ERR_INVALID_ARG, "mg_set_host_format: unknown format");
-  (void)n_threads;
+  if (format != MG_HOST_FULL && format != MG_HOST_PACKED) return fail(MG_ERR_INVALID_ARG, "mg_set_host_format: unknown format");
+  MG_ON_DEVICE(h);
+  if (format == MG_HOST_PACKED) {
+    const size_t n_pad = (size_t)h->p.n_tiles * TILE;
+    if (!h->d_packed) MG_CUDA(cudaMalloc(&h->d_packed, n_pad * PACKED_BYTES));
+    if (!h->h_packed) MG_CUDA(cudaHostAlloc(&h->h_packed, n_pad * PACKED_BYTES, cudaHostAllocDefault));
+    int want = n_threads > 0 ? n_threads : usable_host_threads();
+    if (want > 64) want = 64;
+    if ((int64_t)want * 256 > h->p.n_envs) want = (int)(h->p.n_envs / 256 > 0 ? h->p.n_envs / 256 : 1);  // no point in slices of a few envs
+    if (!h->pool || h->pool->threads() != want) {
+      delete h->pool;
+      h->pool = new HostPool(want);
+    }
+    // chunks: enough of them that the expansion of chunk c overlaps the copy of chunk c + 1, each still a large copy
+    int chunks = (int)(h->p.n_envs / 16384);
+    chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+    for (int c = 0; c < chunks; ++c)
+      if (!h->chunk_ev[c]) MG_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
+    h->n_chunks = chunks;
+  }
+  h->host_format = format;
   return MG_OK;
 }
-int64_t mg_host_d2h_bytes(const mg_env *h) { return h ? (int64_t)h->p.n_envs * (OBS_BYTES + 4 + 8 + 1 + 1) : 0; }
-int mg_host_threads(const mg_env *h) { return h ? 0 : 0; }
+int64_t mg_host_d2h_bytes(const mg_env *h) {
+  if (!h) return 0;
+  return h->host_format == MG_HOST_PACKED ? (int64_t)h->p.n_envs * PACKED_BYTES : (int64_t)h->p.n_envs * (OBS_BYTES + 4 + 8 + 1 + 1);
+}
+int mg_host_threads(const mg_env *h) { return (h && h->host_format == MG_HOST_PACKED && h->pool) ? h->pool->threads() : 0; }
+
+// MG_HOST_PACKED step: H2D actions, K1 writing 52-byte records, D2H in chunks; the pool expands chunk c into the
+// caller's arrays while chunk c + 1 is still on the bus.
+static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, int32_t *dir_host, double *reward_host,
+                            uint8_t *term_host, uint8_t *trunc_host) {
+  const size_t n = (size_t)h->p.n_envs;
+  cudaStream_t s = h->hstream;
+  ExpandJob job;
+  job.packed = h->h_packed; job.max_steps = h->p.max_steps; job.reward_lut = h->h_reward_lut;
+  job.obs = obs_host; job.dir = dir_host; job.reward = reward_host; job.term = term_host; job.trunc = trunc_host;
+  int64_t bounds[17];
+  const int C = h->n_chunks;
+  for (int c = 0; c <= C; ++c) bounds[c] = (int64_t)((n * (size_t)c / (size_t)C) / TILE * TILE);
+  bounds[C] = (int64_t)n;
+  h->pool->begin(job, bounds, C);  // the workers wake up while the copy and the kernel run
+  cudaError_t e = cudaMemcpyAsync(h->d_actions, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    e = launch_step(h->p, h->plan, h->d_actions, MG_ACT_I32, nullptr, nullptr, nullptr, nullptr, nullptr, h->d_packed, s);
+  h->launches += 1;
+  for (int c = 0; c < C && e == cudaSuccess; ++c) {
+    const size_t off = (size_t)bounds[c] * PACKED_BYTES, len = (size_t)(bounds[c + 1] - bounds[c]) * PACKED_BYTES;
+    e = cudaMemcpyAsync(h->h_packed + off, reinterpret_cast<const uint8_t *>(h->d_packed) + off, len, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaEventRecord(h->chunk_ev[c], s);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_err, h->p.err, sizeof(int), cudaMemcpyDeviceToHost, s);
+  int released = 0;
+  for (int c = 0; c < C && e == cudaSuccess; ++c) {
+    e = cudaEventSynchronize(h->chunk_ev[c]);
+    if (e == cudaSuccess) { h->pool->chunk_ready(); ++released; }
+  }
+  if (e != cudaSuccess) h->pool->abort_chunks(C);  // let the workers run through (their output is discarded by the error)
+  (void)released;
+  h->pool->wait();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) return fail(MG_ERR_CUDA, std::string("mg_step_host (packed): ") + cudaGetErrorString(e));
+  if (*h->h_err & ERR_PACKED_RANGE) {
+    MG_CUDA(launch_clear_err(h->p, ERR_PACKED_RANGE, s));
+    return fail(MG_ERR_INVALID_ARG, "mg_step_host: a rewarded step count exceeds what the packed record holds (2^19 - 1); use MG_HOST_FULL");
+  }
+  if (*h->h_err & ERR_BAD_ACTION) {
+    MG_CUDA(launch_clear_err(h->p, ERR_BAD_ACTION, s));
+    return fail(MG_ERR_INVALID_ACTION, "Unknown action: outside 0..6 (minigrid_env.py:584-585)");
+  }
+  return MG_OK;
+}
 
 int mg_reset_host(mg_env *h, uint8_t *obs_host, int32_t *dir_host) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_reset_host: NULL handle");
@@ -516,6 +597,8 @@ int mg_step_host(mg_env *h, const int32_t *actions_host, uint8_t *obs_host, int3
     src = h->h_actions;
   }
   order_after_caller(h);
+  if (h->host_format == MG_HOST_PACKED)
+    return step_host_packed(h, src, obs_host, dir_host, reward_host, terminated_host, truncated_host);
   MG_CUDA(cudaMemcpyAsync(h->d_actions, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, h->hstream));
   uint8_t *d_obs, *d_term, *d_trunc; double *d_rew; int32_t *d_dir;
   host_dev_ptrs(h, &d_obs, &d_rew, &d_dir, &d_term, &d_trunc);

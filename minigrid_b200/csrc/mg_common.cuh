@@ -69,7 +69,7 @@ enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS
 constexpr int KIND_COUNT = 15;  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
 enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
 // bits of the sticky device error word (Params::err)
-enum : int { ERR_BAD_ACTION = 1, ERR_BAD_STATE = 2 };
+enum : int { ERR_BAD_ACTION = 1, ERR_BAD_STATE = 2, ERR_PACKED_RANGE = 4 };
 
 // (type, colour, state) -> cell code. None/unseen/agent all mean "no object" (WorldObj.decode,
 // world_object.py:77-78) and encode as (1,0,0) (grid.py:258-261).

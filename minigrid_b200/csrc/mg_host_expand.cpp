@@ -1,0 +1,240 @@
+// mg_host_expand.cpp — host side of MG_HOST_PACKED (include/minigrid_b200.h): the end-to-end path is PCIe-bound
+// (161 B per env-step at ~55 GB/s), so K1 ships 52 B per env-step — the view's 49 one-byte cell codes, i.e. the image
+// BEFORE Grid.encode's (type, colour, state) table (grid.py:244-268, world_object.py:65-67,196-212), plus direction,
+// flags and the step count the reward is a function of — and the table lookup, which is host-computed data in both
+// formats, runs here on the host cores while the next chunk is still crossing the bus. Bit-identical by construction:
+// the same 256-entry table (decode_cell) and the same IEEE-double reward expression (minigrid_env.py:240-245).
+// Host code only; no CUDA in this file.
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <immintrin.h>
+#include <sched.h>
+
+#include "../../include/minigrid_b200.h"
+#include "mg_host_expand.h"
+
+namespace mg {
+
+namespace {
+
+constexpr int kObsBytes = 147, kPacked = 52, kCells = 49;
+
+// WorldObj.encode / Door.encode of a cell code: bits 0-3 t4 (type with the door state folded in: 4 open, 11 closed,
+// 12 locked), bits 4-6 colour. Same function as decode_cell() in mg_common.cuh, restated for a host-only file.
+inline uint32_t decode_code(uint32_t code) {
+  const uint32_t t4 = code & 15u, color = (code >> 4) & 7u;
+  if (t4 == 0) return 0;
+  if (t4 == 1) return 1;
+  if (t4 == 11) return 4u | (color << 8) | (1u << 16);
+  if (t4 == 12) return 4u | (color << 8) | (2u << 16);
+  return t4 | (color << 8);
+}
+
+struct Tables {
+  uint32_t lut[256];
+  Tables() {
+    for (uint32_t c = 0; c < 256; ++c) lut[c] = decode_code(c);
+  }
+};
+const Tables &tables() {
+  static const Tables t;
+  return t;
+}
+
+inline double reward_of(uint32_t steps, int max_steps) {
+  // _reward(): 1 - 0.9 * (step_count / max_steps), evaluated like Python does: three separately rounded operations
+  volatile double q = (double)steps / (double)max_steps;
+  volatile double m = 0.9 * q;
+  return 1.0 - m;
+}
+
+inline void expand_tail(const uint8_t *rec, int64_t i, const ExpandJob &j) {
+  const uint32_t f = rec[49];
+  if (j.dir) j.dir[i] = (int32_t)(f & 3u);
+  if (j.term) j.term[i] = (uint8_t)((f >> 2) & 1u);
+  if (j.trunc) j.trunc[i] = (uint8_t)((f >> 3) & 1u);
+  if (j.reward) {
+    double r = 0.0;
+    if (f & 16u) {
+      const uint32_t steps = (uint32_t)rec[50] | ((uint32_t)rec[51] << 8) | ((f >> 5) << 16);
+      r = (j.reward_lut && (int)steps <= j.max_steps) ? j.reward_lut[steps] : reward_of(steps, j.max_steps);
+    }
+    j.reward[i] = r;
+  }
+}
+
+void expand_scalar(const ExpandJob &j, int64_t lo, int64_t hi) {
+  const uint32_t *lut = tables().lut;
+  for (int64_t i = lo; i < hi; ++i) {
+    const uint8_t *rec = j.packed + i * kPacked;
+    if (j.obs) {
+      uint8_t *o = j.obs + i * kObsBytes;
+      for (int q = 0; q < kCells - 1; ++q) {  // 4-byte stores, the 4th byte is overwritten by the next triple
+        const uint32_t t = lut[rec[q]];
+        memcpy(o + 3 * q, &t, 4);
+      }
+      const uint32_t t = lut[rec[kCells - 1]];
+      o[144] = (uint8_t)t; o[145] = (uint8_t)(t >> 8); o[146] = (uint8_t)(t >> 16);
+    }
+    expand_tail(rec, i, j);
+  }
+}
+
+// 16 codes -> 48 image bytes with three 16-entry byte tables on t4 and byte shuffles for the 3-way interleave
+__attribute__((target("ssse3"))) void expand_ssse3(const ExpandJob &j, int64_t lo, int64_t hi) {
+  const __m128i type_lut = _mm_setr_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 4, 4, 13, 14, 15);
+  const __m128i state_lut = _mm_setr_epi8(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 0, 0, 0);
+  const __m128i cmask_lut = _mm_setr_epi8(0, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+  const __m128i low4 = _mm_set1_epi8(15), low3 = _mm_set1_epi8(7);
+  // output bytes 0..15 / 16..31 / 32..47 of (t0 c0 s0 t1 c1 s1 ...): shuffle masks per source plane (0x80 = zero)
+  const __m128i Z = _mm_set1_epi8((char)0x80);
+  (void)Z;
+  const __m128i t_a = _mm_setr_epi8(0, -128, -128, 1, -128, -128, 2, -128, -128, 3, -128, -128, 4, -128, -128, 5);
+  const __m128i c_a = _mm_setr_epi8(-128, 0, -128, -128, 1, -128, -128, 2, -128, -128, 3, -128, -128, 4, -128, -128);
+  const __m128i s_a = _mm_setr_epi8(-128, -128, 0, -128, -128, 1, -128, -128, 2, -128, -128, 3, -128, -128, 4, -128);
+  const __m128i t_b = _mm_setr_epi8(-128, -128, 6, -128, -128, 7, -128, -128, 8, -128, -128, 9, -128, -128, 10, -128);
+  const __m128i c_b = _mm_setr_epi8(5, -128, -128, 6, -128, -128, 7, -128, -128, 8, -128, -128, 9, -128, -128, 10);
+  const __m128i s_b = _mm_setr_epi8(-128, 5, -128, -128, 6, -128, -128, 7, -128, -128, 8, -128, -128, 9, -128, -128);
+  const __m128i t_c = _mm_setr_epi8(-128, 11, -128, -128, 12, -128, -128, 13, -128, -128, 14, -128, -128, 15, -128, -128);
+  const __m128i c_c = _mm_setr_epi8(-128, -128, 11, -128, -128, 12, -128, -128, 13, -128, -128, 14, -128, -128, 15, -128);
+  const __m128i s_c = _mm_setr_epi8(10, -128, -128, 11, -128, -128, 12, -128, -128, 13, -128, -128, 14, -128, -128, 15);
+  const uint32_t *lut = tables().lut;
+  for (int64_t i = lo; i < hi; ++i) {
+    const uint8_t *rec = j.packed + i * kPacked;
+    if (j.obs) {
+      uint8_t *o = j.obs + i * kObsBytes;
+#pragma GCC unroll 3
+      for (int blk = 0; blk < 3; ++blk) {
+        const __m128i code = _mm_loadu_si128(reinterpret_cast<const __m128i *>(rec + 16 * blk));
+        const __m128i t4 = _mm_and_si128(code, low4);
+        const __m128i ty = _mm_shuffle_epi8(type_lut, t4);
+        const __m128i st = _mm_shuffle_epi8(state_lut, t4);
+        const __m128i co = _mm_and_si128(_mm_and_si128(_mm_srli_epi16(code, 4), low3), _mm_shuffle_epi8(cmask_lut, t4));
+        const __m128i a = _mm_or_si128(_mm_or_si128(_mm_shuffle_epi8(ty, t_a), _mm_shuffle_epi8(co, c_a)), _mm_shuffle_epi8(st, s_a));
+        const __m128i b = _mm_or_si128(_mm_or_si128(_mm_shuffle_epi8(ty, t_b), _mm_shuffle_epi8(co, c_b)), _mm_shuffle_epi8(st, s_b));
+        const __m128i c = _mm_or_si128(_mm_or_si128(_mm_shuffle_epi8(ty, t_c), _mm_shuffle_epi8(co, c_c)), _mm_shuffle_epi8(st, s_c));
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(o + 48 * blk), a);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(o + 48 * blk + 16), b);
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(o + 48 * blk + 32), c);
+      }
+      const uint32_t t = lut[rec[kCells - 1]];
+      o[144] = (uint8_t)t; o[145] = (uint8_t)(t >> 8); o[146] = (uint8_t)(t >> 16);
+    }
+    expand_tail(rec, i, j);
+  }
+}
+
+}  // namespace
+
+void expand_range(const ExpandJob &j, int64_t lo, int64_t hi) {
+  static const bool have_ssse3 = __builtin_cpu_supports("ssse3");
+  static const bool force_scalar = getenv("MINIGRID_B200_EXPAND_SCALAR") != nullptr;
+  if (have_ssse3 && !force_scalar) expand_ssse3(j, lo, hi);
+  else expand_scalar(j, lo, hi);
+}
+
+int usable_host_threads() {
+  int n = (int)std::thread::hardware_concurrency();
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+    const int a = CPU_COUNT(&set);
+    if (a > 0 && (n <= 0 || a < n)) n = a;
+  }
+  if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {  // cgroup v2 CPU quota
+    char quota[32];
+    long period = 0;
+    if (fscanf(f, "%31s %ld", quota, &period) == 2 && strcmp(quota, "max") != 0 && period > 0) {
+      const long q = (atol(quota) + period - 1) / period;
+      if (q > 0 && q < n) n = (int)q;
+    }
+    fclose(f);
+  }
+  return n < 1 ? 1 : n;
+}
+
+// ---- a small persistent pool: workers park on a condition variable between steps, and inside a step wait (spinning
+// briefly) for the chunk the copy engine is still delivering ----
+struct HostPool::Impl {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv_start, cv_done;
+  uint64_t generation = 0;
+  bool stop = false;
+  ExpandJob job{};
+  std::vector<int64_t> bounds;       // chunk c = envs [bounds[c], bounds[c + 1])
+  std::atomic<int> ready{0};         // chunks whose bytes have arrived on the host
+  int done = 0;
+
+  void worker(int w, int T) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_start.wait(lk, [&] { return stop || generation != seen; });
+        if (stop) return;
+        seen = generation;
+      }
+      const int n_chunks = (int)bounds.size() - 1;
+      for (int c = 0; c < n_chunks; ++c) {
+        int spins = 0;
+        while (ready.load(std::memory_order_acquire) <= c) {
+          if (++spins < 2000) _mm_pause();
+          else { std::this_thread::yield(); spins = 0; }
+        }
+        const int64_t lo = bounds[c], len = bounds[c + 1] - bounds[c];
+        expand_range(job, lo + len * w / T, lo + len * (w + 1) / T);
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (++done == T) cv_done.notify_one();
+      }
+    }
+  }
+};
+
+HostPool::HostPool(int n_threads) : impl_(new Impl), n_threads_(n_threads < 1 ? 1 : n_threads) {
+  for (int w = 0; w < n_threads_; ++w) impl_->threads.emplace_back([this, w] { impl_->worker(w, n_threads_); });
+}
+HostPool::~HostPool() {
+  {
+    std::lock_guard<std::mutex> lk(impl_->mu);
+    impl_->stop = true;
+  }
+  impl_->cv_start.notify_all();
+  for (auto &t : impl_->threads) t.join();
+  delete impl_;
+}
+void HostPool::begin(const ExpandJob &job, const int64_t *bounds, int n_chunks) {
+  std::lock_guard<std::mutex> lk(impl_->mu);
+  impl_->job = job;
+  impl_->bounds.assign(bounds, bounds + n_chunks + 1);
+  impl_->ready.store(0, std::memory_order_release);
+  impl_->done = 0;
+  impl_->generation += 1;
+  impl_->cv_start.notify_all();
+}
+void HostPool::chunk_ready() { impl_->ready.fetch_add(1, std::memory_order_release); }
+void HostPool::abort_chunks(int n_chunks) { impl_->ready.store(n_chunks, std::memory_order_release); }
+void HostPool::wait() {
+  std::unique_lock<std::mutex> lk(impl_->mu);
+  impl_->cv_done.wait(lk, [&] { return impl_->done == n_threads_; });
+}
+
+}  // namespace mg
+
+extern "C" int mg_expand_packed(const uint8_t *packed, int64_t n_envs, int32_t max_steps, uint8_t *obs, int32_t *dir,
+                                double *reward, uint8_t *terminated, uint8_t *truncated) {
+  if (!packed || n_envs < 0 || max_steps < 1) return MG_ERR_INVALID_ARG;
+  mg::ExpandJob j{};
+  j.packed = packed; j.max_steps = max_steps; j.reward_lut = nullptr;
+  j.obs = obs; j.dir = dir; j.reward = reward; j.term = terminated; j.trunc = truncated;
+  mg::expand_range(j, 0, n_envs);
+  return MG_OK;
+}

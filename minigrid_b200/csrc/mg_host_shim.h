@@ -21,6 +21,10 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift)
   const uint64_t v = ((uint64_t)hi << 32) | lo;
   return (uint32_t)(v >> (shift & 31u));
 }
+static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t shift) {  // shf.r.clamp
+  const uint64_t v = ((uint64_t)hi << 32) | lo;
+  return (uint32_t)(v >> (shift > 32u ? 32u : shift));
+}
 static inline uint32_t __brev(uint32_t v) {
   uint32_t r = 0;
   for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);

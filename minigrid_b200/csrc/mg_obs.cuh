@@ -107,13 +107,14 @@ MG_D void process_vis_tbl(const uint16_t *tbl, uint32_t oplo, uint32_t ophi, uin
   }
 }
 
-// Produces the 147-byte image of one env as 37 little-endian words S (byte 147 is zero).
-//   acc    word accessor (AccTiled / AccFlat), lut: 256-entry decode table (shared or global)
+// gen_obs up to and including the carry overlay: the 49 cell CODES of the view (0 = unseen), column vx in
+// (clo[vx], chi[vx]): byte j of clo = view row vy = j, byte j of chi = view row 4 + j (its top byte is zero).
+//   acc    word accessor (AccTiled / AccFlat)
 //   VIS    VIS_NONE: see_through_walls (minigrid_env.py:616-621); VIS_ALU: bit tricks; VIS_TBL: vis_tbl lookups
 constexpr int VIS_NONE = 0, VIS_ALU = 1, VIS_TBL = 2;
 template <int VIS, class Acc>
-MG_D void gen_obs_words(const Geom &g, const Acc &acc, const uint32_t *lut, const uint16_t *vis_tbl,
-                        int ax, int ay, int dir, uint32_t carry, uint32_t (&S)[OBS_WORDS]) {
+MG_D void gather_view(const Geom &g, const Acc &acc, const uint16_t *vis_tbl, int ax, int ay, int dir, uint32_t carry,
+                      uint32_t (&clo)[VIEW], uint32_t (&chi)[VIEW]) {
   const bool useC = dir & 1;
   const bool rev = dir < 2;
   const int lc = useC ? ax : ay;       // line coordinate of the agent in the chosen array
@@ -135,7 +136,6 @@ MG_D void gen_obs_words(const Geom &g, const Acc &acc, const uint32_t *lut, cons
   const uint32_t selLo = rev ? 0x3456u : 0x3210u;
   const uint32_t selHi = rev ? 0x7012u : 0x7654u;
 
-  uint32_t clo[VIEW], chi[VIEW];
   uint32_t oplo = 0, ophi = 0;
 #pragma unroll
   for (int vx = 0; vx < VIEW; ++vx) {
@@ -169,8 +169,101 @@ MG_D void gen_obs_words(const Geom &g, const Acc &acc, const uint32_t *lut, cons
   }
   // the agent's own view cell (3,6) shows what it carries, else empty (minigrid_env.py:623-630)
   chi[3] = prmt(chi[3], carry ? carry : CODE_EMPTY, 0x3410u);
+}
 
-  // Grid.encode: image[vx][vy][c], i.e. triple q = 7*vx + vy occupies stream bytes 3q..3q+2
+// ---- LAYOUT_WINDOW (large grids): the view's words are loaded straight into registers, geometry applied later ----
+// Which 7 lines the view needs is known BEFORE the transition (a turn depends on the action alone and a forward move
+// never changes the line coordinate of the array the agent faces along); only the position inside the lines can still
+// shift by one byte (forward move). So each lane loads, per line, the 3 words that cover the 8 bytes of both cases —
+// 21 independent 4-byte loads, 7 sectors, ONE memory round trip per step — and the transition reads its front cell out
+// of the same words (the cell in front is view cell (3, 5) unless the agent turns, in which case it is not needed).
+struct ViewWords {
+  uint32_t w[VIEW][3];
+  int ws;       // index of w[.][0] inside a line (may be negative: clamped words only ever supply masked bytes)
+};
+// first byte position the loaded words must cover, for an agent at (ax, ay) that will face `dirn` after the action
+MG_D int view_first_pos(int ax, int ay, int dirn) {
+  const int pc = (dirn & 1) ? ay : ax;
+  return (dirn < 2) ? pc : pc - 7;  // facing +: run starts at pc (pc + 1 after a move); facing -: pc - 6 (pc - 7 after a move)
+}
+template <class Load>
+MG_D void load_view_words(const Geom &g, int ax, int ay, int dirn, ViewWords &vw, Load &&load) {
+  const bool useC = dirn & 1;
+  const int lc = useC ? ax : ay;
+  const int lstep = (dirn == 0 || dirn == 3) ? 1 : -1;
+  const int abase = useC ? g.offC : 0;
+  const int ws = view_first_pos(ax, ay, dirn) >> 2;
+  const int k0 = clampi(ws, 0, WIN_LINE_WORDS - 1), k1 = clampi(ws + 1, 0, WIN_LINE_WORDS - 1), k2 = clampi(ws + 2, 0, WIN_LINE_WORDS - 1);
+  vw.ws = ws;
+#pragma unroll
+  for (int vx = 0; vx < VIEW; ++vx) {
+    const int rw = abase + (lc + lstep * (vx - 3) + g.ring) * WIN_LINE_WORDS;  // ring = 3 lines: lc +- 3 always exists
+    vw.w[vx][0] = load(rw + k0);
+    vw.w[vx][1] = load(rw + k1);
+    vw.w[vx][2] = load(rw + k2);
+  }
+}
+// the byte at position `pos` of the agent's own line (view column 3); pos must lie in the 12 bytes loaded
+MG_D uint32_t view_words_byte(const ViewWords &vw, int pos) {
+  const int o = pos - 4 * vw.ws;
+  const uint32_t w = o < 4 ? vw.w[3][0] : (o < 8 ? vw.w[3][1] : vw.w[3][2]);
+  return (w >> (8 * (o & 3))) & 0xFFu;
+}
+MG_D void view_words_set_byte(ViewWords &vw, int pos, uint32_t code) {
+  const int o = pos - 4 * vw.ws;
+  const uint32_t sh = 8u * (uint32_t)(o & 3), m = 0xFFu << sh, v = (code & 0xFFu) << sh;
+  if (o < 4) vw.w[3][0] = (vw.w[3][0] & ~m) | v;
+  else if (o < 8) vw.w[3][1] = (vw.w[3][1] & ~m) | v;
+  else vw.w[3][2] = (vw.w[3][2] & ~m) | v;
+}
+// gather_view on preloaded words: (ax, ay, dir) is the state AFTER the transition; the words were loaded for this
+// direction and cover its run of 7 bytes
+template <int VIS>
+MG_D void gather_from_words(const Geom &g, const ViewWords &vw, const uint16_t *vis_tbl, int ax, int ay, int dir, uint32_t carry,
+                            uint32_t (&clo)[VIEW], uint32_t (&chi)[VIEW]) {
+  const bool useC = dir & 1;
+  const bool rev = dir < 2;
+  const int pc = useC ? ay : ax;
+  const int plen = useC ? g.H : g.W;
+  const int p0 = rev ? pc : pc - 6;
+  const uint32_t sh = (uint32_t)(p0 - 4 * vw.ws) * 8u;  // 0..32: the clamping funnel shift returns the upper word at 32
+  uint32_t valid7 = ((((1u << plen) - 1u) << 6) >> (p0 + 6)) & 0x7Fu;
+  if (rev) valid7 = __brev(valid7) >> 25;
+  const uint32_t mlo = spread4(valid7 & 0xFu) * 0xFFu;
+  const uint32_t mhi = spread4(valid7 >> 4) * 0xFFu;
+  const uint32_t selLo = rev ? 0x3456u : 0x3210u;
+  const uint32_t selHi = rev ? 0x7012u : 0x7654u;
+  uint32_t oplo = 0, ophi = 0;
+#pragma unroll
+  for (int vx = 0; vx < VIEW; ++vx) {
+    const uint32_t a = __funnelshift_rc(vw.w[vx][0], vw.w[vx][1], sh);
+    const uint32_t b = __funnelshift_rc(vw.w[vx][1], vw.w[vx][2], sh);
+    uint32_t lo = prmt(a, b, selLo);
+    uint32_t hi = prmt(a, b, selHi);
+    lo = (lo & mlo) | (CODE_WALL4 & ~mlo);
+    hi = (hi & mhi) | ((CODE_WALL4 & 0x00FFFFFFu) & ~mhi);
+    clo[vx] = lo; chi[vx] = hi;
+    if (VIS != VIS_NONE) {
+      oplo |= ((lo >> 7) & 0x01010101u) << vx;
+      ophi |= ((hi >> 7) & 0x01010101u) << vx;
+    }
+  }
+  if (VIS != VIS_NONE) {
+    uint32_t vlo, vhi;
+    if (VIS == VIS_TBL) process_vis_tbl(vis_tbl, oplo, ophi, vlo, vhi);
+    else process_vis(oplo, ophi, vlo, vhi);
+#pragma unroll
+    for (int vx = 0; vx < VIEW; ++vx) {
+      clo[vx] &= prmt(vlo << (7 - vx), 0u, 0xBA98u);
+      chi[vx] &= prmt(vhi << (7 - vx), 0u, 0xBA98u);
+    }
+  }
+  chi[3] = prmt(chi[3], carry ? carry : CODE_EMPTY, 0x3410u);
+}
+
+// Grid.encode on the gathered codes: the 147-byte image of one env as 37 little-endian words S (byte 147 is zero).
+// image[vx][vy][c], i.e. triple q = 7*vx + vy occupies stream bytes 3q..3q+2; lut: 256-entry decode table.
+MG_D void encode_stream(const uint32_t *lut, const uint32_t (&clo)[VIEW], const uint32_t (&chi)[VIEW], uint32_t (&S)[OBS_WORDS]) {
   uint32_t T[VIEW * VIEW + 1];
 #pragma unroll
   for (int vx = 0; vx < VIEW; ++vx) {
@@ -187,6 +280,44 @@ MG_D void gen_obs_words(const Geom &g, const Acc &acc, const uint32_t *lut, cons
     const int a = (4 * j) / 3, r = 4 * j - 3 * a;
     S[j] = prmt(T[a], T[a + 1], r == 0 ? 0x4210u : (r == 1 ? 0x5421u : 0x6542u));
   }
+}
+
+template <int VIS, class Acc>
+MG_D void gen_obs_words(const Geom &g, const Acc &acc, const uint32_t *lut, const uint16_t *vis_tbl,
+                        int ax, int ay, int dir, uint32_t carry, uint32_t (&S)[OBS_WORDS]) {
+  uint32_t clo[VIEW], chi[VIEW];
+  gather_view<VIS>(g, acc, vis_tbl, ax, ay, dir, carry, clo, chi);
+  encode_stream(lut, clo, chi, S);
+}
+
+// The packed record of the host path (MG_HOST_PACKED, include/minigrid_b200.h): 52 bytes = 13 words per env.
+//   bytes 0..48  the view's cell codes in image order (q = 7*vx + vy), i.e. the image before Grid.encode's table
+//   byte  49     dir | terminated << 2 | truncated << 3 | rewarded << 4 | (step_count >> 16) << 5
+//   bytes 50-51  step_count & 0xFFFF (the reward is the host-side table entry of this step count when `rewarded`)
+constexpr int PACKED_WORDS = 13, PACKED_BYTES = 52, PACKED_TILE_BYTES = PACKED_BYTES * TILE;  // 1664, a multiple of 16
+constexpr uint32_t PACKED_MAX_STEPS = (1u << 19) - 1u;
+MG_D void pack_codes(const uint32_t (&clo)[VIEW], const uint32_t (&chi)[VIEW], uint32_t tail, uint32_t (&P)[PACKED_WORDS]) {
+#pragma unroll
+  for (int j = 0; j < PACKED_WORDS; ++j) {
+    // output byte b = 4j + k comes from column b / 7, row b % 7: at most two source words per output word
+    uint32_t sel = 0, src[2] = {0u, 0u};
+    int nsrc = 0, id[2] = {-1, -1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int b = 4 * j + k;
+      if (b >= VIEW * VIEW) { sel |= 0x8u << (4 * k); continue; }  // filled from `tail` below
+      const int vx = b / VIEW, vy = b % VIEW;
+      const int wid = 2 * vx + (vy >= 4);
+      int slot = (id[0] == wid) ? 0 : ((id[1] == wid) ? 1 : -1);
+      if (slot < 0) { slot = nsrc++; id[slot] = wid; src[slot] = (vy < 4) ? clo[vx] : chi[vx]; }
+      sel |= (uint32_t)(4 * slot + (vy & 3)) << (4 * k);
+    }
+    if (j < PACKED_WORDS - 1) P[j] = prmt(src[0], src[1], sel);
+    else P[j] = ((chi[VIEW - 1] >> 16) & 0xFFu) | (tail << 8);  // byte 48 = cell (6, 6), then the three tail bytes
+  }
+}
+MG_HD uint32_t packed_tail(int dir, uint32_t terminated, uint32_t truncated, uint32_t rewarded, uint32_t steps) {
+  return (uint32_t)dir | (terminated << 2) | (truncated << 3) | (rewarded << 4) | (((steps >> 16) & 7u) << 5) | ((steps & 0xFFFFu) << 8);
 }
 
 // Stage one warp's 32 images into shared memory exactly as they lie in the [n][7][7][3] output

@@ -55,7 +55,7 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
       if (!win && want_nbuf && nbuf != want_nbuf) continue;
       const int mode = win ? MODE_WINDOW : (nbuf == 2 ? MODE_TILED2 : MODE_TILED1);
       StepKernel k = step_kernel(p.kind, vis, mode);
-      const int wcap = nbuf == 2 ? 20 : 32;  // __launch_bounds__ of the variants
+      const int wcap = (nbuf == 2 || win) ? 20 : 32;  // __launch_bounds__ of the variants
       int wmax = 0;
       for (int w = wcap; w >= 1; --w)
         if (step_smem_bytes(p.g, vis, w, nbuf) <= 227 * 1024 - 1024) { wmax = w; break; }
@@ -75,7 +75,7 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
         const int resident = ctas * w;
         const double rounds = tiles_per_sm / resident;
         const double fill = rounds <= 1.0 ? 1.0 : rounds / (double)(long long)(rounds + 0.999999);  // last-round efficiency
-        const int cap = win ? 32 : 20;  // the window layout has two dependent HBM latencies per tile to hide
+        const int cap = 20;  // the window layout has one exposed HBM round trip per tile to hide
         const double score = (resident < cap ? resident : cap) * fill * (vis == VIS_TBL ? 1.3 : 1.0) * (nbuf == 2 ? 1.25 : 1.0);
         if (score > best_score + 1e-9) {
           best_score = score;
@@ -93,7 +93,7 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
 }
 
 cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
-                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, cudaStream_t stream) {
+                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, uint32_t *packed, cudaStream_t stream) {
   int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
 #ifdef MG_TIMELINE
   static int launch_no = 0;
@@ -111,7 +111,7 @@ cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actio
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k, p, actions, action_dtype, obs, dir, reward, term, trunc, tma_ok);
+  return cudaLaunchKernelEx(&cfg, k, p, actions, action_dtype, obs, dir, reward, term, trunc, packed, tma_ok);
 }
 
 }  // namespace mg

@@ -35,7 +35,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 // per-warp buffer: holds the staged tile (or the 32 lanes' view windows), then, once the gather has consumed it,
 // the warp's 4704-byte observation block in output layout.
 __host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
-  uint32_t b = g.layout == LAYOUT_TILED ? (uint32_t)g.wpe * 128u : (uint32_t)(TILE * WIN_LANE_BYTES);
+  uint32_t b = g.layout == LAYOUT_TILED ? (uint32_t)g.wpe * 128u : 0u;  // window layout: the view words live in registers
   if (b < (uint32_t)OBS_TILE_BYTES) b = OBS_TILE_BYTES;
   return (b + 127u) & ~127u;
 }
@@ -176,10 +176,10 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
 // MODE_TILED2: each warp owns two buffers and prefetches its next tile (TMA + agent records + actions) before it
 // processes the current one, so HBM transfers overlap compute instead of alternating with it in GPU-wide bursts.
 template <int KIND, int VIS, int MODE>
-__global__ void __launch_bounds__(MODE == MODE_TILED2 ? 640 : 1024, 1)  // one CTA per SM: <= 20 warps (96 regs) or <= 32 (64 regs)
+__global__ void __launch_bounds__(MODE == MODE_TILED2 ? 640 : (MODE == MODE_TILED1 ? 1024 : 640), 1)  // one CTA per SM: <= 20 warps (96 regs; the window mode keeps 21 view words live) or <= 32 (64 regs)
 k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
        int32_t *__restrict__ dir_out, double *__restrict__ reward_out, uint8_t *__restrict__ term_out,
-       uint8_t *__restrict__ trunc_out, int obs_tma_ok) {
+       uint8_t *__restrict__ trunc_out, uint32_t *__restrict__ packed_out, int obs_tma_ok) {
   constexpr int NBUF = (MODE == MODE_TILED2) ? 2 : 1;
   constexpr bool WIN = (MODE == MODE_WINDOW);
   constexpr bool PREF = (MODE != MODE_TILED1);  // agent records / actions / tile index are fetched one tile ahead
@@ -335,33 +335,19 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
         }
       }
     }
-    // LAYOUT_WINDOW: the 7 lines of the view are 224 contiguous bytes of array R (facing +-x) or C (+-y), one bulk
-    // copy per lane. Which lines is known before the transition: a turn depends on the action alone and a
-    // forward move never changes the line coordinate of the array it faces along, so the window and the
-    // front-cell byte are requested together (one HBM round trip per tile).
-    uint32_t *win = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(gtile) + lane * WIN_LANE_BYTES);
-    auto load_window = [&](int d, bool wrote_any) {
-      const bool useC = d & 1;
-      const int w0 = (useC ? g.offC : 0) + ((useC ? ax : ay) - 3 + g.ring) * WIN_LINE_WORDS;
-      // generic-proxy writes of this step (autoreset fill, a mutated cell) must be visible to the bulk copy
-      if (__ballot_sync(0xFFFFFFFFu, wrote_any)) asm volatile("fence.proxy.async;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_expect_tx(bar0, TILE * WIN_BYTES);
-      tma_load_1d(smem_u32(win), p.grid + grid_word(g, env, w0), WIN_BYTES, bar0);  // one mbarrier per warp
+    // LAYOUT_WINDOW: the view's words go straight to registers (mg_obs.cuh: load_view_words): 21 independent loads,
+    // one memory round trip per step; the transition reads its front cell out of the same words.
+    ViewWords vw;
+    const uint32_t *envw = p.grid + (size_t)env * g.wpe;
+    auto ldw = [&](int w) {
+      uint32_t v;
+      asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(envw + w));  // plain (coherent) load: this warp may just have regenerated the env
+      return v;
     };
-    auto wait_window = [&]() {
-      mbar_wait(bar0, phase & 1u);
-      phase ^= 1u;
-    };
-    uint32_t fc_win = CODE_WALL;
     if (WIN) {
-      int dirn = dir, fx0, fy0;
+      int dirn = dir;
       if (stepping && !fresh) dirn = (dir + (action == A_LEFT ? 3 : 0) + (action == A_RIGHT ? 1 : 0)) & 3;
-      front_pos(g, ax, ay, dir, fx0, fy0);
-      const uint8_t *fcp = gb + grid_word(g, env, r_word(g, fx0, fy0)) * 4 + (fx0 & 3);
-      asm volatile("ld.global.u8 %0, [%1];" : "=r"(fc_win) : "l"(fcp));  // in flight together with the window
-      load_window(dirn, wrote);
-      wait_window();
+      load_view_words(g, ax, ay, dirn, vw, ldw);
     }
     if (stepping && !fresh) {
       // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
@@ -370,7 +356,8 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       front_pos(g, ax, ay, dir, fx, fy);
       const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
       uint32_t fc;
-      if (WIN) fc = fc_win;
+      const int fpos = ((dir & 1) ? ay : ax) + ((dir < 2) ? 1 : -1);  // the front cell's position on the agent's own line
+      if (WIN) fc = view_words_byte(vw, fpos);  // meaningless after a turn (other array loaded), and then unused
       else fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
       const uint32_t carry_before = carry;
       const int act = pre_filter<KIND>(action);
@@ -387,8 +374,8 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
           uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
           sb[(rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)newc;
           sb[(cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)newc;
-        } else {  // pickup / drop / toggle do not turn: the front cell is on the window's centre line
-          reinterpret_cast<uint8_t *>(win)[3 * 32 + ((dir & 1) ? fy : fx)] = (uint8_t)newc;
+        } else {  // pickup / drop / toggle do not turn: the front cell is on the loaded centre line
+          view_words_set_byte(vw, fpos, newc);
         }
         if (!WIN) {  // tile-relative addressing: 32-bit index math on the common path
           uint8_t *tb = reinterpret_cast<uint8_t *>(p.grid + (size_t)tile * g.wpe * 32);
@@ -442,45 +429,66 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
           ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0;
           if (PF) { tx = ro.tx; ty = ro.ty; flags = (flags & 0xFFu) | (ro.aux << 8); }
         }
-        if (WIN) {  // the regenerated levels invalidate the staged windows
-          load_window(dir, true);
-          wait_window();
-        }
+        if (WIN && again) load_view_words(g, ax, ay, dir, vw, ldw);  // the regenerated level replaces the loaded words
       }
     }
 
     // ---- gen_obs ----
-    if (obs != nullptr) {
-      uint32_t S[OBS_WORDS];
+    if (obs != nullptr || packed_out != nullptr) {
       if (VIS == VIS_TBL && first) mbar_wait(tbl_bar, 0);  // the visibility table, requested in the prologue
+      uint32_t clo[VIEW], chi[VIEW];
       if (WIN) {
-        const bool useC = dir & 1;
-        const int w0 = (useC ? g.offC : 0) + ((useC ? ax : ay) - 3 + g.ring) * WIN_LINE_WORDS;
-        const AccFlat acc = {win - w0};
-        gen_obs_words<VIS>(g, acc, lut, vis_tbl, ax, ay, dir, carry, S);
+        gather_from_words<VIS>(g, vw, vis_tbl, ax, ay, dir, carry, clo, chi);
       } else {
         const AccTiled acc = {base, true};
-        gen_obs_words<VIS>(g, acc, lut, vis_tbl, ax, ay, dir, carry, S);
+        gather_view<VIS>(g, acc, vis_tbl, ax, ay, dir, carry, clo, chi);
       }
-      // stage the 32 images in output layout in the consumed buffer, then ONE bulk store of the 4704-byte block.
-      // (The ragged last tile / an unaligned obs pointer copy the valid bytes out of the stage instead: keeping the
-      // stream words out of any byte-store path stops the compiler from spilling S to local memory on every tile.)
       const int nvalid = min(TILE, p.n_envs - tile * TILE);
-      const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);
-      __syncwarp();  // orders memory among the lanes: every lane is past its tile / window reads before the stage overwrites them
-      emit_obs_staged(gtile, lane, S, n0);
-      if (nvalid == TILE && (obs_tma_ok & 1)) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_1d(obs + (size_t)tile * OBS_TILE_BYTES, smem_u32(gtile), OBS_TILE_BYTES);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (packed_out == nullptr) {
+        uint32_t S[OBS_WORDS];
+        encode_stream(lut, clo, chi, S);
+        // stage the 32 images in output layout in the consumed buffer, then ONE bulk store of the 4704-byte block.
+        // (The ragged last tile / an unaligned obs pointer copy the valid bytes out of the stage instead: keeping the
+        // stream words out of any byte-store path stops the compiler from spilling S to local memory on every tile.)
+        const uint32_t n0 = __shfl_down_sync(0xFFFFFFFFu, S[0], 1);
+        __syncwarp();  // orders memory among the lanes: every lane is past its tile / window reads before the stage overwrites them
+        emit_obs_staged(gtile, lane, S, n0);
+        if (nvalid == TILE && (obs_tma_ok & 1)) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_1d(obs + (size_t)tile * OBS_TILE_BYTES, smem_u32(gtile), OBS_TILE_BYTES);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          __syncwarp();
+          const uint8_t *sbytes = reinterpret_cast<const uint8_t *>(gtile);
+          uint8_t *dst = obs + (size_t)tile * OBS_TILE_BYTES;
+          for (int i = lane; i < nvalid * OBS_BYTES; i += 32) dst[i] = sbytes[i];
         }
       } else {
+        // host path, MG_HOST_PACKED: 13 words per env (cell codes + flags + step count) instead of the 147-byte image
+        // and the four result arrays; the host expands them (mg_host_expand.cpp)
+        uint32_t P[PACKED_WORDS];
+        const uint32_t rewarded = reward != 0.0 ? 1u : 0u;
+        if (rewarded && (uint32_t)steps > PACKED_MAX_STEPS) atomicOr(p.err, ERR_PACKED_RANGE);
+        pack_codes(clo, chi, packed_tail(dir, terminated, truncated, rewarded, (uint32_t)steps), P);
         __syncwarp();
-        const uint8_t *sbytes = reinterpret_cast<const uint8_t *>(gtile);
-        uint8_t *dst = obs + (size_t)tile * OBS_TILE_BYTES;
-        for (int i = lane; i < nvalid * OBS_BYTES; i += 32) dst[i] = sbytes[i];
+        uint32_t *dstw = gtile + PACKED_WORDS * lane;  // odd word stride: conflict-free
+#pragma unroll
+        for (int j = 0; j < PACKED_WORDS; ++j) dstw[j] = P[j];
+        if (nvalid == TILE) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_1d(packed_out + (size_t)tile * (PACKED_WORDS * TILE), smem_u32(gtile), PACKED_TILE_BYTES);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          __syncwarp();
+          uint32_t *dst = packed_out + (size_t)tile * (PACKED_WORDS * TILE);
+          for (int i = lane; i < nvalid * PACKED_WORDS; i += 32) dst[i] = gtile[i];
+        }
       }
     }
     if (active) {
@@ -521,7 +529,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
 }
 
 
-typedef void (*StepKernel)(Params, const void *, int, uint8_t *, int32_t *, double *, uint8_t *, uint8_t *, int);
+typedef void (*StepKernel)(Params, const void *, int, uint8_t *, int32_t *, double *, uint8_t *, uint8_t *, uint32_t *, int);
 
 template <int VIS, int MODE>
 static StepKernel pick_kind(int kind) {

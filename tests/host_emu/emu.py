@@ -35,6 +35,8 @@ def lib():
         L.emu_reset.argtypes = [p, p, p]
         L.emu_step.restype = C.c_int
         L.emu_step.argtypes = [p] * 7
+        L.emu_step_packed.restype = C.c_int
+        L.emu_step_packed.argtypes = [p, p, p]
         L.emu_full_obs.argtypes = [p, p, C.c_int]
         L.emu_get_state.argtypes = [p] * 4
         L.emu_set_state.argtypes = [p] * 3
@@ -50,6 +52,7 @@ class EmuVecEnv:
     def __init__(self, spec, num_envs, autoreset="next_step", layout=-1):
         kind, W, H, max_steps, see_through, params = spec
         self.width, self.height, self.num_envs = W, H, int(num_envs)
+        self._max_steps = max_steps
         prm = np.asarray(list(params), dtype=np.int32)
         self._h = lib().emu_create(KIND[kind], W, H, max_steps, int(see_through), _ptr(prm), len(prm), self.num_envs,
                                    AUTORESET[autoreset], layout)
@@ -77,6 +80,23 @@ class EmuVecEnv:
         rc = lib().emu_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.dir), _ptr(self.reward), _ptr(self.terminated), _ptr(self.truncated))
         if rc != 0:
             raise ValueError("Unknown action")
+        return self.obs, self.dir, self.reward, self.terminated.astype(bool), self.truncated.astype(bool)
+
+    def step_packed(self, actions):
+        """The packed host path: K1's 52-byte records (device header code), expanded by the PRODUCT's host expander
+        (mg_expand_packed in libminigrid_b200.so: host code, no GPU needed)."""
+        from minigrid_b200 import _lib
+
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        packed = np.zeros((self.num_envs, 52), np.uint8)
+        rc = lib().emu_step_packed(self._h, _ptr(a), _ptr(packed))
+        if rc != 0:
+            raise ValueError("Unknown action")
+        L = _lib.load()
+        max_steps = self._max_steps
+        rc = L.mg_expand_packed(_ptr(packed), self.num_envs, max_steps, _ptr(self.obs), _ptr(self.dir), _ptr(self.reward),
+                                _ptr(self.terminated), _ptr(self.truncated))
+        assert rc == 0
         return self.obs, self.dir, self.reward, self.terminated.astype(bool), self.truncated.astype(bool)
 
     def gen_obs(self):

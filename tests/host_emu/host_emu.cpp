@@ -33,6 +33,7 @@ struct Emu {
   std::vector<uint32_t> tmpl;
   int use_tbl;
   int err;
+  uint32_t *packed_out = nullptr;  // MG_HOST_PACKED: 13 words per env instead of the image and the result arrays
 };
 
 template <int KIND>
@@ -219,6 +220,18 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
           }
       }
     }
+    std::vector<ViewWords> vws(32);
+    if (WIN)  // K1's window branch: the view words of the post-action direction, loaded before the transition
+      for (int lane = 0; lane < 32; ++lane) {
+        const int env = tile * TILE + lane;
+        int dirn = dir[lane];
+        if (stepping && !fresh[lane]) {
+          const int action = emu_pre_filter(p.kind, active[lane] ? actions[env] : A_DONE);
+          dirn = (dir[lane] + (action == A_LEFT ? 3 : 0) + (action == A_RIGHT ? 1 : 0)) & 3;
+        }
+        const uint32_t *envw = p.grid + (size_t)env * g.wpe;
+        load_view_words(g, ax[lane], ay[lane], dirn, vws[lane], [&](int w) { return envw[w]; });
+      }
     for (int lane = 0; lane < 32; ++lane) {
       if (!(stepping && !fresh[lane])) continue;
       const int env = tile * TILE + lane;
@@ -230,7 +243,8 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
       front_pos(g, ax[lane], ay[lane], dir[lane], fx, fy);
       const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
       uint32_t fc;
-      if (WIN) fc = gb[grid_word(g, env, rw) * 4 + (fx & 3)];
+      const int fpos = ((dir[lane] & 1) ? ay[lane] : ax[lane]) + ((dir[lane] < 2) ? 1 : -1);
+      if (WIN) fc = view_words_byte(vws[lane], fpos);
       else fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
       const StepOut so = transition(action, fc, fx, fy, ax[lane], ay[lane], dir[lane], carry[lane]);
       terminated[lane] = so.terminated;
@@ -244,6 +258,8 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
           uint8_t *sb = reinterpret_cast<uint8_t *>(gtile.data());
           sb[((size_t)rw * 32 + lane) * 4 + (fx & 3)] = (uint8_t)so.newc;
           sb[((size_t)cw * 32 + lane) * 4 + (fy & 3)] = (uint8_t)so.newc;
+        } else {
+          view_words_set_byte(vws[lane], fpos, so.newc);
         }
         gb[grid_word(g, env, rw) * 4 + (fx & 3)] = (uint8_t)so.newc;
         gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)so.newc;
@@ -284,20 +300,33 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
           if (again[lane]) {
             ax[lane] = ro[lane].ax; ay[lane] = ro[lane].ay; dir[lane] = ro[lane].dir; carry[lane] = 0; steps[lane] = 0;
             tx[lane] = ro[lane].tx; ty[lane] = ro[lane].ty; flags[lane] = (flags[lane] & 0xFFu) | (ro[lane].aux << 8);
+            if (WIN) {
+              const uint32_t *envw = p.grid + (size_t)(tile * TILE + lane) * g.wpe;
+              load_view_words(g, ax[lane], ay[lane], dir[lane], vws[lane], [&](int w) { return envw[w]; });
+            }
           }
       }
     }
-    if (obs) {
+    if (e->packed_out) {  // K1's packed branch: gather_view + pack_codes, 13 words per lane
+      for (int lane = 0; lane < 32; ++lane) {
+        const int env = tile * TILE + lane;
+        uint32_t clo[VIEW], chi[VIEW], P[PACKED_WORDS];
+        if (WIN) {
+          gather_from_words<VIS>(g, vws[lane], p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], clo, chi);
+        } else {
+          const AccTiled acc = {gtile.data() + lane, true};
+          gather_view<VIS>(g, acc, p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], clo, chi);
+        }
+        pack_codes(clo, chi, packed_tail(dir[lane], terminated[lane], truncated[lane], reward[lane] != 0.0 ? 1u : 0u, (uint32_t)steps[lane]), P);
+        if (active[lane]) memcpy(e->packed_out + (size_t)env * PACKED_WORDS, P, sizeof(P));
+      }
+    } else if (obs) {
       for (int lane = 0; lane < 32; ++lane) {
         uint32_t(&S)[OBS_WORDS] = *reinterpret_cast<uint32_t(*)[OBS_WORDS]>(&S_all[lane * OBS_WORDS]);
-        if (WIN) {  // the lane's 7-line window, copied as the cp.async loop does
-          const int env = tile * TILE + lane;
-          const bool useC = dir[lane] & 1;
-          const int w0 = (useC ? g.offC : 0) + ((useC ? ax[lane] : ay[lane]) - 3 + g.ring) * WIN_LINE_WORDS;
-          uint32_t *win = gtile.data() + lane * (WIN_LANE_BYTES / 4);
-          memcpy(win, p.grid + grid_word(g, env, w0), WIN_BYTES);
-          const AccFlat acc = {win - w0};
-          gen_obs_words<VIS>(g, acc, p.cell_lut, p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], S);
+        if (WIN) {  // the lane's preloaded view words
+          uint32_t clo[VIEW], chi[VIEW];
+          gather_from_words<VIS>(g, vws[lane], p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], clo, chi);
+          encode_stream(p.cell_lut, clo, chi, S);
         } else {
           const AccTiled acc = {gtile.data() + lane, true};
           gen_obs_words<VIS>(g, acc, p.cell_lut, p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], S);
@@ -400,6 +429,13 @@ int emu_step(void *h, const int32_t *actions, uint8_t *obs, int32_t *dir, double
   else step_tiles<VIS_ALU>(e, actions, obs, dir, reward, term, trunc);
   const int bad = e->err; e->err = 0;
   return bad ? -1 : 0;
+}
+int emu_step_packed(void *h, const int32_t *actions, uint32_t *packed) {  // mg_step_host with MG_HOST_PACKED: K1 with packed_out
+  Emu *e = (Emu *)h;
+  e->packed_out = packed;
+  const int rc = emu_step(h, actions, nullptr, nullptr, nullptr, nullptr, nullptr);
+  e->packed_out = nullptr;
+  return rc;
 }
 void emu_full_obs(void *h, uint8_t *out, int with_agent) {  // k_full_obs body
   Emu *e = (Emu *)h;

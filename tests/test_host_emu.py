@@ -47,3 +47,43 @@ def test_emu_fixture_in_both_layouts(path, layout):
         parity.check_rollout_fixture(mk, g)
     else:
         parity.check_inject_fixture(mk, g)
+
+
+@pytest.mark.parametrize("layout", [0, 1], ids=["tiled", "window"])
+@pytest.mark.parametrize("env_id", ["MiniGrid-DoorKey-8x8-v0", "MiniGrid-FourRooms-v0", "MiniGrid-Empty-5x5-v0",
+                                    "MiniGrid-Fetch-8x8-N3-v0", "MiniGrid-GoToDoor-5x5-v0"])
+@pytest.mark.parametrize("scalar", [False, True], ids=["ssse3", "scalar"])
+def test_packed_host_format_expands_to_the_same_arrays(env_id, layout, scalar, monkeypatch):
+    """MG_HOST_PACKED: K1's 52-byte records (pack_codes, device header) + the product's host expander == the oracle's
+    obs / dir / reward / flags, bit for bit, with both expander code paths."""
+    import subprocess
+
+    code = f"""
+import sys, os
+sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r}); sys.path.insert(0, {os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu")!r})
+import numpy as np
+from emu import EmuVecEnv
+from oracle.oracle import ENV_SPECS, OracleVecEnv
+n = 77
+emu = EmuVecEnv(ENV_SPECS[{env_id!r}], n, autoreset="next_step", layout={layout})
+orc = OracleVecEnv({env_id!r}, n)
+emu.reset(seed=5); orc.reset(seed=5)
+rng = np.random.default_rng(0)
+seen_reward = 0
+for t in range(400):
+    a = rng.integers(0, 7, n).astype(np.int32)
+    if t % 3 == 0: a[:] = np.where(rng.random(n) < 0.6, 2, a)  # mostly forward: reach goals
+    e = emu.step_packed(a); o = orc.step(a)
+    assert np.array_equal(e[0], o[0]), t
+    assert np.array_equal(e[1], o[1]) and e[2].tobytes() == o[2].tobytes()
+    assert np.array_equal(e[3], o[3]) and np.array_equal(e[4], o[4])
+    seen_reward += int((o[2] != 0).sum())
+print("rewards", seen_reward)
+"""
+    env = dict(os.environ)
+    if scalar:
+        env["MINIGRID_B200_EXPAND_SCALAR"] = "1"  # read once per process: hence the subprocess
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stderr[-3000:]
+    if env_id == "MiniGrid-Empty-5x5-v0":
+        assert int(r.stdout.split()[-1]) > 0  # the reward path was exercised
