@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--graph", type=int, default=1, help="replay the step loop as CUDA graphs (0 = eager launches)")
     ap.add_argument("--sync-episodes", action="store_true", help="do NOT desynchronise the episodes (round-1 behaviour: no autoreset in the timed region)")
-    ap.add_argument("--host-format", default="full", choices=["packed", "full"], help="D2H format of the e2e leg (packed: 52 B/env expanded on the host)")
+    ap.add_argument("--host-format", default="packed", choices=["packed", "full"], help="D2H format of the e2e leg (packed: 52 B/env expanded on the host)")
     return ap.parse_args()
 
 
@@ -397,7 +397,7 @@ def main():
     Ke = max(1, min(args.e2e_steps, K))
     host_actions = torch.randint(0, 7, (min(Ke, 64), n), dtype=torch.int32).pin_memory()
     for b in batches:
-        b.set_host_format(args.host_format)
+        b.set_host_format(args.host_format, max(1, usable_cores() // max(1, world)))
     for t in range(max(3, 2 * R)):  # every batch allocates its pinned staging on first use: keep that out of the timing
         batches[t % R].step_host(host_actions[t % host_actions.shape[0]])
     barrier()
@@ -410,6 +410,18 @@ def main():
     h2d = n * 4
     d2h = batches[0].host_d2h_bytes_per_step
     e2e_threads = batches[0].host_threads
+    e2e_full = None
+    if args.host_format != "full":  # the same loop with the arrays crossing PCIe as they are, for comparison
+        for b in batches:
+            b.set_host_format("full")
+        for t in range(max(3, 2 * R)):
+            batches[t % R].step_host(host_actions[t % host_actions.shape[0]])
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(Ke):
+            batches[t % R].step_host(host_actions[t % host_actions.shape[0]])
+        torch.cuda.synchronize()
+        e2e_full = {"value": total * Ke / max_over_ranks(time.perf_counter() - t0), "d2h_bytes_per_step": batches[0].host_d2h_bytes_per_step}
 
     # ---- the other BASELINE configs, the synchronised long run and the autoreset cost (one batch, L2-resident) ----
     configs, sync_wave, autoreset_cost, full_obs = [], None, None, None
@@ -481,7 +493,7 @@ def main():
                     "autoreset_fraction_per_step": head["autoreset_fraction_per_step"]},
             "clocks": {k: head["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "format": args.host_format, "host_threads": e2e_threads},
+                    "format": args.host_format, "host_threads": e2e_threads, "full_format": e2e_full},
             "gpu_launches": int(launches),
             "host_enqueue_us_per_step": head["host_enqueue_us_per_step"],
         }

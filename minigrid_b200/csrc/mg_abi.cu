@@ -137,6 +137,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   p.see_through = see_through_walls ? 1 : 0;
   p.mode = autoreset_mode;
   p.kind = kind;
+  p.hot_first = 1;
+  if (const char *e = getenv("MINIGRID_B200_HOTFIRST")) p.hot_first = atoi(e) != 0;  // tuning knob (same-box A/B)
   for (int i = 0; i < 8; ++i) p.kp[i] = (params && i < n_params) ? params[i] : 0;
   if (kind == MG_KIND_EMPTY && !p.kp[0] && n_params < 4) { p.kp[1] = 1; p.kp[2] = 1; p.kp[3] = 0; }
   if (kind == MG_KIND_CROSSING && n_params < 2) { p.kp[0] = 1; p.kp[1] = (int)T_LAVA; }
@@ -165,7 +167,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   const size_t sz_rng = align_up(n_pad * sizeof(RngRec), 256);
   const size_t sz_lut_r = align_up((size_t)(max_steps + 1) * sizeof(double), 256);
   const size_t sz_tmpl = align_up((size_t)p.g.wpe * 4, 256);
-  const size_t total = sz_grid + sz_agent + sz_rng + 256 /*err*/ + sz_lut_r + 1024 + VIS_TBL_BYTES + sz_tmpl;
+  const size_t sz_hot = align_up((size_t)p.n_tiles, 256);
+  const size_t total = sz_grid + sz_agent + sz_rng + 256 /*err*/ + sz_lut_r + 1024 + VIS_TBL_BYTES + sz_tmpl + sz_hot;
   cudaError_t e = cudaMalloc(&h->d_arena, total);
   if (e != cudaSuccess) { delete h; return fail(MG_ERR_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); }
   uint8_t *base = (uint8_t *)h->d_arena;
@@ -176,7 +179,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   double *d_rl = (double *)base; base += sz_lut_r;
   uint32_t *d_cl = (uint32_t *)base; base += 1024;
   uint16_t *d_vt = (uint16_t *)base; base += VIS_TBL_BYTES;
-  uint32_t *d_tm = (uint32_t *)base;
+  uint32_t *d_tm = (uint32_t *)base; base += sz_tmpl;
+  p.tile_hot = base;
   p.reward_lut = d_rl; p.cell_lut = d_cl; p.vis_tbl = d_vt; p.tmpl = d_tm;
 
   // _reward(): 1 - 0.9 * (step_count / max_steps) in host IEEE double, never contracted (minigrid_env.py:245)
@@ -193,6 +197,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     for (uint32_t c = 0; c < 256; ++c) cl[c] = decode_cell(c);
     if (e == cudaSuccess) e = cudaMemcpy(d_cl, cl, sizeof(cl), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(p.err, 0, 256);
+    if (e == cudaSuccess) e = cudaMemset(p.tile_hot, 0, sz_hot);
     uint16_t *vt = (uint16_t *)malloc(VIS_TBL_BYTES);
     build_vis_table(vt);
     if (e == cudaSuccess) e = cudaMemcpy(d_vt, vt, VIS_TBL_BYTES, cudaMemcpyHostToDevice);

@@ -147,6 +147,8 @@ struct Params {
   const uint16_t *vis_tbl;  // [128 * 128] process_vis row table (mg_obs.cuh: build_vis_table)
   const uint32_t *tmpl;     // [wpe] level template: the words of a blank draw (mg_levels.cuh)
   int *err;                 // sticky error word
+  int hot_first;            // visit the tiles flagged in tile_hot right after a CTA's first round (MINIGRID_B200_HOTFIRST=0 turns it off)
+  uint8_t *tile_hot;        // [n_tiles] 1 = an env of the tile ended in the last step (K1's scheduling hint, never semantics)
 };
 
 struct StepPlan {  // launch shape of K1, chosen once per handle (mg_step.cu: configure_step)

@@ -39,9 +39,14 @@ __host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
   if (b < (uint32_t)OBS_TILE_BYTES) b = OBS_TILE_BYTES;
   return (b + 127u) & ~127u;
 }
-// [cell table 1 KB][visibility table 32 KB, VIS_TBL only][warps x nbuf x buffer][mbarriers][tile counter]
+// Tiles whose environments regenerate in this step (NEXT_STEP autoreset: the previous step flagged them) take several
+// dependent memory round trips longer than a plain tile. Left in place they end up in a CTA's last round every few
+// steps and the whole grid waits for one warp, so each CTA visits them right after its first round: the order of up to
+// ORDER_CAP tiles behind the first round is a list in shared memory, flagged tiles first.
+constexpr int ORDER_CAP = 1024;
+// [cell table 1 KB][visibility table 32 KB, VIS_TBL only][warps x nbuf x buffer][mbarriers][tile counter][list barrier][order list]
 __host__ __device__ inline size_t step_smem_bytes(const Geom &g, int vis, int warps, int nbuf) {
-  return 1024 + (vis == VIS_TBL ? VIS_TBL_BYTES : 0) + (size_t)warps * nbuf * step_buf_bytes(g) + 16 * (size_t)warps + 16;
+  return 1024 + (vis == VIS_TBL ? VIS_TBL_BYTES : 0) + (size_t)warps * nbuf * step_buf_bytes(g) + 16 * (size_t)warps + 32 + 2 * ORDER_CAP;
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -49,6 +54,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -199,6 +207,8 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + TBL + (size_t)WARPS * NBUF * buf_bytes);
   const uint32_t bar0 = smem_u32(bars + 2 * warp), tbl_bar = smem_u32(bars + 2 * WARPS);
   int *s_next = reinterpret_cast<int *>(bars + 2 * WARPS + 1);
+  const uint32_t list_bar = smem_u32(bars + 2 * WARPS + 2);
+  uint16_t *s_order = reinterpret_cast<uint16_t *>(bars + 2 * WARPS + 3);
 
   // Programmatic dependent launch: let the next kernel in the stream start its prologue while this grid drains,
   // and do our own prologue (nothing the previous step wrote is touched) before waiting for it to complete.
@@ -213,8 +223,13 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
   const unsigned tq = (unsigned)p.n_tiles / gridDim.x, tr = (unsigned)p.n_tiles % gridDim.x;
   const int t_lo = (int)(blockIdx.x * tq + min(blockIdx.x, tr));
   const int t_hi = t_lo + (int)tq + (blockIdx.x < tr ? 1 : 0);
+  // pull index k of a CTA: its k-th tile. k < WARPS: the static first round; behind it, the order list (flagged tiles first)
+  const int n_my = t_hi - t_lo;
+  const int m_ord = min(max(n_my - WARPS, 0), ORDER_CAP);
+  const bool use_order = stepping && p.mode == AUTORESET_NEXT_STEP && p.hot_first && m_ord > 0;
   if (threadIdx.x == 0) {
-    *s_next = t_lo + (PREF ? 2 : 1) * WARPS;
+    *s_next = (PREF ? 2 : 1) * WARPS;
+    mbar_init(list_bar, 1);
     if (VIS == VIS_TBL) {  // the table is immutable after mg_create: its copy may run ahead of griddepcontrol.wait
       mbar_init(tbl_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -223,9 +238,18 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     }
   }
   int tile = t_lo + warp;
-  int next = PREF ? t_lo + WARPS + warp : p.n_tiles;
+  int next = p.n_tiles;  // PREF: resolved through the order list at the warp's first prefetch
   if (tile >= t_hi) tile = p.n_tiles;
-  if (next >= t_hi) next = p.n_tiles;
+  bool list_ok = !use_order;
+  auto map_tile = [&](int k) -> int {
+    if (k >= n_my) return p.n_tiles;
+    int off = k;
+    if (use_order && k >= WARPS && k - WARPS < m_ord) {
+      if (!list_ok) { mbar_wait(list_bar, 0); list_ok = true; }
+      off = s_order[k - WARPS];
+    }
+    return t_lo + off;
+  };
   if (lane == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -251,6 +275,42 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     if (stepping && env0 < p.n_envs) action = load_action(actions, act_dtype, env0);
   }
 
+  if (use_order && warp == WARPS - 1) {
+    // the last warp builds the list (its own first tile is already on its way): tiles WARPS .. WARPS + m_ord - 1 of this
+    // CTA, those flagged by the previous step first. Ballots are kept in registers (lane c: chunk c) so that both passes
+    // see the same flags whatever is written to them meanwhile.
+    const uint8_t *hot = p.tile_hot + t_lo + WARPS;
+    unsigned mybal = 0;
+    const int chunks = (m_ord + 31) >> 5;
+    for (int c = 0; c < chunks; ++c) {
+      const int idx = 32 * c + lane;
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, idx < m_ord && hot[idx] != 0);
+      if (lane == c) mybal = bal;
+    }
+    int pre = __popc(mybal);  // inclusive scan over lanes of the chunks' hot counts
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, pre, d);
+      if (lane >= d) pre += v;
+    }
+    const int hot_total = __shfl_sync(0xFFFFFFFFu, pre, 31);
+    const int excl = pre - __popc(mybal);
+    for (int c = 0; c < chunks; ++c) {
+      const unsigned bal = __shfl_sync(0xFFFFFFFFu, mybal, c);
+      const int hb = __shfl_sync(0xFFFFFFFFu, excl, c);
+      const int idx = 32 * c + lane;
+      if (idx < m_ord) {
+        const unsigned lt = (1u << lane) - 1u;
+        const bool is_hot = (bal >> lane) & 1u;
+        const int pos = is_hot ? hb + __popc(bal & lt) : hot_total + (32 * c - hb) + __popc(~bal & lt);
+        s_order[pos] = (uint16_t)(WARPS + idx);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(list_bar);  // release: the list is visible to whoever observes the phase
+    list_ok = true;
+  }
+
   uint8_t *gb = reinterpret_cast<uint8_t *>(p.grid);
   uint32_t phase = 0;  // bit b = parity to wait for on buffer b
   int b = 0;
@@ -259,6 +319,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     int action_n = A_DONE, nn = p.n_tiles;
     // prefetch the next tile (into the other buffer), its agent records and actions, and the index of the tile after it
     auto prefetch = [&]() {
+      if (first) next = map_tile(WARPS + warp);
       if (next < p.n_tiles) {
         if (lane == 0) {
           if (NBUF == 2) {
@@ -267,8 +328,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
             mbar_expect_tx(nb, tile_bytes);
             tma_load_1d(smem_u32(bufs + (size_t)(b ^ 1) * buf_bytes), p.grid + (size_t)next * g.wpe * 32, tile_bytes, nb);
           }
-          nn = atomicAdd(s_next, 1);  // shared-memory atomic, consumed one tile later
-          if (nn >= t_hi) nn = p.n_tiles;
+          nn = map_tile(atomicAdd(s_next, 1));  // shared-memory atomic, consumed one tile later
         }
         const int env_n = next * TILE + lane;
         rec_n = ldg_rec(p.agent + env_n);
@@ -278,7 +338,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     // A warp's first tile: every warp of the GPU is fetching its first tile at this moment, and nothing can be
     // computed anywhere until those arrive, so the second tile is requested only once the first is here (its fetch
     // then overlaps the first tile's compute like every later one) instead of doubling the opening burst.
-    const bool defer = (NBUF == 2) && first;
+    const bool defer = (NBUF == 2 || WIN) && first;  // (window mode: behind the first view loads, the order list is on its way)
     if (PREF) {
       if (WIN && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left
       if (!defer) prefetch();
@@ -287,8 +347,6 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left the buffer
         mbar_expect_tx(bar0, tile_bytes);
         tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
-        nn = atomicAdd(s_next, 1);  // consumed at the end of this tile
-        if (nn >= t_hi) nn = p.n_tiles;
       }
       const int env0 = tile * TILE + lane;
       rec = ldg_rec(p.agent + env0);
@@ -348,6 +406,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       int dirn = dir;
       if (stepping && !fresh) dirn = (dir + (action == A_LEFT ? 3 : 0) + (action == A_RIGHT ? 1 : 0)) & 3;
       load_view_words(g, ax, ay, dirn, vw, ldw);
+      if (defer) prefetch();
     }
     if (stepping && !fresh) {
       // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
@@ -505,6 +564,10 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       if (term_out) term_out[env] = (uint8_t)terminated;
       if (trunc_out) trunc_out[env] = (uint8_t)truncated;
     }
+    if (stepping && p.mode == AUTORESET_NEXT_STEP) {  // scheduling hint for the next step (see ORDER_CAP)
+      const unsigned anyp = __ballot_sync(0xFFFFFFFFu, active && (flags & FLAG_PENDING));
+      if (lane == 0) p.tile_hot[tile] = anyp ? 1 : 0;
+    }
     __syncwarp();  // lanes may still be reading this buffer (partial-tile path) before it is refilled
 #ifdef MG_TIMELINE
     if (first) MG_TL(4);
@@ -517,6 +580,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       action = action_n;
       if (NBUF == 2) b ^= 1;
     } else {
+      if (lane == 0) nn = map_tile(atomicAdd(s_next, 1));
       tile = __shfl_sync(0xFFFFFFFFu, nn, 0);
     }
   }

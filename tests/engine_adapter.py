@@ -7,8 +7,11 @@ from minigrid_b200 import MinigridVecEnv, specs
 
 
 class EngineAdapter:
-    def __init__(self, env_id=None, num_envs=1, mode="next_step", spec=None, host=False, action_dtype=torch.int32):
+    def __init__(self, env_id=None, num_envs=1, mode="next_step", spec=None, host=False, action_dtype=torch.int32,
+                 host_format="full", host_threads=0):
         self.e = MinigridVecEnv(env_id, num_envs, spec=spec, autoreset_mode=mode)
+        if host_format != "full":
+            self.e.set_host_format(host_format, host_threads)
         self.num_envs = num_envs
         self.host = host
         self.action_dtype = action_dtype
