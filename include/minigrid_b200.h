@@ -53,6 +53,8 @@ extern "C" {
 #define MG_KIND_GOTOOBJECT 12   /* envs/gotoobject.py: params {numObjs} */
 #define MG_KIND_PUTNEAR 13      /* envs/putnear.py: params {numObjs} */
 #define MG_KIND_MEMORY 14       /* envs/memory.py: params {random_length}; odd height */
+/* RNG draws inside step */
+#define MG_KIND_DYNOBS 15       /* envs/dynamicobstacles.py: params {n_obstacles, random_start, start_x, start_y, start_dir} */
 
 /* gymnasium.vector.AutoresetMode */
 #define MG_AUTORESET_NEXT_STEP 0
@@ -135,6 +137,9 @@ int mg_set_host_format(mg_env *env, int format, int n_threads);
  * (any output may be NULL). Single-threaded: split n over threads by offsetting the pointers. */
 int mg_expand_packed(const uint8_t *packed, int64_t n_envs, int32_t max_steps, uint8_t *obs, int32_t *dir,
                      double *reward, uint8_t *terminated, uint8_t *truncated);
+/* the same on n_threads host threads (0 = all the process may use); one call at a time per process */
+int mg_expand_packed_mt(const uint8_t *packed, int64_t n_envs, int32_t max_steps, uint8_t *obs, int32_t *dir,
+                        double *reward, uint8_t *terminated, uint8_t *truncated, int n_threads);
 int64_t mg_host_d2h_bytes(const mg_env *env);
 int mg_host_threads(const mg_env *env);
 

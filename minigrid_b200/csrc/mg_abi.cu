@@ -107,6 +107,11 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     return fail(MG_ERR_INVALID_ARG, "redbluedoors is 2 size x size (redbluedoors.py:60-72)");
   if (kind == MG_KIND_MEMORY && (height % 2 == 0 || height < 7 || width < 7))
     return fail(MG_ERR_INVALID_ARG, "memory needs an odd height and at least 7 x 7 (memory.py:98)");
+  if (kind == MG_KIND_DYNOBS) {
+    if (n_params < 5 || params[0] < 0 || params[0] > 8)
+      return fail(MG_ERR_INVALID_ARG, "dynamic obstacles need params {n_obstacles (0..8), random_start, start_x, start_y, start_dir}");
+    if (width > 16 || height > 16) return fail(MG_ERR_INVALID_ARG, "dynamic obstacles: at most 16 x 16 (the obstacles move inside the staged tile)");
+  }
   if (kind == MG_KIND_LOCKEDROOM && (width != height || width < 13))
     return fail(MG_ERR_INVALID_ARG, "lockedroom needs a square grid of at least 13 x 13 (lockedroom.py:108-173)");
   if (kind == MG_KIND_PLAYGROUND && (width != 19 || height != 19))
@@ -129,6 +134,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     // small grids: whole tiles through TMA; large grids: env-major lines and per-lane view windows (mg_common.cuh)
     int layout = make_geom(width, height, LAYOUT_TILED).wpe * 4 > 512 ? LAYOUT_WINDOW : LAYOUT_TILED;
     if (const char *e = getenv("MINIGRID_B200_LAYOUT")) layout = atoi(e) ? LAYOUT_WINDOW : LAYOUT_TILED;  // tuning / test knob
+    if (kind == MG_KIND_DYNOBS) layout = LAYOUT_TILED;  // its obstacles move through cells all over the grid: whole tiles only
     p.g = make_geom(width, height, layout);
   }
   p.n_envs = (int)n_envs;
@@ -153,6 +159,11 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   if (kind == MG_KIND_DISTSHIFT && n_params < 4) { if (n_params < 1) p.kp[0] = 2; p.kp[1] = 1; p.kp[2] = 1; p.kp[3] = 0; }
   // a fixed agent start (agent_start_pos / agent_start_dir, empty.py:75-76, distshift.py:68-69) must lie inside the
   // border walls: K1 trusts the agent record
+  if (kind == MG_KIND_DYNOBS && !p.kp[1] &&
+      (p.kp[2] < 1 || p.kp[2] > width - 2 || p.kp[3] < 1 || p.kp[3] > height - 2 || p.kp[4] < 0 || p.kp[4] > 3)) {
+    delete h;
+    return fail(MG_ERR_INVALID_ARG, "agent start must satisfy 1 <= x <= width - 2, 1 <= y <= height - 2, 0 <= dir <= 3");
+  }
   if ((kind == MG_KIND_EMPTY && !p.kp[0]) || kind == MG_KIND_DISTSHIFT) {
     if (p.kp[1] < 1 || p.kp[1] > width - 2 || p.kp[2] < 1 || p.kp[2] > height - 2 || p.kp[3] < 0 || p.kp[3] > 3) {
       delete h;
@@ -168,7 +179,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   const size_t sz_lut_r = align_up((size_t)(max_steps + 1) * sizeof(double), 256);
   const size_t sz_tmpl = align_up((size_t)p.g.wpe * 4, 256);
   const size_t sz_hot = align_up((size_t)p.n_tiles, 256);
-  const size_t total = sz_grid + sz_agent + sz_rng + 256 /*err*/ + sz_lut_r + 1024 + VIS_TBL_BYTES + sz_tmpl + sz_hot;
+  const size_t sz_extra = kind == MG_KIND_DYNOBS ? align_up(n_pad * sizeof(uint4), 256) : 0;
+  const size_t total = sz_grid + sz_agent + sz_rng + 256 /*err*/ + sz_lut_r + 1024 + VIS_TBL_BYTES + sz_tmpl + sz_hot + sz_extra;
   cudaError_t e = cudaMalloc(&h->d_arena, total);
   if (e != cudaSuccess) { delete h; return fail(MG_ERR_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)); }
   uint8_t *base = (uint8_t *)h->d_arena;
@@ -180,7 +192,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   uint32_t *d_cl = (uint32_t *)base; base += 1024;
   uint16_t *d_vt = (uint16_t *)base; base += VIS_TBL_BYTES;
   uint32_t *d_tm = (uint32_t *)base; base += sz_tmpl;
-  p.tile_hot = base;
+  p.tile_hot = base; base += sz_hot;
+  p.extra = sz_extra ? (uint4 *)base : nullptr;
   p.reward_lut = d_rl; p.cell_lut = d_cl; p.vis_tbl = d_vt; p.tmpl = d_tm;
 
   // _reward(): 1 - 0.9 * (step_count / max_steps) in host IEEE double, never contracted (minigrid_env.py:245)
@@ -198,6 +211,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     if (e == cudaSuccess) e = cudaMemcpy(d_cl, cl, sizeof(cl), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(p.err, 0, 256);
     if (e == cudaSuccess) e = cudaMemset(p.tile_hot, 0, sz_hot);
+    if (e == cudaSuccess && sz_extra) e = cudaMemset(p.extra, 0, sz_extra);
     uint16_t *vt = (uint16_t *)malloc(VIS_TBL_BYTES);
     build_vis_table(vt);
     if (e == cudaSuccess) e = cudaMemcpy(d_vt, vt, VIS_TBL_BYTES, cudaMemcpyHostToDevice);
@@ -541,7 +555,7 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   job.obs = obs_host; job.dir = dir_host; job.reward = reward_host; job.term = term_host; job.trunc = trunc_host;
   int64_t bounds[17];
   const int C = h->n_chunks;
-  for (int c = 0; c <= C; ++c) bounds[c] = (int64_t)((n * (size_t)c / (size_t)C) / TILE * TILE);
+  for (int c = 0; c <= C; ++c) bounds[c] = (int64_t)((n * (size_t)c / (size_t)C) / 64 * 64);  // whole tiles, and whole cache lines on the host
   bounds[C] = (int64_t)n;
   h->pool->begin(job, bounds, C);  // the workers wake up while the copy and the kernel run
   cudaError_t e = cudaMemcpyAsync(h->d_actions, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, s);

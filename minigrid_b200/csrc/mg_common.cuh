@@ -65,8 +65,10 @@ enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS
              // are not instantiated for them yet and mg_create rejects them (KIND_COUNT)
              KIND_LOCKEDROOM = 7, KIND_PLAYGROUND = 8,
              KIND_GOTODOOR = 9, KIND_FETCH = 10, KIND_REDBLUEDOORS = 11, KIND_GOTOOBJECT = 12, KIND_PUTNEAR = 13,
-             KIND_MEMORY = 14 };
-constexpr int KIND_COUNT = 15;  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
+             KIND_MEMORY = 14,
+             // RNG draws inside step (envs/dynamicobstacles.py)
+             KIND_DYNOBS = 15 };
+constexpr int KIND_COUNT = 16;  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
 enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
 // bits of the sticky device error word (Params::err)
 enum : int { ERR_BAD_ACTION = 1, ERR_BAD_STATE = 2, ERR_PACKED_RANGE = 4 };
@@ -141,6 +143,7 @@ struct Params {
   int kp[8];                // generator parameters (see include/minigrid_b200.h)
   uint32_t *grid;           // n_tiles * 32 * wpe words, see grid_word()
   uint4 *agent;             // [n_tiles * 32]
+  uint4 *extra;             // [n_tiles * 32], KIND_DYNOBS only: the obstacles in list order, 16 bits each (x | y << 8)
   RngRec *rng;              // [n_tiles * 32]
   const double *reward_lut; // [max_steps + 1], 1 - 0.9 * (k / max_steps) computed on the host in IEEE double
   const uint32_t *cell_lut; // [256] decode_cell()

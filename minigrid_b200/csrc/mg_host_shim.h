@@ -33,3 +33,4 @@ static inline uint32_t __brev(uint32_t v) {
 static inline int __ffs(uint32_t v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }

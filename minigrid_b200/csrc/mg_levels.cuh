@@ -234,8 +234,26 @@ MG_D uint32_t cell_memory(const Geom &g, const Level &L, int x, int y) {
   return CODE_EMPTY;
 }
 
+// envs/dynamicobstacles.py:107-133: border walls, goal at (W - 2, H - 2), nrooms blue balls (Ball() defaults to blue)
+// in the object records of rm03 (x:5 y:5 kind:2 colour:3, see play_obj)
+MG_D uint32_t cell_dynobs(const Geom &g, const Level &L, int x, int y) {
+  if (on_border(g, x, y)) return CODE_WALL;
+  if (x == g.W - 2 && y == g.H - 2) return CODE_GOAL;
+  return cell_objroom(g, L, x, y);
+}
+// the obstacle list as kept between steps (Params::extra): 8 x (x | y << 8)
+MG_D void dynobs_pack(const Level &L, uint32_t (&ex)[4]) {
+  ex[0] = ex[1] = ex[2] = ex[3] = 0;
+  for (int k = 0; k < 8; ++k)
+    if (k < L.nrooms) {
+      const uint32_t o = play_obj(L, k);
+      ex[k >> 1] |= ((o & 31u) | (((o >> 5) & 31u) << 8)) << (16 * (k & 1));
+    }
+}
+
 template <int KIND>
 MG_D uint32_t cell_of(const Params &p, const Level &L, int x, int y) {
+  if (KIND == KIND_DYNOBS) return cell_dynobs(p.g, L, x, y);
   if (KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR) return cell_objroom(p.g, L, x, y);
   if (KIND == KIND_GOTODOOR) return cell_gotodoor(p.g, L, x, y);
   if (KIND == KIND_REDBLUEDOORS) return cell_redbluedoors(p.g, L, x, y);
@@ -340,6 +358,27 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
       L.e = x; L.f = y;
       break;
     }
+  } else if (KIND == KIND_DYNOBS) {
+    // dynamicobstacles.py:107-133. kp = {n_obstacles, random_start, start_x, start_y, start_dir}
+    if (!p.kp[1]) { L.ax = p.kp[2]; L.ay = p.kp[3]; L.adir = p.kp[4]; }
+    else {  // place_agent() over the whole grid
+      for (;;) {
+        const int x = rng_integers(r, 0, W), y = rng_integers(r, 0, H);
+        if (cell_dynobs(g, L, x, y) != CODE_EMPTY) continue;
+        L.ax = x; L.ay = y;
+        break;
+      }
+      L.adir = rng_integers(r, 0, 4);
+    }
+    for (int k = 0; k < p.kp[0]; ++k)  // place_obj(Ball(), max_tries=100): 101 attempts, then RecursionError (not modelled: never seen)
+      for (int tries = 0; tries <= 100; ++tries) {
+        const int x = rng_integers(r, 0, W), y = rng_integers(r, 0, H);
+        if (cell_dynobs(g, L, x, y) != CODE_EMPTY) continue;
+        if (x == L.ax && y == L.ay) continue;
+        L.rm03 |= (u128)((uint32_t)x | ((uint32_t)y << 5) | (1u << 10) | ((uint32_t)C_BLUE << 12)) << (15 * L.nrooms);
+        L.nrooms += 1;
+        break;
+      }
   } else if (KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR) {
     // gotoobject.py:100-139, fetch.py:127-160, putnear.py:108-166. kp[0] = numObjs.
     const int n_objs = p.kp[0];
@@ -665,7 +704,7 @@ MG_D void patch_level(const Params &p, const Level &L, int lane, Put &&put) {
       }
     }
     if (lane == 0) put(L.e, L.f);
-  } else if (KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR) {
+  } else if (KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR || KIND == KIND_DYNOBS) {
     if (lane < L.nrooms) { const uint32_t o = play_obj(L, lane); put((int)(o & 31u), (int)((o >> 5) & 31u)); }
   } else if (KIND == KIND_REDBLUEDOORS) {
     if (lane == 0) put(g.H / 2, L.a);

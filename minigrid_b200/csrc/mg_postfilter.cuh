@@ -7,6 +7,7 @@
 // call these yet (next/README.md).
 #pragma once
 #include "mg_common.cuh"
+#include "mg_pcg64.cuh"
 
 namespace mg {
 
@@ -66,6 +67,32 @@ MG_HD PostOut post_filter(const PostIn &in, uint32_t terminated) {
     }
   }
   return o;
+}
+
+// ---- DynamicObstaclesEnv.step (dynamicobstacles.py:135-167), the part that runs BEFORE super().step ----
+// Every obstacle is re-placed inside the 3 x 3 box around its old position (place_obj(top=old - 1, size=(3, 3),
+// max_tries=100): up to 101 attempts of two draws each, minigrid_env.py:313-372; a RecursionError leaves it where it
+// is), then its old cell is cleared. The draws continue the env's own numpy stream, so the RNG record is on the step
+// path for this kind. get(x, y) reads a cell code, put(x, y, code) writes one (both arrays); ex = Params::extra.
+constexpr uint32_t CODE_OBSTACLE = T_BALL | (C_BLUE << 4);
+template <class Get, class Put>
+MG_D void dynobs_move(const Geom &g, Pcg &r, int n_obst, uint32_t (&ex)[4], int ax, int ay, Get &&get, Put &&put) {
+  for (int i = 0; i < n_obst; ++i) {
+    const uint32_t rec = (ex[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+    const int ox = (int)(rec & 0xFFu), oy = (int)(rec >> 8);
+    const int tx = max(ox - 1, 0), ty = max(oy - 1, 0);
+    const int hx = min(tx + 3, g.W), hy = min(ty + 3, g.H);
+    for (int tries = 0; tries <= 100; ++tries) {
+      const int x = rng_integers(r, tx, hx), y = rng_integers(r, ty, hy);
+      if (get(x, y) != CODE_EMPTY) continue;   // the old position is still occupied: an obstacle never stays
+      if (x == ax && y == ay) continue;
+      put(x, y, CODE_OBSTACLE);
+      put(ox, oy, CODE_EMPTY);
+      const uint32_t nrec = (uint32_t)x | ((uint32_t)y << 8);
+      ex[i >> 1] = (ex[i >> 1] & ~(0xFFFFu << (16 * (i & 1)))) | (nrec << (16 * (i & 1)));
+      break;
+    }
+  }
 }
 
 template <int KIND>

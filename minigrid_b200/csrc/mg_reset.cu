@@ -42,6 +42,11 @@ k_reset(Params p, const uint8_t *__restrict__ mask, uint8_t *__restrict__ obs, i
       rec.x |= ((uint32_t)level_tx(L) << 16) | ((uint32_t)level_ty(L) << 24);
       rec.y |= level_aux(L) << 16;
     }
+    if (KIND == KIND_DYNOBS) {
+      uint32_t ex[4];
+      dynobs_pack(L, ex);
+      p.extra[env] = make_uint4(ex[0], ex[1], ex[2], ex[3]);
+    }
     rec.z = 0;  // carrying = None
     rec.w = 0;  // step_count = 0
     p.agent[env] = rec;
@@ -72,6 +77,7 @@ cudaError_t launch_reset(const Params &p, const uint8_t *mask, uint8_t *obs, int
     case KIND_GOTOOBJECT: k_reset<KIND_GOTOOBJECT><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
     case KIND_PUTNEAR: k_reset<KIND_PUTNEAR><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
     case KIND_MEMORY: k_reset<KIND_MEMORY><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_DYNOBS: k_reset<KIND_DYNOBS><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
     default: k_reset<KIND_FOURROOMS><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
   }
   return cudaGetLastError();
@@ -102,6 +108,7 @@ cudaError_t launch_template(const Params &p, uint32_t *tmpl, cudaStream_t stream
     case KIND_GOTOOBJECT: k_template<KIND_GOTOOBJECT><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     case KIND_PUTNEAR: k_template<KIND_PUTNEAR><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     case KIND_MEMORY: k_template<KIND_MEMORY><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_DYNOBS: k_template<KIND_DYNOBS><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     default: k_template<KIND_FOURROOMS><<<blocks, 64, 0, stream>>>(p, tmpl); break;
   }
   return cudaGetLastError();

@@ -8,21 +8,49 @@ __device__ __forceinline__ uint32_t load_code(const Params &p, int env, int x, i
   return reinterpret_cast<const uint8_t *>(p.grid)[cell_byte_C(p.g, env, x, y)];
 }
 
-// out[n][W][H][3] = grid.encode(), agent cell = (OBJECT_TO_IDX["agent"], COLOR_TO_IDX["red"], agent_dir).
-// One thread per (env, cell); array C is [x][y] ordered like the output.
-__global__ void k_full_obs(Params p, uint8_t *__restrict__ out, int with_agent) {
-  const int cells = p.g.W * p.g.H;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)p.n_envs * cells) return;
-  const int env = (int)(gid / cells), c = (int)(gid % cells);
-  const int x = c / p.g.H, y = c % p.g.H;
-  uint32_t t = __ldg(p.cell_lut + load_code(p, env, x, y));
-  if (with_agent) {
-    const uint4 rec = p.agent[env];
-    if ((int)(rec.x & 0xFF) == x && (int)((rec.x >> 8) & 0xFF) == y) t = T_AGENT | (C_RED << 8) | ((rec.y & 3u) << 16);
+// K3. out[n][W][H][3] = grid.encode(), agent cell = (OBJECT_TO_IDX["agent"], COLOR_TO_IDX["red"], agent_dir).
+// One CTA per tile of 32 environments: array C is [x][y] ordered like the output, so consecutive threads read
+// consecutive bytes of a line, look the (type, colour, state) triple up and put it into a shared-memory stage that
+// holds the tile's 32 x 3WH output bytes exactly as they lie in `out`; the stage then leaves in 16-byte stores
+// (the block is contiguous and a multiple of 96 bytes). HBM-bound: W*H code bytes + the agent record in, 3*W*H out.
+__global__ void __launch_bounds__(256)
+k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with_agent) {
+  extern __shared__ __align__(16) uint8_t fo_smem[];
+  uint32_t *s_lut = reinterpret_cast<uint32_t *>(fo_smem);           // 256 words
+  uint32_t *s_agent = s_lut + 256;                                    // 32 words: x | y << 8 | dir << 16
+  uint8_t *stage = fo_smem + 1024 + 128;
+  const Geom &g = p.g;
+  const int WH = g.W * g.H, env_bytes = 3 * WH;
+  const int tile = blockIdx.x;
+  const int nvalid = min(TILE, p.n_envs - tile * TILE);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = decode_cell((uint32_t)i);
+  if (threadIdx.x < TILE) {
+    const uint4 rec = p.agent[tile * TILE + threadIdx.x];
+    s_agent[threadIdx.x] = with_agent ? ((rec.x & 0xFFFFu) | ((rec.y & 3u) << 16)) : 0xFFFFFFFFu;
   }
-  uint8_t *o = out + gid * 3;
-  o[0] = (uint8_t)t; o[1] = (uint8_t)(t >> 8); o[2] = (uint8_t)(t >> 16);
+  __syncthreads();
+  const float inv_h = 1.0f / (float)g.H, inv_wh = 1.0f / (float)WH;
+  const uint8_t *gb = reinterpret_cast<const uint8_t *>(p.grid);
+  for (int idx = threadIdx.x; idx < nvalid * WH; idx += blockDim.x) {
+    // exact small-integer divisions: (i + 0.5) / d is never within rounding of an integer
+    const int e = (int)(((float)idx + 0.5f) * inv_wh), c = idx - e * WH;
+    const int x = (int)(((float)c + 0.5f) * inv_h), y = c - x * g.H;
+    const uint32_t ag = s_agent[e];
+    uint32_t t = s_lut[gb[cell_byte_C(g, tile * TILE + e, x, y)]];
+    if ((ag & 0xFFFFu) == ((uint32_t)x | ((uint32_t)y << 8))) t = T_AGENT | (C_RED << 8) | (ag & 0x30000u);
+    uint8_t *o = stage + 3 * idx;
+    o[0] = (uint8_t)t; o[1] = (uint8_t)(t >> 8); o[2] = (uint8_t)(t >> 16);
+  }
+  __syncthreads();
+  uint8_t *dst = out + (size_t)tile * TILE * env_bytes;
+  const int total = nvalid * env_bytes;
+  if (nvalid == TILE && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (int i = threadIdx.x; i < total / 16; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = stage[i];
+  }
 }
 
 __global__ void k_get_agent(Params p, int32_t *__restrict__ agent, uint64_t *__restrict__ rng, uint8_t *__restrict__ pending) {
@@ -106,8 +134,16 @@ __global__ void k_init(Params p) {
 }
 
 cudaError_t launch_full_obs(const Params &p, uint8_t *out, int with_agent, cudaStream_t stream) {
-  const long long total = (long long)p.n_envs * p.g.W * p.g.H;
-  k_full_obs<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p, out, with_agent);
+  const size_t smem = 1024 + 128 + (size_t)TILE * 3 * p.g.W * p.g.H;  // <= 66 KB at 26 x 26
+  static bool attr_set[64] = {false};  // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_full_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 128 + TILE * 3 * MAX_DIM * MAX_DIM);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  k_full_obs<<<(unsigned)p.n_tiles, 256, smem, stream>>>(p, out, with_agent);
   return cudaGetLastError();
 }
 cudaError_t launch_get_state(const Params &p, uint8_t *grid, int32_t *agent, uint64_t *rng, uint8_t *pending, cudaStream_t stream) {

@@ -18,7 +18,7 @@ namespace mg {
 enum : int { MODE_TILED1 = 0, MODE_TILED2 = 1, MODE_WINDOW = 2 };  // buffers per warp / layout of K1
 
 #ifdef MG_TIMELINE  // debug build only (scripts/timeline.py): per-CTA %globaltimer stamps of the last two launches
-static __device__ unsigned long long g_tl[2][160][8];
+static __device__ unsigned long long g_tl[2][160][16];  // 0-7: CTA stamps; 8: regenerating tiles, 9 / 10: longest regenerating / plain tile (ns), 11: end of the last regenerating tile, 12: its pull index, 13: list ready
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -115,6 +115,11 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
     Pcg r = load_rng(rr);
     draw_level<KIND>(p, r, L);
     store_rng(rr, r);
+    if (KIND == KIND_DYNOBS) {  // the obstacle list of the new episode
+      uint32_t ex[4];
+      dynobs_pack(L, ex);
+      p.extra[(size_t)tile * TILE + lane] = make_uint4(ex[0], ex[1], ex[2], ex[3]);
+    }
   }
   constexpr bool PF = has_post_filter<KIND>();
   const ResetOut out = {L.ax, L.ay, L.adir, PF ? level_tx(L) : 0, PF ? level_ty(L) : 0, PF ? level_aux(L) : 0u};
@@ -156,7 +161,7 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
     B.e = __shfl_sync(0xFFFFFFFFu, L.e, src); B.f = __shfl_sync(0xFFFFFFFFu, L.f, src);
     B.rv = __shfl_sync(0xFFFFFFFFu, L.rv, src); B.rh = __shfl_sync(0xFFFFFFFFu, L.rh, src);
     B.ov = __shfl_sync(0xFFFFFFFFu, L.ov, src); B.oh = __shfl_sync(0xFFFFFFFFu, L.oh, src);
-    if (KIND == KIND_MULTIROOM || KIND == KIND_PLAYGROUND || KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR) {
+    if (KIND == KIND_MULTIROOM || KIND == KIND_PLAYGROUND || KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR || KIND == KIND_DYNOBS) {
       const unsigned long long lo = __shfl_sync(0xFFFFFFFFu, (unsigned long long)L.rm03, src);
       const unsigned long long hi = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(L.rm03 >> 64), src);
       B.rm03 = ((u128)hi << 64) | lo;
@@ -214,7 +219,10 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
   // and do our own prologue (nothing the previous step wrote is touched) before waiting for it to complete.
   asm volatile("griddepcontrol.launch_dependents;");
 #ifdef MG_TIMELINE
-  if (threadIdx.x == 0) { g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][6] = 0ull; g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][7] = ~0ull; }
+  if (threadIdx.x == 0) {
+    g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][6] = 0ull; g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][7] = ~0ull;
+    for (int i = 8; i < 16; ++i) g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][i] = 0ull;
+  }
 #endif
   MG_TL(0);
   const bool stepping = actions != nullptr;  // nullptr: observation-only pass (MiniGridEnv.gen_obs), state untouched
@@ -309,6 +317,9 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     __syncwarp();
     if (lane == 0) mbar_arrive(list_bar);  // release: the list is visible to whoever observes the phase
     list_ok = true;
+#ifdef MG_TIMELINE
+    if (lane == 0) g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][13] = gtime();
+#endif
   }
 
   uint8_t *gb = reinterpret_cast<uint8_t *>(p.grid);
@@ -352,6 +363,10 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       rec = ldg_rec(p.agent + env0);
       action = (stepping && env0 < p.n_envs) ? load_action(actions, act_dtype, env0) : A_DONE;
     }
+#ifdef MG_TIMELINE
+    const unsigned long long tl_t0 = gtime();
+    bool tl_hot = false;
+#endif
     uint32_t *gtile = reinterpret_cast<uint32_t *>(bufs + (size_t)b * buf_bytes);
     const int env = tile * TILE + lane;
     const bool active = env < p.n_envs;
@@ -377,6 +392,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     const uint32_t *base = gtile + lane;
     double reward = 0.0;
     uint32_t terminated = 0, truncated = 0;
+    int rsteps = 0;  // the step count the reward was computed from (a SAME_STEP autoreset zeroes `steps` afterwards)
     // NEXT_STEP autoreset (gymnasium >= 1.0 SyncVectorEnv): an env that ended last step ignores its action,
     // is reset now, and returns the reset obs with reward 0 / False / False
     bool fresh = false;
@@ -386,6 +402,9 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       const unsigned pend = __ballot_sync(0xFFFFFFFFu, fresh);
       if (pend) {
         wrote = true;
+#ifdef MG_TIMELINE
+        tl_hot = true;
+#endif
         const ResetOut ro = warp_reset<KIND>(p, pend, tile, WIN ? nullptr : gtile, lane);
         if (fresh) {
           ax = ro.ax; ay = ro.ay; dir = ro.dir; carry = 0; steps = 0; flags &= ~FLAG_PENDING;
@@ -414,6 +433,32 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       int fx, fy;
       front_pos(g, ax, ay, dir, fx, fy);
       const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
+      bool not_clear = false;
+      if (KIND == KIND_DYNOBS && !WIN) {
+        // DynamicObstaclesEnv.step (dynamicobstacles.py:135-158): actions beyond forward count as left, the front cell is
+        // looked at BEFORE the obstacles move, then every obstacle is re-placed with draws from the env's own stream
+        if (action >= 3) action = A_LEFT;
+        const uint32_t fc0 = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
+        not_clear = fc0 != CODE_EMPTY && (fc0 & 15u) != T_GOAL;
+        if (active) {
+          RngRec *rr = p.rng + env;
+          Pcg r = load_rng(rr);
+          const uint4 e4 = p.extra[env];
+          uint32_t ex[4] = {e4.x, e4.y, e4.z, e4.w};
+          uint8_t *sb = reinterpret_cast<uint8_t *>(gtile);
+          uint8_t *tb = reinterpret_cast<uint8_t *>(p.grid + (size_t)tile * g.wpe * 32);
+          dynobs_move(g, r, p.kp[0], ex, ax, ay,
+                      [&](int x, int y) { return (tile_word<true>(base, r_word(g, x, y)) >> (8 * (x & 3))) & 0xFFu; },
+                      [&](int x, int y, uint32_t code) {
+                        const int o_r = (r_word(g, x, y) * 32 + lane) * 4 + (x & 3), o_c = (c_word(g, x, y) * 32 + lane) * 4 + (y & 3);
+                        sb[o_r] = (uint8_t)code; sb[o_c] = (uint8_t)code;
+                        tb[o_r] = (uint8_t)code; tb[o_c] = (uint8_t)code;
+                      });
+          store_rng(rr, r);
+          p.extra[env] = make_uint4(ex[0], ex[1], ex[2], ex[3]);
+          wrote = true;
+        }
+      }
       uint32_t fc;
       const int fpos = ((dir & 1) ? ay : ax) + ((dir < 2) ? 1 : -1);  // the front cell's position on the agent's own line
       if (WIN) fc = view_words_byte(vw, fpos);  // meaningless after a turn (other array loaded), and then unused
@@ -445,6 +490,10 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
           gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)newc;
         }
       }
+      if (KIND == KIND_DYNOBS && action == A_FORWARD && not_clear) {  // walked into an obstacle or a wall: :161-165
+        reward = -1.0;
+        terminated = 1u;
+      }
       if (PF) {  // the env's own step(): a few predicates on top of MiniGridEnv.step (mg_postfilter.cuh)
         PostIn in;
         in.action = act; in.ax = ax; in.ay = ay; in.dir = dir;
@@ -474,6 +523,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
                                         : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
       }
       truncated = steps >= p.max_steps;
+      rsteps = steps;
       const bool done = (terminated | truncated) != 0;
       if (p.mode == AUTORESET_NEXT_STEP) flags = done ? (flags | FLAG_PENDING) : (flags & ~FLAG_PENDING);
     }
@@ -530,8 +580,9 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
         // and the four result arrays; the host expands them (mg_host_expand.cpp)
         uint32_t P[PACKED_WORDS];
         const uint32_t rewarded = reward != 0.0 ? 1u : 0u;
-        if (rewarded && (uint32_t)steps > PACKED_MAX_STEPS) atomicOr(p.err, ERR_PACKED_RANGE);
-        pack_codes(clo, chi, packed_tail(dir, terminated, truncated, rewarded, (uint32_t)steps), P);
+        if (rewarded && (uint32_t)rsteps >= PACKED_MAX_STEPS) atomicOr(p.err, ERR_PACKED_RANGE);
+        // (the only negative reward, Dynamic-Obstacles' -1, travels as the reserved step count PACKED_MAX_STEPS)
+        pack_codes(clo, chi, packed_tail(dir, terminated, truncated, rewarded, reward < 0.0 ? PACKED_MAX_STEPS : (uint32_t)rsteps), P);
         __syncwarp();
         uint32_t *dstw = gtile + PACKED_WORDS * lane;  // odd word stride: conflict-free
 #pragma unroll
@@ -571,6 +622,12 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     __syncwarp();  // lanes may still be reading this buffer (partial-tile path) before it is refilled
 #ifdef MG_TIMELINE
     if (first) MG_TL(4);
+    if (lane == 0) {
+      unsigned long long *tl = g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x];
+      const unsigned long long t1 = gtime();
+      if (tl_hot) { atomicAdd(&tl[8], 1ull); atomicMax(&tl[9], t1 - tl_t0); atomicMax(&tl[11], t1); atomicMax(&tl[12], (unsigned long long)(tile - t_lo)); }
+      else atomicMax(&tl[10], t1 - tl_t0);
+    }
 #endif
     first = false;
     if (PREF) {
@@ -612,6 +669,7 @@ static StepKernel pick_kind(int kind) {
     case KIND_GOTOOBJECT: return (StepKernel)k_step<KIND_GOTOOBJECT, VIS, MODE>;
     case KIND_PUTNEAR: return (StepKernel)k_step<KIND_PUTNEAR, VIS, MODE>;
     case KIND_MEMORY: return (StepKernel)k_step<KIND_MEMORY, VIS, MODE>;
+    case KIND_DYNOBS: return (StepKernel)k_step<KIND_DYNOBS, VIS, MODE>;
     default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, MODE>;
   }
 }

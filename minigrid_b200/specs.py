@@ -13,6 +13,7 @@ from dataclasses import dataclass, field
 KIND_EMPTY, KIND_DOORKEY, KIND_CROSSING, KIND_FOURROOMS, KIND_LAVAGAP, KIND_DISTSHIFT, KIND_MULTIROOM = 0, 1, 2, 3, 4, 5, 6
 KIND_LOCKEDROOM, KIND_PLAYGROUND = 7, 8
 KIND_GOTODOOR, KIND_FETCH, KIND_REDBLUEDOORS, KIND_GOTOOBJECT, KIND_PUTNEAR, KIND_MEMORY = 9, 10, 11, 12, 13, 14
+KIND_DYNOBS = 15
 T_WALL, T_LAVA = 2, 9
 
 
@@ -115,6 +116,15 @@ def memory(size=8, random_length=False, max_steps=None):
                    "go to the matching object at the end of the hallway")
 
 
+def dynobstacles(size=8, agent_start_pos=(1, 1), agent_start_dir=0, n_obstacles=4, max_steps=None):
+    """envs/dynamicobstacles.py:72-105 (4 * size^2 steps, see_through_walls=True; too many obstacles are reduced)."""
+    n_obst = int(n_obstacles) if n_obstacles <= size / 2 + 1 else int(size / 2)
+    random_start = agent_start_pos is None
+    sx, sy = (0, 0) if random_start else agent_start_pos
+    return EnvSpec(KIND_DYNOBS, size, size, max_steps or 4 * size * size, True,
+                   (n_obst, int(random_start), sx, sy, agent_start_dir), "get to the green goal square")
+
+
 REGISTRY = {
     # BASELINE.json configs
     "MiniGrid-Empty-5x5-v0": empty(size=5),
@@ -170,6 +180,13 @@ REGISTRY = {
     "MiniGrid-MemoryS11-v0": memory(11),
     "MiniGrid-MemoryS9-v0": memory(9),
     "MiniGrid-MemoryS7-v0": memory(7),
+    # RNG inside step: __init__.py:117-153
+    "MiniGrid-Dynamic-Obstacles-5x5-v0": dynobstacles(5, n_obstacles=2),
+    "MiniGrid-Dynamic-Obstacles-Random-5x5-v0": dynobstacles(5, agent_start_pos=None, n_obstacles=2),
+    "MiniGrid-Dynamic-Obstacles-6x6-v0": dynobstacles(6, n_obstacles=3),
+    "MiniGrid-Dynamic-Obstacles-Random-6x6-v0": dynobstacles(6, agent_start_pos=None, n_obstacles=3),
+    "MiniGrid-Dynamic-Obstacles-8x8-v0": dynobstacles(8),
+    "MiniGrid-Dynamic-Obstacles-16x16-v0": dynobstacles(16, n_obstacles=8),
 }
 
 

@@ -53,10 +53,10 @@ ROLLOUTS = {  # id -> (N, T, seed)
     "MiniGrid-PutNear-8x8-N3-v0": (8, 300, 73),
     "MiniGrid-MemoryS13Random-v0": (6, 600, 79),
     "MiniGrid-MemoryS7-v0": (6, 400, 83),
-}
-NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist yet: next_rollout_<id>.npz (oracle only)
     "MiniGrid-Dynamic-Obstacles-Random-6x6-v0": (8, 400, 89),
     "MiniGrid-Dynamic-Obstacles-8x8-v0": (8, 500, 97),
+}
+NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist yet: next_rollout_<id>.npz (oracle only)
 }
 INJECTS = {  # id (host env whose size/see_through/max_steps are used) -> (N, T)
     "MiniGrid-DoorKey-8x8-v0": (16, 120),

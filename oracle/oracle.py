@@ -65,6 +65,12 @@ ENV_SPECS = {
     "MiniGrid-MemoryS11-v0": ("memory", 11, 11, 605, False, [0]),
     "MiniGrid-MemoryS9-v0": ("memory", 9, 9, 405, False, [0]),
     "MiniGrid-MemoryS7-v0": ("memory", 7, 7, 245, False, [0]),
+    "MiniGrid-Dynamic-Obstacles-5x5-v0": ("dynobstacles", 5, 5, 100, True, [2, 0, 1, 1, 0]),
+    "MiniGrid-Dynamic-Obstacles-Random-5x5-v0": ("dynobstacles", 5, 5, 100, True, [2, 1, 0, 0, 0]),
+    "MiniGrid-Dynamic-Obstacles-6x6-v0": ("dynobstacles", 6, 6, 144, True, [3, 0, 1, 1, 0]),
+    "MiniGrid-Dynamic-Obstacles-Random-6x6-v0": ("dynobstacles", 6, 6, 144, True, [3, 1, 0, 0, 0]),
+    "MiniGrid-Dynamic-Obstacles-8x8-v0": ("dynobstacles", 8, 8, 256, True, [4, 0, 1, 1, 0]),
+    "MiniGrid-Dynamic-Obstacles-16x16-v0": ("dynobstacles", 16, 16, 1024, True, [8, 0, 1, 1, 0]),
 }
 
 # SURVEY 8(f-1) generators restated ahead of their device kernels: the oracle and its fixtures exist, the product does
@@ -78,12 +84,6 @@ NEXT_SPECS = {
     # memory.py:67-88 (5 * size^2 steps, see_through_walls=False), __init__.py:323-357; params {random_length}
     # dynamicobstacles.py:72-105 (4 * size^2 steps, see_through_walls=True), __init__.py:117-153;
     # params {n_obstacles, random_start, start_x, start_y, start_dir}
-    "MiniGrid-Dynamic-Obstacles-5x5-v0": ("dynobstacles", 5, 5, 100, True, [2, 0, 1, 1, 0]),
-    "MiniGrid-Dynamic-Obstacles-Random-5x5-v0": ("dynobstacles", 5, 5, 100, True, [2, 1, 0, 0, 0]),
-    "MiniGrid-Dynamic-Obstacles-6x6-v0": ("dynobstacles", 6, 6, 144, True, [3, 0, 1, 1, 0]),
-    "MiniGrid-Dynamic-Obstacles-Random-6x6-v0": ("dynobstacles", 6, 6, 144, True, [3, 1, 0, 0, 0]),
-    "MiniGrid-Dynamic-Obstacles-8x8-v0": ("dynobstacles", 8, 8, 256, True, [4, 0, 1, 1, 0]),
-    "MiniGrid-Dynamic-Obstacles-16x16-v0": ("dynobstacles", 16, 16, 1024, True, [8, 0, 1, 1, 0]),
 }
 
 

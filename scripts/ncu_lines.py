@@ -8,7 +8,7 @@ rep, mangled = sys.argv[1], sys.argv[2]
 n_tiles = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "minigrid_b200", "libminigrid_b200.so")], cwd=tmp, capture_output=True)
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("NCU_LINES_LIB", os.path.join(root, "minigrid_b200", "libminigrid_b200.so"))], cwd=tmp, capture_output=True)
 sass = []
 for cub in sorted(f for f in os.listdir(tmp) if f.startswith("mg_step")):  # K1 is instantiated in several translation units
     out = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cub)], capture_output=True, text=True).stdout

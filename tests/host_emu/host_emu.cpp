@@ -27,6 +27,7 @@ struct Emu {
   std::vector<uint32_t> grid;
   std::vector<uint4> agent;
   std::vector<RngRec> rng;
+  std::vector<uint4> extra;
   std::vector<double> reward_lut;
   std::vector<uint32_t> cell_lut;
   std::vector<uint16_t> vis_tbl;
@@ -47,11 +48,16 @@ static void reset_env(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {  // k_r
   uint4 rec;
   rec.x = (uint32_t)L.ax | ((uint32_t)L.ay << 8);
   rec.y = (uint32_t)L.adir;
-  if (KIND >= KIND_GOTODOOR) {  // post-filter targets
+  if (has_post_filter<KIND>()) {  // post-filter targets
     rec.x |= ((uint32_t)level_tx(L) << 16) | ((uint32_t)level_ty(L) << 24);
     rec.y |= level_aux(L) << 16;
   }
   rec.z = 0; rec.w = 0;
+  if (KIND == KIND_DYNOBS) {
+    uint32_t ex[4];
+    dynobs_pack(L, ex);
+    p.extra[env] = make_uint4(ex[0], ex[1], ex[2], ex[3]);
+  }
   p.agent[env] = rec;
   if (dir_out) dir_out[env] = L.adir;
   if (obs) {
@@ -85,6 +91,7 @@ static void reset_one(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {
     case KIND_GOTOOBJECT: reset_env<KIND_GOTOOBJECT>(e, env, obs, dir_out); break;
     case KIND_PUTNEAR: reset_env<KIND_PUTNEAR>(e, env, obs, dir_out); break;
     case KIND_MEMORY: reset_env<KIND_MEMORY>(e, env, obs, dir_out); break;
+    case KIND_DYNOBS: reset_env<KIND_DYNOBS>(e, env, obs, dir_out); break;
     default: reset_env<KIND_FOURROOMS>(e, env, obs, dir_out); break;
   }
 }
@@ -101,10 +108,15 @@ static void warp_reset_k(Emu *e, unsigned pend, int tile, uint32_t *gtile, Reset
       Pcg r = load_rng(&e->rng[env]);
       draw_level<KIND>(p, r, Ls[lane]);
       store_rng(&e->rng[env], r);
+      if (KIND == KIND_DYNOBS) {
+        uint32_t ex[4];
+        dynobs_pack(Ls[lane], ex);
+        p.extra[env] = make_uint4(ex[0], ex[1], ex[2], ex[3]);
+      }
     }
   for (int lane = 0; lane < 32; ++lane) {
     out[lane].ax = Ls[lane].ax; out[lane].ay = Ls[lane].ay; out[lane].dir = Ls[lane].adir;
-    const bool pf = KIND >= KIND_GOTODOOR;  // kinds with a post-filter: their targets ride in Level::ov
+    const bool pf = has_post_filter<KIND>();  // kinds with a post-filter: their targets ride in Level::ov
     out[lane].tx = pf ? level_tx(Ls[lane]) : 0; out[lane].ty = pf ? level_ty(Ls[lane]) : 0; out[lane].aux = pf ? level_aux(Ls[lane]) : 0u;
   }
   if (__builtin_popcount(pend) >= 4) {  // DENSE_RESET_MIN: every pending lane fills its own env
@@ -164,6 +176,7 @@ static void warp_reset(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOu
     case KIND_GOTOOBJECT: warp_reset_k<KIND_GOTOOBJECT>(e, pend, tile, gtile, out); break;
     case KIND_PUTNEAR: warp_reset_k<KIND_PUTNEAR>(e, pend, tile, gtile, out); break;
     case KIND_MEMORY: warp_reset_k<KIND_MEMORY>(e, pend, tile, gtile, out); break;
+    case KIND_DYNOBS: warp_reset_k<KIND_DYNOBS>(e, pend, tile, gtile, out); break;
     default: warp_reset_k<KIND_FOURROOMS>(e, pend, tile, gtile, out); break;
   }
 }
@@ -194,7 +207,7 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
   for (int tile = 0; tile < p.n_tiles; ++tile) {
     if (!WIN) memcpy(gtile.data(), p.grid + (size_t)tile * g.wpe * 32, (size_t)g.wpe * 128);  // the TMA bulk load
     const bool full = (tile + 1) * TILE <= p.n_envs;
-    int ax[32], ay[32], dir[32], steps[32], tx[32], ty[32];
+    int ax[32], ay[32], dir[32], steps[32], tx[32], ty[32], rsteps[32] = {0};
     uint32_t flags[32], carry[32], terminated[32] = {0}, truncated[32] = {0};
     double reward[32] = {0};
     bool active[32], fresh[32] = {false};
@@ -235,13 +248,35 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
     for (int lane = 0; lane < 32; ++lane) {
       if (!(stepping && !fresh[lane])) continue;
       const int env = tile * TILE + lane;
-      const int action = emu_pre_filter(p.kind, active[lane] ? actions[env] : A_DONE);
+      int action = emu_pre_filter(p.kind, active[lane] ? actions[env] : A_DONE);
       const uint32_t carry_before = carry[lane];
       const uint32_t *base = gtile.data() + lane;
       steps[lane] += 1;
       int fx, fy;
       front_pos(g, ax[lane], ay[lane], dir[lane], fx, fy);
       const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
+      bool not_clear = false;
+      if (p.kind == KIND_DYNOBS && !WIN) {  // K1's Dynamic-Obstacles block
+        if (action >= 3) action = A_LEFT;
+        const uint32_t fc0 = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
+        not_clear = fc0 != CODE_EMPTY && (fc0 & 15u) != T_GOAL;
+        if (active[lane]) {
+          Pcg r = load_rng(&e->rng[env]);
+          const uint4 e4 = p.extra[env];
+          uint32_t ex[4] = {e4.x, e4.y, e4.z, e4.w};
+          uint8_t *sb = reinterpret_cast<uint8_t *>(gtile.data());
+          uint8_t *tb = reinterpret_cast<uint8_t *>(p.grid + (size_t)tile * g.wpe * 32);
+          dynobs_move(g, r, p.kp[0], ex, ax[lane], ay[lane],
+                      [&](int x, int y) { return (tile_word<true>(base, r_word(g, x, y)) >> (8 * (x & 3))) & 0xFFu; },
+                      [&](int x, int y, uint32_t code) {
+                        const int o_r = (r_word(g, x, y) * 32 + lane) * 4 + (x & 3), o_c = (c_word(g, x, y) * 32 + lane) * 4 + (y & 3);
+                        sb[o_r] = (uint8_t)code; sb[o_c] = (uint8_t)code;
+                        tb[o_r] = (uint8_t)code; tb[o_c] = (uint8_t)code;
+                      });
+          store_rng(&e->rng[env], r);
+          p.extra[env] = make_uint4(ex[0], ex[1], ex[2], ex[3]);
+        }
+      }
       uint32_t fc;
       const int fpos = ((dir[lane] & 1) ? ay[lane] : ax[lane]) + ((dir[lane] < 2) ? 1 : -1);
       if (WIN) fc = view_words_byte(vws[lane], fpos);
@@ -264,7 +299,8 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
         gb[grid_word(g, env, rw) * 4 + (fx & 3)] = (uint8_t)so.newc;
         gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)so.newc;
       }
-      if (p.kind >= KIND_GOTODOOR) {  // step post-filter
+      if (p.kind == KIND_DYNOBS && action == A_FORWARD && not_clear) { reward[lane] = -1.0; terminated[lane] = 1u; }
+      if (p.kind >= KIND_GOTODOOR && p.kind <= KIND_MEMORY) {  // step post-filter
         PostIn in;
         in.action = action; in.ax = ax[lane]; in.ay = ay[lane]; in.dir = dir[lane];
         in.carry_before = carry_before; in.carry = carry[lane];
@@ -286,6 +322,7 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
         }
       }
       truncated[lane] = steps[lane] >= p.max_steps;
+      rsteps[lane] = steps[lane];
       const bool done = (terminated[lane] | truncated[lane]) != 0;
       if (p.mode == AUTORESET_NEXT_STEP) flags[lane] = done ? (flags[lane] | FLAG_PENDING) : (flags[lane] & ~FLAG_PENDING);
     }
@@ -317,7 +354,8 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
           const AccTiled acc = {gtile.data() + lane, true};
           gather_view<VIS>(g, acc, p.vis_tbl, ax[lane], ay[lane], dir[lane], carry[lane], clo, chi);
         }
-        pack_codes(clo, chi, packed_tail(dir[lane], terminated[lane], truncated[lane], reward[lane] != 0.0 ? 1u : 0u, (uint32_t)steps[lane]), P);
+        pack_codes(clo, chi, packed_tail(dir[lane], terminated[lane], truncated[lane], reward[lane] != 0.0 ? 1u : 0u,
+                                         reward[lane] < 0.0 ? PACKED_MAX_STEPS : (uint32_t)rsteps[lane]), P);
         if (active[lane]) memcpy(e->packed_out + (size_t)env * PACKED_WORDS, P, sizeof(P));
       }
     } else if (obs) {
@@ -368,6 +406,7 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
   Params &p = e->p;
   memset(&p, 0, sizeof(p));
   if (layout < 0) layout = make_geom(W, H, LAYOUT_TILED).wpe * 4 > 512 ? LAYOUT_WINDOW : LAYOUT_TILED;  // mg_create rule
+  if (kind == KIND_DYNOBS) layout = LAYOUT_TILED;
   p.g = make_geom(W, H, layout);
   p.n_envs = n_envs; p.n_tiles = (n_envs + 31) / 32;
   p.max_steps = max_steps; p.see_through = see_through; p.mode = mode; p.kind = kind;
@@ -375,6 +414,8 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
   const size_t n_pad = (size_t)p.n_tiles * 32;
   e->grid.assign((size_t)p.n_tiles * p.g.wpe * 32 + 64, CODE_WALL4);
   e->agent.assign(n_pad, make_uint4(1u | (1u << 8), 0, 0, 0));
+  e->extra.assign(n_pad, make_uint4(0, 0, 0, 0));
+  p.extra = e->extra.data();
   e->rng.resize(n_pad);
   memset(e->rng.data(), 0, n_pad * sizeof(RngRec));
   e->reward_lut.resize(max_steps + 1);
@@ -404,6 +445,7 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
         case KIND_GOTOOBJECT: e->tmpl[w] = level_word<KIND_GOTOOBJECT>(p, L, w); break;
         case KIND_PUTNEAR: e->tmpl[w] = level_word<KIND_PUTNEAR>(p, L, w); break;
         case KIND_MEMORY: e->tmpl[w] = level_word<KIND_MEMORY>(p, L, w); break;
+        case KIND_DYNOBS: e->tmpl[w] = level_word<KIND_DYNOBS>(p, L, w); break;
         default: e->tmpl[w] = level_word<KIND_FOURROOMS>(p, L, w); break;
       }
     p.tmpl = e->tmpl.data();

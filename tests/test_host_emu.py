@@ -29,7 +29,10 @@ def test_emu_inject_fixture(path):
 
 
 @pytest.mark.parametrize("env_id", ["MiniGrid-DoorKey-8x8-v0", "MiniGrid-FourRooms-v0", "MiniGrid-LavaCrossingS9N1-v0",
-                                    "MiniGrid-Empty-5x5-v0", "MiniGrid-LavaCrossingS11N5-v0"])
+                                    "MiniGrid-Empty-5x5-v0", "MiniGrid-LavaCrossingS11N5-v0",
+                                    "MiniGrid-Dynamic-Obstacles-5x5-v0", "MiniGrid-Dynamic-Obstacles-Random-6x6-v0",
+                                    "MiniGrid-Dynamic-Obstacles-8x8-v0", "MiniGrid-Dynamic-Obstacles-16x16-v0",
+                                    "MiniGrid-RedBlueDoors-8x8-v0", "MiniGrid-PutNear-6x6-N2-v0", "MiniGrid-LockedRoom-v0"])
 @pytest.mark.parametrize("mode,n", [("next_step", 96), ("same_step", 45)])
 def test_emu_lockstep_vs_oracle(env_id, mode, n):
     emu = make_emu(env_id, n, mode)
@@ -49,11 +52,13 @@ def test_emu_fixture_in_both_layouts(path, layout):
         parity.check_inject_fixture(mk, g)
 
 
-@pytest.mark.parametrize("layout", [0, 1], ids=["tiled", "window"])
-@pytest.mark.parametrize("env_id", ["MiniGrid-DoorKey-8x8-v0", "MiniGrid-FourRooms-v0", "MiniGrid-Empty-5x5-v0",
-                                    "MiniGrid-Fetch-8x8-N3-v0", "MiniGrid-GoToDoor-5x5-v0"])
-@pytest.mark.parametrize("scalar", [False, True], ids=["ssse3", "scalar"])
-def test_packed_host_format_expands_to_the_same_arrays(env_id, layout, scalar, monkeypatch):
+@pytest.mark.parametrize("env_id,layout,scalar,mode", [
+    ("MiniGrid-DoorKey-8x8-v0", 0, False, "next_step"), ("MiniGrid-DoorKey-8x8-v0", 1, False, "same_step"),
+    ("MiniGrid-FourRooms-v0", 1, False, "next_step"), ("MiniGrid-FourRooms-v0", 0, True, "same_step"),
+    ("MiniGrid-Empty-5x5-v0", 0, False, "same_step"), ("MiniGrid-Empty-5x5-v0", 1, True, "next_step"),
+    ("MiniGrid-Fetch-8x8-N3-v0", 0, False, "next_step"), ("MiniGrid-GoToDoor-5x5-v0", 1, False, "same_step"),
+    ("MiniGrid-Dynamic-Obstacles-6x6-v0", 0, False, "same_step"), ("MiniGrid-Dynamic-Obstacles-6x6-v0", 0, True, "next_step")])
+def test_packed_host_format_expands_to_the_same_arrays(env_id, layout, scalar, mode, monkeypatch):
     """MG_HOST_PACKED: K1's 52-byte records (pack_codes, device header) + the product's host expander == the oracle's
     obs / dir / reward / flags, bit for bit, with both expander code paths."""
     import subprocess
@@ -65,12 +70,12 @@ import numpy as np
 from emu import EmuVecEnv
 from oracle.oracle import ENV_SPECS, OracleVecEnv
 n = 77
-emu = EmuVecEnv(ENV_SPECS[{env_id!r}], n, autoreset="next_step", layout={layout})
-orc = OracleVecEnv({env_id!r}, n)
+emu = EmuVecEnv(ENV_SPECS[{env_id!r}], n, autoreset={mode!r}, layout={layout})
+orc = OracleVecEnv({env_id!r}, n, autoreset={mode!r})
 emu.reset(seed=5); orc.reset(seed=5)
 rng = np.random.default_rng(0)
 seen_reward = 0
-for t in range(400):
+for t in range(300):
     a = rng.integers(0, 7, n).astype(np.int32)
     if t % 3 == 0: a[:] = np.where(rng.random(n) < 0.6, 2, a)  # mostly forward: reach goals
     e = emu.step_packed(a); o = orc.step(a)
