@@ -9,47 +9,58 @@ __device__ __forceinline__ uint32_t load_code(const Params &p, int env, int x, i
 }
 
 // K3. out[n][W][H][3] = grid.encode(), agent cell = (OBJECT_TO_IDX["agent"], COLOR_TO_IDX["red"], agent_dir).
-// One CTA per tile of 32 environments: array C is [x][y] ordered like the output, so consecutive threads read
-// consecutive bytes of a line, look the (type, colour, state) triple up and put it into a shared-memory stage that
-// holds the tile's 32 x 3WH output bytes exactly as they lie in `out`; the stage then leaves in 16-byte stores
-// (the block is contiguous and a multiple of 96 bytes). HBM-bound: W*H code bytes + the agent record in, 3*W*H out.
+// One CTA per tile of 32 environments, whose output block (32 x 3WH bytes, a multiple of 96) is contiguous: a thread
+// produces one 4-byte WORD of it — the word's bytes belong to two consecutive cells (array C is [x][y] ordered like
+// the output), so it reads two cell codes (L1-resident lines), looks the (type, colour, state) triples up and merges
+// them with one byte permute, exactly like the image stream of K1 — and stores it, 128 contiguous bytes per warp.
+// HBM-bound: W*H code bytes + the agent record in, 3*W*H out. No staging, no byte stores.
 __global__ void __launch_bounds__(256)
 k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with_agent) {
-  extern __shared__ __align__(16) uint8_t fo_smem[];
-  uint32_t *s_lut = reinterpret_cast<uint32_t *>(fo_smem);           // 256 words
-  uint32_t *s_agent = s_lut + 256;                                    // 32 words: x | y << 8 | dir << 16
-  uint8_t *stage = fo_smem + 1024 + 128;
+  __shared__ uint32_t s_lut[256];
+  __shared__ uint32_t s_agent[TILE];                // agent cell index x * H + y | dir << 16 (no agent: never matches)
+  __shared__ uint16_t s_off[MAX_DIM * MAX_DIM + 1]; // cell c = x * H + y -> byte offset of the cell inside the env's part of array C
   const Geom &g = p.g;
   const int WH = g.W * g.H, env_bytes = 3 * WH;
   const int tile = blockIdx.x;
   const int nvalid = min(TILE, p.n_envs - tile * TILE);
+  const bool tiled = g.layout == LAYOUT_TILED;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = decode_cell((uint32_t)i);
   if (threadIdx.x < TILE) {
     const uint4 rec = p.agent[tile * TILE + threadIdx.x];
-    s_agent[threadIdx.x] = with_agent ? ((rec.x & 0xFFFFu) | ((rec.y & 3u) << 16)) : 0xFFFFFFFFu;
+    s_agent[threadIdx.x] = with_agent ? ((rec.x & 0xFFu) * (uint32_t)g.H + ((rec.x >> 8) & 0xFFu)) | ((rec.y & 3u) << 16) : 0xFFFFu;
+  }
+  const float inv_h = 1.0f / (float)g.H;
+  for (int c = threadIdx.x; c < WH; c += blockDim.x) {
+    const int x = (int)(((float)c + 0.5f) * inv_h), y = c - x * g.H;  // exact: (c + 0.5) / H is never within rounding of an integer
+    // tiled: word cw of lane e sits at (cw * 32 + e) * 4 of the tile block; window: env-major words
+    s_off[c] = (uint16_t)(tiled ? c_word(g, x, y) * 128 + (y & 3) : c_word(g, x, y) * 4 + (y & 3));
   }
   __syncthreads();
-  const float inv_h = 1.0f / (float)g.H, inv_wh = 1.0f / (float)WH;
-  const uint8_t *gb = reinterpret_cast<const uint8_t *>(p.grid);
-  for (int idx = threadIdx.x; idx < nvalid * WH; idx += blockDim.x) {
-    // exact small-integer divisions: (i + 0.5) / d is never within rounding of an integer
-    const int e = (int)(((float)idx + 0.5f) * inv_wh), c = idx - e * WH;
-    const int x = (int)(((float)c + 0.5f) * inv_h), y = c - x * g.H;
+  const uint8_t *tb = reinterpret_cast<const uint8_t *>(p.grid) + (size_t)tile * g.wpe * 128;  // both layouts: 32 envs x wpe words
+  const uint32_t estride = tiled ? 4u : (uint32_t)g.wpe * 4u;
+  const float inv_eb = 1.0f / (float)env_bytes;
+  // (type | colour << 8 | state << 16) of the cell that holds byte B of the tile's output block, and B's place in the triple
+  auto triple = [&](int e, int c) -> uint32_t {
+    if (e >= nvalid) return 0u;
     const uint32_t ag = s_agent[e];
-    uint32_t t = s_lut[gb[cell_byte_C(g, tile * TILE + e, x, y)]];
-    if ((ag & 0xFFFFu) == ((uint32_t)x | ((uint32_t)y << 8))) t = T_AGENT | (C_RED << 8) | (ag & 0x30000u);
-    uint8_t *o = stage + 3 * idx;
-    o[0] = (uint8_t)t; o[1] = (uint8_t)(t >> 8); o[2] = (uint8_t)(t >> 16);
-  }
-  __syncthreads();
+    if ((ag & 0xFFFFu) == (uint32_t)c) return T_AGENT | (C_RED << 8) | (ag & 0x30000u);
+    return s_lut[tb[(uint32_t)e * estride + s_off[c]]];
+  };
+  auto word_at = [&](int B) -> uint32_t {  // bytes B .. B + 3
+    const int e = (int)(((float)B + 0.5f) * inv_eb), b = B - e * env_bytes;
+    const int c = (b * 0xAAABu) >> 17, r = b - 3 * c;  // b / 3 for b < 2^15
+    const bool wrap = c + 1 == WH;
+    const uint32_t t0 = triple(e, c), t1 = triple(wrap ? e + 1 : e, wrap ? 0 : c + 1);
+    return prmt(t0, t1, r == 0 ? 0x4210u : (r == 1 ? 0x5421u : 0x6542u));
+  };
   uint8_t *dst = out + (size_t)tile * TILE * env_bytes;
   const int total = nvalid * env_bytes;
-  if (nvalid == TILE && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
-    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-    for (int i = threadIdx.x; i < total / 16; i += blockDim.x) d4[i] = s4[i];
+  if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    for (int J = threadIdx.x; J < total / 4; J += blockDim.x) d32[J] = word_at(4 * J);
+    for (int B = (total & ~3) + threadIdx.x; B < total; B += blockDim.x) dst[B] = (uint8_t)word_at(B);  // ragged last tile
   } else {
-    for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = stage[i];
+    for (int B = threadIdx.x; B < total; B += blockDim.x) dst[B] = (uint8_t)word_at(B);
   }
 }
 
@@ -134,16 +145,7 @@ __global__ void k_init(Params p) {
 }
 
 cudaError_t launch_full_obs(const Params &p, uint8_t *out, int with_agent, cudaStream_t stream) {
-  const size_t smem = 1024 + 128 + (size_t)TILE * 3 * p.g.W * p.g.H;  // <= 66 KB at 26 x 26
-  static bool attr_set[64] = {false};  // the attribute is per device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_full_obs, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 128 + TILE * 3 * MAX_DIM * MAX_DIM);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
-  k_full_obs<<<(unsigned)p.n_tiles, 256, smem, stream>>>(p, out, with_agent);
+  k_full_obs<<<(unsigned)p.n_tiles, 256, 0, stream>>>(p, out, with_agent);
   return cudaGetLastError();
 }
 cudaError_t launch_get_state(const Params &p, uint8_t *grid, int32_t *agent, uint64_t *rng, uint8_t *pending, cudaStream_t stream) {

@@ -21,7 +21,11 @@
 namespace mg {
 
 #ifdef MG_TIMELINE
-extern "C" int mg_debug_timeline(void *out) {  // out: unsigned long long[2][160][8]
+int debug_timeline_window(void *out);
+int debug_timeline_tiled1(void *out);
+extern "C" int mg_debug_timeline(void *out, int mode) {  // out: unsigned long long[2][160][16]; mode: MODE_* of the handle's plan
+  if (mode == MODE_WINDOW) return debug_timeline_window(out);
+  if (mode == MODE_TILED1) return debug_timeline_tiled1(out);
   return (int)cudaMemcpyFromSymbol(out, g_tl, sizeof(g_tl));
 }
 #endif

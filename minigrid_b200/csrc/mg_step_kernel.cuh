@@ -18,7 +18,8 @@ namespace mg {
 enum : int { MODE_TILED1 = 0, MODE_TILED2 = 1, MODE_WINDOW = 2 };  // buffers per warp / layout of K1
 
 #ifdef MG_TIMELINE  // debug build only (scripts/timeline.py): per-CTA %globaltimer stamps of the last two launches
-static __device__ unsigned long long g_tl[2][160][16];  // 0-7: CTA stamps; 8: regenerating tiles, 9 / 10: longest regenerating / plain tile (ns), 11: end of the last regenerating tile, 12: its pull index, 13: list ready
+static __device__ unsigned long long g_tl[2][160][16];  // one per translation unit: mg_debug_timeline(mode) reads the right one
+//  // 0-7: CTA stamps; 8: regenerating tiles, 9 / 10: longest regenerating / plain tile (ns), 11: end of the last regenerating tile, 12: its pull index, 13: list ready
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -39,10 +40,12 @@ __host__ __device__ inline uint32_t step_buf_bytes(const Geom &g) {
   if (b < (uint32_t)OBS_TILE_BYTES) b = OBS_TILE_BYTES;
   return (b + 127u) & ~127u;
 }
-// Tiles whose environments regenerate in this step (NEXT_STEP autoreset: the previous step flagged them) take several
-// dependent memory round trips longer than a plain tile. Left in place they end up in a CTA's last round every few
-// steps and the whole grid waits for one warp, so each CTA visits them right after its first round: the order of up to
-// ORDER_CAP tiles behind the first round is a list in shared memory, flagged tiles first.
+// Tiles whose environments regenerate in this step (NEXT_STEP autoreset: the previous step flagged them) take twice as
+// long as a plain tile (9 us against 4.7 us, profiles/r02c_timeline.txt: the numpy-exact draws are one lane's serial
+// chain). Left where they are they end up in a CTA's last round every step and the whole grid waits for one warp, so
+// each CTA visits them FIRST: the order of its (up to ORDER_CAP) tiles is a list in shared memory, flagged tiles in
+// front. The list is built in the prologue, i.e. before griddepcontrol.wait, from flags the previous launch may still
+// be writing: a stale flag only costs the tile its place in the order, never correctness.
 constexpr int ORDER_CAP = 1024;
 // [cell table 1 KB][visibility table 32 KB, VIS_TBL only][warps x nbuf x buffer][mbarriers][tile counter][list barrier][order list]
 __host__ __device__ inline size_t step_smem_bytes(const Geom &g, int vis, int warps, int nbuf) {
@@ -212,7 +215,6 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 1024 + TBL + (size_t)WARPS * NBUF * buf_bytes);
   const uint32_t bar0 = smem_u32(bars + 2 * warp), tbl_bar = smem_u32(bars + 2 * WARPS);
   int *s_next = reinterpret_cast<int *>(bars + 2 * WARPS + 1);
-  const uint32_t list_bar = smem_u32(bars + 2 * WARPS + 2);
   uint16_t *s_order = reinterpret_cast<uint16_t *>(bars + 2 * WARPS + 3);
 
   // Programmatic dependent launch: let the next kernel in the stream start its prologue while this grid drains,
@@ -233,11 +235,10 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
   const int t_hi = t_lo + (int)tq + (blockIdx.x < tr ? 1 : 0);
   // pull index k of a CTA: its k-th tile. k < WARPS: the static first round; behind it, the order list (flagged tiles first)
   const int n_my = t_hi - t_lo;
-  const int m_ord = min(max(n_my - WARPS, 0), ORDER_CAP);
-  const bool use_order = stepping && p.mode == AUTORESET_NEXT_STEP && p.hot_first && m_ord > 0;
+  const int m_ord = min(n_my, ORDER_CAP);
+  const bool use_order = stepping && p.mode == AUTORESET_NEXT_STEP && p.hot_first && m_ord > WARPS;
   if (threadIdx.x == 0) {
     *s_next = (PREF ? 2 : 1) * WARPS;
-    mbar_init(list_bar, 1);
     if (VIS == VIS_TBL) {  // the table is immutable after mg_create: its copy may run ahead of griddepcontrol.wait
       mbar_init(tbl_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -245,54 +246,21 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       tma_load_1d(smem_u32(vis_tbl), p.vis_tbl, TBL, tbl_bar);
     }
   }
-  int tile = t_lo + warp;
-  int next = p.n_tiles;  // PREF: resolved through the order list at the warp's first prefetch
-  if (tile >= t_hi) tile = p.n_tiles;
-  bool list_ok = !use_order;
-  auto map_tile = [&](int k) -> int {
+  auto map_tile = [&](int k) -> int {  // the CTA's k-th tile
     if (k >= n_my) return p.n_tiles;
-    int off = k;
-    if (use_order && k >= WARPS && k - WARPS < m_ord) {
-      if (!list_ok) { mbar_wait(list_bar, 0); list_ok = true; }
-      off = s_order[k - WARPS];
-    }
-    return t_lo + off;
+    return t_lo + ((use_order && k < m_ord) ? (int)s_order[k] : k);
   };
-  if (lane == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  // the 256-entry (type, colour, state) table is pure arithmetic: no global load anywhere near the critical path
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = decode_cell((uint32_t)i);
-  __syncthreads();
-  MG_TL(1);
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads state the previous step wrote
-  MG_TL(2);
-  bool first = true;  // first tile of this warp
-
-  uint4 rec = make_uint4(0, 0, 0, 0);
-  int action = A_DONE;
-  if (PREF && tile < p.n_tiles) {
-    if (NBUF == 2 && lane == 0) {
-      mbar_expect_tx(bar0, tile_bytes);
-      tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
-    }
-    const int env0 = tile * TILE + lane;
-    rec = ldg_rec(p.agent + env0);
-    if (stepping && env0 < p.n_envs) action = load_action(actions, act_dtype, env0);
-  }
-
   if (use_order && warp == WARPS - 1) {
-    // the last warp builds the list (its own first tile is already on its way): tiles WARPS .. WARPS + m_ord - 1 of this
-    // CTA, those flagged by the previous step first. Ballots are kept in registers (lane c: chunk c) so that both passes
-    // see the same flags whatever is written to them meanwhile.
-    const uint8_t *hot = p.tile_hot + t_lo + WARPS;
+    // tiles 0 .. m_ord - 1 of this CTA, those flagged by the previous step first. Ballots are kept in registers (lane c:
+    // chunk c) so that both passes see the same flags whatever is written to them meanwhile.
+    const uint8_t *hot = p.tile_hot + t_lo;
     unsigned mybal = 0;
     const int chunks = (m_ord + 31) >> 5;
     for (int c = 0; c < chunks; ++c) {
       const int idx = 32 * c + lane;
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, idx < m_ord && hot[idx] != 0);
+      uint32_t f = 0;
+      if (idx < m_ord) asm volatile("ld.global.relaxed.gpu.u8 %0, [%1];" : "=r"(f) : "l"(hot + idx));
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, f != 0);
       if (lane == c) mybal = bal;
     }
     int pre = __popc(mybal);  // inclusive scan over lanes of the chunks' hot counts
@@ -311,15 +279,35 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
         const unsigned lt = (1u << lane) - 1u;
         const bool is_hot = (bal >> lane) & 1u;
         const int pos = is_hot ? hb + __popc(bal & lt) : hot_total + (32 * c - hb) + __popc(~bal & lt);
-        s_order[pos] = (uint16_t)(WARPS + idx);
+        s_order[pos] = (uint16_t)idx;
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(list_bar);  // release: the list is visible to whoever observes the phase
-    list_ok = true;
-#ifdef MG_TIMELINE
-    if (lane == 0) g_tl[(obs_tma_ok >> 1) & 1][blockIdx.x][13] = gtime();
-#endif
+  }
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the 256-entry (type, colour, state) table is pure arithmetic: no global load anywhere near the critical path
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = decode_cell((uint32_t)i);
+  __syncthreads();
+  MG_TL(1);
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads state the previous step wrote
+  MG_TL(2);
+  bool first = true;  // first tile of this warp
+  int tile = map_tile(warp);
+  int next = PREF ? map_tile(WARPS + warp) : p.n_tiles;
+
+  uint4 rec = make_uint4(0, 0, 0, 0);
+  int action = A_DONE;
+  if (PREF && tile < p.n_tiles) {
+    if (NBUF == 2 && lane == 0) {
+      mbar_expect_tx(bar0, tile_bytes);
+      tma_load_1d(smem_u32(bufs), p.grid + (size_t)tile * g.wpe * 32, tile_bytes, bar0);
+    }
+    const int env0 = tile * TILE + lane;
+    rec = ldg_rec(p.agent + env0);
+    if (stepping && env0 < p.n_envs) action = load_action(actions, act_dtype, env0);
   }
 
   uint8_t *gb = reinterpret_cast<uint8_t *>(p.grid);
@@ -330,7 +318,6 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     int action_n = A_DONE, nn = p.n_tiles;
     // prefetch the next tile (into the other buffer), its agent records and actions, and the index of the tile after it
     auto prefetch = [&]() {
-      if (first) next = map_tile(WARPS + warp);
       if (next < p.n_tiles) {
         if (lane == 0) {
           if (NBUF == 2) {
@@ -349,7 +336,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     // A warp's first tile: every warp of the GPU is fetching its first tile at this moment, and nothing can be
     // computed anywhere until those arrive, so the second tile is requested only once the first is here (its fetch
     // then overlaps the first tile's compute like every later one) instead of doubling the opening burst.
-    const bool defer = (NBUF == 2 || WIN) && first;  // (window mode: behind the first view loads, the order list is on its way)
+    const bool defer = (NBUF == 2) && first;
     if (PREF) {
       if (WIN && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous obs block has left
       if (!defer) prefetch();
@@ -425,7 +412,6 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       int dirn = dir;
       if (stepping && !fresh) dirn = (dir + (action == A_LEFT ? 3 : 0) + (action == A_RIGHT ? 1 : 0)) & 3;
       load_view_words(g, ax, ay, dirn, vw, ldw);
-      if (defer) prefetch();
     }
     if (stepping && !fresh) {
       // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----

@@ -5,4 +5,8 @@ namespace mg {
 
 StepKernel step_kernel_tiled1(int kind, int vis) { return pick_vis<MODE_TILED1>(kind, vis); }
 
+#ifdef MG_TIMELINE
+int debug_timeline_tiled1(void *out) { return (int)cudaMemcpyFromSymbol(out, g_tl, sizeof(g_tl)); }
+#endif
+
 }  // namespace mg

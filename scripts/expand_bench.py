@@ -1,5 +1,5 @@
 """Host-side expansion of the packed step records (mg_expand_packed_mt): milliseconds per 262144-env step against the
-number of threads, with and without non-temporal stores (MINIGRID_B200_EXPAND_NOSTREAM). CPU only."""
+number of threads, with plain and with non-temporal stores (MINIGRID_B200_EXPAND_STREAM=1). CPU only."""
 import ctypes as C
 import os
 import subprocess
@@ -36,7 +36,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(" ".join(out), "(pinned)" if pin else "(pageable)")
 else:
     threads = sys.argv[1] if len(sys.argv) > 1 else "1,2,4,8,12,15,16,24,32"
-    for name, env in (("stream", {}), ("nostream", {"MINIGRID_B200_EXPAND_NOSTREAM": "1"})):
+    for name, env in (("plain stores", {}), ("streaming stores", {"MINIGRID_B200_EXPAND_STREAM": "1"})):
         e = dict(os.environ)
         e.update(env)
         r = subprocess.run([sys.executable, __file__, "child", threads], capture_output=True, text=True, env=e)
