@@ -147,6 +147,31 @@ int mg_host_threads(const mg_env *env);
  * (10, 0, agent_dir). out_dev: uint8[n][W][H][3]. */
 int mg_full_obs(mg_env *env, uint8_t *out_dev, void *stream);
 
+/* The reference's observation wrappers (minigrid/wrappers.py) for the whole batch, on the device. `image_dev` is the
+ * observation image the last mg_step / mg_reset / mg_gen_obs wrote (uint8[n][V][V][3]).
+ *  mg_obs_view         ViewSizeWrapper.observation (:663-673): gen_obs with agent_view_size = view_size (odd, 3..15);
+ *                      out_dev uint8[n][V][V][3]
+ *  mg_obs_onehot       OneHotPartialObsWrapper.observation (:268-284): out_dev uint8[n][V][V][20]
+ *  mg_obs_flat         FlatObsWrapper.observation (:589-626): out_dev uint8[n][image_bytes + mission_bytes], the image
+ *                      followed by the one-hot mission characters (mission_dev: uint8[mission_bytes], the same for
+ *                      every env: only ids with a constant mission string)
+ *  mg_obs_symbolic     SymbolicObsWrapper.observation (:762-782): out_dev int64[n][W][H][3] = (x, y, type | -1), the
+ *                      agent's cell carries OBJECT_TO_IDX["agent"]
+ *  mg_obs_rgb_partial  RGBImgPartialObsWrapper.observation (:371-380), tile_size 8: out_dev uint8[n][56][56][3]
+ *  mg_obs_rgb_full     RGBImgObsWrapper.observation (:325-331), tile_size 8: out_dev uint8[n][8 H][8 W][3]; image_dev
+ *                      supplies the highlight (the visible cells of the agent's view)
+ * tiles_dev uint8[T][8][8][3] and index_dev uint16[128][5][2] (cell code, 0 no agent | 1 + agent_dir, highlight) are the
+ * tile atlas rendered once by the reference's Grid.render_tile (grid.py:145-198; minigrid_b200/data/tile_atlas.npz). */
+int mg_obs_view(mg_env *env, int view_size, uint8_t *out_dev, void *stream);
+int mg_obs_onehot(mg_env *env, const uint8_t *image_dev, int view_size, uint8_t *out_dev, void *stream);
+int mg_obs_flat(mg_env *env, const uint8_t *image_dev, int image_bytes, const uint8_t *mission_dev, int mission_bytes,
+                uint8_t *out_dev, void *stream);
+int mg_obs_symbolic(mg_env *env, int64_t *out_dev, void *stream);
+int mg_obs_rgb_partial(mg_env *env, const uint8_t *image_dev, const uint8_t *tiles_dev, const uint16_t *index_dev,
+                       uint8_t *out_dev, void *stream);
+int mg_obs_rgb_full(mg_env *env, const uint8_t *image_dev, const uint8_t *tiles_dev, const uint16_t *index_dev,
+                    uint8_t *out_dev, void *stream);
+
 /* Replaces: pickling / inspecting env objects (tests/test_envs.py:185-195) and lets tests inject states.
  * grid_dev: Grid.encode() uint8[n][W][H][3]; agent_dev: int32[n][6] {x, y, dir, carry_type (-1 none),
  * carry_color, step_count}; rng_dev: uint64[n][6] {state_hi, state_lo, inc_hi, inc_lo, has_uint32,

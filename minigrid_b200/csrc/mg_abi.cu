@@ -25,6 +25,13 @@ cudaError_t launch_set_state(const Params &p, const uint8_t *grid, const int32_t
                              const uint8_t *pending, cudaStream_t stream);
 cudaError_t launch_init(const Params &p, cudaStream_t stream);
 cudaError_t launch_clear_err(const Params &p, int bits, cudaStream_t stream);
+cudaError_t launch_view(const Params &p, int V, uint8_t *out, cudaStream_t s);
+cudaError_t launch_onehot(const uint8_t *img, uint8_t *out, long long n_cells, cudaStream_t s);
+cudaError_t launch_flat(const uint8_t *img, const uint8_t *mission, uint8_t *out, int img_bytes, int mission_bytes, long long n_envs,
+                        cudaStream_t s);
+cudaError_t launch_symbolic(const Params &p, long long *out, cudaStream_t s);
+cudaError_t launch_rgb_partial(const uint8_t *img, const uint8_t *tiles, const uint16_t *index, uint8_t *out, long long n_envs, cudaStream_t s);
+cudaError_t launch_rgb_full(const Params &p, const uint8_t *img, const uint8_t *tiles, const uint16_t *index, uint8_t *out, cudaStream_t s);
 cudaError_t launch_template(const Params &p, uint32_t *tmpl, cudaStream_t stream);
 }  // namespace mg
 
@@ -394,6 +401,59 @@ int mg_full_obs(mg_env *h, uint8_t *out_dev, void *stream) {
   MG_ON_DEVICE(h);
   note_stream(h, (cudaStream_t)stream);
   MG_CUDA(launch_full_obs(h->p, out_dev, 1, (cudaStream_t)stream));
+  h->launches += 1;
+  return MG_OK;
+}
+
+// ---- observation wrappers on the device (mg_wrappers.cu) ----
+int mg_obs_view(mg_env *h, int view_size, uint8_t *out_dev, void *stream) {
+  if (!h || !out_dev) return fail(MG_ERR_INVALID_ARG, "mg_obs_view: NULL argument");
+  if (view_size < 3 || view_size > 15 || view_size % 2 == 0)
+    return fail(MG_ERR_INVALID_ARG, "mg_obs_view: agent_view_size must be odd and in 3..15 (wrappers.py:650-651)");
+  MG_ON_DEVICE(h);
+  note_stream(h, (cudaStream_t)stream);
+  MG_CUDA(launch_view(h->p, view_size, out_dev, (cudaStream_t)stream));
+  h->launches += 1;
+  return MG_OK;
+}
+int mg_obs_onehot(mg_env *h, const uint8_t *image_dev, int view_size, uint8_t *out_dev, void *stream) {
+  if (!h || !image_dev || !out_dev || view_size < 1) return fail(MG_ERR_INVALID_ARG, "mg_obs_onehot: bad argument");
+  MG_ON_DEVICE(h);
+  MG_CUDA(launch_onehot(image_dev, out_dev, (long long)h->p.n_envs * view_size * view_size, (cudaStream_t)stream));
+  h->launches += 1;
+  return MG_OK;
+}
+int mg_obs_flat(mg_env *h, const uint8_t *image_dev, int image_bytes, const uint8_t *mission_dev, int mission_bytes, uint8_t *out_dev,
+                void *stream) {
+  if (!h || !image_dev || !mission_dev || !out_dev || image_bytes < 1 || mission_bytes < 0)
+    return fail(MG_ERR_INVALID_ARG, "mg_obs_flat: bad argument");
+  MG_ON_DEVICE(h);
+  MG_CUDA(launch_flat(image_dev, mission_dev, out_dev, image_bytes, mission_bytes, h->p.n_envs, (cudaStream_t)stream));
+  h->launches += 1;
+  return MG_OK;
+}
+int mg_obs_symbolic(mg_env *h, int64_t *out_dev, void *stream) {
+  if (!h || !out_dev) return fail(MG_ERR_INVALID_ARG, "mg_obs_symbolic: NULL argument");
+  MG_ON_DEVICE(h);
+  note_stream(h, (cudaStream_t)stream);
+  MG_CUDA(launch_symbolic(h->p, (long long *)out_dev, (cudaStream_t)stream));
+  h->launches += 1;
+  return MG_OK;
+}
+int mg_obs_rgb_partial(mg_env *h, const uint8_t *image_dev, const uint8_t *tiles_dev, const uint16_t *index_dev, uint8_t *out_dev,
+                       void *stream) {
+  if (!h || !image_dev || !tiles_dev || !index_dev || !out_dev) return fail(MG_ERR_INVALID_ARG, "mg_obs_rgb_partial: NULL argument");
+  MG_ON_DEVICE(h);
+  MG_CUDA(launch_rgb_partial(image_dev, tiles_dev, index_dev, out_dev, h->p.n_envs, (cudaStream_t)stream));
+  h->launches += 1;
+  return MG_OK;
+}
+int mg_obs_rgb_full(mg_env *h, const uint8_t *image_dev, const uint8_t *tiles_dev, const uint16_t *index_dev, uint8_t *out_dev,
+                    void *stream) {
+  if (!h || !image_dev || !tiles_dev || !index_dev || !out_dev) return fail(MG_ERR_INVALID_ARG, "mg_obs_rgb_full: NULL argument");
+  MG_ON_DEVICE(h);
+  note_stream(h, (cudaStream_t)stream);
+  MG_CUDA(launch_rgb_full(h->p, image_dev, tiles_dev, index_dev, out_dev, (cudaStream_t)stream));
   h->launches += 1;
   return MG_OK;
 }

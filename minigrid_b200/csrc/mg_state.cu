@@ -44,7 +44,7 @@ k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with
     if (e >= nvalid) return 0u;
     const uint32_t ag = s_agent[e];
     if ((ag & 0xFFFFu) == (uint32_t)c) return T_AGENT | (C_RED << 8) | (ag & 0x30000u);
-    return s_lut[tb[(uint32_t)e * estride + s_off[c]]];
+    return s_lut[__ldg(tb + (uint32_t)e * estride + s_off[c])];  // read-only path: the loads of an unrolled batch run ahead of its stores
   };
   auto word_at = [&](int B) -> uint32_t {  // bytes B .. B + 3
     const int e = (int)(((float)B + 0.5f) * inv_eb), b = B - e * env_bytes;
@@ -57,7 +57,14 @@ k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with
   const int total = nvalid * env_bytes;
   if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
     uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-    for (int J = threadIdx.x; J < total / 4; J += blockDim.x) d32[J] = word_at(4 * J);
+    const int nw = total / 4;
+    int J = threadIdx.x;
+    for (; J + 3 * (int)blockDim.x < nw; J += 4 * blockDim.x) {  // four independent words per thread: their 8 cell loads overlap
+      const uint32_t w0 = word_at(4 * J), w1 = word_at(4 * (J + blockDim.x)), w2 = word_at(4 * (J + 2 * blockDim.x)),
+                     w3 = word_at(4 * (J + 3 * blockDim.x));
+      d32[J] = w0; d32[J + blockDim.x] = w1; d32[J + 2 * blockDim.x] = w2; d32[J + 3 * blockDim.x] = w3;
+    }
+    for (; J < nw; J += blockDim.x) d32[J] = word_at(4 * J);
     for (int B = (total & ~3) + threadIdx.x; B < total; B += blockDim.x) dst[B] = (uint8_t)word_at(B);  // ragged last tile
   } else {
     for (int B = threadIdx.x; B < total; B += blockDim.x) dst[B] = (uint8_t)word_at(B);

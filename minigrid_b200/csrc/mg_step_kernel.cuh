@@ -113,6 +113,11 @@ template <int KIND>
 __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int tile, uint32_t *gtile, int lane) {
   const Geom &g = p.g;
   Level L = blank_level();
+  // pending envs per tile from which every pending lane fills its own env (a truncation wave) instead of the warp going
+  // through them one at a time. 8: by chance (LavaCrossing: 0.85 % of the envs end per step) 4 of 32 happen once per
+  // step somewhere in a 262144-env batch, and that one tile then cost 35 us and set the step time (profiles/r02d_gpu_call.log)
+  constexpr int DENSE_RESET_MIN = 8;
+  const bool dense = __popc(pend) >= DENSE_RESET_MIN;
   if ((pend >> lane) & 1u) {
     RngRec *rr = p.rng + (size_t)tile * TILE + lane;
     Pcg r = load_rng(rr);
@@ -123,6 +128,28 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
       dynobs_pack(L, ex);
       p.extra[(size_t)tile * TILE + lane] = make_uint4(ex[0], ex[1], ex[2], ex[3]);
     }
+  } else if (!dense) {
+    // Sparse case: the draws are one lane's serial chain of a few microseconds. The other lanes use that time (divergent
+    // paths of a warp interleave where one stalls) to copy the level template over the pending envs, four independent
+    // loads at a time.
+    const unsigned idle = ~pend;
+    const int n_idle = __popc(idle), rank = __popc(idle & ((1u << lane) - 1u));
+    for (unsigned m = pend; m; m &= m - 1) {
+      const int src = __ffs(m) - 1;
+      uint32_t *genv = p.grid + grid_word(g, tile * TILE + src, 0);
+      const int gs = g.layout == LAYOUT_TILED ? 32 : 1;  // stride of an env's consecutive words
+      int w = rank;
+      for (; w + 3 * n_idle < g.wpe; w += 4 * n_idle) {
+        const uint32_t a = __ldg(p.tmpl + w), b = __ldg(p.tmpl + w + n_idle), c = __ldg(p.tmpl + w + 2 * n_idle), d = __ldg(p.tmpl + w + 3 * n_idle);
+        if (gtile) { gtile[w * 32 + src] = a; gtile[(w + n_idle) * 32 + src] = b; gtile[(w + 2 * n_idle) * 32 + src] = c; gtile[(w + 3 * n_idle) * 32 + src] = d; }
+        genv[(size_t)w * gs] = a; genv[(size_t)(w + n_idle) * gs] = b; genv[(size_t)(w + 2 * n_idle) * gs] = c; genv[(size_t)(w + 3 * n_idle) * gs] = d;
+      }
+      for (; w < g.wpe; w += n_idle) {
+        const uint32_t a = __ldg(p.tmpl + w);
+        if (gtile) gtile[w * 32 + src] = a;
+        genv[(size_t)w * gs] = a;
+      }
+    }
   }
   constexpr bool PF = has_post_filter<KIND>();
   const ResetOut out = {L.ax, L.ay, L.adir, PF ? level_tx(L) : 0, PF ? level_ty(L) : 0, PF ? level_aux(L) : 0u};
@@ -132,8 +159,7 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
   // same step): every pending lane fills ITS OWN env — template words (one broadcast load per word; in the tiled
   // layout the 32 lanes' stores of a word index are one 128-byte line), then all patch cells of its own level —
   // instead of the warp going through the environments one at a time.
-  constexpr int DENSE_RESET_MIN = 4;  // pending envs per tile from which the lane-parallel fill is used
-  if (__popc(pend) >= DENSE_RESET_MIN) {
+  if (dense) {
     if ((pend >> lane) & 1u) {
       const int env = tile * TILE + lane;
       for (int w = 0; w < g.wpe; ++w) {
@@ -171,12 +197,7 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
       B.rm45 = __shfl_sync(0xFFFFFFFFu, L.rm45, src);
       B.nrooms = __shfl_sync(0xFFFFFFFFu, L.nrooms, src);
     } else { B.rm03 = 0; B.rm45 = 0; B.nrooms = 0; }
-    for (int w = lane; w < g.wpe; w += 32) {
-      const uint32_t word = __ldg(p.tmpl + w);
-      if (gtile) gtile[w * 32 + src] = word;
-      p.grid[grid_word(g, env, w)] = word;
-    }
-    __syncwarp();  // template words land before the byte patches other lanes write into them
+    // (the template words were written by the idle lanes during the draws, ordered before this point by __syncwarp)
     patch_level<KIND>(p, B, lane, [&](int x, int y) {
       const uint8_t code = (uint8_t)cell_of<KIND>(p, B, x, y);
       const int rw = r_word(g, x, y), cw = c_word(g, x, y);

@@ -166,6 +166,43 @@ def gen_inject(env_id, n, t_steps, seed=99):
                 width=W, height=H, max_steps=e0.max_steps, see_through=e0.see_through_walls)
 
 
+WRAPPER_FIXTURES = {  # id -> (N, steps before the snapshot): the reference's observation wrappers on the same states
+    "MiniGrid-DoorKey-8x8-v0": (6, 90),
+    "MiniGrid-FourRooms-v0": (5, 40),
+    "MiniGrid-Playground-v0": (5, 60),
+    "MiniGrid-Empty-5x5-v0": (4, 7),
+    "MiniGrid-LavaCrossingS9N1-v0": (4, 12),
+}
+
+
+def gen_wrappers(env_id, n, t_steps, seed=77):
+    """State after t_steps random steps + what the reference's wrapper classes (minigrid/wrappers.py) return on it."""
+    ref = ReferenceVecEnv(env_id, n, autoreset="next_step")
+    ref.reset(seed=seed)
+    rng = np.random.default_rng(4)
+    obs = None
+    for t in range(t_steps):
+        obs = ref.step(rng.integers(0, 6, n))  # no `done`: keeps the post-filter envs of other fixtures out of this one
+    st = ref.get_state()
+    out = dict(env_id=env_id, seed=seed, grid=st["grid"], agent=st["agent"], obs=obs[0], one_hot=ref.one_hot_obs(),
+               symbolic=ref.symbolic_obs(), rgb_partial=ref.rgb_partial_obs(), rgb_full=ref.rgb_full_obs(), full_obs=ref.full_obs())
+    for V in (3, 5, 9, 11):
+        out[f"view{V}"] = ref.view_obs(V)
+    try:
+        out["flat"] = ref.flat_obs()
+    except Exception:  # noqa: BLE001  (missions with characters FlatObsWrapper rejects)
+        pass
+    return out
+
+
+def main_wrappers():
+    os.makedirs(OUT, exist_ok=True)
+    for env_id, (n, t) in WRAPPER_FIXTURES.items():
+        d = gen_wrappers(env_id, n, t)
+        np.savez_compressed(os.path.join(OUT, f"wrappers_{env_id}.npz"), **d)
+        print("wrappers", env_id, {k: v.shape for k, v in d.items() if hasattr(v, "shape") and k.startswith(("rgb", "flat", "view9"))})
+
+
 def main_next():
     os.makedirs(OUT, exist_ok=True)
     for env_id, (n, t, seed) in NEXT_ROLLOUTS.items():
@@ -199,6 +236,9 @@ def main():
 if __name__ == "__main__":
     if sys.argv[1:] == ["next"]:   # python -m oracle.gen_golden next: only the next_rollout_* fixtures
         main_next()
+    elif sys.argv[1:] == ["wrappers"]:
+        main_wrappers()
     else:
         main()
         main_next()
+        main_wrappers()

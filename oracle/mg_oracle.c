@@ -826,6 +826,60 @@ static void env_gen_obs(const mgo_vec *v, const env_t *e, uint8_t *image, int32_
   *direction = e->agent_dir;
 }
 
+/* ViewSizeWrapper.observation (wrappers.py:663-673) = gen_obs_grid(agent_view_size) + grid.encode(vis_mask) for an odd
+ * view size V >= 3 (minigrid_env.py:453-484, 597-630; grid.py:110-143, 291-328): the same pipeline as env_gen_obs with
+ * the 7 replaced by V. image: [V][V][3] */
+#define MAX_VIEW 15
+static void env_gen_obs_view(const mgo_vec *v, const env_t *e, int V, uint8_t *image) {
+  int topX, topY;
+  switch (e->agent_dir) {
+    case 0: topX = e->agent_x; topY = e->agent_y - V / 2; break;
+    case 1: topX = e->agent_x - V / 2; topY = e->agent_y; break;
+    case 2: topX = e->agent_x - V + 1; topY = e->agent_y - V / 2; break;
+    default: topX = e->agent_x - V / 2; topY = e->agent_y - V + 1; break;
+  }
+  cell_t a[MAX_VIEW * MAX_VIEW], b[MAX_VIEW * MAX_VIEW]; /* row-major j * V + i */
+  for (int j = 0; j < V; j++)
+    for (int i = 0; i < V; i++) {
+      int x = topX + i, y = topY + j;
+      a[j * V + i] = (x >= 0 && x < e->grid.width && y >= 0 && y < e->grid.height) ? grid_get(&e->grid, x, y) : WALL_GREY;
+    }
+  cell_t *cur = a, *other = b;
+  for (int r = 0; r < e->agent_dir + 1; r++) { /* rotate_left: out(j, V - 1 - i) = in(i, j) */
+    for (int i = 0; i < V; i++)
+      for (int j = 0; j < V; j++) other[(V - 1 - i) * V + j] = cur[j * V + i];
+    cell_t *t = cur; cur = other; other = t;
+  }
+  uint8_t mask[MAX_VIEW][MAX_VIEW];
+  if (!v->see_through) {
+    memset(mask, 0, sizeof(mask));
+    mask[V / 2][V - 1] = 1;
+    for (int j = V - 1; j >= 0; j--) {
+      for (int i = 0; i < V - 1; i++) {
+        if (!mask[i][j]) continue;
+        cell_t c = cur[j * V + i];
+        if (!cell_is_none(c) && !see_behind(c)) continue;
+        mask[i + 1][j] = 1;
+        if (j > 0) { mask[i + 1][j - 1] = 1; mask[i][j - 1] = 1; }
+      }
+      for (int i = V - 1; i >= 1; i--) {
+        if (!mask[i][j]) continue;
+        cell_t c = cur[j * V + i];
+        if (!cell_is_none(c) && !see_behind(c)) continue;
+        mask[i - 1][j] = 1;
+        if (j > 0) { mask[i - 1][j - 1] = 1; mask[i][j - 1] = 1; }
+      }
+    }
+  } else memset(mask, 1, sizeof(mask));
+  cur[(V - 1) * V + V / 2] = e->carrying ? e->carry : CELL_NONE;
+  for (int i = 0; i < V; i++)
+    for (int j = 0; j < V; j++) {
+      uint8_t *o = image + (i * V + j) * 3;
+      if (mask[i][j]) encode_cell(cur[j * V + i], o);
+      else { o[0] = 0; o[1] = 0; o[2] = 0; }
+    }
+}
+
 /* minigrid_env.py:240-245; compiled with -ffp-contract=off so no FMA is formed */
 static double env_reward(const mgo_vec *v, const env_t *e) {
   volatile double q = (double)e->step_count / (double)v->max_steps;
@@ -1053,6 +1107,28 @@ int mgo_vec_step(mgo_vec *v, const int32_t *actions, uint8_t *obs, int32_t *dir,
   job_t j; memset(&j, 0, sizeof(j));
   j.v = v; j.op = 1; j.actions = actions; j.obs = obs; j.dir = dir; j.reward = reward; j.term = terminated; j.trunc = truncated; j.mode = mode;
   return run_jobs(j, clamp_threads(v, n_threads)) ? -1 : 0;
+}
+/* ViewSizeWrapper: image [n][V][V][3]; returns -1 for an unsupported size */
+int mgo_vec_gen_obs_view(mgo_vec *v, int V, uint8_t *obs) {
+  if (V < 3 || V > MAX_VIEW || V % 2 == 0) return -1;
+  for (int i = 0; i < v->n; i++) env_gen_obs_view(v, &v->envs[i], V, obs + (size_t)i * V * V * 3);
+  return 0;
+}
+/* SymbolicObsWrapper.observation (wrappers.py:762-782): [n][W][H][3] int64 = (x, y, OBJECT_TO_IDX[type] or -1), the
+ * agent's cell gets OBJECT_TO_IDX["agent"] */
+void mgo_vec_symbolic_obs(mgo_vec *v, int64_t *out) {
+  int W = v->width, H = v->height;
+  for (int n = 0; n < v->n; n++) {
+    env_t *e = &v->envs[n];
+    int64_t *o = out + (size_t)n * W * H * 3;
+    for (int i = 0; i < W; i++)
+      for (int j = 0; j < H; j++) {
+        cell_t c = grid_get(&e->grid, i, j);
+        int64_t *t = o + (i * H + j) * 3;
+        t[0] = i; t[1] = j; t[2] = cell_is_none(c) ? -1 : c.type;
+      }
+    o[(e->agent_x * H + e->agent_y) * 3 + 2] = T_AGENT;
+  }
 }
 /* wrappers.py:419-426 */
 void mgo_vec_full_obs(mgo_vec *v, uint8_t *out) {

@@ -60,6 +60,10 @@ int mgo_vec_step(mgo_vec *v, const int32_t *actions, uint8_t *obs, int32_t *dir,
                  uint8_t *terminated, uint8_t *truncated, int autoreset_mode, int n_threads);
 /* FullyObsWrapper.observation: [n][W][H][3] */
 void mgo_vec_full_obs(mgo_vec *v, uint8_t *out);
+/* ViewSizeWrapper.observation: gen_obs with agent_view_size V (odd, 3..15): [n][V][V][3]; -1 if V is unsupported */
+int mgo_vec_gen_obs_view(mgo_vec *v, int V, uint8_t *obs);
+/* SymbolicObsWrapper.observation: int64 [n][W][H][3] = (x, y, type or -1), agent cell type 10 */
+void mgo_vec_symbolic_obs(mgo_vec *v, int64_t *out);
 /* gen_obs() of the current state, no transition */
 void mgo_vec_gen_obs(mgo_vec *v, uint8_t *obs, int32_t *dir);
 

@@ -114,6 +114,9 @@ def lib():
         L.mgo_vec_step.argtypes = [p] * 7 + [C.c_int, C.c_int]
         L.mgo_vec_full_obs.argtypes = [p, p]
         L.mgo_vec_gen_obs.argtypes = [p, p, p]
+        L.mgo_vec_gen_obs_view.restype = C.c_int
+        L.mgo_vec_gen_obs_view.argtypes = [p, C.c_int, p]
+        L.mgo_vec_symbolic_obs.argtypes = [p, p]
         L.mgo_vec_get_state.argtypes = [p] * 5
         L.mgo_vec_set_state.argtypes = [p] * 5
         L.mgo_rng_integers.restype = C.c_int64
@@ -188,6 +191,30 @@ class OracleVecEnv:
     def gen_obs(self):
         lib().mgo_vec_gen_obs(self._h, _ptr(self.obs), _ptr(self.dir))
         return self.obs, self.dir
+
+    def gen_obs_view(self, view_size):
+        """ViewSizeWrapper.observation: uint8[n, V, V, 3]."""
+        out = np.zeros((self.num_envs, view_size, view_size, 3), np.uint8)
+        if lib().mgo_vec_gen_obs_view(self._h, int(view_size), _ptr(out)) != 0:
+            raise ValueError("view size must be odd and in 3..15")
+        return out
+
+    def symbolic_obs(self):
+        """SymbolicObsWrapper.observation: int64[n, W, H, 3]."""
+        out = np.zeros((self.num_envs, self.width, self.height, 3), np.int64)
+        lib().mgo_vec_symbolic_obs(self._h, _ptr(out))
+        return out
+
+    @staticmethod
+    def one_hot(image):
+        """OneHotPartialObsWrapper.observation (wrappers.py:268-284) on uint8[..., 3] images: 11 + 6 + 3 channels."""
+        img = np.asarray(image)
+        out = np.zeros(img.shape[:-1] + (20,), np.uint8)
+        idx = np.indices(img.shape[:-1])
+        out[(*idx, img[..., 0])] = 1
+        out[(*idx, 11 + img[..., 1])] = 1
+        out[(*idx, 17 + img[..., 2])] = 1
+        return out
 
     def full_obs(self):
         out = np.zeros((self.num_envs, self.width, self.height, 3), np.uint8)

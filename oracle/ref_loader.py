@@ -101,3 +101,45 @@ class ReferenceVecEnv:
 
         np = self.np
         return np.stack([FullyObsWrapper(e).observation({})["image"] for e in self.envs])
+
+    # ---- observation wrappers of the reference, applied to the current state of every env (wrappers.py) ----
+    def _last_obs(self, e):
+        return e.gen_obs()
+
+    def view_obs(self, view_size):
+        """ViewSizeWrapper.observation (wrappers.py:663-673)."""
+        from minigrid.wrappers import ViewSizeWrapper
+
+        np = self.np
+        return np.stack([ViewSizeWrapper(e, agent_view_size=view_size).observation(self._last_obs(e))["image"] for e in self.envs])
+
+    def symbolic_obs(self):
+        """SymbolicObsWrapper.observation (wrappers.py:762-782)."""
+        from minigrid.wrappers import SymbolicObsWrapper
+
+        np = self.np
+        return np.stack([np.asarray(SymbolicObsWrapper(e).observation(self._last_obs(e))["image"]) for e in self.envs])
+
+    def one_hot_obs(self):
+        """OneHotPartialObsWrapper.observation (wrappers.py:268-284)."""
+        from minigrid.wrappers import OneHotPartialObsWrapper
+
+        np = self.np
+        return np.stack([OneHotPartialObsWrapper(e).observation(self._last_obs(e))["image"] for e in self.envs])
+
+    def flat_obs(self):
+        """FlatObsWrapper.observation (wrappers.py:589-626)."""
+        from minigrid.wrappers import FlatObsWrapper
+
+        np = self.np
+        return np.stack([FlatObsWrapper(e).observation(self._last_obs(e)) for e in self.envs])
+
+    def rgb_partial_obs(self, tile_size=8):
+        """RGBImgPartialObsWrapper.observation (wrappers.py:371-380): get_frame(tile_size, agent_pov=True)."""
+        np = self.np
+        return np.stack([e.get_frame(tile_size=tile_size, agent_pov=True) for e in self.envs])
+
+    def rgb_full_obs(self, tile_size=8):
+        """RGBImgObsWrapper.observation (wrappers.py:325-331): get_frame(highlight=True, tile_size)."""
+        np = self.np
+        return np.stack([e.get_frame(highlight=True, tile_size=tile_size) for e in self.envs])

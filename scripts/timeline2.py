@@ -37,6 +37,9 @@ for desync in (False, True):
     t0 = A[:, 2].min()  # release of griddepcontrol.wait
     us = lambda x: x / 1e3
     print(f"== {env_id} n={n} desync={desync}: {ncta} CTAs; period {us(tl[b,:,0].min() - tl[a,:,0].min()):.2f} us")
+    B = tl[b]
+    for nm, k in (("entry", 0), ("prologue done", 1), ("wait released", 2), ("warp0 first tile in", 3), ("warp0 exit", 5), ("last warp exit", 6)):
+        print(f"   A {nm:22s} min {us(A[:,k].min()-t0):7.2f} med {us(np.median(A[:,k])-t0):7.2f} max {us(A[:,k].max()-t0):7.2f}   |  B min {us(B[:,k].min()-t0):7.2f} med {us(np.median(B[:,k])-t0):7.2f} max {us(B[:,k].max()-t0):7.2f}")
     print(f"   last warp exit (rel. to wait release): min {us(A[:,6].min()-t0):.2f} med {us(np.median(A[:,6])-t0):.2f} max {us(A[:,6].max()-t0):.2f}")
     print(f"   order list ready: med {us(np.median(A[:,13][A[:,13]>0]) - t0) if (A[:,13]>0).any() else -1:.2f}")
     hot = A[:, 8]

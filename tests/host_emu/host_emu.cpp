@@ -119,7 +119,7 @@ static void warp_reset_k(Emu *e, unsigned pend, int tile, uint32_t *gtile, Reset
     const bool pf = has_post_filter<KIND>();  // kinds with a post-filter: their targets ride in Level::ov
     out[lane].tx = pf ? level_tx(Ls[lane]) : 0; out[lane].ty = pf ? level_ty(Ls[lane]) : 0; out[lane].aux = pf ? level_aux(Ls[lane]) : 0u;
   }
-  if (__builtin_popcount(pend) >= 4) {  // DENSE_RESET_MIN: every pending lane fills its own env
+  if (__builtin_popcount(pend) >= 8) {  // DENSE_RESET_MIN: every pending lane fills its own env
     uint8_t *sb = reinterpret_cast<uint8_t *>(gtile), *gb = reinterpret_cast<uint8_t *>(p.grid);
     for (int lane = 0; lane < 32; ++lane) {
       if (!((pend >> lane) & 1u)) continue;

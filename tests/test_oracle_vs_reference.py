@@ -68,3 +68,28 @@ def test_lockstep_rollout_at_unregistered_sizes(base_id, kind, size, max_steps, 
     rs, os_ = ref.get_state(), orc.get_state()
     for k in rs:
         np.testing.assert_array_equal(rs[k], os_[k], err_msg=k)
+
+
+@pytest.mark.parametrize("env_id", ["MiniGrid-DoorKey-8x8-v0", "MiniGrid-FourRooms-v0", "MiniGrid-Empty-5x5-v0", "MiniGrid-MultiRoom-N6-v0",
+                                    "MiniGrid-Playground-v0", "MiniGrid-Dynamic-Obstacles-6x6-v0"])
+def test_observation_wrappers_against_live_reference(env_id):
+    """ViewSizeWrapper (V = 3, 5, 9, 11), SymbolicObsWrapper and OneHotPartialObsWrapper restated in the
+    oracle (gen_obs_view, symbolic_obs, one_hot) against the reference's own wrapper classes on the same states."""
+    n = 6
+    ref = ref_loader.ReferenceVecEnv(env_id, n)
+    orc = OracleVecEnv(env_id, n)
+    ref.reset(seed=31)
+    orc.reset(seed=31)
+    rng = np.random.default_rng(5)
+    for t in range(120):
+        a = rng.integers(0, 7, n)
+        r = ref.step(a)
+        q = orc.step(a)
+        np.testing.assert_array_equal(r[0], q[0])
+        if t % 6 == 0:
+            for V in (3, 5, 7, 9, 11):
+                np.testing.assert_array_equal(ref.view_obs(V), orc.gen_obs_view(V), err_msg=f"view {V} t={t}")
+            sym = ref.symbolic_obs()
+            assert sym.dtype == np.int64
+            np.testing.assert_array_equal(sym, orc.symbolic_obs(), err_msg=f"symbolic t={t}")
+            np.testing.assert_array_equal(ref.one_hot_obs(), OracleVecEnv.one_hot(q[0]), err_msg=f"one-hot t={t}")
