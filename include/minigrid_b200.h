@@ -54,6 +54,9 @@ extern "C" {
 #define MG_KIND_PUTNEAR 13      /* envs/putnear.py: params {numObjs} */
 #define MG_KIND_MEMORY 14       /* envs/memory.py: params {random_length}; odd height */
 /* RNG draws inside step */
+#define MG_KIND_ROOMGRID 16     /* core/roomgrid.py + envs/unlock.py, unlockpickup.py, blockedunlockpickup.py, keycorridor.py:
+                                   params {variant (0 Unlock, 1 UnlockPickup, 2 BlockedUnlockPickup, 3 KeyCorridor), room_size,
+                                   num_rows, num_cols} */
 #define MG_KIND_DYNOBS 15       /* envs/dynamicobstacles.py: params {n_obstacles, random_start, start_x, start_y, start_dir} */
 
 /* gymnasium.vector.AutoresetMode */

@@ -114,6 +114,15 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
     return fail(MG_ERR_INVALID_ARG, "redbluedoors is 2 size x size (redbluedoors.py:60-72)");
   if (kind == MG_KIND_MEMORY && (height % 2 == 0 || height < 7 || width < 7))
     return fail(MG_ERR_INVALID_ARG, "memory needs an odd height and at least 7 x 7 (memory.py:98)");
+  if (kind == MG_KIND_ROOMGRID) {
+    if (n_params < 4 || params[0] < 0 || params[0] > 3 || params[1] < 3 || params[1] > 8 || params[2] < 1 || params[3] < 1 ||
+        params[2] * params[3] > 9 || width != (params[1] - 1) * params[3] + 1 || height != (params[1] - 1) * params[2] + 1)
+      return fail(MG_ERR_INVALID_ARG, "roomgrid needs params {variant 0..3, room_size 3..8, num_rows, num_cols} with at most 9 rooms, "
+                                      "width = (room_size - 1) num_cols + 1 and height = (room_size - 1) num_rows + 1 (roomgrid.py:83-84)");
+    if (params[0] == 3 && params[3] != 3) return fail(MG_ERR_INVALID_ARG, "keycorridor has 3 columns of rooms (keycorridor.py:104-126)");
+    if (params[0] != 3 && (params[2] != 1 || params[3] != 2)) return fail(MG_ERR_INVALID_ARG, "unlock / unlockpickup / blockedunlockpickup are 1 x 2 rooms");
+    if (params[0] == 2 && params[1] < 4) return fail(MG_ERR_INVALID_ARG, "blockedunlockpickup needs room_size >= 4 (a cell in front of the door)");
+  }
   if (kind == MG_KIND_DYNOBS) {
     if (n_params < 5 || params[0] < 0 || params[0] > 8)
       return fail(MG_ERR_INVALID_ARG, "dynamic obstacles need params {n_obstacles (0..8), random_start, start_x, start_y, start_dir}");

@@ -67,8 +67,11 @@ enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS
              KIND_GOTODOOR = 9, KIND_FETCH = 10, KIND_REDBLUEDOORS = 11, KIND_GOTOOBJECT = 12, KIND_PUTNEAR = 13,
              KIND_MEMORY = 14,
              // RNG draws inside step (envs/dynamicobstacles.py)
-             KIND_DYNOBS = 15 };
-constexpr int KIND_COUNT = 16;  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
+             KIND_DYNOBS = 15,
+             // SURVEY 8(f-2), second half: core/roomgrid.py with unlock.py, unlockpickup.py, blockedunlockpickup.py, keycorridor.py
+             KIND_ROOMGRID = 16 };
+constexpr int KIND_COUNT = 17;
+enum : int { RG_UNLOCK = 0, RG_UNLOCKPICKUP = 1, RG_BLOCKEDUNLOCKPICKUP = 2, RG_KEYCORRIDOR = 3 };  // kp[0] of KIND_ROOMGRID  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
 enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
 // bits of the sticky device error word (Params::err)
 enum : int { ERR_BAD_ACTION = 1, ERR_BAD_STATE = 2, ERR_PACKED_RANGE = 4 };

@@ -234,6 +234,41 @@ MG_D uint32_t cell_memory(const Geom &g, const Level &L, int x, int y) {
   return CODE_EMPTY;
 }
 
+// core/roomgrid.py:123-177 (RoomGrid._gen_grid) and the envs on it. kp = {variant, room_size S, num_rows, num_cols}; rooms
+// are S x S with shared walls on the lines x, y = k (S - 1). A door descriptor is 8 bits: off:3 (door cell = first
+// interior cell + off, drawn for every wall between two rooms whether or not a door is put there) colour:3 locked:1
+// exists:1. oh = the doors in the vertical walls (index j (cols - 1) + i for the wall right of room (i, j)), rm45 = those
+// in the horizontal walls (index j cols + i for the wall below room (i, j)); the objects are records in rm03 like
+// Playground's (x:5 y:5 kind:2 colour:3), nrooms = their number. KeyCorridor removes the walls between the rooms of
+// the middle column (keycorridor.py:107-109).
+MG_D uint32_t rg_vdoor(const Level &L, int idx) { return (uint32_t)(L.oh >> (8 * idx)) & 0xFFu; }
+MG_D uint32_t rg_hdoor(const Level &L, int idx) { return (uint32_t)(L.rm45 >> (8 * idx)) & 0xFFu; }
+MG_D uint32_t rg_door_code(uint32_t dsc) {
+  return ((dsc & 0x40u) ? T4_DOOR_LOCKED : T4_DOOR_CLOSED) | (((dsc >> 3) & 7u) << 4) | OPAQUE_BIT;  // Door(color, is_locked)
+}
+MG_D uint32_t cell_roomgrid(const Geom &g, const int *kp, const Level &L, int x, int y) {
+  const int S1 = kp[1] - 1, cols = kp[3];
+  const int i = x / S1, j = y / S1, lx = x - i * S1, ly = y - j * S1;
+  if (lx == 0 && ly == 0) return CODE_WALL;
+  if (lx == 0) {  // the vertical wall left of room (i, j) = right of room (i - 1, j)
+    if (i == 0 || x == g.W - 1) return CODE_WALL;
+    const uint32_t dsc = rg_vdoor(L, j * (cols - 1) + (i - 1));
+    return ((dsc & 0x80u) && ly - 1 == (int)(dsc & 7u)) ? rg_door_code(dsc) : CODE_WALL;
+  }
+  if (ly == 0) {  // the horizontal wall above room (i, j) = below room (i, j - 1)
+    if (j == 0 || y == g.H - 1) return CODE_WALL;
+    if (kp[0] == RG_KEYCORRIDOR && i == 1) return CODE_EMPTY;  // remove_wall(1, j, 3), j >= 1
+    const uint32_t dsc = rg_hdoor(L, (j - 1) * cols + i);
+    return ((dsc & 0x80u) && lx - 1 == (int)(dsc & 7u)) ? rg_door_code(dsc) : CODE_WALL;
+  }
+  for (int k = 0; k < 4; ++k)
+    if (k < L.nrooms) {
+      const uint32_t o = play_obj(L, k);
+      if ((int)(o & 31u) == x && (int)((o >> 5) & 31u) == y) return (T_KEY + ((o >> 10) & 3u)) | (((o >> 12) & 7u) << 4);
+    }
+  return CODE_EMPTY;
+}
+
 // envs/dynamicobstacles.py:107-133: border walls, goal at (W - 2, H - 2), nrooms blue balls (Ball() defaults to blue)
 // in the object records of rm03 (x:5 y:5 kind:2 colour:3, see play_obj)
 MG_D uint32_t cell_dynobs(const Geom &g, const Level &L, int x, int y) {
@@ -253,6 +288,7 @@ MG_D void dynobs_pack(const Level &L, uint32_t (&ex)[4]) {
 
 template <int KIND>
 MG_D uint32_t cell_of(const Params &p, const Level &L, int x, int y) {
+  if (KIND == KIND_ROOMGRID) return cell_roomgrid(p.g, p.kp, L, x, y);
   if (KIND == KIND_DYNOBS) return cell_dynobs(p.g, L, x, y);
   if (KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR) return cell_objroom(p.g, L, x, y);
   if (KIND == KIND_GOTODOOR) return cell_gotodoor(p.g, L, x, y);
@@ -357,6 +393,122 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
       if (x == L.ax && y == L.ay) continue;
       L.e = x; L.f = y;
       break;
+    }
+  } else if (KIND == KIND_ROOMGRID) {
+    // RoomGrid._gen_grid (roomgrid.py:123-177), then the env's own _gen_grid (unlock.py:72-84, unlockpickup.py:80-93,
+    // blockedunlockpickup.py:87-103, keycorridor.py:104-126) with RoomGrid's helpers restated as lambdas
+    const int variant = p.kp[0], S = p.kp[1], rows = p.kp[2], cols = p.kp[3], S1 = S - 1;
+    for (int j = 0; j < rows; ++j)
+      for (int i = 0; i < cols; ++i) {  // door_pos draws: right wall (y), then bottom wall (x)
+        if (i < cols - 1) L.oh |= (unsigned long long)rng_integers(r, 0, S - 2) << (8 * (j * (cols - 1) + i));
+        if (j < rows - 1) L.rm45 |= (unsigned long long)rng_integers(r, 0, S - 2) << (8 * (j * cols + i));
+      }
+    L.ax = (cols / 2) * S1 + S / 2; L.ay = (rows / 2) * S1 + S / 2; L.adir = 0;  // "the agent starts in the middle, facing right"
+    unsigned long long conn = 0;  // Room.doors[k] is truthy: bit 4 q + k of room q = j cols + i (k: right, down, left, up)
+    uint32_t locked_rooms = 0;    // Room.locked
+    auto nbr = [&](int i, int j, int k, int &ni, int &nj) -> bool {
+      ni = i + (k == 0) - (k == 2); nj = j + (k == 1) - (k == 3);
+      return ni >= 0 && ni < cols && nj >= 0 && nj < rows;
+    };
+    // descriptor slot of the wall on side k of room (i, j): vertical walls in oh, horizontal walls in rm45
+    auto add_door = [&](int i, int j, int k, int color, int lockd, int &px, int &py) -> int {  // roomgrid.py:226-273
+      int ni, nj;
+      if (k < 0)
+        for (;;) {
+          k = rng_integers(r, 0, 4);
+          if (nbr(i, j, k, ni, nj) && !((conn >> (4 * (j * cols + i) + k)) & 1ull)) break;
+        }
+      if (color < 0) color = (int)color_name_idx(rng_integers(r, 0, 6));
+      if (lockd < 0) lockd = rng_integers(r, 0, 2) == 0;
+      if (lockd) locked_rooms |= 1u << (j * cols + i); else locked_rooms &= ~(1u << (j * cols + i));
+      nbr(i, j, k, ni, nj);
+      const bool vertical = (k == 0 || k == 2);
+      const int wi = vertical ? (k == 0 ? i : i - 1) : i, wj = vertical ? j : (k == 1 ? j : j - 1);
+      const int idx = vertical ? wj * (cols - 1) + wi : wj * cols + wi;
+      const unsigned long long set = (unsigned long long)(0x80u | (lockd ? 0x40u : 0u) | ((uint32_t)color << 3)) << (8 * idx);
+      if (vertical) { L.oh |= set; px = (wi + 1) * S1; py = wj * S1 + 1 + (int)(rg_vdoor(L, idx) & 7u); }
+      else { L.rm45 |= set; px = wi * S1 + 1 + (int)(rg_hdoor(L, idx) & 7u); py = (wj + 1) * S1; }
+      conn |= 1ull << (4 * (j * cols + i) + k);
+      conn |= 1ull << (4 * (nj * cols + ni) + ((k + 2) & 3));
+      return color;
+    };
+    auto add_object = [&](int i, int j, int kind, int color) -> uint32_t {  // roomgrid.py:196-224 + place_in_room :179-194
+      if (kind < 0) kind = rng_integers(r, 0, 3);  // _rand_elem(["key", "ball", "box"])
+      if (color < 0) color = (int)color_name_idx(rng_integers(r, 0, 6));
+      for (;;) {  // place_obj(top, size, reject_fn=reject_next_to, max_tries=1000)
+        const int x = rng_integers(r, i * S1, min(i * S1 + S, W)), y = rng_integers(r, j * S1, min(j * S1 + S, H));
+        if (cell_roomgrid(g, p.kp, L, x, y) != CODE_EMPTY) continue;
+        if (x == L.ax && y == L.ay) continue;
+        const int ddx = L.ax - x, ddy = L.ay - y;
+        if ((ddx < 0 ? -ddx : ddx) + (ddy < 0 ? -ddy : ddy) < 2) continue;
+        const uint32_t o = (uint32_t)x | ((uint32_t)y << 5) | ((uint32_t)kind << 10) | ((uint32_t)color << 12);
+        L.rm03 |= (u128)o << (15 * L.nrooms);
+        L.nrooms += 1;
+        return o;
+      }
+    };
+    auto place_agent = [&](int i, int j) {  // roomgrid.py:313-335: until the front cell is None or a wall
+      for (;;) {
+        int x, y;
+        for (;;) {  // MiniGridEnv.place_agent(room.top, room.size): agent_pos = (-1, -1) while placing
+          x = rng_integers(r, i * S1, min(i * S1 + S, W)); y = rng_integers(r, j * S1, min(j * S1 + S, H));
+          if (cell_roomgrid(g, p.kp, L, x, y) == CODE_EMPTY) break;
+        }
+        const int d = rng_integers(r, 0, 4);
+        L.ax = x; L.ay = y; L.adir = d;
+        const uint32_t front = cell_roomgrid(g, p.kp, L, x + (d == 0) - (d == 2), y + (d == 1) - (d == 3));
+        if (front == CODE_EMPTY || front == CODE_WALL) break;
+      }
+    };
+    int dpx = 0, dpy = 0;
+    if (variant == RG_KEYCORRIDOR) {
+      for (int j = 1; j < rows; ++j) {  // remove_wall(1, j, 3): the cells are handled by cell_roomgrid, the rooms become connected
+        conn |= 1ull << (4 * (j * cols + 1) + 3);
+        conn |= 1ull << (4 * ((j - 1) * cols + 1) + 1);
+      }
+      const int room_idx = rng_integers(r, 0, rows);
+      const int door_color = add_door(2, room_idx, 2, -1, 1, dpx, dpy);
+      const uint32_t obj = add_object(2, room_idx, 1, -1);  // kind = self.obj_type = "ball"
+      const int key_row = rng_integers(r, 0, rows);
+      add_object(0, key_row, 0, door_color);
+      place_agent(1, rows / 2);
+      // connect_all (roomgrid.py:337-393): random doors until every room is reachable from the agent's
+      const int start = (L.ay / S1) * cols + (L.ax / S1);
+      for (;;) {
+        uint32_t reach = 0, stack = 1u << start;
+        while (stack) {
+          const int q = __ffs(stack) - 1;
+          stack &= stack - 1;
+          if ((reach >> q) & 1u) continue;
+          reach |= 1u << q;
+          for (int k = 0; k < 4; ++k) {
+            int ni, nj;
+            if (((conn >> (4 * q + k)) & 1ull) && nbr(q % cols, q / cols, k, ni, nj)) stack |= 1u << (nj * cols + ni);
+          }
+        }
+        if (__popc(reach) == rows * cols) break;
+        const int i = rng_integers(r, 0, cols), j = rng_integers(r, 0, rows), k = rng_integers(r, 0, 4);
+        int ni, nj;
+        if (!nbr(i, j, k, ni, nj) || ((conn >> (4 * (j * cols + i) + k)) & 1ull)) continue;  // no door_pos there, or already a door
+        if (((locked_rooms >> (j * cols + i)) & 1u) || ((locked_rooms >> (nj * cols + ni)) & 1u)) continue;
+        const int color = (int)color_name_idx(rng_integers(r, 0, 6));
+        int qx, qy;
+        add_door(i, j, k, color, 0, qx, qy);
+      }
+      level_target(L, (int)(T_KEY + ((obj >> 10) & 3u)), (int)((obj >> 12) & 7u), 0u);
+    } else {
+      uint32_t obj = 0;
+      if (variant != RG_UNLOCK) obj = add_object(1, 0, 2, -1);  // a box in the room on the right
+      const int door_color = add_door(0, 0, 0, -1, 1, dpx, dpy);
+      if (variant == RG_BLOCKEDUNLOCKPICKUP) {  // a ball of a random colour in front of the door (grid.set, no placement draws)
+        const uint32_t col = color_name_idx(rng_integers(r, 0, 6));
+        L.rm03 |= (u128)((uint32_t)(dpx - 1) | ((uint32_t)dpy << 5) | (1u << 10) | (col << 12)) << (15 * L.nrooms);
+        L.nrooms += 1;
+      }
+      add_object(0, 0, 0, door_color);
+      place_agent(0, 0);
+      if (variant == RG_UNLOCK) level_target(L, dpx, dpy, 0u);
+      else level_target(L, (int)(T_KEY + ((obj >> 10) & 3u)), (int)((obj >> 12) & 7u), 0u);
     }
   } else if (KIND == KIND_DYNOBS) {
     // dynamicobstacles.py:107-133. kp = {n_obstacles, random_start, start_x, start_y, start_dir}
@@ -709,8 +861,8 @@ MG_D void patch_level(const Params &p, const Level &L, int lane, Put &&put) {
   } else if (KIND == KIND_REDBLUEDOORS) {
     if (lane == 0) put(g.H / 2, L.a);
     if (lane == 1) put(g.H / 2 + g.H - 1, L.b);
-  } else if (KIND == KIND_GOTODOOR || KIND == KIND_MEMORY) {
-    // the walls themselves are drawn (room size / hallway length): every cell may differ from the template
+  } else if (KIND == KIND_GOTODOOR || KIND == KIND_MEMORY || KIND == KIND_ROOMGRID) {
+    // the walls themselves are drawn (room size / hallway length / where the doors are): every cell may differ from the template
     for (int c = lane; c < g.W * g.H; c += 32) put(c % g.W, c / g.W);
   } else if (KIND == KIND_LOCKEDROOM) {
     const int lw = g.W / 2 - 2, rw = g.W / 2 + 2, h3 = g.H / 3;

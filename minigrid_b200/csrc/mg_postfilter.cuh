@@ -26,6 +26,9 @@ struct PostIn {
   uint32_t aux;                 // level_aux
   // redbluedoors only: is_open of the two doors before and after the transition
   bool red_before, blue_before, red_after, blue_after;
+  // roomgrid only: kp[0], and whether the cell at (tx, ty) is an open door after the transition (Unlock's self.door.is_open)
+  int variant;
+  bool door_open;
 };
 enum : int { POST_KEEP = 0, POST_REWARD = 1, POST_ZERO = 2 };  // what becomes of the step's reward
 struct PostOut { uint32_t terminated; int reward; };
@@ -57,6 +60,14 @@ MG_HD PostOut post_filter(const PostIn &in, uint32_t terminated) {
   } else if (KIND == KIND_MEMORY) {  // memory.py:156-164; aux = failure_pos (x | y << 8)
     if (in.ax == in.tx && in.ay == in.ty) { o.reward = POST_REWARD; o.terminated = 1u; }
     if (in.ax == (int)(in.aux & 255u) && in.ay == (int)((in.aux >> 8) & 255u)) { o.reward = POST_ZERO; o.terminated = 1u; }
+  } else if (KIND == KIND_ROOMGRID) {
+    if (in.variant == RG_UNLOCK) {  // unlock.py:88-96
+      if (in.action == A_TOGGLE && in.door_open) { o.reward = POST_REWARD; o.terminated = 1u; }
+    } else if (in.action == A_PICKUP && in.carry != 0u && (int)(in.carry & 15u) == in.tx && (int)((in.carry >> 4) & 7u) == in.ty) {
+      // "self.carrying and self.carrying == self.obj" (unlockpickup.py:97-105, blockedunlockpickup.py:107-115,
+      // keycorridor.py:128-136): an identity test; these generators make exactly one object of self.obj's type
+      o.reward = POST_REWARD; o.terminated = 1u;
+    }
   } else if (KIND == KIND_REDBLUEDOORS) {  // redbluedoors.py:105-126
     if (in.blue_after) {
       o.reward = in.red_before ? POST_REWARD : POST_ZERO;
@@ -98,7 +109,7 @@ MG_D void dynobs_move(const Geom &g, Pcg &r, int n_obst, uint32_t (&ex)[4], int 
 template <int KIND>
 MG_HD constexpr bool has_post_filter() {
   return KIND == KIND_GOTODOOR || KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR ||
-         KIND == KIND_MEMORY || KIND == KIND_REDBLUEDOORS;
+         KIND == KIND_MEMORY || KIND == KIND_REDBLUEDOORS || KIND == KIND_ROOMGRID;
 }
 
 }  // namespace mg

@@ -6,6 +6,7 @@
 #include "mg_obs.cuh"
 #include "mg_pcg64.cuh"
 #include "mg_levels.cuh"
+#include "mg_postfilter.cuh"
 
 namespace mg {
 
@@ -38,7 +39,7 @@ k_reset(Params p, const uint8_t *__restrict__ mask, uint8_t *__restrict__ obs, i
     uint4 rec;
     rec.x = (uint32_t)L.ax | ((uint32_t)L.ay << 8);
     rec.y = (uint32_t)L.adir;  // flags cleared: SyncVectorEnv.reset() clears _autoreset_envs
-    if (KIND >= KIND_GOTODOOR) {  // post-filter targets in the spare bits (mg_postfilter.cuh)
+    if (has_post_filter<KIND>()) {  // post-filter targets in the spare bits (mg_postfilter.cuh)
       rec.x |= ((uint32_t)level_tx(L) << 16) | ((uint32_t)level_ty(L) << 24);
       rec.y |= level_aux(L) << 16;
     }
@@ -78,6 +79,7 @@ cudaError_t launch_reset(const Params &p, const uint8_t *mask, uint8_t *obs, int
     case KIND_PUTNEAR: k_reset<KIND_PUTNEAR><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
     case KIND_MEMORY: k_reset<KIND_MEMORY><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
     case KIND_DYNOBS: k_reset<KIND_DYNOBS><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
+    case KIND_ROOMGRID: k_reset<KIND_ROOMGRID><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
     default: k_reset<KIND_FOURROOMS><<<blocks, threads, 0, stream>>>(p, mask, obs, dir); break;
   }
   return cudaGetLastError();
@@ -109,6 +111,7 @@ cudaError_t launch_template(const Params &p, uint32_t *tmpl, cudaStream_t stream
     case KIND_PUTNEAR: k_template<KIND_PUTNEAR><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     case KIND_MEMORY: k_template<KIND_MEMORY><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     case KIND_DYNOBS: k_template<KIND_DYNOBS><<<blocks, 64, 0, stream>>>(p, tmpl); break;
+    case KIND_ROOMGRID: k_template<KIND_ROOMGRID><<<blocks, 64, 0, stream>>>(p, tmpl); break;
     default: k_template<KIND_FOURROOMS><<<blocks, 64, 0, stream>>>(p, tmpl); break;
   }
   return cudaGetLastError();

@@ -9,11 +9,11 @@ __device__ __forceinline__ uint32_t load_code(const Params &p, int env, int x, i
 }
 
 // K3. out[n][W][H][3] = grid.encode(), agent cell = (OBJECT_TO_IDX["agent"], COLOR_TO_IDX["red"], agent_dir).
-// One CTA per tile of 32 environments, whose output block (32 x 3WH bytes, a multiple of 96) is contiguous: a thread
-// produces one 4-byte WORD of it — the word's bytes belong to two consecutive cells (array C is [x][y] ordered like
-// the output), so it reads two cell codes (L1-resident lines), looks the (type, colour, state) triples up and merges
-// them with one byte permute, exactly like the image stream of K1 — and stores it, 128 contiguous bytes per warp.
-// HBM-bound: W*H code bytes + the agent record in, 3*W*H out. No staging, no byte stores.
+// One CTA per tile of 32 environments, whose output block (32 x 3WH bytes) is contiguous. Four consecutive cells are
+// twelve output bytes = three aligned words, so a thread takes a GROUP of four cells of the tile's flat cell sequence
+// (array C is [x][y] ordered like the output; a group may straddle two envs): four code bytes through the read-only
+// path (L1-resident lines), four (type, colour, state) lookups, three byte permutes like K1's image stream, three
+// word stores. One division per group, no staging. HBM-bound: W*H code bytes + the agent record in, 3*W*H out.
 __global__ void __launch_bounds__(256)
 k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with_agent) {
   __shared__ uint32_t s_lut[256];
@@ -38,36 +38,40 @@ k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with
   __syncthreads();
   const uint8_t *tb = reinterpret_cast<const uint8_t *>(p.grid) + (size_t)tile * g.wpe * 128;  // both layouts: 32 envs x wpe words
   const uint32_t estride = tiled ? 4u : (uint32_t)g.wpe * 4u;
-  const float inv_eb = 1.0f / (float)env_bytes;
-  // (type | colour << 8 | state << 16) of the cell that holds byte B of the tile's output block, and B's place in the triple
-  auto triple = [&](int e, int c) -> uint32_t {
-    if (e >= nvalid) return 0u;
+  const float inv_wh = 1.0f / (float)WH;
+  auto triple = [&](int e, int c) -> uint32_t {  // type | colour << 8 | state << 16 of cell c of env e
     const uint32_t ag = s_agent[e];
-    if ((ag & 0xFFFFu) == (uint32_t)c) return T_AGENT | (C_RED << 8) | (ag & 0x30000u);
-    return s_lut[__ldg(tb + (uint32_t)e * estride + s_off[c])];  // read-only path: the loads of an unrolled batch run ahead of its stores
-  };
-  auto word_at = [&](int B) -> uint32_t {  // bytes B .. B + 3
-    const int e = (int)(((float)B + 0.5f) * inv_eb), b = B - e * env_bytes;
-    const int c = (b * 0xAAABu) >> 17, r = b - 3 * c;  // b / 3 for b < 2^15
-    const bool wrap = c + 1 == WH;
-    const uint32_t t0 = triple(e, c), t1 = triple(wrap ? e + 1 : e, wrap ? 0 : c + 1);
-    return prmt(t0, t1, r == 0 ? 0x4210u : (r == 1 ? 0x5421u : 0x6542u));
+    const uint32_t t = s_lut[__ldg(tb + (uint32_t)e * estride + s_off[c])];
+    return (ag & 0xFFFFu) == (uint32_t)c ? (T_AGENT | (C_RED << 8) | (ag & 0x30000u)) : t;
   };
   uint8_t *dst = out + (size_t)tile * TILE * env_bytes;
-  const int total = nvalid * env_bytes;
+  const int n_cells = nvalid * WH;
   if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
     uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-    const int nw = total / 4;
-    int J = threadIdx.x;
-    for (; J + 3 * (int)blockDim.x < nw; J += 4 * blockDim.x) {  // four independent words per thread: their 8 cell loads overlap
-      const uint32_t w0 = word_at(4 * J), w1 = word_at(4 * (J + blockDim.x)), w2 = word_at(4 * (J + 2 * blockDim.x)),
-                     w3 = word_at(4 * (J + 3 * blockDim.x));
-      d32[J] = w0; d32[J + blockDim.x] = w1; d32[J + 2 * blockDim.x] = w2; d32[J + 3 * blockDim.x] = w3;
+    for (int gq = threadIdx.x; gq < n_cells / 4; gq += blockDim.x) {
+      const int f0 = 4 * gq;
+      int e = (int)(((float)f0 + 0.5f) * inv_wh), c = f0 - e * WH;  // exact small-integer division
+      uint32_t t[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t[k] = triple(e, c);
+        if (++c == WH) { c = 0; ++e; }
+      }
+      d32[3 * gq] = prmt(t[0], t[1], 0x4210u);
+      d32[3 * gq + 1] = prmt(t[1], t[2], 0x5421u);
+      d32[3 * gq + 2] = prmt(t[2], t[3], 0x6542u);
     }
-    for (; J < nw; J += blockDim.x) d32[J] = word_at(4 * J);
-    for (int B = (total & ~3) + threadIdx.x; B < total; B += blockDim.x) dst[B] = (uint8_t)word_at(B);  // ragged last tile
+    for (int f = (n_cells & ~3) + threadIdx.x; f < n_cells; f += blockDim.x) {  // ragged last tile: up to 3 cells left
+      const int e = f / WH, c = f - e * WH;
+      const uint32_t t = triple(e, c);
+      dst[3 * f] = (uint8_t)t; dst[3 * f + 1] = (uint8_t)(t >> 8); dst[3 * f + 2] = (uint8_t)(t >> 16);
+    }
   } else {
-    for (int B = threadIdx.x; B < total; B += blockDim.x) dst[B] = (uint8_t)word_at(B);
+    for (int f = threadIdx.x; f < n_cells; f += blockDim.x) {
+      const int e = f / WH, c = f - e * WH;
+      const uint32_t t = triple(e, c);
+      dst[3 * f] = (uint8_t)t; dst[3 * f + 1] = (uint8_t)(t >> 8); dst[3 * f + 2] = (uint8_t)(t >> 16);
+    }
   }
 }
 

@@ -190,7 +190,8 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
     B.e = __shfl_sync(0xFFFFFFFFu, L.e, src); B.f = __shfl_sync(0xFFFFFFFFu, L.f, src);
     B.rv = __shfl_sync(0xFFFFFFFFu, L.rv, src); B.rh = __shfl_sync(0xFFFFFFFFu, L.rh, src);
     B.ov = __shfl_sync(0xFFFFFFFFu, L.ov, src); B.oh = __shfl_sync(0xFFFFFFFFu, L.oh, src);
-    if (KIND == KIND_MULTIROOM || KIND == KIND_PLAYGROUND || KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR || KIND == KIND_DYNOBS) {
+    if (KIND == KIND_MULTIROOM || KIND == KIND_PLAYGROUND || KIND == KIND_GOTOOBJECT || KIND == KIND_FETCH || KIND == KIND_PUTNEAR || KIND == KIND_DYNOBS ||
+        KIND == KIND_ROOMGRID) {
       const unsigned long long lo = __shfl_sync(0xFFFFFFFFu, (unsigned long long)L.rm03, src);
       const unsigned long long hi = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(L.rm03 >> 64), src);
       B.rm03 = ((u128)hi << 64) | lo;
@@ -507,6 +508,13 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
         in.carry_before = carry_before; in.carry = carry;
         in.tx = tx; in.ty = ty; in.aux = flags >> 8;
         in.red_before = in.blue_before = in.red_after = in.blue_after = false;
+        in.variant = p.kp[0]; in.door_open = false;
+        if (KIND == KIND_ROOMGRID && p.kp[0] == RG_UNLOCK) {  // self.door.is_open: the cell at the target, after this step's mutation
+          uint32_t cd;
+          if (!WIN) cd = (tile_word<true>(base, r_word(g, tx, ty)) >> (8 * (tx & 3))) & 0xFFu;
+          else cd = gb[grid_word(g, env, r_word(g, tx, ty)) * 4 + (tx & 3)];
+          in.door_open = (cd & 15u) == T_DOOR;
+        }
         if (KIND == KIND_REDBLUEDOORS) {  // a door changes only as the front cell of a toggle
           const int xl = g.H / 2, xr = g.H / 2 + g.H - 1;
           uint32_t cr, cb;
@@ -622,9 +630,14 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       if (term_out) term_out[env] = (uint8_t)terminated;
       if (trunc_out) trunc_out[env] = (uint8_t)truncated;
     }
-    if (stepping && p.mode == AUTORESET_NEXT_STEP) {  // scheduling hint for the next step (see ORDER_CAP)
+    if (stepping && p.mode == AUTORESET_NEXT_STEP) {
+      // scheduling hint (see ORDER_CAP). bit 0: an env of the tile ended in this step, so the tile regenerates in the
+      // next one; bit 1: one will be truncated in the next step, so the tile regenerates in the step after. The next
+      // launch reads these flags in its prologue, while this launch's last tiles are still being processed: a tile whose
+      // byte is still the previous step's then shows its bit 1, which is exactly the truncation it missed.
       const unsigned anyp = __ballot_sync(0xFFFFFFFFu, active && (flags & FLAG_PENDING));
-      if (lane == 0) p.tile_hot[tile] = anyp ? 1 : 0;
+      const unsigned soon = __ballot_sync(0xFFFFFFFFu, active && !(flags & FLAG_PENDING) && steps + 1 >= p.max_steps);
+      if (lane == 0) p.tile_hot[tile] = (uint8_t)((anyp ? 1 : 0) | (soon ? 2 : 0));
     }
     __syncwarp();  // lanes may still be reading this buffer (partial-tile path) before it is refilled
 #ifdef MG_TIMELINE
@@ -677,6 +690,7 @@ static StepKernel pick_kind(int kind) {
     case KIND_PUTNEAR: return (StepKernel)k_step<KIND_PUTNEAR, VIS, MODE>;
     case KIND_MEMORY: return (StepKernel)k_step<KIND_MEMORY, VIS, MODE>;
     case KIND_DYNOBS: return (StepKernel)k_step<KIND_DYNOBS, VIS, MODE>;
+    case KIND_ROOMGRID: return (StepKernel)k_step<KIND_ROOMGRID, VIS, MODE>;
     default: return (StepKernel)k_step<KIND_FOURROOMS, VIS, MODE>;
   }
 }

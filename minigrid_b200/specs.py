@@ -14,6 +14,7 @@ KIND_EMPTY, KIND_DOORKEY, KIND_CROSSING, KIND_FOURROOMS, KIND_LAVAGAP, KIND_DIST
 KIND_LOCKEDROOM, KIND_PLAYGROUND = 7, 8
 KIND_GOTODOOR, KIND_FETCH, KIND_REDBLUEDOORS, KIND_GOTOOBJECT, KIND_PUTNEAR, KIND_MEMORY = 9, 10, 11, 12, 13, 14
 KIND_DYNOBS = 15
+KIND_ROOMGRID = 16
 T_WALL, T_LAVA = 2, 9
 
 
@@ -125,6 +126,17 @@ def dynobstacles(size=8, agent_start_pos=(1, 1), agent_start_dir=0, n_obstacles=
                    (n_obst, int(random_start), sx, sy, agent_start_dir), "get to the green goal square")
 
 
+def roomgrid(variant, room_size, num_rows, num_cols, max_steps, mission):
+    """core/roomgrid.py:66-100: width = (room_size - 1) * num_cols + 1, height likewise; see_through_walls=False."""
+    return EnvSpec(KIND_ROOMGRID, (room_size - 1) * num_cols + 1, (room_size - 1) * num_rows + 1, max_steps, False,
+                   (variant, room_size, num_rows, num_cols), mission)
+
+
+def keycorridor(room_size=6, num_rows=3, max_steps=None):
+    """envs/keycorridor.py:73-97 (obj_type "ball", 3 columns, 30 * room_size^2 steps)."""
+    return roomgrid(3, room_size, num_rows, 3, max_steps or 30 * room_size ** 2, "pick up the {color} ball")
+
+
 REGISTRY = {
     # BASELINE.json configs
     "MiniGrid-Empty-5x5-v0": empty(size=5),
@@ -187,6 +199,16 @@ REGISTRY = {
     "MiniGrid-Dynamic-Obstacles-Random-6x6-v0": dynobstacles(6, agent_start_pos=None, n_obstacles=3),
     "MiniGrid-Dynamic-Obstacles-8x8-v0": dynobstacles(8),
     "MiniGrid-Dynamic-Obstacles-16x16-v0": dynobstacles(16, n_obstacles=8),
+    # RoomGrid family: __init__.py:12-20, 252-290, 555-563 (unlock.py:55-70: 8 * 36 steps; blockedunlockpickup.py:67-85: 16 * 36)
+    "MiniGrid-Unlock-v0": roomgrid(0, 6, 1, 2, 288, "open the door"),
+    "MiniGrid-UnlockPickup-v0": roomgrid(1, 6, 1, 2, 288, "pick up the {color} box"),
+    "MiniGrid-BlockedUnlockPickup-v0": roomgrid(2, 6, 1, 2, 576, "pick up the {color} {type}"),
+    "MiniGrid-KeyCorridorS3R1-v0": keycorridor(3, 1),
+    "MiniGrid-KeyCorridorS3R2-v0": keycorridor(3, 2),
+    "MiniGrid-KeyCorridorS3R3-v0": keycorridor(3, 3),
+    "MiniGrid-KeyCorridorS4R3-v0": keycorridor(4, 3),
+    "MiniGrid-KeyCorridorS5R3-v0": keycorridor(5, 3),
+    "MiniGrid-KeyCorridorS6R3-v0": keycorridor(6, 3),
 }
 
 

@@ -55,6 +55,12 @@ ROLLOUTS = {  # id -> (N, T, seed)
     "MiniGrid-MemoryS7-v0": (6, 400, 83),
     "MiniGrid-Dynamic-Obstacles-Random-6x6-v0": (8, 400, 89),
     "MiniGrid-Dynamic-Obstacles-8x8-v0": (8, 500, 97),
+    "MiniGrid-Unlock-v0": (6, 600, 101),
+    "MiniGrid-UnlockPickup-v0": (6, 600, 103),
+    "MiniGrid-BlockedUnlockPickup-v0": (6, 700, 107),
+    "MiniGrid-KeyCorridorS3R2-v0": (6, 560, 109),
+    "MiniGrid-KeyCorridorS4R3-v0": (4, 500, 113),
+    "MiniGrid-KeyCorridorS6R3-v0": (4, 300, 127),
 }
 NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist yet: next_rollout_<id>.npz (oracle only)
 }

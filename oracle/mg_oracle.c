@@ -666,6 +666,174 @@ static void gen_dynobstacles(const mgo_vec *v, env_t *e) {
     place_obj_tries(e, &BALL_BLUE, 0, 0, W, H, 100, &e->obst_x[i], &e->obst_y[i]);
 }
 
+/* ---- core/roomgrid.py: RoomGrid and the envs built on it (second half) ----
+ * params: {variant, room_size, num_rows, num_cols}; variant 0 Unlock (envs/unlock.py), 1 UnlockPickup
+ * (unlockpickup.py), 2 BlockedUnlockPickup (blockedunlockpickup.py), 3 KeyCorridor (keycorridor.py, obj_type "ball") */
+enum { RG_UNLOCK = 0, RG_UNLOCKPICKUP = 1, RG_BLOCKEDUNLOCKPICKUP = 2, RG_KEYCORRIDOR = 3 };
+typedef struct {
+  int top_x, top_y;          /* Room.top; Room.size = (room_size, room_size) */
+  int door_x[4], door_y[4];  /* Room.door_pos, order right, down, left, up; -1 = None */
+  int doors[4];              /* Room.doors: 0 None, 1 a Door, 2 True (wall removed) */
+  int locked;                /* Room.locked */
+} rg_room_t;
+typedef struct { int S, rows, cols; rg_room_t r[9]; } rg_t; /* room (i, j) = r[j * cols + i] */
+
+static int rg_neighbor(const rg_t *g, int i, int j, int k, int *ni, int *nj) { /* Room.neighbors, roomgrid.py:157-168 */
+  static const int DI[4] = {1, 0, -1, 0}, DJ[4] = {0, 1, 0, -1};
+  *ni = i + DI[k]; *nj = j + DJ[k];
+  return *ni >= 0 && *ni < g->cols && *nj >= 0 && *nj < g->rows;
+}
+/* RoomGrid._gen_grid, roomgrid.py:123-177 */
+static void rg_gen_base(const mgo_vec *v, env_t *e, rg_t *g) {
+  g->S = v->params[1]; g->rows = v->params[2]; g->cols = v->params[3];
+  const int S = g->S;
+  grid_clear(&e->grid);
+  for (int j = 0; j < g->rows; j++)
+    for (int i = 0; i < g->cols; i++) {
+      rg_room_t *r = &g->r[j * g->cols + i];
+      memset(r, 0, sizeof(*r));
+      r->top_x = i * (S - 1); r->top_y = j * (S - 1);
+      for (int k = 0; k < 4; k++) { r->door_x[k] = -1; r->door_y[k] = -1; }
+      grid_wall_rect(&e->grid, r->top_x, r->top_y, S, S);
+    }
+  for (int j = 0; j < g->rows; j++)
+    for (int i = 0; i < g->cols; i++) {
+      rg_room_t *r = &g->r[j * g->cols + i];
+      const int x_l = r->top_x + 1, y_l = r->top_y + 1, x_m = r->top_x + S - 1, y_m = r->top_y + S - 1;
+      if (i < g->cols - 1) { r->door_x[0] = x_m; r->door_y[0] = (int)rand_int(e, y_l, y_m); }
+      if (j < g->rows - 1) { r->door_x[1] = (int)rand_int(e, x_l, x_m); r->door_y[1] = y_m; }
+      if (i > 0) { const rg_room_t *n = &g->r[j * g->cols + i - 1]; r->door_x[2] = n->door_x[0]; r->door_y[2] = n->door_y[0]; }
+      if (j > 0) { const rg_room_t *n = &g->r[(j - 1) * g->cols + i]; r->door_x[3] = n->door_x[1]; r->door_y[3] = n->door_y[1]; }
+    }
+  e->agent_x = (g->cols / 2) * (S - 1) + S / 2; /* "the agent starts in the middle, facing right" */
+  e->agent_y = (g->rows / 2) * (S - 1) + S / 2;
+  e->agent_dir = 0;
+}
+/* RoomGrid.add_door, roomgrid.py:226-273; door_idx / color (COLOR_TO_IDX) / locked: -1 = draw it. Returns the colour. */
+static int rg_add_door(env_t *e, rg_t *g, int i, int j, int door_idx, int color, int locked, int *px, int *py) {
+  rg_room_t *r = &g->r[j * g->cols + i];
+  int ni, nj;
+  if (door_idx < 0)
+    for (;;) {
+      door_idx = (int)rand_int(e, 0, 4);
+      if (rg_neighbor(g, i, j, door_idx, &ni, &nj) && r->doors[door_idx] == 0) break;
+    }
+  if (color < 0) color = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+  if (locked < 0) locked = rand_int(e, 0, 2) == 0; /* _rand_bool */
+  r->locked = locked;
+  cell_t door = {T_DOOR, (uint8_t)color, (uint8_t)(locked ? S_LOCKED : S_CLOSED)};
+  grid_set(&e->grid, r->door_x[door_idx], r->door_y[door_idx], door);
+  rg_neighbor(g, i, j, door_idx, &ni, &nj);
+  r->doors[door_idx] = 1;
+  g->r[nj * g->cols + ni].doors[(door_idx + 2) % 4] = 1;
+  if (px) { *px = r->door_x[door_idx]; *py = r->door_y[door_idx]; }
+  return color;
+}
+/* RoomGrid.place_in_room, roomgrid.py:179-194: place_obj(reject_fn=reject_next_to, max_tries=1000); the RecursionError
+ * after 1001 attempts is not modelled (never seen) */
+static void rg_place_in_room(env_t *e, const rg_t *g, int i, int j, cell_t obj, int *px, int *py) {
+  const rg_room_t *r = &g->r[j * g->cols + i];
+  int hi_x = r->top_x + g->S < e->grid.width ? r->top_x + g->S : e->grid.width;
+  int hi_y = r->top_y + g->S < e->grid.height ? r->top_y + g->S : e->grid.height;
+  for (;;) {
+    int x = (int)rand_int(e, r->top_x, hi_x), y = (int)rand_int(e, r->top_y, hi_y);
+    if (!cell_is_none(grid_get(&e->grid, x, y))) continue;
+    if (x == e->agent_x && y == e->agent_y) continue;
+    if (abs(e->agent_x - x) + abs(e->agent_y - y) < 2) continue; /* reject_next_to, roomgrid.py:11-20 */
+    grid_set(&e->grid, x, y, obj);
+    if (px) { *px = x; *py = y; }
+    return;
+  }
+}
+/* RoomGrid.add_object, roomgrid.py:196-224; kind (T_KEY / T_BALL / T_BOX) / color: -1 = draw it */
+static cell_t rg_add_object(env_t *e, const rg_t *g, int i, int j, int kind, int color, int *px, int *py) {
+  static const int KINDS[3] = {T_KEY, T_BALL, T_BOX};
+  if (kind < 0) kind = KINDS[rand_int(e, 0, 3)];
+  if (color < 0) color = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+  cell_t obj = {(uint8_t)kind, (uint8_t)color, 0};
+  rg_place_in_room(e, g, i, j, obj, px, py);
+  return obj;
+}
+/* RoomGrid.remove_wall, roomgrid.py:275-311 */
+static void rg_remove_wall(env_t *e, rg_t *g, int i, int j, int wall_idx) {
+  rg_room_t *r = &g->r[j * g->cols + i];
+  const int tx = r->top_x, ty = r->top_y, S = g->S;
+  for (int k = 1; k < S - 1; k++) {
+    if (wall_idx == 0) grid_set(&e->grid, tx + S - 1, ty + k, CELL_NONE);
+    else if (wall_idx == 1) grid_set(&e->grid, tx + k, ty + S - 1, CELL_NONE);
+    else if (wall_idx == 2) grid_set(&e->grid, tx, ty + k, CELL_NONE);
+    else grid_set(&e->grid, tx + k, ty, CELL_NONE);
+  }
+  int ni, nj;
+  rg_neighbor(g, i, j, wall_idx, &ni, &nj);
+  r->doors[wall_idx] = 2;
+  g->r[nj * g->cols + ni].doors[(wall_idx + 2) % 4] = 2;
+}
+/* RoomGrid.place_agent, roomgrid.py:313-335 (i, j given, rand_dir=True): retried until the front cell is None or a wall */
+static void rg_place_agent(env_t *e, const rg_t *g, int i, int j) {
+  const rg_room_t *r = &g->r[j * g->cols + i];
+  for (;;) {
+    place_agent(e, r->top_x, r->top_y, g->S, g->S);
+    cell_t front = grid_get(&e->grid, e->agent_x + DIR_X[e->agent_dir], e->agent_y + DIR_Y[e->agent_dir]);
+    if (cell_is_none(front) || front.type == T_WALL) break;
+  }
+}
+/* RoomGrid.connect_all, roomgrid.py:337-393 (door_colors = COLOR_NAMES) */
+static void rg_connect_all(env_t *e, rg_t *g) {
+  const int S = g->S;
+  const int si = e->agent_x / (S - 1), sj = e->agent_y / (S - 1); /* room_from_pos */
+  for (;;) {
+    unsigned reach = 0, stack = 1u << (sj * g->cols + si);
+    while (stack) {
+      const int q = __builtin_ctz(stack);
+      stack &= stack - 1;
+      if ((reach >> q) & 1u) continue;
+      reach |= 1u << q;
+      for (int k = 0; k < 4; k++) {
+        int ni, nj;
+        if (g->r[q].doors[k] && rg_neighbor(g, q % g->cols, q / g->cols, k, &ni, &nj)) stack |= 1u << (nj * g->cols + ni);
+      }
+    }
+    if (__builtin_popcount(reach) == g->rows * g->cols) break;
+    const int i = (int)rand_int(e, 0, g->cols), j = (int)rand_int(e, 0, g->rows), k = (int)rand_int(e, 0, 4);
+    rg_room_t *r = &g->r[j * g->cols + i];
+    if (r->door_x[k] < 0 || r->doors[k]) continue;
+    int ni, nj;
+    rg_neighbor(g, i, j, k, &ni, &nj);
+    if (r->locked || g->r[nj * g->cols + ni].locked) continue;
+    const int color = COLOR_NAMES_IDX[rand_int(e, 0, 6)];
+    rg_add_door(e, g, i, j, k, color, 0, NULL, NULL);
+  }
+}
+static void gen_roomgrid(const mgo_vec *v, env_t *e) {
+  rg_t g;
+  rg_gen_base(v, e, &g);
+  const int variant = v->params[0];
+  if (variant == RG_KEYCORRIDOR) { /* keycorridor.py:104-128 */
+    for (int j = 1; j < g.rows; j++) rg_remove_wall(e, &g, 1, j, 3);
+    const int room_idx = (int)rand_int(e, 0, g.rows);
+    const int door_color = rg_add_door(e, &g, 2, room_idx, 2, -1, 1, NULL, NULL);
+    const cell_t obj = rg_add_object(e, &g, 2, room_idx, T_BALL, -1, NULL, NULL);
+    rg_add_object(e, &g, 0, (int)rand_int(e, 0, g.rows), T_KEY, door_color, NULL, NULL);
+    rg_place_agent(e, &g, 1, g.rows / 2);
+    rg_connect_all(e, &g);
+    e->target_x = obj.type; e->target_y = obj.color;
+  } else {
+    cell_t obj = CELL_NONE;
+    int dx = -1, dy = -1;
+    if (variant != RG_UNLOCK) obj = rg_add_object(e, &g, 1, 0, T_BOX, -1, NULL, NULL); /* unlockpickup.py:85, blockedunlockpickup.py:93 */
+    const int door_color = rg_add_door(e, &g, 0, 0, 0, -1, 1, &dx, &dy);
+    if (variant == RG_BLOCKEDUNLOCKPICKUP) { /* :97-98: a ball in front of the door */
+      cell_t ball = {T_BALL, (uint8_t)COLOR_NAMES_IDX[rand_int(e, 0, 6)], 0};
+      grid_set(&e->grid, dx - 1, dy, ball);
+    }
+    rg_add_object(e, &g, 0, 0, T_KEY, door_color, NULL, NULL);
+    rg_place_agent(e, &g, 0, 0);
+    if (variant == RG_UNLOCK) { e->target_x = dx; e->target_y = dy; } /* self.door */
+    else { e->target_x = obj.type; e->target_y = obj.color; }          /* self.obj */
+  }
+}
+
 /* envs/putnear.py:99-166: like GoToObject, but no object within one cell of an earlier one (reject_fn), and a second,
  * different object as the target. place_obj order of tests: cell empty, not the agent, then reject_fn (:348-361). */
 static void gen_putnear(const mgo_vec *v, env_t *e) {
@@ -793,6 +961,7 @@ static void env_reset(const mgo_vec *v, env_t *e) {
     case MGO_PUTNEAR: gen_putnear(v, e); break;
     case MGO_MEMORY: gen_memory(v, e); break;
     case MGO_DYNOBSTACLES: gen_dynobstacles(v, e); break;
+    case MGO_ROOMGRID: gen_roomgrid(v, e); break;
     default: gen_fourrooms(v, e); break;
   }
   e->carrying = 0;
@@ -955,6 +1124,18 @@ static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint
     }
   }
   if (v->kind == MGO_DYNOBSTACLES && action == A_FORWARD && not_clear) { *reward = -1.0; *terminated = 1; } /* :162-165 */
+  if (v->kind == MGO_ROOMGRID) {
+    if (v->params[0] == RG_UNLOCK) { /* unlock.py:88-96: a toggle with self.door open ends the episode */
+      if (action == A_TOGGLE) {
+        cell_t d = grid_get(&e->grid, e->target_x, e->target_y);
+        if (d.type == T_DOOR && d.state == S_OPEN) { *reward = env_reward(v, e); *terminated = 1; }
+      }
+    } else if (action == A_PICKUP && e->carrying && e->carry.type == e->target_x && e->carry.color == e->target_y) {
+      /* "self.carrying == self.obj" (unlockpickup.py:97-105, blockedunlockpickup.py:107-115, keycorridor.py:128-136): an
+       * identity test; these generators create exactly one object of self.obj's type, so type + colour decide it */
+      *reward = env_reward(v, e); *terminated = 1;
+    }
+  }
   if (v->kind == MGO_PUTNEAR) { /* putnear.py:171-199 */
     int ox = e->agent_x + DIR_X[e->agent_dir], oy = e->agent_y + DIR_Y[e->agent_dir];
     if (action == A_PICKUP && e->carrying && (e->carry.type != e->aux[0] || e->carry.color != e->aux[1])) *terminated = 1;

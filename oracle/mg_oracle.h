@@ -30,7 +30,9 @@ enum { MGO_EMPTY = 0, MGO_DOORKEY = 1, MGO_CROSSING = 2, MGO_FOURROOMS = 3, MGO_
        MGO_GOTOOBJECT = 12 /* gotoobject.py:92-160 */, MGO_PUTNEAR = 13 /* putnear.py:99-199 */,
        MGO_MEMORY = 14 /* memory.py:90-164 */,
        /* RNG draws inside step */
-       MGO_DYNOBSTACLES = 15 /* dynamicobstacles.py:107-167 */ };
+       MGO_DYNOBSTACLES = 15 /* dynamicobstacles.py:107-167 */,
+       /* core/roomgrid.py + unlock.py, unlockpickup.py, blockedunlockpickup.py, keycorridor.py */
+       MGO_ROOMGRID = 16 };
 /* vector autoreset modes (gymnasium.vector.AutoresetMode) */
 enum { MGO_AUTORESET_NEXT_STEP = 0, MGO_AUTORESET_SAME_STEP = 1, MGO_AUTORESET_DISABLED = 2 };
 
@@ -42,7 +44,8 @@ typedef struct mgo_vec mgo_vec;
  *         FOURROOMS {}
  *         LAVAGAP {obstacle_type}; DISTSHIFT {strip2_row, start_x, start_y, start_dir}
  *         MULTIROOM {minNumRooms, maxNumRooms, maxRoomSize}; LOCKEDROOM {}; PLAYGROUND {}; GOTODOOR {}; FETCH {numObjs}; REDBLUEDOORS {}; GOTOOBJECT {numObjs}; PUTNEAR {numObjs};
- *         MEMORY {random_length}; DYNOBSTACLES {n_obstacles, random_start, start_x, start_y, start_dir} */
+ *         MEMORY {random_length}; DYNOBSTACLES {n_obstacles, random_start, start_x, start_y, start_dir};
+ *         ROOMGRID {variant (0 Unlock, 1 UnlockPickup, 2 BlockedUnlockPickup, 3 KeyCorridor), room_size, num_rows, num_cols} */
 mgo_vec *mgo_vec_create(int kind, int width, int height, int max_steps, int see_through_walls,
                         const int32_t *params, int n_params, int n_envs);
 void mgo_vec_destroy(mgo_vec *v);

@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(_HERE, "libmg_oracle.so")
 
 KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6,
         "lockedroom": 7, "playground": 8, "gotodoor": 9, "fetch": 10, "redbluedoors": 11, "gotoobject": 12, "putnear": 13,
-        "memory": 14, "dynobstacles": 15}
+        "memory": 14, "dynobstacles": 15, "roomgrid": 16}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 
 # id -> (kind, width, height, max_steps, see_through_walls, params); restated from
@@ -71,11 +71,23 @@ ENV_SPECS = {
     "MiniGrid-Dynamic-Obstacles-Random-6x6-v0": ("dynobstacles", 6, 6, 144, True, [3, 1, 0, 0, 0]),
     "MiniGrid-Dynamic-Obstacles-8x8-v0": ("dynobstacles", 8, 8, 256, True, [4, 0, 1, 1, 0]),
     "MiniGrid-Dynamic-Obstacles-16x16-v0": ("dynobstacles", 16, 16, 1024, True, [8, 0, 1, 1, 0]),
+    "MiniGrid-Unlock-v0": ("roomgrid", 11, 6, 288, False, [0, 6, 1, 2]),
+    "MiniGrid-UnlockPickup-v0": ("roomgrid", 11, 6, 288, False, [1, 6, 1, 2]),
+    "MiniGrid-BlockedUnlockPickup-v0": ("roomgrid", 11, 6, 576, False, [2, 6, 1, 2]),
+    "MiniGrid-KeyCorridorS3R1-v0": ("roomgrid", 7, 3, 270, False, [3, 3, 1, 3]),
+    "MiniGrid-KeyCorridorS3R2-v0": ("roomgrid", 7, 5, 270, False, [3, 3, 2, 3]),
+    "MiniGrid-KeyCorridorS3R3-v0": ("roomgrid", 7, 7, 270, False, [3, 3, 3, 3]),
+    "MiniGrid-KeyCorridorS4R3-v0": ("roomgrid", 10, 10, 480, False, [3, 4, 3, 3]),
+    "MiniGrid-KeyCorridorS5R3-v0": ("roomgrid", 13, 13, 750, False, [3, 5, 3, 3]),
+    "MiniGrid-KeyCorridorS6R3-v0": ("roomgrid", 16, 16, 1080, False, [3, 6, 3, 3]),
 }
 
 # SURVEY 8(f-1) generators restated ahead of their device kernels: the oracle and its fixtures exist, the product does
 # not register these ids yet (lockedroom.py:74-90 / __init__.py:312-318, playground.py:16-25 / __init__.py:516-522)
 NEXT_SPECS = {
+    # SURVEY 8(f-2), second half: core/roomgrid.py + unlock.py:55-70 (2 rooms of 6, 8 * 36 steps), unlockpickup.py:60-78,
+    # blockedunlockpickup.py:67-85 (16 * 36), keycorridor.py:73-97 (3 columns, 30 * room_size^2); __init__.py:12-20, 252-290, 555-563
+    # params {variant, room_size, num_rows, num_cols}
     # SURVEY 8(f-2), first of the step post-filters: gotodoor.py:65-86 (4 * size^2 steps, see_through_walls=True), __init__.py:218-236
     # fetch.py:72-103 (5 * size^2 steps, see_through_walls=True), __init__.py:196-208; params {numObjs}
     # redbluedoors.py:60-72 (2 size x size, 20 * size^2 steps), __init__.py:541-551

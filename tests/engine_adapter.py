@@ -61,5 +61,5 @@ def make_engine(env_id, n, mode):
 def spec_tuple(env_id):
     s = specs.get(env_id)
     kind = ["empty", "doorkey", "crossing", "fourrooms", "lavagap", "distshift", "multiroom", "lockedroom", "playground",
-            "gotodoor", "fetch", "redbluedoors", "gotoobject", "putnear", "memory", "dynobstacles"][s.kind]
+            "gotodoor", "fetch", "redbluedoors", "gotoobject", "putnear", "memory", "dynobstacles", "roomgrid"][s.kind]
     return (kind, s.width, s.height, s.max_steps, s.see_through_walls, list(s.params))

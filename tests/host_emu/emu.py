@@ -13,7 +13,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "libmg_host_emu.so")
 KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "distshift": 5, "multiroom": 6,
         "lockedroom": 7, "playground": 8,  # 7 and up: device generators checked here before the kernels are instantiated
-        "gotodoor": 9, "fetch": 10, "redbluedoors": 11, "gotoobject": 12, "putnear": 13, "memory": 14, "dynobstacles": 15}
+        "gotodoor": 9, "fetch": 10, "redbluedoors": 11, "gotoobject": 12, "putnear": 13, "memory": 14, "dynobstacles": 15, "roomgrid": 16}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 _lib = None
 

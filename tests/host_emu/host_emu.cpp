@@ -92,6 +92,7 @@ static void reset_one(Emu *e, int env, uint8_t *obs, int32_t *dir_out) {
     case KIND_PUTNEAR: reset_env<KIND_PUTNEAR>(e, env, obs, dir_out); break;
     case KIND_MEMORY: reset_env<KIND_MEMORY>(e, env, obs, dir_out); break;
     case KIND_DYNOBS: reset_env<KIND_DYNOBS>(e, env, obs, dir_out); break;
+    case KIND_ROOMGRID: reset_env<KIND_ROOMGRID>(e, env, obs, dir_out); break;
     default: reset_env<KIND_FOURROOMS>(e, env, obs, dir_out); break;
   }
 }
@@ -177,6 +178,7 @@ static void warp_reset(Emu *e, unsigned pend, int tile, uint32_t *gtile, ResetOu
     case KIND_PUTNEAR: warp_reset_k<KIND_PUTNEAR>(e, pend, tile, gtile, out); break;
     case KIND_MEMORY: warp_reset_k<KIND_MEMORY>(e, pend, tile, gtile, out); break;
     case KIND_DYNOBS: warp_reset_k<KIND_DYNOBS>(e, pend, tile, gtile, out); break;
+    case KIND_ROOMGRID: warp_reset_k<KIND_ROOMGRID>(e, pend, tile, gtile, out); break;
     default: warp_reset_k<KIND_FOURROOMS>(e, pend, tile, gtile, out); break;
   }
 }
@@ -191,6 +193,7 @@ static PostOut emu_post_filter(int kind, const PostIn &in, uint32_t terminated) 
     case KIND_PUTNEAR: return post_filter<KIND_PUTNEAR>(in, terminated);
     case KIND_MEMORY: return post_filter<KIND_MEMORY>(in, terminated);
     case KIND_REDBLUEDOORS: return post_filter<KIND_REDBLUEDOORS>(in, terminated);
+    case KIND_ROOMGRID: return post_filter<KIND_ROOMGRID>(in, terminated);
     default: { PostOut o = {terminated, POST_KEEP}; return o; }
   }
 }
@@ -300,12 +303,14 @@ static void step_tiles(Emu *e, const int32_t *actions, uint8_t *obs, int32_t *di
         gb[grid_word(g, env, cw) * 4 + (fy & 3)] = (uint8_t)so.newc;
       }
       if (p.kind == KIND_DYNOBS && action == A_FORWARD && not_clear) { reward[lane] = -1.0; terminated[lane] = 1u; }
-      if (p.kind >= KIND_GOTODOOR && p.kind <= KIND_MEMORY) {  // step post-filter
+      if ((p.kind >= KIND_GOTODOOR && p.kind <= KIND_MEMORY) || p.kind == KIND_ROOMGRID) {  // step post-filter
         PostIn in;
         in.action = action; in.ax = ax[lane]; in.ay = ay[lane]; in.dir = dir[lane];
         in.carry_before = carry_before; in.carry = carry[lane];
         in.tx = tx[lane]; in.ty = ty[lane]; in.aux = flags[lane] >> 8;
         in.red_before = in.blue_before = in.red_after = in.blue_after = false;
+        in.variant = p.kp[0]; in.door_open = false;
+        if (p.kind == KIND_ROOMGRID && p.kp[0] == RG_UNLOCK) in.door_open = (gb[cell_byte_R(g, env, tx[lane], ty[lane])] & 15u) == T_DOOR;
         if (p.kind == KIND_REDBLUEDOORS) {  // a door changes only as the front cell of a toggle
           const int xl = g.H / 2, xr = g.H / 2 + g.H - 1;
           in.red_after = (gb[cell_byte_R(g, env, xl, tx[lane])] & 15u) == T_DOOR;
@@ -446,6 +451,7 @@ void *emu_create(int kind, int W, int H, int max_steps, int see_through, const i
         case KIND_PUTNEAR: e->tmpl[w] = level_word<KIND_PUTNEAR>(p, L, w); break;
         case KIND_MEMORY: e->tmpl[w] = level_word<KIND_MEMORY>(p, L, w); break;
         case KIND_DYNOBS: e->tmpl[w] = level_word<KIND_DYNOBS>(p, L, w); break;
+        case KIND_ROOMGRID: e->tmpl[w] = level_word<KIND_ROOMGRID>(p, L, w); break;
         default: e->tmpl[w] = level_word<KIND_FOURROOMS>(p, L, w); break;
       }
     p.tmpl = e->tmpl.data();
@@ -522,8 +528,8 @@ void emu_set_state(void *h, const uint8_t *grid, const int32_t *agent) {  // k_s
     if (agent) {
       const int32_t *a = agent + (size_t)env * 6;
       uint4 rec = p.agent[env];
-      rec.x = (uint32_t)(a[0] & 0xFF) | ((uint32_t)(a[1] & 0xFF) << 8);
-      rec.y = (uint32_t)(a[2] & 3);
+      rec.x = (rec.x & 0xFFFF0000u) | (uint32_t)(a[0] & 0xFF) | ((uint32_t)(a[1] & 0xFF) << 8);  // k_set_agent: the post-filter targets stay
+      rec.y = (rec.y & ~3u) | (uint32_t)(a[2] & 3);
       rec.z = a[3] >= 0 ? ((uint32_t)(a[3] & 15) | ((uint32_t)(a[4] & 7) << 4)) : 0u;
       rec.w = (uint32_t)a[5];
       p.agent[env] = rec;

@@ -73,3 +73,22 @@ def check_lockstep_vs_oracle(engine, oracle, n_steps, seed, action_seed=1234, ch
     for k in ("grid", "agent", "rng", "pending"):
         np.testing.assert_array_equal(es[k], os_[k], err_msg=k)
     np.testing.assert_array_equal(engine.full_obs(), oracle.full_obs())
+
+
+def roomgrid_inject_targets(orc):
+    """Agents placed next to their env's target (Unlock: in front of the locked door with its key; the pickup variants:
+    facing the box / ball), from the oracle's state. Returns (agent array, action)."""
+    st = orc.get_state()
+    grid, agent = st["grid"], st["agent"].copy()
+    unlock = orc.params[0] == 0
+    want = 4 if unlock else (6 if orc.params[0] == 3 else 7)  # door | ball (KeyCorridor) | box
+    for i in range(orc.num_envs):
+        xs, ys = np.nonzero((grid[i, :, :, 0] == want) & ((grid[i, :, :, 2] == 2) if unlock else True))
+        tx, ty = int(xs[0]), int(ys[0])
+        for d, (dx, dy) in enumerate([(1, 0), (0, 1), (-1, 0), (0, -1)]):
+            ax, ay = tx - dx, ty - dy
+            if 0 < ax < orc.width - 1 and 0 < ay < orc.height - 1 and grid[i, ax, ay, 0] in ((1,) if unlock else (1, 4)):
+                agent[i, :3] = (ax, ay, d)
+                agent[i, 3:5] = (5, grid[i, tx, ty, 1]) if unlock else (-1, 0)
+                break
+    return agent, (5 if unlock else 3)

@@ -67,7 +67,7 @@ def test_spec_tables_agree():
     from minigrid_b200 import specs
     from oracle.oracle import ENV_SPECS
 
-    kinds = ["empty", "doorkey", "crossing", "fourrooms", "lavagap", "distshift", "multiroom", "lockedroom", "playground", "gotodoor", "fetch", "redbluedoors", "gotoobject", "putnear", "memory", "dynobstacles"]
+    kinds = ["empty", "doorkey", "crossing", "fourrooms", "lavagap", "distshift", "multiroom", "lockedroom", "playground", "gotodoor", "fetch", "redbluedoors", "gotoobject", "putnear", "memory", "dynobstacles", "roomgrid"]
     for env_id, (kind, w, h, ms, st, prm) in ENV_SPECS.items():
         s = specs.get(env_id)
         assert (kinds[s.kind], s.width, s.height, s.max_steps, s.see_through_walls) == (kind, w, h, ms, st), env_id

@@ -92,3 +92,32 @@ print("rewards", seen_reward)
     assert r.returncode == 0, r.stderr[-3000:]
     if env_id == "MiniGrid-Empty-5x5-v0":
         assert int(r.stdout.split()[-1]) > 0  # the reward path was exercised
+
+
+@pytest.mark.parametrize("layout", [0, 1], ids=["tiled", "window"])
+@pytest.mark.parametrize("env_id", ["MiniGrid-Unlock-v0", "MiniGrid-UnlockPickup-v0", "MiniGrid-BlockedUnlockPickup-v0",
+                                    "MiniGrid-KeyCorridorS3R3-v0", "MiniGrid-KeyCorridorS6R3-v0"])
+@pytest.mark.parametrize("mode", ["next_step", "same_step"])
+def test_emu_roomgrid_post_filters(env_id, layout, mode):
+    """The success branches of the RoomGrid step post-filters (unlock.py:88-96, `carrying == self.obj`) through the device
+    headers, against the oracle (itself pinned on these branches against the live reference, tests/test_oracle_next.py)."""
+    n = 40
+    emu = make_emu(env_id, n, mode, layout)
+    orc = OracleVecEnv(env_id, n, autoreset=mode)
+    parity.check_lockstep_vs_oracle(emu, orc, 20, seed=77)
+    agent, act = parity.roomgrid_inject_targets(orc)
+    emu.set_state(agent=agent)
+    orc.set_state(agent=agent)
+    rewarded = 0
+    for a in (np.full(n, act), np.full(n, act), np.full(n, 2), np.full(n, act)):
+        e, o = emu.step(a), orc.step(a)
+        for x, y, name in zip(e, o, ["obs", "dir", "reward", "terminated", "truncated"]):
+            if name == "reward":
+                assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+            else:
+                np.testing.assert_array_equal(np.asarray(x).astype(np.asarray(y).dtype), y, err_msg=name)
+        rewarded += int((o[2] > 0).sum())
+    assert rewarded >= n // 2
+    es, os_ = emu.get_state(), orc.get_state()
+    for k in ("grid", "agent", "rng", "pending"):
+        np.testing.assert_array_equal(es[k], os_[k], err_msg=k)

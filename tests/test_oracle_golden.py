@@ -113,4 +113,4 @@ def test_invalid_action_raises():
 
 def test_spec_table_is_consistent():
     for env_id, (kind, w, h, ms, st, prm) in ENV_SPECS.items():
-        assert kind in ("empty", "doorkey", "crossing", "fourrooms", "lavagap", "distshift", "multiroom", "lockedroom", "playground", "gotodoor", "fetch", "redbluedoors", "gotoobject", "putnear", "memory", "dynobstacles") and w >= 3 and h >= 3 and ms > 0
+        assert kind in ("empty", "doorkey", "crossing", "fourrooms", "lavagap", "distshift", "multiroom", "lockedroom", "playground", "gotodoor", "fetch", "redbluedoors", "gotoobject", "putnear", "memory", "dynobstacles", "roomgrid") and w >= 3 and h >= 3 and ms > 0

@@ -107,3 +107,46 @@ def test_memory_success_and_failure_cells_against_live_reference(env_id):
         ended += int(np.asarray(r[3]).sum())
     rewards = np.concatenate(rewards)
     assert ended >= n and (rewards > 0).any() and ended > int((rewards > 0).sum())  # successes and failures both seen
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("env_id", ["MiniGrid-Unlock-v0", "MiniGrid-UnlockPickup-v0", "MiniGrid-BlockedUnlockPickup-v0",
+                                    "MiniGrid-KeyCorridorS3R3-v0", "MiniGrid-KeyCorridorS6R3-v0"])
+def test_roomgrid_post_filters_fire_against_live_reference(env_id):
+    """Random actions practically never unlock a door or reach the object behind it: put every agent next to its target
+    (the same injection in the reference's env objects and in the oracle) so that the success branches of unlock.py:88-96
+    and of the `carrying == self.obj` filters run in both."""
+    n = 16
+    ref = ref_loader.ReferenceVecEnv(env_id, n)
+    orc = OracleVecEnv(env_id, n)
+    np.testing.assert_array_equal(ref.reset(seed=700)[0], orc.reset(seed=700)[0])
+    from minigrid.core.world_object import Key
+
+    agent = orc.get_state()["agent"].copy()
+    unlock = env_id == "MiniGrid-Unlock-v0"
+    moved = 0
+    for i, e in enumerate(ref.envs):
+        tx, ty = (e.door.cur_pos if unlock else e.obj.cur_pos)
+        for d, (dx, dy) in enumerate([(1, 0), (0, 1), (-1, 0), (0, -1)]):  # stand at target - d, face d
+            ax, ay = tx - dx, ty - dy
+            here = e.grid.get(ax, ay) if 0 < ax < e.width - 1 and 0 < ay < e.height - 1 else False
+            if here is None or (here and here.type == "door" and not unlock):  # (S3 rooms: the only free neighbour is the doorway)
+                e.agent_pos, e.agent_dir = (ax, ay), d
+                e.carrying = Key(e.door.color) if unlock else None
+                agent[i, :3] = (ax, ay, d)
+                agent[i, 3:5] = (5, {"red": 0, "green": 1, "blue": 2, "purple": 3, "yellow": 4, "grey": 5}[e.door.color]) if unlock else (-1, 0)
+                moved += 1
+                break
+    assert moved >= n // 2
+    orc.set_state(agent=agent)
+    act = np.full(n, 5 if unlock else 3)
+    ended = 0
+    for a in (act, act, np.full(n, 2)):
+        r, q = ref.step(a), orc.step(a)
+        for x, y, name in zip(r, q, ["obs", "dir", "reward", "terminated", "truncated"]):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=name)
+        ended += int((np.asarray(r[3]) & (np.asarray(r[2]) > 0)).sum())
+    assert ended >= moved  # every injected env succeeded once
+    rs, os_ = ref.get_state(), orc.get_state()
+    for k in rs:
+        np.testing.assert_array_equal(rs[k], os_[k], err_msg=k)
