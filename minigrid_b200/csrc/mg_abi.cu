@@ -639,7 +639,8 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_err, h->p.err, sizeof(int), cudaMemcpyDeviceToHost, s);
   int released = 0;
   for (int c = 0; c < C && e == cudaSuccess; ++c) {
-    e = cudaEventSynchronize(h->chunk_ev[c]);
+    // poll: a chunk lands every ~30 us, a blocking synchronise would add its wake-up latency to each of them
+    while ((e = cudaEventQuery(h->chunk_ev[c])) == cudaErrorNotReady) {}
     if (e == cudaSuccess) { h->pool->chunk_ready(); ++released; }
   }
   if (e != cudaSuccess) h->pool->abort_chunks(C);  // let the workers run through (their output is discarded by the error)

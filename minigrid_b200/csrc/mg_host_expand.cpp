@@ -222,12 +222,22 @@ struct HostPool::Impl {
   std::atomic<int> ready{0};         // chunks whose bytes have arrived on the host
   int done = 0;
 
+  std::atomic<uint64_t> gen_fast{0};  // mirrors `generation` for the spinning phase
+  std::atomic<int> done_fast{0};
+
   void worker(int w, int T) {
     uint64_t seen = 0;
     for (;;) {
+      // A training loop calls step after step: the next job arrives tens of microseconds after the last one ended, less
+      // than a condition-variable wake-up costs. Spin for it briefly, park only when the caller has gone quiet.
+      bool got = false;
+      for (int spins = 0; spins < 20000; ++spins) {  // ~0.2-0.4 ms
+        if (gen_fast.load(std::memory_order_acquire) != seen) { got = true; break; }
+        _mm_pause();
+      }
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv_start.wait(lk, [&] { return stop || generation != seen; });
+        if (!got) cv_start.wait(lk, [&] { return stop || generation != seen; });
         if (stop) return;
         seen = generation;
       }
@@ -243,6 +253,7 @@ struct HostPool::Impl {
         const int64_t a = w == 0 ? 0 : ((len * w / T) & ~(int64_t)63), b = w == T - 1 ? len : ((len * (w + 1) / T) & ~(int64_t)63);
         expand_range(job, lo + a, lo + b);
       }
+      done_fast.fetch_add(1, std::memory_order_release);
       {
         std::lock_guard<std::mutex> lk(mu);
         if (++done == T) cv_done.notify_one();
@@ -269,12 +280,18 @@ void HostPool::begin(const ExpandJob &job, const int64_t *bounds, int n_chunks) 
   impl_->bounds.assign(bounds, bounds + n_chunks + 1);
   impl_->ready.store(0, std::memory_order_release);
   impl_->done = 0;
+  impl_->done_fast.store(0, std::memory_order_release);
   impl_->generation += 1;
+  impl_->gen_fast.store(impl_->generation, std::memory_order_release);
   impl_->cv_start.notify_all();
 }
 void HostPool::chunk_ready() { impl_->ready.fetch_add(1, std::memory_order_release); }
 void HostPool::abort_chunks(int n_chunks) { impl_->ready.store(n_chunks, std::memory_order_release); }
 void HostPool::wait() {
+  for (int spins = 0; spins < 200000; ++spins) {  // the workers are a few microseconds from done when this is called
+    if (impl_->done_fast.load(std::memory_order_acquire) == n_threads_) break;
+    _mm_pause();
+  }
   std::unique_lock<std::mutex> lk(impl_->mu);
   impl_->cv_done.wait(lk, [&] { return impl_->done == n_threads_; });
 }

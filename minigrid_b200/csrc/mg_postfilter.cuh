@@ -3,8 +3,8 @@
 //   pre_filter   what the subclass does to the action before super().step
 //   post_filter  what it does to (reward, terminated) afterwards
 // The comparison targets are drawn at reset (mg_levels.cuh: level_target) and live in the spare bits of the
-// agent record. STATUS: checked against the oracle in the host emulation (tests/test_oracle_next.py); K1 does not
-// call these yet (next/README.md).
+// agent record. Called by K1 (mg_step_kernel.cuh) for the kinds has_post_filter() names; also replayed by the host
+// emulation (tests/host_emu) against the oracle.
 #pragma once
 #include "mg_common.cuh"
 #include "mg_pcg64.cuh"

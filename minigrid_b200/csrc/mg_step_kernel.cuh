@@ -87,6 +87,10 @@ __device__ __forceinline__ uint4 ldg_rec(const uint4 *ptr) {
   asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
   return v;
 }
+__device__ __forceinline__ void prefetch_rng(const RngRec *r) {  // 48 bytes: two 32-byte sectors
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(r) + 32));
+}
 __device__ __forceinline__ int load_action(const void *actions, int dtype, int env) {
   int v;
   if (dtype == 1) {
@@ -330,6 +334,8 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     const int env0 = tile * TILE + lane;
     rec = ldg_rec(p.agent + env0);
     if (stepping && env0 < p.n_envs) action = load_action(actions, act_dtype, env0);
+    // an env that regenerates in this step starts from its RNG record: bring it in while the tile is on its way
+    if (stepping && ((rec.y >> 8) & FLAG_PENDING)) prefetch_rng(p.rng + env0);
   }
 
   uint8_t *gb = reinterpret_cast<uint8_t *>(p.grid);
@@ -371,6 +377,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       const int env0 = tile * TILE + lane;
       rec = ldg_rec(p.agent + env0);
       action = (stepping && env0 < p.n_envs) ? load_action(actions, act_dtype, env0) : A_DONE;
+      if (stepping && ((rec.y >> 8) & FLAG_PENDING)) prefetch_rng(p.rng + env0);
     }
 #ifdef MG_TIMELINE
     const unsigned long long tl_t0 = gtime();
@@ -651,6 +658,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
 #endif
     first = false;
     if (PREF) {
+      if (stepping && next < p.n_tiles && ((rec_n.y >> 8) & FLAG_PENDING)) prefetch_rng(p.rng + (size_t)next * TILE + lane);
       tile = next;
       next = __shfl_sync(0xFFFFFFFFu, nn, 0);
       rec = rec_n;
