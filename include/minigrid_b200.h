@@ -55,8 +55,10 @@ extern "C" {
 #define MG_KIND_MEMORY 14       /* envs/memory.py: params {random_length}; odd height */
 /* RNG draws inside step */
 #define MG_KIND_ROOMGRID 16     /* core/roomgrid.py + envs/unlock.py, unlockpickup.py, blockedunlockpickup.py, keycorridor.py:
-                                   params {variant (0 Unlock, 1 UnlockPickup, 2 BlockedUnlockPickup, 3 KeyCorridor), room_size,
-                                   num_rows, num_cols} */
+                                   obstructedmaze.py, obstructedmaze_v1.py: params {variant (0 Unlock, 1 UnlockPickup,
+                                   2 BlockedUnlockPickup, 3 KeyCorridor, 4 ObstructedMaze_1Dlhb, 5 ObstructedMaze_Full,
+                                   6 ObstructedMaze_Full_V1), room_size, num_rows, num_cols[, key_in_box, blocked,
+                                   agent_room_i | agent_room_j << 4, num_quarters]} */
 #define MG_KIND_DYNOBS 15       /* envs/dynamicobstacles.py: params {n_obstacles, random_start, start_x, start_y, start_dir} */
 
 /* gymnasium.vector.AutoresetMode */

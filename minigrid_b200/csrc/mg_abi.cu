@@ -1,5 +1,6 @@
 // mg_abi.cu — the C-ABI of include/minigrid_b200.h: handle management, launch sequencing (autoreset
 // modes), and the host-buffer (end-to-end) entry points. No torch types cross this boundary.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,6 +60,8 @@ struct mg_env {
   HostPool *pool;
   cudaEvent_t chunk_ev[16];
   int n_chunks;
+  // MINIGRID_B200_HOST_TRACE=1: where a packed host step spends its time (printed by mg_destroy)
+  int trace; double tr_enqueue, tr_first_chunk, tr_last_chunk, tr_pool, tr_total; int64_t tr_n;
   // optional per-launch timing of K1 (bench.py's roofline leg)
   int profiling;
   std::vector<cudaEvent_t> *prof_events;  // start/stop pairs
@@ -115,12 +118,18 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   if (kind == MG_KIND_MEMORY && (height % 2 == 0 || height < 7 || width < 7))
     return fail(MG_ERR_INVALID_ARG, "memory needs an odd height and at least 7 x 7 (memory.py:98)");
   if (kind == MG_KIND_ROOMGRID) {
-    if (n_params < 4 || params[0] < 0 || params[0] > 3 || params[1] < 3 || params[1] > 8 || params[2] < 1 || params[3] < 1 ||
+    if (n_params < 4 || params[0] < 0 || params[0] > 6 || params[1] < 3 || params[1] > 8 || params[2] < 1 || params[3] < 1 ||
         params[2] * params[3] > 9 || width != (params[1] - 1) * params[3] + 1 || height != (params[1] - 1) * params[2] + 1)
       return fail(MG_ERR_INVALID_ARG, "roomgrid needs params {variant 0..3, room_size 3..8, num_rows, num_cols} with at most 9 rooms, "
                                       "width = (room_size - 1) num_cols + 1 and height = (room_size - 1) num_rows + 1 (roomgrid.py:83-84)");
     if (params[0] == 3 && params[3] != 3) return fail(MG_ERR_INVALID_ARG, "keycorridor has 3 columns of rooms (keycorridor.py:104-126)");
-    if (params[0] != 3 && (params[2] != 1 || params[3] != 2)) return fail(MG_ERR_INVALID_ARG, "unlock / unlockpickup / blockedunlockpickup are 1 x 2 rooms");
+    if (params[0] != 3 && params[0] < 5 && (params[2] != 1 || params[3] != 2))
+      return fail(MG_ERR_INVALID_ARG, "unlock / unlockpickup / blockedunlockpickup / obstructedmaze-1D are 1 x 2 rooms");
+    if (params[0] >= 4) {
+      if (n_params < 8 || params[1] < 4) return fail(MG_ERR_INVALID_ARG, "obstructedmaze needs params {variant, room_size >= 4, num_rows, num_cols, key_in_box, blocked, agent_room_i | agent_room_j << 4, num_quarters}");
+      if (params[0] >= 5 && (params[2] != 3 || params[3] != 3 || params[7] < 1 || params[7] > 4 || (params[6] & 15) > 2 || (params[6] >> 4) > 2))
+        return fail(MG_ERR_INVALID_ARG, "obstructedmaze-Full is 3 x 3 rooms with 1..4 quarters and the agent's room inside the grid");
+    }
     if (params[0] == 2 && params[1] < 4) return fail(MG_ERR_INVALID_ARG, "blockedunlockpickup needs room_size >= 4 (a cell in front of the door)");
   }
   if (kind == MG_KIND_DYNOBS) {
@@ -159,6 +168,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   p.see_through = see_through_walls ? 1 : 0;
   p.mode = autoreset_mode;
   p.kind = kind;
+  h->trace = getenv("MINIGRID_B200_HOST_TRACE") != nullptr;
   p.hot_first = 1;
   if (const char *e = getenv("MINIGRID_B200_HOTFIRST")) p.hot_first = atoi(e) != 0;  // tuning knob (same-box A/B)
   for (int i = 0; i < 8; ++i) p.kp[i] = (params && i < n_params) ? params[i] : 0;
@@ -255,6 +265,11 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
 
 int mg_destroy(mg_env *h) {
   if (!h) return MG_OK;
+  if (h->trace && h->tr_n)
+    fprintf(stderr, "[minigrid_b200] packed host step, mean of %lld (us since entry): enqueued %.1f, first chunk on the host %.1f, last chunk %.1f, "
+                    "expansion done %.1f, return %.1f; %d chunks, %d threads\n", (long long)h->tr_n, h->tr_enqueue / h->tr_n,
+            h->tr_first_chunk / h->tr_n, h->tr_last_chunk / h->tr_n, h->tr_pool / h->tr_n, h->tr_total / h->tr_n, h->n_chunks,
+            h->pool ? h->pool->threads() : 0);
   DeviceGuard guard(h->device);
   if (h->hstream) { cudaStreamSynchronize(h->hstream); cudaStreamDestroy(h->hstream); }
   if (h->ev_order) cudaEventDestroy(h->ev_order);
@@ -600,6 +615,7 @@ int mg_set_host_format(mg_env *h, int format, int n_threads) {
     // chunks: enough of them that the expansion of chunk c overlaps the copy of chunk c + 1, each still a large copy
     int chunks = (int)(h->p.n_envs / 16384);
     chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks);
+    if (const char *e = getenv("MINIGRID_B200_HOST_CHUNKS")) { chunks = atoi(e); chunks = chunks < 1 ? 1 : (chunks > 16 ? 16 : chunks); }  // tuning knob
     for (int c = 0; c < chunks; ++c)
       if (!h->chunk_ev[c]) MG_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
     h->n_chunks = chunks;
@@ -626,6 +642,9 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   const int C = h->n_chunks;
   for (int c = 0; c <= C; ++c) bounds[c] = (int64_t)((n * (size_t)c / (size_t)C) / 64 * 64);  // whole tiles, and whole cache lines on the host
   bounds[C] = (int64_t)n;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
+  double t_enq = 0, t_first = 0, t_last = 0;
   h->pool->begin(job, bounds, C);  // the workers wake up while the copy and the kernel run
   cudaError_t e = cudaMemcpyAsync(h->d_actions, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess)
@@ -638,15 +657,22 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->h_err, h->p.err, sizeof(int), cudaMemcpyDeviceToHost, s);
   int released = 0;
+  t_enq = since();
   for (int c = 0; c < C && e == cudaSuccess; ++c) {
     // poll: a chunk lands every ~30 us, a blocking synchronise would add its wake-up latency to each of them
     while ((e = cudaEventQuery(h->chunk_ev[c])) == cudaErrorNotReady) {}
     if (e == cudaSuccess) { h->pool->chunk_ready(); ++released; }
+    if (c == 0) t_first = since();
   }
+  t_last = since();
   if (e != cudaSuccess) h->pool->abort_chunks(C);  // let the workers run through (their output is discarded by the error)
   (void)released;
   h->pool->wait();
+  if (h->trace) {
+    h->tr_enqueue += t_enq; h->tr_first_chunk += t_first; h->tr_last_chunk += t_last; h->tr_pool += since(); h->tr_n += 1;
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (h->trace) h->tr_total += since();
   if (e != cudaSuccess) return fail(MG_ERR_CUDA, std::string("mg_step_host (packed): ") + cudaGetErrorString(e));
   if (*h->h_err & ERR_PACKED_RANGE) {
     MG_CUDA(launch_clear_err(h->p, ERR_PACKED_RANGE, s));

@@ -43,7 +43,10 @@ constexpr int MAX_DIM = 26;                 // W, H <= 26 (the OOB bit mask is b
 
 // core/constants.py:25-37
 enum : uint32_t { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
-                  T_BOX = 7, T_GOAL = 8, T_LAVA = 9, T_AGENT = 10, T4_DOOR_CLOSED = 11, T4_DOOR_LOCKED = 12 };
+                  T_BOX = 7, T_GOAL = 8, T_LAVA = 9, T_AGENT = 10, T4_DOOR_CLOSED = 11, T4_DOOR_LOCKED = 12,
+                  // Box.contains (world_object.py:273-293) is None everywhere except ObstructedMaze, whose grey boxes hide
+                  // the key of a door: t4 = 13 is "a grey box with a key inside", the colour field is the KEY's colour
+                  T4_BOX_WITH_KEY = 13 };
 enum : uint32_t { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5 };
 // core/actions.py:7-20
 enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
@@ -71,7 +74,10 @@ enum : int { KIND_EMPTY = 0, KIND_DOORKEY = 1, KIND_CROSSING = 2, KIND_FOURROOMS
              // SURVEY 8(f-2), second half: core/roomgrid.py with unlock.py, unlockpickup.py, blockedunlockpickup.py, keycorridor.py
              KIND_ROOMGRID = 16 };
 constexpr int KIND_COUNT = 17;
-enum : int { RG_UNLOCK = 0, RG_UNLOCKPICKUP = 1, RG_BLOCKEDUNLOCKPICKUP = 2, RG_KEYCORRIDOR = 3 };  // kp[0] of KIND_ROOMGRID  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
+// kp[0] of KIND_ROOMGRID; the ObstructedMaze variants (envs/obstructedmaze.py, obstructedmaze_v1.py) also read
+// kp[4] key_in_box, kp[5] blocked, kp[6] agent room i | j << 4, kp[7] num_quarters
+enum : int { RG_UNLOCK = 0, RG_UNLOCKPICKUP = 1, RG_BLOCKEDUNLOCKPICKUP = 2, RG_KEYCORRIDOR = 3, RG_OBSTRUCTED_1D = 4,
+             RG_OBSTRUCTED_FULL = 5, RG_OBSTRUCTED_FULL_V1 = 6 };  // kinds mg_create accepts: the kernels are instantiated for the kinds below this
 enum : int { AUTORESET_NEXT_STEP = 0, AUTORESET_SAME_STEP = 1, AUTORESET_DISABLED = 2 };
 // bits of the sticky device error word (Params::err)
 enum : int { ERR_BAD_ACTION = 1, ERR_BAD_STATE = 2, ERR_PACKED_RANGE = 4 };
@@ -96,6 +102,7 @@ MG_HD uint32_t decode_cell(uint32_t code) {
   if (t4 == T_EMPTY) return T_EMPTY;
   if (t4 == T4_DOOR_CLOSED) return T_DOOR | (color << 8) | (1u << 16);
   if (t4 == T4_DOOR_LOCKED) return T_DOOR | (color << 8) | (2u << 16);
+  if (t4 == T4_BOX_WITH_KEY) return T_BOX | (C_GREY << 8);  // what is inside does not show (Box.encode is WorldObj.encode)
   return t4 | (color << 8);
 }
 

@@ -35,6 +35,7 @@ inline uint32_t decode_code(uint32_t code) {
   if (t4 == 1) return 1;
   if (t4 == 11) return 4u | (color << 8) | (1u << 16);
   if (t4 == 12) return 4u | (color << 8) | (2u << 16);
+  if (t4 == 13) return 7u | (5u << 8);  // a grey box with a key inside (ObstructedMaze): the contents do not show
   return t4 | (color << 8);
 }
 
@@ -93,9 +94,10 @@ void expand_scalar(const ExpandJob &j, const uint8_t *rec, int count, const Dst 
 
 // 16 codes -> 48 image bytes with three 16-entry byte tables on t4 and byte shuffles for the 3-way interleave
 __attribute__((target("ssse3"))) void expand_ssse3(const ExpandJob &j, const uint8_t *rec, int count, const Dst &d) {
-  const __m128i type_lut = _mm_setr_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 4, 4, 13, 14, 15);
+  const __m128i type_lut = _mm_setr_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 4, 4, 7, 14, 15);
+  const __m128i cfix_lut = _mm_setr_epi8(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 5, 0, 0);  // t4 = 13: the colour is the box's (grey)
   const __m128i state_lut = _mm_setr_epi8(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 0, 0, 0);
-  const __m128i cmask_lut = _mm_setr_epi8(0, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+  const __m128i cmask_lut = _mm_setr_epi8(0, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, -1, -1);
   const __m128i low4 = _mm_set1_epi8(15), low3 = _mm_set1_epi8(7);
   // output bytes 0..15 / 16..31 / 32..47 of (t0 c0 s0 t1 c1 s1 ...): shuffle masks per source plane (0x80 = zero)
   const __m128i t_a = _mm_setr_epi8(0, -128, -128, 1, -128, -128, 2, -128, -128, 3, -128, -128, 4, -128, -128, 5);
@@ -117,7 +119,8 @@ __attribute__((target("ssse3"))) void expand_ssse3(const ExpandJob &j, const uin
         const __m128i t4 = _mm_and_si128(code, low4);
         const __m128i ty = _mm_shuffle_epi8(type_lut, t4);
         const __m128i st = _mm_shuffle_epi8(state_lut, t4);
-        const __m128i co = _mm_and_si128(_mm_and_si128(_mm_srli_epi16(code, 4), low3), _mm_shuffle_epi8(cmask_lut, t4));
+        const __m128i co = _mm_or_si128(_mm_and_si128(_mm_and_si128(_mm_srli_epi16(code, 4), low3), _mm_shuffle_epi8(cmask_lut, t4)),
+                                        _mm_shuffle_epi8(cfix_lut, t4));
         const __m128i a = _mm_or_si128(_mm_or_si128(_mm_shuffle_epi8(ty, t_a), _mm_shuffle_epi8(co, c_a)), _mm_shuffle_epi8(st, s_a));
         const __m128i b = _mm_or_si128(_mm_or_si128(_mm_shuffle_epi8(ty, t_b), _mm_shuffle_epi8(co, c_b)), _mm_shuffle_epi8(st, s_b));
         const __m128i c = _mm_or_si128(_mm_or_si128(_mm_shuffle_epi8(ty, t_c), _mm_shuffle_epi8(co, c_c)), _mm_shuffle_epi8(st, s_c));

@@ -28,6 +28,7 @@ struct Level {
   u128 rm03;
   unsigned long long rm45;
   int nrooms;
+  u128 rmx;  // roomgrid: object records 8..15 (ObstructedMaze creates up to 16 before its target ball, which is (e, f))
   // kinds with a step post-filter (mg_postfilter.cuh): what the filter compares against is packed into `ov`
   // (tx | ty << 8 | aux << 16, see level_target) and from there into the spare bits of the agent record
   // (x | y << 8 | tx << 16 | ty << 24, dir | flags << 8 | aux << 16). The struct itself is unchanged: MultiRoom keeps
@@ -241,6 +242,14 @@ MG_D uint32_t cell_memory(const Geom &g, const Level &L, int x, int y) {
 // in the horizontal walls (index j cols + i for the wall below room (i, j)); the objects are records in rm03 like
 // Playground's (x:5 y:5 kind:2 colour:3), nrooms = their number. KeyCorridor removes the walls between the rooms of
 // the middle column (keycorridor.py:107-109).
+// object record k (x:5 y:5 kind:2 colour:3; kind 0 key, 1 ball, 2 box, 3 grey box hiding a key of that colour)
+MG_D uint32_t rg_obj(const Level &L, int k) {
+  return k < 8 ? (uint32_t)(L.rm03 >> (15 * k)) & 0x7FFFu : (uint32_t)(L.rmx >> (15 * (k - 8))) & 0x7FFFu;
+}
+MG_D void rg_obj_append(Level &L, uint32_t o) {
+  if (L.nrooms < 8) L.rm03 |= (u128)o << (15 * L.nrooms); else L.rmx |= (u128)o << (15 * (L.nrooms - 8));
+  L.nrooms += 1;
+}
 MG_D uint32_t rg_vdoor(const Level &L, int idx) { return (uint32_t)(L.oh >> (8 * idx)) & 0xFFu; }
 MG_D uint32_t rg_hdoor(const Level &L, int idx) { return (uint32_t)(L.rm45 >> (8 * idx)) & 0xFFu; }
 MG_D uint32_t rg_door_code(uint32_t dsc) {
@@ -261,10 +270,15 @@ MG_D uint32_t cell_roomgrid(const Geom &g, const int *kp, const Level &L, int x,
     const uint32_t dsc = rg_hdoor(L, (j - 1) * cols + i);
     return ((dsc & 0x80u) && lx - 1 == (int)(dsc & 7u)) ? rg_door_code(dsc) : CODE_WALL;
   }
-  for (int k = 0; k < 4; ++k)
+  if (kp[0] >= RG_OBSTRUCTED_1D && x == L.e && y == L.f) return T_BALL | (C_BLUE << 4);  // self.obj: COLOR_NAMES[0]
+  // the objects in creation order; a later grid.set wins (ObstructedMaze v0 puts blocking balls over earlier keys)
+  for (int k = 15; k >= 0; --k)
     if (k < L.nrooms) {
-      const uint32_t o = play_obj(L, k);
-      if ((int)(o & 31u) == x && (int)((o >> 5) & 31u) == y) return (T_KEY + ((o >> 10) & 3u)) | (((o >> 12) & 7u) << 4);
+      const uint32_t o = rg_obj(L, k);
+      if ((int)(o & 31u) == x && (int)((o >> 5) & 31u) == y) {
+        const uint32_t kind = (o >> 10) & 3u, col = (o >> 12) & 7u;
+        return kind == 3u ? (T4_BOX_WITH_KEY | (col << 4)) : ((T_KEY + kind) | (col << 4));
+      }
     }
   return CODE_EMPTY;
 }
@@ -316,7 +330,7 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
   L.a = L.b = L.c = L.d = L.e = L.f = -1;
   L.rv = L.rh = 0;
   L.ov = L.oh = 0;
-  L.rm03 = 0; L.rm45 = 0; L.nrooms = 0;
+  L.rm03 = 0; L.rm45 = 0; L.nrooms = 0; L.rmx = 0;
   if (KIND == KIND_MULTIROOM) {
     // MultiRoomEnv._gen_grid / _placeRoom (multiroom.py:117-284). _placeRoom returns True as soon as ONE next room
     // has been placed (or after 8 failed tries), so the recursion is a chain without backtracking: room k+1 is
@@ -432,20 +446,24 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
       conn |= 1ull << (4 * (nj * cols + ni) + ((k + 2) & 3));
       return color;
     };
-    auto add_object = [&](int i, int j, int kind, int color) -> uint32_t {  // roomgrid.py:196-224 + place_in_room :179-194
-      if (kind < 0) kind = rng_integers(r, 0, 3);  // _rand_elem(["key", "ball", "box"])
-      if (color < 0) color = (int)color_name_idx(rng_integers(r, 0, 6));
-      for (;;) {  // place_obj(top, size, reject_fn=reject_next_to, max_tries=1000)
-        const int x = rng_integers(r, i * S1, min(i * S1 + S, W)), y = rng_integers(r, j * S1, min(j * S1 + S, H));
+    auto place_in_room = [&](int i, int j, int &x, int &y) {  // roomgrid.py:179-194: place_obj(top, size, reject_fn=reject_next_to, max_tries=1000)
+      for (;;) {
+        x = rng_integers(r, i * S1, min(i * S1 + S, W)); y = rng_integers(r, j * S1, min(j * S1 + S, H));
         if (cell_roomgrid(g, p.kp, L, x, y) != CODE_EMPTY) continue;
         if (x == L.ax && y == L.ay) continue;
         const int ddx = L.ax - x, ddy = L.ay - y;
         if ((ddx < 0 ? -ddx : ddx) + (ddy < 0 ? -ddy : ddy) < 2) continue;
-        const uint32_t o = (uint32_t)x | ((uint32_t)y << 5) | ((uint32_t)kind << 10) | ((uint32_t)color << 12);
-        L.rm03 |= (u128)o << (15 * L.nrooms);
-        L.nrooms += 1;
-        return o;
+        return;
       }
+    };
+    auto add_object = [&](int i, int j, int kind, int color) -> uint32_t {  // roomgrid.py:196-224
+      if (kind < 0) kind = rng_integers(r, 0, 3);  // _rand_elem(["key", "ball", "box"])
+      if (color < 0) color = (int)color_name_idx(rng_integers(r, 0, 6));
+      int x, y;
+      place_in_room(i, j, x, y);
+      const uint32_t o = (uint32_t)x | ((uint32_t)y << 5) | ((uint32_t)kind << 10) | ((uint32_t)color << 12);
+      rg_obj_append(L, o);
+      return o;
     };
     auto place_agent = [&](int i, int j) {  // roomgrid.py:313-335: until the front cell is None or a wall
       for (;;) {
@@ -461,7 +479,57 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
       }
     };
     int dpx = 0, dpy = 0;
-    if (variant == RG_KEYCORRIDOR) {
+    if (variant >= RG_OBSTRUCTED_1D) {
+      // ObstructedMazeEnv._gen_grid (obstructedmaze.py:112-126): door_colors = _rand_subset(COLOR_NAMES, 6), the ball to find
+      // is COLOR_NAMES[0] (blue), blocking balls COLOR_NAMES[1] (green), boxes COLOR_NAMES[2] (grey)
+      const int key_in_box = p.kp[4], blocked = p.kp[5];
+      uint32_t left = 0403512u, colors = 0;  // sorted names as 3-bit colour indices, see color_name_idx
+      for (int k = 0; k < 6; ++k) {
+        const int pick = rng_integers(r, 0, 6 - k);
+        colors |= ((left >> (3 * pick)) & 7u) << (3 * k);
+        left = (left & ((1u << (3 * pick)) - 1u)) | ((left >> (3 * (pick + 1))) << (3 * pick));
+      }
+      auto door_color = [&](int k) { return (int)((colors >> (3 * ((k + 6) % 6))) & 7u); };
+      auto add_locked_door = [&](int i, int j, int k, int color) {  // obstructedmaze_v1.py:77-85 / the door half of obstructedmaze.py:135-165
+        int x, y;
+        add_door(i, j, k, color, 1, x, y);
+        if (blocked) rg_obj_append(L, (uint32_t)(x - ((k == 0) - (k == 2))) | ((uint32_t)(y - ((k == 1) - (k == 3))) << 5) | (1u << 10) | ((uint32_t)C_GREEN << 12));
+      };
+      auto add_key = [&](int i, int j, int color) {  // obstructedmaze_v1.py:87-99 / the key half: a key, or a grey box hiding it
+        int x, y;
+        place_in_room(i, j, x, y);
+        rg_obj_append(L, (uint32_t)x | ((uint32_t)y << 5) | ((key_in_box ? 3u : 0u) << 10) | ((uint32_t)color << 12));
+      };
+      int bx, by;
+      if (variant == RG_OBSTRUCTED_1D) {  // obstructedmaze.py:188-203
+        add_locked_door(0, 0, 0, door_color(0));
+        add_key(0, 0, door_color(0));
+        place_in_room(1, 0, bx, by);
+        L.e = bx; L.f = by;
+        place_agent(0, 0);
+      } else {  // obstructedmaze.py:229-262, obstructedmaze_v1.py:37-75
+        const int nq = p.kp[7];
+        for (int i = 0; i < nq; ++i) {
+          const int si = i == 0 ? 2 : (i == 2 ? 0 : 1), sj = i == 1 ? 2 : (i == 3 ? 0 : 1);  // side_rooms = (2,1) (1,2) (0,1) (1,0)
+          int x, y;
+          add_door(1, 1, i, door_color(i), 0, x, y);
+          if (variant == RG_OBSTRUCTED_FULL) {
+            for (int k = -1; k <= 1; k += 2) {
+              add_locked_door(si, sj, (i + k + 4) % 4, door_color(i + k));
+              add_key(si, sj, door_color(i + k));
+            }
+          } else {
+            for (int k = -1; k <= 1; k += 2) add_locked_door(si, sj, (i + k + 4) % 4, door_color(i + k));
+            for (int k = -1; k <= 1; k += 2) add_key(si, sj, door_color(i + k));
+          }
+        }
+        const int corner = rng_integers(r, 0, nq);  // corners = (2,0) (2,2) (0,2) (0,0)
+        place_in_room(corner < 2 ? 2 : 0, (corner == 1 || corner == 2) ? 2 : 0, bx, by);
+        L.e = bx; L.f = by;
+        place_agent(p.kp[6] & 15, p.kp[6] >> 4);
+      }
+      level_target(L, (int)T_BALL, (int)C_BLUE, 0u);
+    } else if (variant == RG_KEYCORRIDOR) {
       for (int j = 1; j < rows; ++j) {  // remove_wall(1, j, 3): the cells are handled by cell_roomgrid, the rooms become connected
         conn |= 1ull << (4 * (j * cols + 1) + 3);
         conn |= 1ull << (4 * ((j - 1) * cols + 1) + 1);
@@ -502,8 +570,7 @@ MG_D void draw_level(const Params &p, Pcg &r, Level &L) {
       const int door_color = add_door(0, 0, 0, -1, 1, dpx, dpy);
       if (variant == RG_BLOCKEDUNLOCKPICKUP) {  // a ball of a random colour in front of the door (grid.set, no placement draws)
         const uint32_t col = color_name_idx(rng_integers(r, 0, 6));
-        L.rm03 |= (u128)((uint32_t)(dpx - 1) | ((uint32_t)dpy << 5) | (1u << 10) | (col << 12)) << (15 * L.nrooms);
-        L.nrooms += 1;
+        rg_obj_append(L, (uint32_t)(dpx - 1) | ((uint32_t)dpy << 5) | (1u << 10) | (col << 12));
       }
       add_object(0, 0, 0, door_color);
       place_agent(0, 0);
@@ -838,7 +905,7 @@ MG_D Level blank_level() {
   L.a = L.b = L.c = L.d = L.e = L.f = -1;
   L.rv = L.rh = 0;
   L.ov = L.oh = 0;
-  L.rm03 = 0; L.rm45 = 0; L.nrooms = 0;
+  L.rm03 = 0; L.rm45 = 0; L.nrooms = 0; L.rmx = 0;
   return L;
 }
 // calls put(x, y) for this lane's share of the cells that may differ from the template

@@ -82,7 +82,9 @@ __global__ void k_get_agent(Params p, int32_t *__restrict__ agent, uint64_t *__r
   if (agent) {
     int32_t *a = agent + (size_t)env * 6;
     a[0] = rec.x & 0xFF; a[1] = (rec.x >> 8) & 0xFF; a[2] = rec.y & 3;
-    a[3] = rec.z ? (int32_t)(rec.z & 15u) : -1; a[4] = rec.z ? (int32_t)((rec.z >> 4) & 7u) : 0; a[5] = (int32_t)rec.w;
+    const bool boxed = (rec.z & 15u) == T4_BOX_WITH_KEY;  // carrying.encode(): a grey box, whatever is inside
+    a[3] = rec.z ? (boxed ? (int32_t)T_BOX : (int32_t)(rec.z & 15u)) : -1;
+    a[4] = rec.z ? (boxed ? (int32_t)C_GREY : (int32_t)((rec.z >> 4) & 7u)) : 0; a[5] = (int32_t)rec.w;
   }
   if (rng) {
     const RngRec r = p.rng[env];

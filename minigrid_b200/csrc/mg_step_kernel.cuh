@@ -202,6 +202,11 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
       B.rm45 = __shfl_sync(0xFFFFFFFFu, L.rm45, src);
       B.nrooms = __shfl_sync(0xFFFFFFFFu, L.nrooms, src);
     } else { B.rm03 = 0; B.rm45 = 0; B.nrooms = 0; }
+    if (KIND == KIND_ROOMGRID) {
+      const unsigned long long lo = __shfl_sync(0xFFFFFFFFu, (unsigned long long)L.rmx, src);
+      const unsigned long long hi = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(L.rmx >> 64), src);
+      B.rmx = ((u128)hi << 64) | lo;
+    } else B.rmx = 0;
     // (the template words were written by the idle lanes during the draws, ordered before this point by __syncwarp)
     patch_level<KIND>(p, B, lane, [&](int x, int y) {
       const uint8_t code = (uint8_t)cell_of<KIND>(p, B, x, y);

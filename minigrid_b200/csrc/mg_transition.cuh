@@ -35,7 +35,7 @@ MG_HD StepOut transition(int action, uint32_t fc, int fx, int fy, int &ax, int &
   o.goal = (isF && t4 == T_GOAL) ? 1u : 0u;
   o.terminated = (isF && (t4 == T_GOAL || t4 == T_LAVA)) ? 1u : 0u;
   // pickup: can_pickup = Key, Ball, Box, and nothing carried                               :561-566
-  const bool pick = isP && t4 >= T_KEY && t4 <= T_BOX && carry == 0;
+  const bool pick = isP && ((t4 >= T_KEY && t4 <= T_BOX) || t4 == T4_BOX_WITH_KEY) && carry == 0;
   // drop: front cell is None and something is carried                                      :569-573
   const bool drop = isD && t4 == T_EMPTY && carry != 0;
   // toggle: Door.toggle (world_object.py:184-194), Box.toggle with contains == None (:290-293)   :576-578
@@ -48,6 +48,7 @@ MG_HD StepOut transition(int action, uint32_t fc, int fx, int fy, int &ax, int &
   newc = drop ? carry : newc;
   newc = opens ? (T_DOOR | (col << 4)) : newc;
   newc = closes ? (T4_DOOR_CLOSED | (col << 4) | OPAQUE_BIT) : newc;
+  newc = (isT && t4 == T4_BOX_WITH_KEY) ? (T_KEY | (col << 4)) : newc;  // Box.toggle: the box is replaced by its contents
   carry = pick ? (fc & 0x7Fu) : (drop ? 0u : carry);
   o.newc = newc;
   o.bad_action = ((unsigned)action > (unsigned)A_DONE) ? 1u : 0u;  // ValueError, :584-585

@@ -110,7 +110,7 @@ __global__ void k_symbolic(Params p, long long *__restrict__ out) {
   const int x = c / p.g.H, y = c % p.g.H;
   const uint32_t code = reinterpret_cast<const uint8_t *>(p.grid)[cell_byte_C(p.g, env, x, y)];
   const uint32_t t4 = code & 15u;
-  long long type = t4 <= T_EMPTY ? -1 : (t4 >= T4_DOOR_CLOSED ? (long long)T_DOOR : (long long)t4);
+  long long type = t4 <= T_EMPTY ? -1 : (t4 == T4_BOX_WITH_KEY ? (long long)T_BOX : (t4 >= T4_DOOR_CLOSED ? (long long)T_DOOR : (long long)t4));
   const uint4 rec = p.agent[env];
   if ((int)(rec.x & 0xFF) == x && (int)((rec.x >> 8) & 0xFF) == y) type = T_AGENT;
   long long *o = out + gid * 3;

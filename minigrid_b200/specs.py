@@ -126,10 +126,16 @@ def dynobstacles(size=8, agent_start_pos=(1, 1), agent_start_dir=0, n_obstacles=
                    (n_obst, int(random_start), sx, sy, agent_start_dir), "get to the green goal square")
 
 
-def roomgrid(variant, room_size, num_rows, num_cols, max_steps, mission):
+def roomgrid(variant, room_size, num_rows, num_cols, max_steps, mission, extra=()):
     """core/roomgrid.py:66-100: width = (room_size - 1) * num_cols + 1, height likewise; see_through_walls=False."""
     return EnvSpec(KIND_ROOMGRID, (room_size - 1) * num_cols + 1, (room_size - 1) * num_rows + 1, max_steps, False,
-                   (variant, room_size, num_rows, num_cols), mission)
+                   (variant, room_size, num_rows, num_cols) + tuple(extra), mission)
+
+
+def obstructedmaze(variant, num_rows, num_cols, num_rooms_visited, key_in_box, blocked, agent_room=(0, 0), num_quarters=0):
+    """envs/obstructedmaze.py:79-105 (room_size 6, max_steps = 4 * num_rooms_visited * room_size^2), obstructedmaze_v1.py."""
+    return roomgrid(variant, 6, num_rows, num_cols, 4 * num_rooms_visited * 36, "pick up the blue ball",
+                    (int(key_in_box), int(blocked), agent_room[0] | (agent_room[1] << 4), num_quarters))
 
 
 def keycorridor(room_size=6, num_rows=3, max_steps=None):
@@ -209,6 +215,20 @@ REGISTRY = {
     "MiniGrid-KeyCorridorS4R3-v0": keycorridor(4, 3),
     "MiniGrid-KeyCorridorS5R3-v0": keycorridor(5, 3),
     "MiniGrid-KeyCorridorS6R3-v0": keycorridor(6, 3),
+    # ObstructedMaze: __init__.py:387-514 (boxes hide keys: Box.contains)
+    "MiniGrid-ObstructedMaze-1Dl-v0": obstructedmaze(4, 1, 2, 2, False, False),
+    "MiniGrid-ObstructedMaze-1Dlh-v0": obstructedmaze(4, 1, 2, 2, True, False),
+    "MiniGrid-ObstructedMaze-1Dlhb-v0": obstructedmaze(4, 1, 2, 2, True, True),
+    "MiniGrid-ObstructedMaze-2Dl-v0": obstructedmaze(5, 3, 3, 4, False, False, (2, 1), 1),
+    "MiniGrid-ObstructedMaze-2Dlh-v0": obstructedmaze(5, 3, 3, 4, True, False, (2, 1), 1),
+    "MiniGrid-ObstructedMaze-2Dlhb-v0": obstructedmaze(5, 3, 3, 4, True, True, (2, 1), 1),
+    "MiniGrid-ObstructedMaze-1Q-v0": obstructedmaze(5, 3, 3, 5, True, True, (1, 1), 1),
+    "MiniGrid-ObstructedMaze-2Q-v0": obstructedmaze(5, 3, 3, 11, True, True, (2, 1), 2),
+    "MiniGrid-ObstructedMaze-Full-v0": obstructedmaze(5, 3, 3, 25, True, True, (1, 1), 4),
+    "MiniGrid-ObstructedMaze-2Dlhb-v1": obstructedmaze(6, 3, 3, 4, True, True, (2, 1), 1),
+    "MiniGrid-ObstructedMaze-1Q-v1": obstructedmaze(6, 3, 3, 5, True, True, (1, 1), 1),
+    "MiniGrid-ObstructedMaze-2Q-v1": obstructedmaze(6, 3, 3, 11, True, True, (2, 1), 2),
+    "MiniGrid-ObstructedMaze-Full-v1": obstructedmaze(6, 3, 3, 25, True, True, (1, 1), 4),
 }
 
 

@@ -61,6 +61,11 @@ ROLLOUTS = {  # id -> (N, T, seed)
     "MiniGrid-KeyCorridorS3R2-v0": (6, 560, 109),
     "MiniGrid-KeyCorridorS4R3-v0": (4, 500, 113),
     "MiniGrid-KeyCorridorS6R3-v0": (4, 300, 127),
+    "MiniGrid-ObstructedMaze-1Dlhb-v0": (6, 600, 131),
+    "MiniGrid-ObstructedMaze-2Dlh-v0": (4, 600, 137),
+    "MiniGrid-ObstructedMaze-2Q-v0": (4, 400, 139),
+    "MiniGrid-ObstructedMaze-Full-v0": (4, 300, 149),
+    "MiniGrid-ObstructedMaze-Full-v1": (4, 300, 151),
 }
 NEXT_ROLLOUTS = {  # SURVEY 8(f-1) generators whose device kernels do not exist yet: next_rollout_<id>.npz (oracle only)
 }

@@ -36,8 +36,9 @@ static const int DIR_Y[4] = {0, 1, 0, -1};
 
 /* A grid slot: the reference stores WorldObj|None (grid.py:35). `None` is type T_EMPTY here, which is
  * also what Grid.encode emits for None (grid.py:258-261); an object is (type, colour, door state).
- * Box.contains is always None in the four generators, so it is not modelled. */
-typedef struct { uint8_t type, color, state; } cell_t;
+ * Box.contains (world_object.py:273-293) is None everywhere except ObstructedMaze, whose boxes hide a key:
+ * inner = 1 + the colour of the contained Key, 0 = nothing inside. It is not part of encode(). */
+typedef struct { uint8_t type, color, state, inner; } cell_t;
 static const cell_t CELL_NONE = {T_EMPTY, 0, 0};
 
 static int cell_is_none(cell_t c) { return c.type == T_EMPTY; }
@@ -669,7 +670,11 @@ static void gen_dynobstacles(const mgo_vec *v, env_t *e) {
 /* ---- core/roomgrid.py: RoomGrid and the envs built on it (second half) ----
  * params: {variant, room_size, num_rows, num_cols}; variant 0 Unlock (envs/unlock.py), 1 UnlockPickup
  * (unlockpickup.py), 2 BlockedUnlockPickup (blockedunlockpickup.py), 3 KeyCorridor (keycorridor.py, obj_type "ball") */
-enum { RG_UNLOCK = 0, RG_UNLOCKPICKUP = 1, RG_BLOCKEDUNLOCKPICKUP = 2, RG_KEYCORRIDOR = 3 };
+enum { RG_UNLOCK = 0, RG_UNLOCKPICKUP = 1, RG_BLOCKEDUNLOCKPICKUP = 2, RG_KEYCORRIDOR = 3,
+       /* envs/obstructedmaze.py, obstructedmaze_v1.py: params {variant, room_size, num_rows, num_cols, key_in_box, blocked,
+        * agent_room_i | agent_room_j << 4, num_quarters (Full only)} */
+       RG_OBSTRUCTED_1D = 4 /* ObstructedMaze_1Dlhb */, RG_OBSTRUCTED_FULL = 5 /* ObstructedMaze_Full */,
+       RG_OBSTRUCTED_FULL_V1 = 6 /* ObstructedMaze_Full_V1 */ };
 typedef struct {
   int top_x, top_y;          /* Room.top; Room.size = (room_size, room_size) */
   int door_x[4], door_y[4];  /* Room.door_pos, order right, down, left, up; -1 = None */
@@ -805,10 +810,65 @@ static void rg_connect_all(env_t *e, rg_t *g) {
     rg_add_door(e, g, i, j, k, color, 0, NULL, NULL);
   }
 }
+/* ObstructedMazeEnv (obstructedmaze.py:112-176): colours fixed by COLOR_NAMES' order, door colours a random permutation */
+static const int OM_BALL_TO_FIND = C_BLUE, OM_BLOCKING_BALL = C_GREEN, OM_BOX = C_GREY; /* COLOR_NAMES[0], [1], [2] */
+static void om_add_locked_door(env_t *e, rg_t *g, int i, int j, int door_idx, int color, int blocked) { /* v1 :77-85; also the door half of v0's add_door */
+  int dx, dy;
+  rg_add_door(e, g, i, j, door_idx, color, 1, &dx, &dy);
+  if (blocked) { /* grid.set: whatever was there is overwritten */
+    cell_t ball = {T_BALL, (uint8_t)OM_BLOCKING_BALL, 0, 0};
+    grid_set(&e->grid, dx - DIR_X[door_idx], dy - DIR_Y[door_idx], ball);
+  }
+}
+static void om_add_key(env_t *e, const rg_t *g, int i, int j, int color, int key_in_box) { /* v1 :87-99; the key half of v0's add_door */
+  cell_t obj = {T_KEY, (uint8_t)color, 0, 0};
+  if (key_in_box) { obj.type = T_BOX; obj.color = (uint8_t)OM_BOX; obj.inner = (uint8_t)(color + 1); }
+  rg_place_in_room(e, g, i, j, obj, NULL, NULL);
+}
+static void gen_obstructedmaze(const mgo_vec *v, env_t *e, rg_t *g) {
+  const int variant = v->params[0], key_in_box = v->params[4], blocked = v->params[5];
+  /* door_colors = _rand_subset(COLOR_NAMES, 6): _rand_elem on the shrinking list (minigrid_env.py:277-292) */
+  int left[6], colors[6], nleft = 6;
+  for (int c = 0; c < 6; c++) left[c] = COLOR_NAMES_IDX[c];
+  for (int k = 0; k < 6; k++) {
+    const int pick = (int)rand_int(e, 0, nleft);
+    colors[k] = left[pick];
+    for (int c = pick; c < nleft - 1; c++) left[c] = left[c + 1];
+    nleft--;
+  }
+  cell_t obj;
+  if (variant == RG_OBSTRUCTED_1D) { /* obstructedmaze.py:188-203 */
+    om_add_locked_door(e, g, 0, 0, 0, colors[0], blocked);
+    om_add_key(e, g, 0, 0, colors[0], key_in_box);
+    obj = rg_add_object(e, g, 1, 0, T_BALL, OM_BALL_TO_FIND, NULL, NULL);
+    rg_place_agent(e, g, 0, 0);
+  } else { /* obstructedmaze.py:229-262, obstructedmaze_v1.py:37-75 */
+    static const int SIDE[4][2] = {{2, 1}, {1, 2}, {0, 1}, {1, 0}}, CORNER[4][2] = {{2, 0}, {2, 2}, {0, 2}, {0, 0}};
+    const int nq = v->params[7];
+    for (int i = 0; i < nq; i++) {
+      rg_add_door(e, g, 1, 1, i, colors[i], 0, NULL, NULL);
+      if (variant == RG_OBSTRUCTED_FULL) {
+        for (int k = -1; k <= 1; k += 2) {
+          om_add_locked_door(e, g, SIDE[i][0], SIDE[i][1], (i + k + 4) % 4, colors[(i + k + 6) % 6], blocked);
+          om_add_key(e, g, SIDE[i][0], SIDE[i][1], colors[(i + k + 6) % 6], key_in_box);
+        }
+      } else {
+        for (int k = -1; k <= 1; k += 2) om_add_locked_door(e, g, SIDE[i][0], SIDE[i][1], (i + k + 4) % 4, colors[(i + k + 6) % 6], blocked);
+        for (int k = -1; k <= 1; k += 2) om_add_key(e, g, SIDE[i][0], SIDE[i][1], colors[(i + k + 6) % 6], key_in_box);
+      }
+    }
+    const int corner = (int)rand_int(e, 0, nq);
+    obj = rg_add_object(e, g, CORNER[corner][0], CORNER[corner][1], T_BALL, OM_BALL_TO_FIND, NULL, NULL);
+    rg_place_agent(e, g, v->params[6] & 15, v->params[6] >> 4);
+  }
+  e->target_x = obj.type; e->target_y = obj.color;
+}
+
 static void gen_roomgrid(const mgo_vec *v, env_t *e) {
   rg_t g;
   rg_gen_base(v, e, &g);
   const int variant = v->params[0];
+  if (variant >= RG_OBSTRUCTED_1D) { gen_obstructedmaze(v, e, &g); return; }
   if (variant == RG_KEYCORRIDOR) { /* keycorridor.py:104-128 */
     for (int j = 1; j < g.rows; j++) rg_remove_wall(e, &g, 1, j, 3);
     const int room_idx = (int)rand_int(e, 0, g.rows);
@@ -1106,8 +1166,10 @@ static int env_step(const mgo_vec *v, env_t *e, int action, double *reward, uint
           if (fwd.state == S_LOCKED) {
             if (e->carrying && e->carry.type == T_KEY && e->carry.color == fwd.color) { fwd.state = S_OPEN; grid_set(&e->grid, fx, fy, fwd); }
           } else { fwd.state = (fwd.state == S_OPEN) ? S_CLOSED : S_OPEN; grid_set(&e->grid, fx, fy, fwd); }
-        } else if (fwd.type == T_BOX) { /* Box.toggle :290-293, contains == None */
-          grid_set(&e->grid, fx, fy, CELL_NONE);
+        } else if (fwd.type == T_BOX) { /* Box.toggle :290-293: the box is replaced by its contents (None, or the hidden key) */
+          cell_t inside = CELL_NONE;
+          if (fwd.inner) { inside.type = T_KEY; inside.color = (uint8_t)(fwd.inner - 1); inside.state = 0; inside.inner = 0; }
+          grid_set(&e->grid, fx, fy, inside);
         }
       }
       break;

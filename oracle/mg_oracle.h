@@ -45,7 +45,9 @@ typedef struct mgo_vec mgo_vec;
  *         LAVAGAP {obstacle_type}; DISTSHIFT {strip2_row, start_x, start_y, start_dir}
  *         MULTIROOM {minNumRooms, maxNumRooms, maxRoomSize}; LOCKEDROOM {}; PLAYGROUND {}; GOTODOOR {}; FETCH {numObjs}; REDBLUEDOORS {}; GOTOOBJECT {numObjs}; PUTNEAR {numObjs};
  *         MEMORY {random_length}; DYNOBSTACLES {n_obstacles, random_start, start_x, start_y, start_dir};
- *         ROOMGRID {variant (0 Unlock, 1 UnlockPickup, 2 BlockedUnlockPickup, 3 KeyCorridor), room_size, num_rows, num_cols} */
+ *         ROOMGRID {variant (0 Unlock, 1 UnlockPickup, 2 BlockedUnlockPickup, 3 KeyCorridor, 4 ObstructedMaze_1Dlhb,
+ *         5 ObstructedMaze_Full, 6 ObstructedMaze_Full_V1), room_size, num_rows, num_cols[, key_in_box, blocked,
+ *         agent_room_i | agent_room_j << 4, num_quarters]} */
 mgo_vec *mgo_vec_create(int kind, int width, int height, int max_steps, int see_through_walls,
                         const int32_t *params, int n_params, int n_envs);
 void mgo_vec_destroy(mgo_vec *v);

@@ -19,6 +19,12 @@ KIND = {"empty": 0, "doorkey": 1, "crossing": 2, "fourrooms": 3, "lavagap": 4, "
         "memory": 14, "dynobstacles": 15, "roomgrid": 16}
 AUTORESET = {"next_step": 0, "same_step": 1, "disabled": 2}
 
+def _om(variant, rows, cols, visited, key_in_box, blocked, agent_room=(0, 0), quarters=0):
+    """envs/obstructedmaze.py:79-105: room_size 6, max_steps = 4 * num_rooms_visited * 36"""
+    return ("roomgrid", 5 * cols + 1, 5 * rows + 1, 4 * visited * 36, False,
+            [variant, 6, rows, cols, int(key_in_box), int(blocked), agent_room[0] | (agent_room[1] << 4), quarters])
+
+
 # id -> (kind, width, height, max_steps, see_through_walls, params); restated from
 # /root/reference/minigrid/__init__.py:25-28,106-109,159-162,183-185,214-216 and the env
 # constructors (empty.py:69-90, doorkey.py:62-68, crossing.py:89-116, fourrooms.py:55-67).
@@ -80,11 +86,25 @@ ENV_SPECS = {
     "MiniGrid-KeyCorridorS4R3-v0": ("roomgrid", 10, 10, 480, False, [3, 4, 3, 3]),
     "MiniGrid-KeyCorridorS5R3-v0": ("roomgrid", 13, 13, 750, False, [3, 5, 3, 3]),
     "MiniGrid-KeyCorridorS6R3-v0": ("roomgrid", 16, 16, 1080, False, [3, 6, 3, 3]),
+    "MiniGrid-ObstructedMaze-1Dl-v0": _om(4, 1, 2, 2, False, False),
+    "MiniGrid-ObstructedMaze-1Dlh-v0": _om(4, 1, 2, 2, True, False),
+    "MiniGrid-ObstructedMaze-1Dlhb-v0": _om(4, 1, 2, 2, True, True),
+    "MiniGrid-ObstructedMaze-2Dl-v0": _om(5, 3, 3, 4, False, False, (2, 1), 1),
+    "MiniGrid-ObstructedMaze-2Dlh-v0": _om(5, 3, 3, 4, True, False, (2, 1), 1),
+    "MiniGrid-ObstructedMaze-2Dlhb-v0": _om(5, 3, 3, 4, True, True, (2, 1), 1),
+    "MiniGrid-ObstructedMaze-1Q-v0": _om(5, 3, 3, 5, True, True, (1, 1), 1),
+    "MiniGrid-ObstructedMaze-2Q-v0": _om(5, 3, 3, 11, True, True, (2, 1), 2),
+    "MiniGrid-ObstructedMaze-Full-v0": _om(5, 3, 3, 25, True, True, (1, 1), 4),
+    "MiniGrid-ObstructedMaze-2Dlhb-v1": _om(6, 3, 3, 4, True, True, (2, 1), 1),
+    "MiniGrid-ObstructedMaze-1Q-v1": _om(6, 3, 3, 5, True, True, (1, 1), 1),
+    "MiniGrid-ObstructedMaze-2Q-v1": _om(6, 3, 3, 11, True, True, (2, 1), 2),
+    "MiniGrid-ObstructedMaze-Full-v1": _om(6, 3, 3, 25, True, True, (1, 1), 4),
 }
 
 # SURVEY 8(f-1) generators restated ahead of their device kernels: the oracle and its fixtures exist, the product does
 # not register these ids yet (lockedroom.py:74-90 / __init__.py:312-318, playground.py:16-25 / __init__.py:516-522)
 NEXT_SPECS = {
+    # envs/obstructedmaze.py + obstructedmaze_v1.py, __init__.py:387-514
     # SURVEY 8(f-2), second half: core/roomgrid.py + unlock.py:55-70 (2 rooms of 6, 8 * 36 steps), unlockpickup.py:60-78,
     # blockedunlockpickup.py:67-85 (16 * 36), keycorridor.py:73-97 (3 columns, 30 * room_size^2); __init__.py:12-20, 252-290, 555-563
     # params {variant, room_size, num_rows, num_cols}

@@ -23,6 +23,8 @@ def decode_code(code):
         return None
     if colour > 5 or t4 == 10 or t4 > 12:
         return "invalid"
+    if t4 == 13:
+        return 7, 5, 0  # a grey box with a key inside (ObstructedMaze): rendered like any grey box
     if t4 == 11:
         return 4, colour, 1
     if t4 == 12:

@@ -505,7 +505,9 @@ void emu_get_state(void *h, int32_t *agent, uint64_t *rng, uint8_t *pending) {  
     const uint4 rec = e->agent[env];
     int32_t *a = agent + (size_t)env * 6;
     a[0] = rec.x & 0xFF; a[1] = (rec.x >> 8) & 0xFF; a[2] = rec.y & 3;
-    a[3] = rec.z ? (int32_t)(rec.z & 15u) : -1; a[4] = rec.z ? (int32_t)((rec.z >> 4) & 7u) : 0; a[5] = (int32_t)rec.w;
+    const bool boxed = (rec.z & 15u) == T4_BOX_WITH_KEY;  // k_get_agent: a grey box, whatever is inside
+    a[3] = rec.z ? (boxed ? (int32_t)T_BOX : (int32_t)(rec.z & 15u)) : -1;
+    a[4] = rec.z ? (boxed ? (int32_t)C_GREY : (int32_t)((rec.z >> 4) & 7u)) : 0; a[5] = (int32_t)rec.w;
     const RngRec r = e->rng[env];
     uint64_t *o = rng + (size_t)env * 6;
     o[0] = r.state_hi; o[1] = r.state_lo; o[2] = r.inc_hi; o[3] = r.inc_lo; o[4] = r.has_uint32; o[5] = r.uinteger;

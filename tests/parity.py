@@ -92,3 +92,24 @@ def roomgrid_inject_targets(orc):
                 agent[i, 3:5] = (5, grid[i, tx, ty, 1]) if unlock else (-1, 0)
                 break
     return agent, (5 if unlock else 3)
+
+
+def face_first_cell_of_type(orc, want_type):
+    """Agent records that put every agent next to (and facing) the first cell of the given type of its env, from the
+    oracle's state; envs without such a cell or without a free neighbour keep their record."""
+    st = orc.get_state()
+    grid, agent = st["grid"], st["agent"].copy()
+    moved = np.zeros(orc.num_envs, bool)
+    for i in range(orc.num_envs):
+        xs, ys = np.nonzero(grid[i, :, :, 0] == want_type)
+        if len(xs) == 0:
+            continue
+        tx, ty = int(xs[0]), int(ys[0])
+        for d, (dx, dy) in enumerate([(1, 0), (0, 1), (-1, 0), (0, -1)]):
+            ax, ay = tx - dx, ty - dy
+            if 0 < ax < orc.width - 1 and 0 < ay < orc.height - 1 and grid[i, ax, ay, 0] == 1:
+                agent[i, :3] = (ax, ay, d)
+                agent[i, 3:5] = (-1, 0)
+                moved[i] = True
+                break
+    return agent, moved

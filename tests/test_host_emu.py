@@ -57,7 +57,8 @@ def test_emu_fixture_in_both_layouts(path, layout):
     ("MiniGrid-FourRooms-v0", 1, False, "next_step"), ("MiniGrid-FourRooms-v0", 0, True, "same_step"),
     ("MiniGrid-Empty-5x5-v0", 0, False, "same_step"), ("MiniGrid-Empty-5x5-v0", 1, True, "next_step"),
     ("MiniGrid-Fetch-8x8-N3-v0", 0, False, "next_step"), ("MiniGrid-GoToDoor-5x5-v0", 1, False, "same_step"),
-    ("MiniGrid-Dynamic-Obstacles-6x6-v0", 0, False, "same_step"), ("MiniGrid-Dynamic-Obstacles-6x6-v0", 0, True, "next_step")])
+    ("MiniGrid-Dynamic-Obstacles-6x6-v0", 0, False, "same_step"), ("MiniGrid-Dynamic-Obstacles-6x6-v0", 0, True, "next_step"),
+    ("MiniGrid-ObstructedMaze-1Dlh-v0", 0, False, "next_step"), ("MiniGrid-ObstructedMaze-1Dlh-v0", 1, True, "next_step")])  # cell code 13
 def test_packed_host_format_expands_to_the_same_arrays(env_id, layout, scalar, mode, monkeypatch):
     """MG_HOST_PACKED: K1's 52-byte records (pack_codes, device header) + the product's host expander == the oracle's
     obs / dir / reward / flags, bit for bit, with both expander code paths."""
@@ -121,3 +122,29 @@ def test_emu_roomgrid_post_filters(env_id, layout, mode):
     es, os_ = emu.get_state(), orc.get_state()
     for k in ("grid", "agent", "rng", "pending"):
         np.testing.assert_array_equal(es[k], os_[k], err_msg=k)
+
+
+@pytest.mark.parametrize("layout", [0, 1], ids=["tiled", "window"])
+@pytest.mark.parametrize("env_id", ["MiniGrid-ObstructedMaze-1Dlh-v0", "MiniGrid-ObstructedMaze-Full-v1"])
+def test_emu_boxes_hide_keys(env_id, layout):
+    """Box.contains (world_object.py:273-293): toggling a box of ObstructedMaze leaves its key; a box that is picked up
+    and dropped again keeps it. Device headers (cell code 13) against the oracle."""
+    n = 24
+    emu = make_emu(env_id, n, "next_step", layout)
+    orc = OracleVecEnv(env_id, n)
+    parity.check_lockstep_vs_oracle(emu, orc, 5, seed=11)
+    agent, moved = parity.face_first_cell_of_type(orc, 7)
+    assert moved.sum() >= n // 2
+    emu.set_state(agent=agent)
+    orc.set_state(agent=agent)
+    half = np.arange(n) % 2 == 0
+    # even envs: toggle (box -> key), pickup (the key); odd envs: pickup (the box), turn, drop, toggle, pickup
+    script = [np.where(half, 5, 3), np.where(half, 3, 0), np.where(half, 6, 4), np.where(half, 6, 5), np.where(half, 4, 3), np.full(n, 2)]
+    for a in script:
+        e, o = emu.step(a), orc.step(a)
+        for x, y, name in zip(e, o, ["obs", "dir", "reward", "terminated", "truncated"]):
+            np.testing.assert_array_equal(np.asarray(x).astype(np.asarray(y).dtype), y, err_msg=name)
+    es, os_ = emu.get_state(), orc.get_state()
+    for k in ("grid", "agent", "rng", "pending"):
+        np.testing.assert_array_equal(es[k], os_[k], err_msg=k)
+    assert (os_["agent"][moved, 3] == 5).sum() >= moved.sum() // 4  # keys did come out of boxes

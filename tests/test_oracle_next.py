@@ -150,3 +150,29 @@ def test_roomgrid_post_filters_fire_against_live_reference(env_id):
     rs, os_ = ref.get_state(), orc.get_state()
     for k in rs:
         np.testing.assert_array_equal(rs[k], os_[k], err_msg=k)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+@pytest.mark.parametrize("env_id", ["MiniGrid-ObstructedMaze-1Dlh-v0", "MiniGrid-ObstructedMaze-Full-v1"])
+def test_boxes_hide_keys_against_live_reference(env_id):
+    """Box.contains / Box.toggle (world_object.py:273-293) in the oracle: agents put in front of a box in the reference's
+    env objects and in the oracle, then toggle / pick up / drop scripts."""
+    n = 24
+    ref = ref_loader.ReferenceVecEnv(env_id, n)
+    orc = OracleVecEnv(env_id, n)
+    np.testing.assert_array_equal(ref.reset(seed=11)[0], orc.reset(seed=11)[0])
+    agent, moved = parity.face_first_cell_of_type(orc, 7)
+    assert moved.sum() >= n // 2
+    for i, e in enumerate(ref.envs):
+        e.agent_pos, e.agent_dir, e.carrying = (int(agent[i, 0]), int(agent[i, 1])), int(agent[i, 2]), None
+    orc.set_state(agent=agent)
+    half = np.arange(n) % 2 == 0
+    script = [np.where(half, 5, 3), np.where(half, 3, 0), np.where(half, 6, 4), np.where(half, 6, 5), np.where(half, 4, 3), np.full(n, 2)]
+    for a in script:
+        r, q = ref.step(a), orc.step(a)
+        for x, y, name in zip(r, q, ["obs", "dir", "reward", "terminated", "truncated"]):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=name)
+    rs, os_ = ref.get_state(), orc.get_state()
+    for k in rs:
+        np.testing.assert_array_equal(rs[k], os_[k], err_msg=k)
+    assert (os_["agent"][moved, 3] == 5).sum() >= moved.sum() // 4
