@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -15,7 +16,8 @@
 
 namespace mg {
 cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
-                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, uint32_t *packed, cudaStream_t stream);
+                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, uint32_t *packed, int step_parity,
+                        cudaStream_t stream);
 cudaError_t configure_step(const Params &p, StepPlan *plan);
 cudaError_t launch_reset(const Params &p, const uint8_t *mask, uint8_t *obs, int32_t *dir, cudaStream_t stream);
 cudaError_t launch_seed(const Params &p, const uint8_t *mask, const uint64_t *seeds_dev, uint64_t base, cudaStream_t stream);
@@ -57,7 +59,7 @@ struct mg_env {
   int host_format;
   uint32_t *d_packed; uint8_t *h_packed;   // device records, pinned landing buffer
   double *h_reward_lut;                    // host copy of the reward table
-  HostPool *pool;
+  int pool_threads;                        // what this handle asked for (the pool itself is process-wide)
   cudaEvent_t chunk_ev[16];
   int n_chunks;
   // MINIGRID_B200_HOST_TRACE=1: where a packed host step spends its time (printed by mg_destroy)
@@ -68,6 +70,12 @@ struct mg_env {
 };
 
 static thread_local std::string g_err;
+
+// The host threads that expand packed step records are ONE pool per process, shared by every handle: a training process
+// that cycles through several handles (bench.py rotates four) must not keep four sets of workers spinning. A step takes
+// the pool for its duration; handles driven from different host threads serialise on it.
+static std::mutex g_pool_mu;       // guards g_pool and serialises its use
+static HostPool *g_pool = nullptr;
 const char *mg_last_error(void) { return g_err.c_str(); }
 
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -269,7 +277,7 @@ int mg_destroy(mg_env *h) {
     fprintf(stderr, "[minigrid_b200] packed host step, mean of %lld (us since entry): enqueued %.1f, first chunk on the host %.1f, last chunk %.1f, "
                     "expansion done %.1f, return %.1f; %d chunks, %d threads\n", (long long)h->tr_n, h->tr_enqueue / h->tr_n,
             h->tr_first_chunk / h->tr_n, h->tr_last_chunk / h->tr_n, h->tr_pool / h->tr_n, h->tr_total / h->tr_n, h->n_chunks,
-            h->pool ? h->pool->threads() : 0);
+            h->pool_threads);
   DeviceGuard guard(h->device);
   if (h->hstream) { cudaStreamSynchronize(h->hstream); cudaStreamDestroy(h->hstream); }
   if (h->ev_order) cudaEventDestroy(h->ev_order);
@@ -283,7 +291,6 @@ int mg_destroy(mg_env *h) {
   cudaFree(h->d_packed);
   cudaFreeHost(h->h_packed);
   free(h->h_reward_lut);
-  delete h->pool;
   for (int c = 0; c < 16; ++c)
     if (h->chunk_ev[c]) cudaEventDestroy(h->chunk_ev[c]);
   if (h->prof_events) {
@@ -376,7 +383,7 @@ int mg_step(mg_env *h, const void *actions_dev, int action_dtype, uint8_t *obs_d
   }
   // one launch: transition + autoreset (either mode) + observation
   MG_CUDA(launch_step(p, h->plan, actions_dev, action_dtype, obs_dev, dir_dev, reward_dev, terminated_dev,
-                      truncated_dev, nullptr, s));
+                      truncated_dev, nullptr, (int)(h->launches & 1), s));
   h->launches += 1;
   if (h->profiling) {
     MG_CUDA(cudaEventRecord(ev1, s));
@@ -390,7 +397,7 @@ int mg_gen_obs(mg_env *h, uint8_t *obs_dev, int32_t *dir_dev, void *stream) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_gen_obs: NULL handle");
   MG_ON_DEVICE(h);
   note_stream(h, (cudaStream_t)stream);
-  MG_CUDA(launch_step(h->p, h->plan, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr, nullptr,
+  MG_CUDA(launch_step(h->p, h->plan, nullptr, MG_ACT_I32, obs_dev, dir_dev, nullptr, nullptr, nullptr, nullptr, 0,
                       (cudaStream_t)stream));
   h->launches += 1;
   return MG_OK;
@@ -608,9 +615,13 @@ int mg_set_host_format(mg_env *h, int format, int n_threads) {
     int want = n_threads > 0 ? n_threads : usable_host_threads();
     if (want > 64) want = 64;
     if ((int64_t)want * 256 > h->p.n_envs) want = (int)(h->p.n_envs / 256 > 0 ? h->p.n_envs / 256 : 1);  // no point in slices of a few envs
-    if (!h->pool || h->pool->threads() != want) {
-      delete h->pool;
-      h->pool = new HostPool(want);
+    h->pool_threads = want;
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      if (!g_pool || g_pool->threads() != want) {
+        delete g_pool;
+        g_pool = new HostPool(want);
+      }
     }
     // chunks: enough of them that the expansion of chunk c overlaps the copy of chunk c + 1, each still a large copy
     int chunks = (int)(h->p.n_envs / 16384);
@@ -627,7 +638,7 @@ int64_t mg_host_d2h_bytes(const mg_env *h) {
   if (!h) return 0;
   return h->host_format == MG_HOST_PACKED ? (int64_t)h->p.n_envs * PACKED_BYTES : (int64_t)h->p.n_envs * (OBS_BYTES + 4 + 8 + 1 + 1);
 }
-int mg_host_threads(const mg_env *h) { return (h && h->host_format == MG_HOST_PACKED && h->pool) ? h->pool->threads() : 0; }
+int mg_host_threads(const mg_env *h) { return (h && h->host_format == MG_HOST_PACKED) ? h->pool_threads : 0; }
 
 // MG_HOST_PACKED step: H2D actions, K1 writing 52-byte records, D2H in chunks; the pool expands chunk c into the
 // caller's arrays while chunk c + 1 is still on the bus.
@@ -635,6 +646,9 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
                             uint8_t *term_host, uint8_t *trunc_host) {
   const size_t n = (size_t)h->p.n_envs;
   cudaStream_t s = h->hstream;
+  std::lock_guard<std::mutex> pool_lock(g_pool_mu);
+  if (!g_pool) g_pool = new HostPool(h->pool_threads > 0 ? h->pool_threads : 1);
+  HostPool *pool = g_pool;
   ExpandJob job;
   job.packed = h->h_packed; job.max_steps = h->p.max_steps; job.reward_lut = h->h_reward_lut;
   job.obs = obs_host; job.dir = dir_host; job.reward = reward_host; job.term = term_host; job.trunc = trunc_host;
@@ -645,10 +659,10 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   const auto t0 = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
   double t_enq = 0, t_first = 0, t_last = 0;
-  h->pool->begin(job, bounds, C);  // the workers wake up while the copy and the kernel run
+  pool->begin(job, bounds, C);  // the workers wake up while the copy and the kernel run
   cudaError_t e = cudaMemcpyAsync(h->d_actions, src, n * sizeof(int32_t), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess)
-    e = launch_step(h->p, h->plan, h->d_actions, MG_ACT_I32, nullptr, nullptr, nullptr, nullptr, nullptr, h->d_packed, s);
+    e = launch_step(h->p, h->plan, h->d_actions, MG_ACT_I32, nullptr, nullptr, nullptr, nullptr, nullptr, h->d_packed, (int)(h->launches & 1), s);
   h->launches += 1;
   for (int c = 0; c < C && e == cudaSuccess; ++c) {
     const size_t off = (size_t)bounds[c] * PACKED_BYTES, len = (size_t)(bounds[c + 1] - bounds[c]) * PACKED_BYTES;
@@ -661,13 +675,13 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   for (int c = 0; c < C && e == cudaSuccess; ++c) {
     // poll: a chunk lands every ~30 us, a blocking synchronise would add its wake-up latency to each of them
     while ((e = cudaEventQuery(h->chunk_ev[c])) == cudaErrorNotReady) {}
-    if (e == cudaSuccess) { h->pool->chunk_ready(); ++released; }
+    if (e == cudaSuccess) { pool->chunk_ready(); ++released; }
     if (c == 0) t_first = since();
   }
   t_last = since();
-  if (e != cudaSuccess) h->pool->abort_chunks(C);  // let the workers run through (their output is discarded by the error)
+  if (e != cudaSuccess) pool->abort_chunks(C);  // let the workers run through (their output is discarded by the error)
   (void)released;
-  h->pool->wait();
+  pool->wait();
   if (h->trace) {
     h->tr_enqueue += t_enq; h->tr_first_chunk += t_first; h->tr_last_chunk += t_last; h->tr_pool += since(); h->tr_n += 1;
   }

@@ -97,8 +97,10 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
 }
 
 cudaError_t launch_step(const Params &p, const StepPlan &plan, const void *actions, int action_dtype, uint8_t *obs,
-                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, uint32_t *packed, cudaStream_t stream) {
+                        int32_t *dir, double *reward, uint8_t *term, uint8_t *trunc, uint32_t *packed, int step_parity,
+                        cudaStream_t stream) {
   int tma_ok = ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) ? 1 : 0;
+  tma_ok |= (step_parity & 1) << 2;  // direction of the unflagged tiles in K1's order list
 #ifdef MG_TIMELINE
   static int launch_no = 0;
   tma_ok |= (launch_no++ & 1) << 1;

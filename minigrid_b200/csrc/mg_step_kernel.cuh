@@ -309,7 +309,10 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       if (idx < m_ord) {
         const unsigned lt = (1u << lane) - 1u;
         const bool is_hot = (bal >> lane) & 1u;
-        const int pos = is_hot ? hb + __popc(bal & lt) : hot_total + (32 * c - hb) + __popc(~bal & lt);
+        // the unflagged tiles alternate their direction from step to step (bit 2 of obs_tma_ok): the tiles a CTA finished
+        // last in the previous step are the ones whose flags this prologue may have read too early, and they come first now
+        const int cold_rank = (32 * c - hb) + __popc(~bal & lt);
+        const int pos = is_hot ? hb + __popc(bal & lt) : hot_total + ((obs_tma_ok & 4) ? (m_ord - hot_total - 1 - cold_rank) : cold_rank);
         s_order[pos] = (uint16_t)idx;
       }
     }
