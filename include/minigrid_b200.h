@@ -189,6 +189,21 @@ int mg_get_state(mg_env *env, uint8_t *grid_dev, int32_t *agent_dev, uint64_t *r
 int mg_set_state(mg_env *env, const uint8_t *grid_dev, const int32_t *agent_dev, const uint64_t *rng_dev,
                  const uint8_t *pending_dev, void *stream);
 
+/* The reference's reward wrappers, as a SyncVectorEnv of wrapped envs applies them (they change `terminated`, so they
+ * live inside the step and its autoreset, not behind it). Order: the bonus wrapper is the outermost.
+ *   mg_set_no_death  NoDeath(env, no_death_types, death_cost) (wrappers.py:809-882): type_mask bit t set = the
+ *                    OBJECT_TO_IDX type t (constants.py:25-37: 2 wall, 4 door, 5 key, 6 ball, 7 box, 9 lava ...) is a
+ *                    death cell; a step that terminated while moving into / standing on such a cell returns
+ *                    terminated = False and reward + death_cost, and the episode goes on. Bit 8 (goal) is refused
+ *                    (the wrapper's assert, :845). type_mask 0 removes the wrapper.
+ *   mg_set_bonus     mode 1: ActionBonus(env) (wrappers.py:68-125), reward += 1 / sqrt(count[(agent_pos, agent_dir,
+ *                    action)]); mode 2: PositionBonus(env) (:128-184), reward += 1 / sqrt(count[agent_pos]) (its scale is
+ *                    the constant 1, :157); counts are per environment, start at zero when the call is made and live as
+ *                    long as the wrapper (they are not cleared by resets, like the wrappers' dicts); mode 0 removes it.
+ * Both are incompatible with MG_HOST_PACKED (the packed record carries no reward value). */
+int mg_set_no_death(mg_env *env, int type_mask, double death_cost);
+int mg_set_bonus(mg_env *env, int mode);
+
 /* Measurement aid (no reference counterpart): while enabled, every K1 (step+obs) launch is bracketed by CUDA
  * events on the launching stream; mg_profile_read synchronises them, returns the summed kernel milliseconds
  * and the number of launches since the last read, and clears the list. */

@@ -290,6 +290,7 @@ int mg_destroy(mg_env *h) {
   cudaFreeHost(h->h_err);
   cudaFree(h->d_packed);
   cudaFreeHost(h->h_packed);
+  cudaFree(h->p.counts);
   free(h->h_reward_lut);
   for (int c = 0; c < 16; ++c)
     if (h->chunk_ev[c]) cudaEventDestroy(h->chunk_ev[c]);
@@ -298,6 +299,36 @@ int mg_destroy(mg_env *h) {
     delete h->prof_events;
   }
   delete h;
+  return MG_OK;
+}
+
+// NoDeath / ActionBonus / PositionBonus (wrappers.py:68-184, 809-882): parameters of K1, see include/minigrid_b200.h
+int mg_set_no_death(mg_env *h, int type_mask, double death_cost) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_set_no_death: NULL handle");
+  if (type_mask < 0 || type_mask >= (1 << 11)) return fail(MG_ERR_INVALID_ARG, "mg_set_no_death: type_mask has bits beyond OBJECT_TO_IDX (0..10)");
+  if (type_mask & (1 << T_GOAL)) return fail(MG_ERR_INVALID_ARG, "goal cannot be a death cell (wrappers.py:845)");
+  if (type_mask && h->host_format == MG_HOST_PACKED)
+    return fail(MG_ERR_INVALID_ARG, "mg_set_no_death: the packed host format carries no reward value; use MG_HOST_FULL");
+  h->p.no_death_mask = type_mask;
+  h->p.death_cost = death_cost;
+  return MG_OK;
+}
+int mg_set_bonus(mg_env *h, int mode) {
+  if (!h) return fail(MG_ERR_INVALID_ARG, "mg_set_bonus: NULL handle");
+  if (mode < 0 || mode > 2) return fail(MG_ERR_INVALID_ARG, "mg_set_bonus: mode is 0 (none), 1 (ActionBonus) or 2 (PositionBonus)");
+  if (mode && h->host_format == MG_HOST_PACKED)
+    return fail(MG_ERR_INVALID_ARG, "mg_set_bonus: the packed host format carries no reward value; use MG_HOST_FULL");
+  MG_ON_DEVICE(h);
+  MG_CUDA(cudaDeviceSynchronize());  // no step of this handle may still be counting
+  if (h->p.counts) { MG_CUDA(cudaFree(h->p.counts)); h->p.counts = nullptr; }
+  h->p.bonus_mode = 0;
+  if (mode) {
+    const size_t entries = (size_t)h->p.n_envs * (size_t)h->p.g.W * (size_t)h->p.g.H * (mode == 1 ? 28u : 1u);
+    MG_CUDA(cudaMalloc(&h->p.counts, entries * sizeof(uint32_t)));
+    MG_CUDA(cudaMemset(h->p.counts, 0, entries * sizeof(uint32_t)));
+    MG_CUDA(cudaDeviceSynchronize());
+    h->p.bonus_mode = mode;
+  }
   return MG_OK;
 }
 
@@ -608,6 +639,8 @@ int mg_set_host_format(mg_env *h, int format, int n_threads) {
   if (!h) return fail(MG_ERR_INVALID_ARG, "mg_set_host_format: NULL handle");
   if (format != MG_HOST_FULL && format != MG_HOST_PACKED) return fail(MG_ERR_INVALID_ARG, "mg_set_host_format: unknown format");
   MG_ON_DEVICE(h);
+  if (format == MG_HOST_PACKED && (h->p.no_death_mask || h->p.bonus_mode))
+    return fail(MG_ERR_INVALID_ARG, "mg_set_host_format: the packed record carries no reward value, and NoDeath / the bonus wrappers change it");
   if (format == MG_HOST_PACKED) {
     const size_t n_pad = (size_t)h->p.n_tiles * TILE;
     if (!h->d_packed) MG_CUDA(cudaMalloc(&h->d_packed, n_pad * PACKED_BYTES));

@@ -106,6 +106,15 @@ __device__ __forceinline__ int load_action(const void *actions, int dtype, int e
   return v;
 }
 
+// 1 / math.sqrt(new_count) of ActionBonus / PositionBonus (wrappers.py:122, 180): correctly rounded sqrt and division,
+// like CPython's. Out of line: the wrappers are rare, the hot loop must not carry their registers.
+static __device__ __noinline__ double bonus_of(uint32_t count) { return __ddiv_rn(1.0, __dsqrt_rn((double)count)); }
+// OBJECT_TO_IDX type of a cell code (door states and the key-hiding box folded back)
+__device__ __forceinline__ uint32_t code_type(uint32_t code) {
+  const uint32_t t4 = code & 15u;
+  return (t4 == T4_DOOR_CLOSED || t4 == T4_DOOR_LOCKED) ? (uint32_t)T_DOOR : (t4 == T4_BOX_WITH_KEY ? (uint32_t)T_BOX : t4);
+}
+
 // MiniGridEnv.reset() for the lanes in `pend`. Phase 1: every pending lane replays the numpy-exact draws of ITS
 // environment (lane per env; only the rejection loops diverge). Phase 2, one environment at a time with the whole
 // warp: the owner's drawn integers are broadcast, lane L copies words L, L+32, ... of the level template into HBM
@@ -453,16 +462,19 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
     if (stepping && !fresh) {
       // ---- MiniGridEnv.step, minigrid_env.py:525-588 ----
       steps += 1;
+      const int action_raw = action;  // what the wrappers saw (Dynamic-Obstacles remaps it below)
       int fx, fy;
       front_pos(g, ax, ay, dir, fx, fy);
       const int rw = r_word(g, fx, fy), cw = c_word(g, fx, fy);
       bool not_clear = false;
+      uint32_t fc_before = 0;  // Dynamic-Obstacles: the front cell before the obstacles moved
       if (KIND == KIND_DYNOBS && !WIN) {
         // DynamicObstaclesEnv.step (dynamicobstacles.py:135-158): actions beyond forward count as left, the front cell is
         // looked at BEFORE the obstacles move, then every obstacle is re-placed with draws from the env's own stream
         if (action >= 3) action = A_LEFT;
         const uint32_t fc0 = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
         not_clear = fc0 != CODE_EMPTY && (fc0 & 15u) != T_GOAL;
+        fc_before = fc0;
         if (active) {
           RngRec *rr = p.rng + env;
           Pcg r = load_rng(rr);
@@ -486,6 +498,12 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       const int fpos = ((dir & 1) ? ay : ax) + ((dir < 2) ? 1 : -1);  // the front cell's position on the agent's own line
       if (WIN) fc = view_words_byte(vw, fpos);  // meaningless after a turn (other array loaded), and then unused
       else fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
+      // NoDeath.step (wrappers.py:855-861): the cell in front BEFORE the env steps (Dynamic-Obstacles: before its balls move)
+      bool going_to_death = false;
+      if (p.no_death_mask) {
+        const uint32_t f0 = (KIND == KIND_DYNOBS && !WIN) ? fc_before : fc;
+        going_to_death = action_raw == A_FORWARD && f0 != CODE_EMPTY && ((p.no_death_mask >> code_type(f0)) & 1);
+      }
       const uint32_t carry_before = carry;
       const int act = pre_filter<KIND>(action);
       const StepOut so = transition(act, fc, fx, fy, ax, ay, dir, carry);
@@ -551,6 +569,25 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
         if (po.reward == POST_REWARD)
           reward = steps <= p.max_steps ? p.reward_lut[steps]
                                         : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
+      }
+      if (p.no_death_mask) {  // NoDeath.step after env.step (wrappers.py:863-872): also an agent that stays on a death cell
+        uint32_t cur;
+        if (WIN) cur = view_words_byte(vw, (dir & 1) ? ay : ax);
+        else cur = (tile_word<true>(base, r_word(g, ax, ay)) >> (8 * (ax & 3))) & 0xFFu;
+        const bool in_death = cur != CODE_EMPTY && ((p.no_death_mask >> code_type(cur)) & 1);
+        if (terminated && (going_to_death || in_death)) {
+          terminated = 0u;
+          reward = __dadd_rn(reward, p.death_cost);
+        }
+      }
+      if (p.bonus_mode && active && (unsigned)action_raw <= (unsigned)A_DONE) {  // ActionBonus / PositionBonus.step: the state after the step
+        uint32_t key = (uint32_t)(ay * g.W + ax);
+        uint32_t per = (uint32_t)(g.W * g.H);
+        if (p.bonus_mode == 1) { key = (key * 4u + (uint32_t)dir) * 7u + (uint32_t)action_raw; per *= 28u; }
+        uint32_t *cnt = p.counts + (size_t)env * per + key;
+        const uint32_t c = *cnt + 1u;
+        *cnt = c;
+        reward = __dadd_rn(reward, bonus_of(c));
       }
       truncated = steps >= p.max_steps;
       rsteps = steps;

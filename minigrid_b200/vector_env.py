@@ -282,6 +282,23 @@ class MinigridVecEnv(_VectorEnvBase):
             _lib.check(self._L.mg_set_state(self._h, self._p(g), self._p(a), self._p(r), self._p(p), self._stream()))
             torch.cuda.current_stream(self.device).synchronize()  # g/a/r/p may be temporaries
 
+    # ---- the reference's reward wrappers (they change `terminated`, so they live inside the step: wrappers.py) ----
+    OBJECT_TO_IDX = {"unseen": 0, "empty": 1, "wall": 2, "floor": 3, "door": 4, "key": 5, "ball": 6, "box": 7, "goal": 8, "lava": 9, "agent": 10}
+
+    def set_no_death(self, no_death_types=(), death_cost: float = -1.0):
+        """NoDeath(env, no_death_types, death_cost) around every env (wrappers.py:809-882); () removes it."""
+        assert "goal" not in no_death_types, "goal cannot be a death cell"
+        mask = 0
+        for t in no_death_types:
+            mask |= 1 << self.OBJECT_TO_IDX[t]
+        _lib.check(self._L.mg_set_no_death(self._h, mask, float(death_cost)))
+
+    def set_bonus(self, kind):
+        """kind: None, "action" (ActionBonus, wrappers.py:68-125) or "position" (PositionBonus, :128-184): a fresh wrapper
+        (zeroed per-env counts) around every env, outside NoDeath."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.mg_set_bonus(self._h, {None: 0, "action": 1, "position": 2}[kind]))
+
     def profile_kernels(self, enable: bool):
         """Bracket every step+obs kernel launch with CUDA events on the launching stream (measurement aid)."""
         _lib.check(self._L.mg_profile(self._h, int(bool(enable))))

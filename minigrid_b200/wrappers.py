@@ -11,6 +11,11 @@ SymbolicObsWrapper       :729-782  obs["image"] = int64 (W, H, 3): (x, y, type o
 RGBImgPartialObsWrapper  :334-380  obs["image"] = the agent's view rendered with 8 x 8 tiles, (56, 56, 3).
 RGBImgObsWrapper         :287-331  obs["image"] = the whole grid rendered, the agent's view highlighted, (8 H, 8 W, 3).
 The two RGB wrappers copy tiles that the reference's own Grid.render_tile drew (data/tile_atlas.npz).
+
+Reward wrappers (they act inside the engine's step kernel, because NoDeath decides whether an episode ends):
+NoDeath                  :809-882  a terminated step into / on a death cell continues with reward + death_cost.
+ActionBonus              :68-125   reward += 1 / sqrt(visits of (agent_pos, agent_dir, action)), per env.
+PositionBonus            :128-184  reward += 1 / sqrt(visits of agent_pos), per env.
 """
 from __future__ import annotations
 
@@ -49,6 +54,49 @@ class _VecWrapper:
 
     def close(self):
         return self.env.close()
+
+
+class _RewardWrapper(_VecWrapper):
+    """The wrapper is a setting of the batch's step kernel; the object only scopes it (close() / remove() take it off)."""
+
+    def observation(self, obs):
+        return obs
+
+    def remove(self):
+        raise NotImplementedError
+
+    def close(self):
+        self.remove()
+        return self.env.close()
+
+
+class NoDeath(_RewardWrapper):
+    def __init__(self, env, no_death_types, death_cost: float = -1.0):
+        super().__init__(env)
+        self.no_death_types, self.death_cost = tuple(no_death_types), float(death_cost)
+        self.unwrapped.set_no_death(self.no_death_types, self.death_cost)
+
+    def remove(self):
+        self.unwrapped.set_no_death(())
+
+
+class ActionBonus(_RewardWrapper):
+    def __init__(self, env):
+        super().__init__(env)
+        self.unwrapped.set_bonus("action")
+
+    def remove(self):
+        self.unwrapped.set_bonus(None)
+
+
+class PositionBonus(_RewardWrapper):
+    def __init__(self, env, scale=1):
+        super().__init__(env)
+        self.scale = 1  # as the reference: the argument is ignored (wrappers.py:157)
+        self.unwrapped.set_bonus("position")
+
+    def remove(self):
+        self.unwrapped.set_bonus(None)
 
 
 class ImgObsWrapper(_VecWrapper):

@@ -79,12 +79,43 @@ INJECTS = {  # id (host env whose size/see_through/max_steps are used) -> (N, T)
 }
 
 
-def gen_rollout(env_id, n, t_steps, seed, mode="next_step"):
-    ref = ReferenceVecEnv(env_id, n, autoreset=mode)
+# the reference's reward wrappers around every env (wrappers.py:68-184, 809-882), bonus outermost:
+# rewardwrap_<name>.npz = a rollout fixture + the wrapper configuration. name -> (id, N, T, seed, no_death_types, death_cost, bonus, mode)
+REWARD_WRAPS = {
+    "nodeath_lava": ("MiniGrid-LavaCrossingS9N1-v0", 8, 500, 2, ("lava",), -1.0, None, "next_step"),
+    "nodeath_lava_action": ("MiniGrid-DistShift1-v0", 8, 400, 3, ("lava",), -0.75, "action", "next_step"),
+    "nodeath_ball": ("MiniGrid-Dynamic-Obstacles-6x6-v0", 8, 400, 2, ("ball",), -1.0, None, "next_step"),
+    "nodeath_ball_position_samestep": ("MiniGrid-Dynamic-Obstacles-8x8-v0", 8, 400, 5, ("ball",), -2.5, "position", "same_step"),
+    "action_doorkey": ("MiniGrid-DoorKey-8x8-v0", 8, 800, 7, (), 0.0, "action", "next_step"),
+    "position_fourrooms": ("MiniGrid-FourRooms-v0", 8, 330, 31, (), 0.0, "position", "next_step"),
+    "action_fourrooms_samestep": ("MiniGrid-FourRooms-v0", 8, 330, 33, (), 0.0, "action", "same_step"),
+}
+
+
+def reward_wrap(no_death, death_cost, bonus):
+    load()
+    from minigrid.wrappers import ActionBonus, NoDeath, PositionBonus
+
+    def w(e):
+        if no_death:
+            e = NoDeath(e, no_death_types=tuple(no_death), death_cost=death_cost)
+        if bonus == "action":
+            e = ActionBonus(e)
+        elif bonus == "position":
+            e = PositionBonus(e)
+        return e
+    return w
+
+
+def gen_rollout(env_id, n, t_steps, seed, mode="next_step", wrap=None, forward_share=0.0):
+    ref = ReferenceVecEnv(env_id, n, autoreset=mode, wrap=wrap)
     obs0, dir0 = ref.reset(seed=seed)
     state0 = ref.get_state()
     full0 = ref.full_obs()
-    actions = np.random.default_rng(1234).integers(0, 7, (t_steps, n)).astype(np.int32)
+    rng = np.random.default_rng(1234)
+    actions = rng.integers(0, 7, (t_steps, n)).astype(np.int32)
+    if forward_share > 0:  # walk into things more often than uniform actions do
+        actions = np.where(rng.random((t_steps, n)) < forward_share, 2, actions).astype(np.int32)
     obs = np.zeros((t_steps, n, 7, 7, 3), np.uint8)
     dirs = np.zeros((t_steps, n), np.int32)
     rew = np.zeros((t_steps, n), np.float64)
@@ -214,6 +245,16 @@ def main_wrappers():
         print("wrappers", env_id, {k: v.shape for k, v in d.items() if hasattr(v, "shape") and k.startswith(("rgb", "flat", "view9"))})
 
 
+def main_reward_wrappers():
+    os.makedirs(OUT, exist_ok=True)
+    for name, (env_id, n, t, seed, no_death, cost, bonus, mode) in REWARD_WRAPS.items():
+        d = gen_rollout(env_id, n, t, seed, mode=mode, wrap=reward_wrap(no_death, cost, bonus), forward_share=0.4)
+        d.update(no_death=np.array(list(no_death), dtype="U8"), death_cost=cost, bonus=bonus or "")
+        np.savez_compressed(os.path.join(OUT, f"rewardwrap_{name}.npz"), **d)
+        print("rewardwrap", name, "episodes ended:", int((d["terminated"] | d["truncated"]).sum()),
+              "negative rewards on live envs:", int(((d["reward"] < 0) & ~d["terminated"]).sum()))
+
+
 def main_next():
     os.makedirs(OUT, exist_ok=True)
     for env_id, (n, t, seed) in NEXT_ROLLOUTS.items():
@@ -249,7 +290,10 @@ if __name__ == "__main__":
         main_next()
     elif sys.argv[1:] == ["wrappers"]:
         main_wrappers()
+    elif sys.argv[1:] == ["reward_wrappers"]:
+        main_reward_wrappers()
     else:
         main()
         main_next()
         main_wrappers()
+        main_reward_wrappers()

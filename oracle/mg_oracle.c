@@ -18,6 +18,7 @@
 #include <pthread.h>
 #include <time.h>
 #include <unistd.h>
+#include <math.h>
 
 typedef unsigned __int128 u128;
 
@@ -242,6 +243,10 @@ struct mgo_vec {
   cell_t *arena;
   /* scratch for rollout */
   uint8_t *s_obs; int32_t *s_dir; double *s_rew; uint8_t *s_term, *s_trunc;
+  /* reward wrappers around each env, as a SyncVectorEnv of wrapped envs has them (wrappers.py:68-184, 809-882) */
+  int no_death_mask; double death_cost; /* NoDeath: bit t set = OBJECT_TO_IDX type t is in no_death_types */
+  int bonus_mode;                        /* 0 none, 1 ActionBonus, 2 PositionBonus (outermost wrapper) */
+  uint32_t *counts;                      /* [n][W*H*4*7] / [n][W*H]: the wrappers' self.counts dicts, dense */
 };
 
 static int64_t rand_int(env_t *e, int64_t lo, int64_t hi) { return rng_integers(&e->rng, lo, hi); } /* :247-252 */
@@ -1248,8 +1253,25 @@ mgo_vec *mgo_vec_create(int kind, int width, int height, int max_steps, int see_
   }
   return v;
 }
+/* NoDeath(env, no_death_types, death_cost), wrappers.py:836-850: type_mask bit t = OBJECT_TO_IDX value t; 0 removes it */
+int mgo_vec_set_no_death(mgo_vec *v, int type_mask, double death_cost) {
+  if (type_mask & (1 << T_GOAL)) return -1; /* assert "goal" not in no_death_types, :845 */
+  v->no_death_mask = type_mask; v->death_cost = death_cost;
+  return 0;
+}
+/* ActionBonus(env) (mode 1) / PositionBonus(env) (mode 2), wrappers.py:97-104, 148-157: fresh, empty counts */
+int mgo_vec_set_bonus(mgo_vec *v, int mode) {
+  free(v->counts); v->counts = NULL; v->bonus_mode = 0;
+  if (mode == 0) return 0;
+  if (mode != 1 && mode != 2) return -1;
+  v->counts = (uint32_t *)calloc((size_t)v->n * v->width * v->height * (mode == 1 ? 28 : 1), sizeof(uint32_t));
+  if (!v->counts) return -1;
+  v->bonus_mode = mode;
+  return 0;
+}
 void mgo_vec_destroy(mgo_vec *v) {
   if (!v) return;
+  free(v->counts);
   free(v->s_obs); free(v->s_dir); free(v->s_rew); free(v->s_term); free(v->s_trunc);
   free(v->arena); free(v->envs); free(v);
 }
@@ -1282,17 +1304,53 @@ static void reset_range(mgo_vec *v, int lo, int hi, uint8_t *obs, int32_t *dir) 
     env_gen_obs(v, e, obs + (size_t)i * 147, dir + i);
   }
 }
+/* the wrapped env's step(): BonusWrapper(NoDeath(env)).step(action). A wrapper that is not configured is absent. */
+static int wrapped_step(mgo_vec *v, int i, int action, double *reward, uint8_t *terminated, uint8_t *truncated) {
+  env_t *e = &v->envs[i];
+  /* NoDeath.step, wrappers.py:852-882: the cell in front BEFORE the env steps (Dynamic-Obstacles moves its balls inside step) */
+  int going_to_death = 0;
+  if (v->no_death_mask) {
+    int fx = e->agent_x + DIR_X[e->agent_dir], fy = e->agent_y + DIR_Y[e->agent_dir]; /* front_pos; always inside the walls */
+    cell_t front = grid_get(&e->grid, fx, fy);
+    going_to_death = action == A_FORWARD && !cell_is_none(front) && ((v->no_death_mask >> front.type) & 1);
+  }
+  int rc = env_step(v, e, action, reward, terminated, truncated);
+  if (rc != 0) return rc;
+  if (v->no_death_mask) {
+    cell_t cur = grid_get(&e->grid, e->agent_x, e->agent_y);
+    int in_death = !cell_is_none(cur) && ((v->no_death_mask >> cur.type) & 1);
+    if (*terminated && (going_to_death || in_death)) {
+      *terminated = 0;
+      volatile double r = *reward + v->death_cost; /* reward += self.death_cost */
+      *reward = r;
+    }
+  }
+  if (v->bonus_mode) {
+    /* ActionBonus.step wrappers.py:106-125: key (agent_pos, agent_dir, action) after the step;
+     * PositionBonus.step :163-184: key agent_pos, bonus * self.scale with self.scale = 1 (:157) */
+    size_t per = (size_t)v->width * v->height * (v->bonus_mode == 1 ? 28 : 1);
+    size_t key = (size_t)e->agent_y * v->width + e->agent_x;
+    if (v->bonus_mode == 1) key = (key * 4 + (size_t)e->agent_dir) * 7 + (size_t)action;
+    uint32_t c = ++v->counts[(size_t)i * per + key];
+    volatile double sq = sqrt((double)c);
+    volatile double bonus = 1.0 / sq;
+    volatile double r = *reward + bonus;
+    *reward = r;
+  }
+  return 0;
+}
+
 static int step_range(mgo_vec *v, int lo, int hi, const int32_t *actions, uint8_t *obs, int32_t *dir,
                       double *reward, uint8_t *terminated, uint8_t *truncated, int mode) {
   int bad = 0;
   for (int i = lo; i < hi; i++) {
     env_t *e = &v->envs[i];
     if (mode == MGO_AUTORESET_NEXT_STEP && e->pending_reset) {
-      env_reset(v, e); /* action ignored; unseeded reset: the RNG stream continues */
+      env_reset(v, e); /* action ignored; unseeded reset: the RNG stream continues (the wrappers' reset() is the env's) */
       reward[i] = 0.0; terminated[i] = 0; truncated[i] = 0;
       e->pending_reset = 0;
     } else {
-      if (env_step(v, e, actions[i], &reward[i], &terminated[i], &truncated[i]) != 0) bad = 1;
+      if (wrapped_step(v, i, actions[i], &reward[i], &terminated[i], &truncated[i]) != 0) bad = 1;
       int done = terminated[i] | truncated[i];
       if (mode == MGO_AUTORESET_NEXT_STEP) e->pending_reset = (uint8_t)done;
       else if (mode == MGO_AUTORESET_SAME_STEP && done) env_reset(v, e);

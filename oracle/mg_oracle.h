@@ -51,6 +51,9 @@ typedef struct mgo_vec mgo_vec;
 mgo_vec *mgo_vec_create(int kind, int width, int height, int max_steps, int see_through_walls,
                         const int32_t *params, int n_params, int n_envs);
 void mgo_vec_destroy(mgo_vec *v);
+/* reward wrappers around every env of the vector (wrappers.py:68-184, 809-882); bonus wrappers are outermost */
+int mgo_vec_set_no_death(mgo_vec *v, int type_mask, double death_cost);
+int mgo_vec_set_bonus(mgo_vec *v, int mode); /* 0 none, 1 ActionBonus, 2 PositionBonus */
 
 /* np_random = Generator(PCG64(SeedSequence(seed[i]))) for env i (gymnasium Env.reset(seed=...)) */
 void mgo_vec_seed(mgo_vec *v, const uint64_t *seeds);

@@ -138,6 +138,8 @@ def lib():
         L.mgo_vec_create.restype = p
         L.mgo_vec_create.argtypes = [C.c_int] * 5 + [p, C.c_int, C.c_int]
         L.mgo_vec_destroy.argtypes = [p]
+        L.mgo_vec_set_no_death.argtypes = [p, C.c_int, C.c_double]
+        L.mgo_vec_set_bonus.argtypes = [p, C.c_int]
         L.mgo_vec_seed.argtypes = [p, p]
         L.mgo_vec_reset.argtypes = [p, p, p, C.c_int]
         L.mgo_vec_seed_masked.argtypes = [p, p, p]
@@ -219,6 +221,22 @@ class OracleVecEnv:
         if rc != 0:
             raise ValueError("Unknown action")
         return self.obs, self.dir, self.reward, self.terminated.astype(bool), self.truncated.astype(bool)
+
+    # ---- reward wrappers around every env (wrappers.py:68-184, 809-882); the bonus wrapper is the outermost ----
+    OBJECT_TO_IDX = {"unseen": 0, "empty": 1, "wall": 2, "floor": 3, "door": 4, "key": 5, "ball": 6, "box": 7, "goal": 8, "lava": 9, "agent": 10}
+
+    def set_no_death(self, no_death_types, death_cost=-1.0):
+        """NoDeath(env, no_death_types, death_cost); an empty tuple removes the wrapper."""
+        mask = 0
+        for t in no_death_types:
+            mask |= 1 << self.OBJECT_TO_IDX[t]
+        if lib().mgo_vec_set_no_death(self._h, mask, float(death_cost)) != 0:
+            raise AssertionError("goal cannot be a death cell")
+
+    def set_bonus(self, kind):
+        """kind: None, "action" (ActionBonus) or "position" (PositionBonus): a fresh wrapper with empty counts."""
+        if lib().mgo_vec_set_bonus(self._h, {None: 0, "action": 1, "position": 2}[kind]) != 0:
+            raise MemoryError("bonus counts")
 
     def gen_obs(self):
         lib().mgo_vec_gen_obs(self._h, _ptr(self.obs), _ptr(self.dir))

@@ -39,12 +39,15 @@ class ReferenceVecEnv:
     (gymnasium >= 1.0: NEXT_STEP default; SAME_STEP optional). Implemented here so the result does
     not depend on which gymnasium (if any) is installed."""
 
-    def __init__(self, env_id, num_envs, autoreset="next_step", **kwargs):
+    def __init__(self, env_id, num_envs, autoreset="next_step", wrap=None, **kwargs):
+        """wrap: optional callable env -> wrapped env (the reference's NoDeath / ActionBonus / PositionBonus, as a
+        SyncVectorEnv of wrapped envs would hold them): step() and reset() then go through the wrapper."""
         import numpy as np
 
         gym, _ = load()
         self.np = np
         self.envs = [gym.make(env_id, **kwargs).unwrapped for _ in range(num_envs)]
+        self.wrapped = [wrap(e) for e in self.envs] if wrap is not None else self.envs
         self.num_envs = num_envs
         self.autoreset = autoreset
         self.pending = [False] * num_envs
@@ -52,7 +55,7 @@ class ReferenceVecEnv:
     def reset(self, seed=None):
         np = self.np
         obs, dirs = [], []
-        for i, e in enumerate(self.envs):
+        for i, e in enumerate(self.wrapped):
             s = None if seed is None else (int(seed) + i if np.isscalar(seed) else int(seed[i]))
             o, _ = e.reset(seed=s)
             obs.append(o["image"]); dirs.append(o["direction"])
@@ -62,7 +65,7 @@ class ReferenceVecEnv:
     def step(self, actions):
         np = self.np
         obs, dirs, rew, term, trunc = [], [], [], [], []
-        for i, e in enumerate(self.envs):
+        for i, e in enumerate(self.wrapped):
             if self.autoreset == "next_step" and self.pending[i]:
                 o, _ = e.reset()
                 r, te, tr = 0.0, False, False

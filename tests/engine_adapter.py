@@ -38,6 +38,12 @@ class EngineAdapter:
         return (self._np(obs["image"]).copy(), self._np(obs["direction"]).copy(), self._np(r).copy(),
                 self._np(te).copy(), self._np(tr).copy())
 
+    def set_no_death(self, no_death_types, death_cost=-1.0):
+        self.e.set_no_death(tuple(no_death_types), death_cost)
+
+    def set_bonus(self, kind):
+        self.e.set_bonus(kind)
+
     def gen_obs(self):
         obs = self.e.gen_obs()
         return self._np(obs["image"]).copy(), self._np(obs["direction"]).copy()

@@ -36,6 +36,25 @@ def test_rollout_matches_reference_fixture(path):
     np.testing.assert_array_equal(o.full_obs(), g["full_obs"])
 
 
+def make_oracle_wrapped(g):
+    """make_env for parity.check_rollout_fixture: the oracle with the fixture's reward wrappers."""
+    def make(env_id, n, mode):
+        o = OracleVecEnv(env_id, n, autoreset=mode)
+        o.set_no_death([str(t) for t in g["no_death"]], float(g["death_cost"]))
+        o.set_bonus(str(g["bonus"]) or None)
+        return o
+    return make
+
+
+@pytest.mark.parametrize("path", golden_files("rewardwrap"), ids=os.path.basename)
+def test_reward_wrappers_match_reference_fixture(path):
+    """NoDeath / ActionBonus / PositionBonus (wrappers.py:68-184, 809-882) applied by the reference itself (oracle/gen_golden.py)."""
+    import parity
+
+    g = load_golden(path)
+    parity.check_rollout_fixture(make_oracle_wrapped(g), g)
+
+
 @pytest.mark.parametrize("path", golden_files("inject"), ids=os.path.basename)
 def test_injected_states_match_reference_fixture(path):
     g = load_golden(path)

@@ -93,3 +93,74 @@ def test_observation_wrappers_against_live_reference(env_id):
             assert sym.dtype == np.int64
             np.testing.assert_array_equal(sym, orc.symbolic_obs(), err_msg=f"symbolic t={t}")
             np.testing.assert_array_equal(ref.one_hot_obs(), OracleVecEnv.one_hot(q[0]), err_msg=f"one-hot t={t}")
+
+
+# ---- SURVEY 8(f-4), second half: the reward wrappers (wrappers.py:68-184, 809-882) ----
+def _wrap(no_death, bonus):
+    ref_loader.load()
+    from minigrid.wrappers import ActionBonus, NoDeath, PositionBonus
+
+    def w(e):
+        if no_death:
+            e = NoDeath(e, no_death_types=no_death, death_cost=-1.5)
+        if bonus == "action":
+            e = ActionBonus(e)
+        elif bonus == "position":
+            e = PositionBonus(e)
+        return e
+    return w
+
+
+@pytest.mark.parametrize("env_id,no_death,bonus", [
+    ("MiniGrid-LavaCrossingS9N1-v0", ("lava",), None),
+    ("MiniGrid-LavaCrossingS9N3-v0", ("lava",), "action"),
+    ("MiniGrid-DistShift1-v0", ("lava",), "position"),
+    ("MiniGrid-LavaGapS5-v0", ("lava", "wall"), None),
+    ("MiniGrid-Dynamic-Obstacles-5x5-v0", ("ball",), None),
+    ("MiniGrid-Dynamic-Obstacles-6x6-v0", ("ball",), "action"),
+    ("MiniGrid-Empty-5x5-v0", (), "action"),
+    ("MiniGrid-DoorKey-5x5-v0", (), "position"),
+    ("MiniGrid-FourRooms-v0", (), "action"),
+    ("MiniGrid-GoToDoor-5x5-v0", ("door",), "position"),
+])
+@pytest.mark.parametrize("mode", ["next_step", "same_step"])
+def test_reward_wrappers_against_live_reference(env_id, no_death, bonus, mode):
+    """NoDeath, ActionBonus and PositionBonus as a SyncVectorEnv of wrapped envs applies them (bonus outermost), restated
+    in the oracle (wrapped_step): rewards bit for bit, and the episodes NoDeath keeps alive stay alive."""
+    n, t_steps = 6, 400
+    ref = ref_loader.ReferenceVecEnv(env_id, n, autoreset=mode, wrap=_wrap(no_death, bonus))
+    orc = OracleVecEnv(env_id, n, autoreset=mode)
+    orc.set_no_death(no_death, -1.5)
+    orc.set_bonus(bonus)
+    ref.reset(seed=2)
+    orc.reset(seed=2)
+    rng = np.random.default_rng(11)
+    saved = 0
+    for t in range(t_steps):
+        # forward-heavy actions: walk into lava / obstacles often
+        a = np.where(rng.random(n) < 0.5, 2, rng.integers(0, 7, n))
+        r = ref.step(a)
+        q = orc.step(a)
+        for x, y, name in zip(r, q, ["obs", "dir", "reward", "terminated", "truncated"]):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=f"{name} t={t}")
+        assert r[2].tobytes() == q[2].tobytes()
+        saved += int(((r[2] < -0.4) & ~r[3]).sum())  # a negative reward on a live env: the death cost
+    if no_death and "Empty" not in env_id and "GoToDoor" not in env_id:
+        assert saved > 0, "NoDeath never triggered: the test does not cover it"
+
+
+def test_reward_wrapper_known_answers():
+    """The reference's own doctests: wrappers.py:81-93 (ActionBonus 1.0, 1.0), :137-145 (PositionBonus 1.0, 0.7071067811865475),
+    :818-834 (NoDeath: LavaCrossingS9N1 seed 2 -> (-1.0, False); Dynamic-Obstacles-5x5 seed 2 -> (-2.0, False))."""
+    o = OracleVecEnv("MiniGrid-Empty-5x5-v0", 1); o.set_bonus("action"); o.reset(seed=0)
+    assert [float(o.step([1])[2][0]) for _ in range(2)] == [1.0, 1.0]
+    o = OracleVecEnv("MiniGrid-Empty-5x5-v0", 1); o.set_bonus("position"); o.reset(seed=0)
+    assert [float(o.step([1])[2][0]) for _ in range(2)] == [1.0, 0.7071067811865475]
+    o = OracleVecEnv("MiniGrid-LavaCrossingS9N1-v0", 1); o.reset(seed=2); o.step([1])
+    r = o.step([2]); assert (float(r[2][0]), bool(r[3][0])) == (0.0, True)
+    o = OracleVecEnv("MiniGrid-LavaCrossingS9N1-v0", 1); o.set_no_death(("lava",), -1.0); o.reset(seed=2); o.step([1])
+    r = o.step([2]); assert (float(r[2][0]), bool(r[3][0])) == (-1.0, False)
+    o = OracleVecEnv("MiniGrid-Dynamic-Obstacles-5x5-v0", 1); o.reset(seed=2)
+    r = o.step([2]); assert (float(r[2][0]), bool(r[3][0])) == (-1.0, True)
+    o = OracleVecEnv("MiniGrid-Dynamic-Obstacles-5x5-v0", 1); o.set_no_death(("ball",), -1.0); o.reset(seed=2)
+    r = o.step([2]); assert (float(r[2][0]), bool(r[3][0])) == (-2.0, False)
