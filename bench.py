@@ -256,6 +256,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # torch's CPU thread pool is not used by anything measured here, but its workers keep spinning for a while after any
+    # parallel CPU op (OpenMP block time) — next to the host threads that expand packed step records in the e2e leg
+    torch.set_num_threads(1)
     # pinned host buffers (the e2e leg) should live on the GPU's own NUMA node: with 8 ranks copying at once, remote
     # pinned memory costs a quarter of the D2H bandwidth (round 1: 37 instead of 50 GB/s per GPU at N = 8)
     numa = bind_to_gpu_numa_node(dev)
@@ -395,33 +398,33 @@ def main():
 
     # ---- end to end through the host-buffer API: pinned host actions in, pinned host obs/reward/flags out ----
     Ke = max(1, min(args.e2e_steps, K))
-    host_actions = torch.randint(0, 7, (min(Ke, 64), n), dtype=torch.int32).pin_memory()
-    for b in batches:
-        b.set_host_format(args.host_format, max(1, usable_cores() // max(1, world)))
-    for t in range(max(3, 2 * R)):  # every batch allocates its pinned staging on first use: keep that out of the timing
-        batches[t % R].step_host(host_actions[t % host_actions.shape[0]])
-    barrier()
-    t0 = time.perf_counter()
-    for t in range(Ke):
-        batches[t % R].step_host(host_actions[t % host_actions.shape[0]])
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = total * Ke / e2e_s
+    host_actions = torch.from_numpy(np.random.default_rng(4321 + rank).integers(0, 7, (min(Ke, 64), n)).astype(np.int32)).pin_memory()
+    act_views = [host_actions[i] for i in range(host_actions.shape[0])]
+
+    def e2e_run(fmt):
+        """Ke synchronous step_host calls (pinned host actions in, host arrays out), three times; the median repetition."""
+        for b in batches:
+            b.set_host_format(fmt, max(1, usable_cores() // max(1, world)))
+        for t in range(max(3, 2 * R)):  # every batch allocates its pinned staging on first use: keep that out of the timing
+            batches[t % R].step_host(act_views[t % len(act_views)])
+        reps = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for t in range(Ke):
+                batches[t % R].step_host(act_views[t % len(act_views)])
+            torch.cuda.synchronize()
+            reps.append(total * Ke / max_over_ranks(time.perf_counter() - t0))
+        return float(np.median(reps)), reps
+
+    e2e_value, e2e_reps = e2e_run(args.host_format)
     h2d = n * 4
     d2h = batches[0].host_d2h_bytes_per_step
     e2e_threads = batches[0].host_threads
     e2e_full = None
     if args.host_format != "full":  # the same loop with the arrays crossing PCIe as they are, for comparison
-        for b in batches:
-            b.set_host_format("full")
-        for t in range(max(3, 2 * R)):
-            batches[t % R].step_host(host_actions[t % host_actions.shape[0]])
-        barrier()
-        t0 = time.perf_counter()
-        for t in range(Ke):
-            batches[t % R].step_host(host_actions[t % host_actions.shape[0]])
-        torch.cuda.synchronize()
-        e2e_full = {"value": total * Ke / max_over_ranks(time.perf_counter() - t0), "d2h_bytes_per_step": batches[0].host_d2h_bytes_per_step}
+        v_full, reps_full = e2e_run("full")
+        e2e_full = {"value": v_full, "repetitions": reps_full, "d2h_bytes_per_step": batches[0].host_d2h_bytes_per_step}
 
     # ---- the other BASELINE configs, the synchronised long run and the autoreset cost (one batch, L2-resident) ----
     configs, sync_wave, autoreset_cost, full_obs = [], None, None, None
@@ -493,7 +496,8 @@ def main():
                     "autoreset_fraction_per_step": head["autoreset_fraction_per_step"]},
             "clocks": {k: head["clocks"][k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                    "format": args.host_format, "host_threads": e2e_threads, "full_format": e2e_full},
+                    "format": args.host_format, "host_threads": e2e_threads, "repetitions": e2e_reps,
+                    "protocol": "3 repetitions of `steps` synchronous step_host calls, the median", "full_format": e2e_full},
             "gpu_launches": int(launches),
             "host_enqueue_us_per_step": head["host_enqueue_us_per_step"],
         }

@@ -75,8 +75,11 @@ def load(build_if_missing: bool = True):
     L.mg_get_state.argtypes = [p] * 6
     L.mg_set_state.argtypes = [p] * 6
     L.mg_check_error.argtypes = [p, p]
-    L.mg_set_no_death.argtypes = [p, i32, C.c_double]
-    L.mg_set_bonus.argtypes = [p, i32]
+    try:
+        L.mg_set_no_death.argtypes = [p, i32, C.c_double]
+        L.mg_set_bonus.argtypes = [p, i32]
+    except AttributeError:  # an older build loaded through MINIGRID_B200_LIB for an A/B run
+        pass
     L.mg_profile.argtypes = [p, i32]
     L.mg_profile_read.argtypes = [p, C.POINTER(C.c_double), C.POINTER(i64)]
     for name in EXPORTS:

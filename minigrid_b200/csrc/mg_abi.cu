@@ -62,6 +62,13 @@ struct mg_env {
   int pool_threads;                        // what this handle asked for (the pool itself is process-wide)
   cudaEvent_t chunk_ev[16];
   int n_chunks;
+  // store form of the host expansion (mg_host_expand.cpp: expand_range): calibrated per handle, because it depends on
+  // whether the caller's output arrays stay in the host's last-level cache. Steps 2..13 of a calibration alternate the
+  // two forms and time the whole call; the faster one is kept for the next 8192 steps.
+  int stream_fixed;            // -1 calibrate, 0 / 1 forced by MINIGRID_B200_EXPAND_STREAM
+  int stream_mode;             // the form in use outside a calibration
+  int64_t packed_steps;        // packed host steps so far
+  double cal_us[2]; int cal_n[2];
   // MINIGRID_B200_HOST_TRACE=1: where a packed host step spends its time (printed by mg_destroy)
   int trace; double tr_enqueue, tr_first_chunk, tr_last_chunk, tr_pool, tr_total; int64_t tr_n;
   // optional per-launch timing of K1 (bench.py's roofline leg)
@@ -177,6 +184,8 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   p.mode = autoreset_mode;
   p.kind = kind;
   h->trace = getenv("MINIGRID_B200_HOST_TRACE") != nullptr;
+  h->stream_fixed = -1;
+  if (const char *es = getenv("MINIGRID_B200_EXPAND_STREAM")) h->stream_fixed = atoi(es) != 0;
   p.hot_first = 1;
   if (const char *e = getenv("MINIGRID_B200_HOTFIRST")) p.hot_first = atoi(e) != 0;  // tuning knob (same-box A/B)
   for (int i = 0; i < 8; ++i) p.kp[i] = (params && i < n_params) ? params[i] : 0;
@@ -684,6 +693,12 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   HostPool *pool = g_pool;
   ExpandJob job;
   job.packed = h->h_packed; job.max_steps = h->p.max_steps; job.reward_lut = h->h_reward_lut;
+  const int64_t cal_pos = h->packed_steps % 8192;  // a calibration opens every 8192 steps
+  const bool calibrating = h->stream_fixed < 0 && cal_pos < 14;
+  if (h->stream_fixed >= 0) job.stream = h->stream_fixed;
+  else if (calibrating) job.stream = (int)(cal_pos & 1);
+  else job.stream = h->stream_mode;
+  if (calibrating && cal_pos == 0) { h->cal_us[0] = h->cal_us[1] = 0.0; h->cal_n[0] = h->cal_n[1] = 0; }
   job.obs = obs_host; job.dir = dir_host; job.reward = reward_host; job.term = term_host; job.trunc = trunc_host;
   int64_t bounds[17];
   const int C = h->n_chunks;
@@ -720,6 +735,15 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (h->trace) h->tr_total += since();
+  if (calibrating && cal_pos >= 2) {  // (the first two steps warm the buffers up)
+    h->cal_us[job.stream] += since(); h->cal_n[job.stream] += 1;
+    if (cal_pos == 13) {
+      h->stream_mode = h->cal_us[1] * h->cal_n[0] < h->cal_us[0] * h->cal_n[1] ? 1 : 0;
+      if (h->trace) fprintf(stderr, "[minigrid_b200] host expansion: plain %.1f us, streaming %.1f us per step -> %s stores\n",
+                            h->cal_us[0] / h->cal_n[0], h->cal_us[1] / h->cal_n[1], h->stream_mode ? "streaming" : "plain");
+    }
+  }
+  h->packed_steps += 1;
   if (e != cudaSuccess) return fail(MG_ERR_CUDA, std::string("mg_step_host (packed): ") + cudaGetErrorString(e));
   if (*h->h_err & ERR_PACKED_RANGE) {
     MG_CUDA(launch_clear_err(h->p, ERR_PACKED_RANGE, s));

@@ -109,13 +109,11 @@ MG_HD uint32_t decode_cell(uint32_t code) {
 // Two HBM layouts of the per-env words (same words, same r_word / c_word indices):
 //   LAYOUT_TILED   tile[w][lane] for 32 consecutive envs (small grids): one TMA bulk copy stages a whole tile and
 //                  per-lane gathers are bank-conflict free.
-//   LAYOUT_WINDOW  env-major, 32-byte lines, 3 ring lines (large grids): a step only touches the 7 lines of the
-//                  egocentric view, 224 contiguous bytes of one array, which each lane copies with cp.async;
-//                  HBM traffic per env-step no longer grows with the grid.
+//   LAYOUT_WINDOW  env-major, lines of ceil(W / 4) words, 3 ring lines (large grids): a step only touches the 7 lines of
+//                  the egocentric view, contiguous in one array, which each lane gathers straight into registers;
+//                  HBM traffic per env-step grows with the grid's side, not its area.
 enum : int { LAYOUT_TILED = 0, LAYOUT_WINDOW = 1 };
-constexpr int WIN_LINE_WORDS = 8;   // 32-byte lines (W, H <= 26)
-constexpr int WIN_BYTES = 7 * 32;   // the 7 view lines
-constexpr int WIN_LANE_BYTES = 240; // per-lane shared-memory stride (16-byte aligned, 60 words: 4-way bank spread)
+constexpr int WIN_LANE_BYTES = 240; // (host emulation of the round-1 window staging only)
 
 struct Geom {
   int W, H;
@@ -130,9 +128,13 @@ MG_HD Geom make_geom(int W, int H, int layout) {
   Geom g;
   g.W = W; g.H = H; g.layout = layout;
   if (layout == LAYOUT_TILED) { g.lswR = (W + 3) >> 2; g.lswC = (H + 3) >> 2; g.ring = 1; }
-  else { g.lswR = WIN_LINE_WORDS; g.lswC = WIN_LINE_WORDS; g.ring = 3; }
+  else { g.lswR = (W + 3) >> 2; g.lswC = (H + 3) >> 2; g.ring = 3; }  // lines as wide as the grid: a step's 7 lines are 7 * lsw words
   g.offC = (H + 2 * g.ring) * g.lswR;
   g.wpe = g.offC + (W + 2 * g.ring) * g.lswC;
+  if (layout != LAYOUT_TILED) {  // both arrays of every env start on 16 bytes (K3 stages array C with bulk copies)
+    g.offC = (g.offC + 3) & ~3;
+    g.wpe = (g.offC + (W + 2 * g.ring) * g.lswC + 3) & ~3;
+  }
   return g;
 }
 // index in the grid arena (in words) of word w of environment env

@@ -169,10 +169,13 @@ void expand_block64(const ExpandJob &j, int64_t i0) {
 }  // namespace
 
 void expand_range(const ExpandJob &j, int64_t lo, int64_t hi) {
-  // measured on the B200 host (profiles/r02c_gpu_call.log, 262144 envs, 16 threads): 0.195 ms with plain stores,
-  // 0.248 ms with the streaming block path — the 64-env staging pass costs more than the avoided read-for-ownership
-  // saves there, so streaming is opt-in (MINIGRID_B200_EXPAND_STREAM=1)
-  static const bool no_stream = getenv("MINIGRID_B200_EXPAND_STREAM") == nullptr;
+  // Which store form is faster depends on where the caller's arrays live (profiles/r02n_gpu_call.log, 262144 envs, 16
+  // threads): one set of output arrays (42 MB) stays in the host's last-level cache and plain stores win (7.4e8 against
+  // 5.7e8 env-steps/s end to end); four sets cycled (bench.py's rotating batches) live in DRAM, where plain stores pay a
+  // read-for-ownership per line and streaming wins (7.1e8 against 4.5e8). The caller says which (mg_abi.cu calibrates per
+  // handle over its first steps); -1 = the environment variable, else plain.
+  static const bool env_stream = [] { const char *e = getenv("MINIGRID_B200_EXPAND_STREAM"); return e && atoi(e) != 0; }();
+  const bool no_stream = j.stream < 0 ? !env_stream : j.stream == 0;
   auto aligned = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 63u) == 0; };
   const bool stream = !no_stream && aligned(j.obs) && aligned(j.dir) && aligned(j.reward) && aligned(j.term) && aligned(j.trunc);
   auto plain = [&](int64_t a, int64_t b) {
@@ -213,22 +216,45 @@ int usable_host_threads() {
 }
 
 // ---- a small persistent pool: workers park on a condition variable between steps, and inside a step wait (spinning
-// briefly) for the chunk the copy engine is still delivering ----
+// briefly) for the chunk the copy engine is still delivering. Work is handed out in SLICES of 1024 records through one
+// counter per chunk: a worker the OS has descheduled (the pool may be as wide as the process's CPU quota, and the
+// calling thread is polling CUDA events next to it) then holds up one slice, not a sixteenth of every chunk, and the
+// calling thread expands slices itself once the last chunk has landed. Counters carry the job's generation, so a worker
+// that is late leaving job g can never take (or skip) a slice of job g + 1.
 struct HostPool::Impl {
+  static constexpr int64_t SLICE = 1024;  // records; a multiple of 64 (whole cache lines of every output array)
+  static constexpr int MAX_CHUNKS = 16;
   std::vector<std::thread> threads;
   std::mutex mu;
-  std::condition_variable cv_start, cv_done;
+  std::condition_variable cv_start;
   uint64_t generation = 0;
   bool stop = false;
   ExpandJob job{};
-  std::vector<int64_t> bounds;       // chunk c = envs [bounds[c], bounds[c + 1])
-  std::atomic<int> ready{0};         // chunks whose bytes have arrived on the host
-  int done = 0;
+  int64_t bounds[MAX_CHUNKS + 1] = {0};  // chunk c = envs [bounds[c], bounds[c + 1])
+  int n_chunks = 0;
+  int64_t total_slices = 0;
+  std::atomic<int> ready{0};                    // chunks whose bytes have arrived on the host
+  std::atomic<uint64_t> next[MAX_CHUNKS];       // generation << 32 | next slice of the chunk
+  std::atomic<int64_t> finished{0};             // slices of the current job that are done
+  std::atomic<uint64_t> gen_fast{0};            // mirrors `generation` for the spinning phase
 
-  std::atomic<uint64_t> gen_fast{0};  // mirrors `generation` for the spinning phase
-  std::atomic<int> done_fast{0};
+  static int64_t slices_of(int64_t len) { return (len + SLICE - 1) / SLICE; }
 
-  void worker(int w, int T) {
+  // take slices of chunk c of job `gen` until there are none left (or the job is no longer `gen`)
+  void drain_chunk(const ExpandJob &j, const int64_t *bnd, int c, uint64_t gen) {
+    const int64_t lo = bnd[c], hi = bnd[c + 1], n = slices_of(hi - lo);
+    for (;;) {
+      uint64_t cur = next[c].load(std::memory_order_acquire);
+      if ((cur >> 32) != (gen & 0xFFFFFFFFu) || (int64_t)(cur & 0xFFFFFFFFu) >= n) return;
+      if (!next[c].compare_exchange_weak(cur, cur + 1, std::memory_order_acq_rel)) continue;
+      const int64_t s = (int64_t)(cur & 0xFFFFFFFFu);
+      const int64_t a = lo + s * SLICE, b = a + SLICE < hi ? a + SLICE : hi;
+      expand_range(j, a, b);
+      finished.fetch_add(1, std::memory_order_release);
+    }
+  }
+
+  void worker() {
     uint64_t seen = 0;
     for (;;) {
       // A training loop calls step after step: the next job arrives tens of microseconds after the last one ended, less
@@ -238,35 +264,35 @@ struct HostPool::Impl {
         if (gen_fast.load(std::memory_order_acquire) != seen) { got = true; break; }
         _mm_pause();
       }
+      ExpandJob j;
+      int64_t bnd[MAX_CHUNKS + 1];
+      int nc;
       {
         std::unique_lock<std::mutex> lk(mu);
         if (!got) cv_start.wait(lk, [&] { return stop || generation != seen; });
         if (stop) return;
         seen = generation;
+        j = job; nc = n_chunks;
+        for (int c = 0; c <= nc; ++c) bnd[c] = bounds[c];
       }
-      const int n_chunks = (int)bounds.size() - 1;
-      for (int c = 0; c < n_chunks; ++c) {
+      for (int c = 0; c < nc; ++c) {
         int spins = 0;
+        bool stale = false;
         while (ready.load(std::memory_order_acquire) <= c) {
+          if (gen_fast.load(std::memory_order_acquire) != seen) { stale = true; break; }  // the job ended without us
           if (++spins < 2000) _mm_pause();
           else { std::this_thread::yield(); spins = 0; }
         }
-        // slices start on multiples of 64 records (whole cache lines of every output array, see expand_block64)
-        const int64_t lo = bounds[c], len = bounds[c + 1] - bounds[c];
-        const int64_t a = w == 0 ? 0 : ((len * w / T) & ~(int64_t)63), b = w == T - 1 ? len : ((len * (w + 1) / T) & ~(int64_t)63);
-        expand_range(job, lo + a, lo + b);
-      }
-      done_fast.fetch_add(1, std::memory_order_release);
-      {
-        std::lock_guard<std::mutex> lk(mu);
-        if (++done == T) cv_done.notify_one();
+        if (stale) break;
+        drain_chunk(j, bnd, c, seen);
       }
     }
   }
 };
 
 HostPool::HostPool(int n_threads) : impl_(new Impl), n_threads_(n_threads < 1 ? 1 : n_threads) {
-  for (int w = 0; w < n_threads_; ++w) impl_->threads.emplace_back([this, w] { impl_->worker(w, n_threads_); });
+  for (int c = 0; c < Impl::MAX_CHUNKS; ++c) impl_->next[c].store(0);
+  for (int w = 0; w < n_threads_; ++w) impl_->threads.emplace_back([this] { impl_->worker(); });
 }
 HostPool::~HostPool() {
   {
@@ -279,24 +305,32 @@ HostPool::~HostPool() {
 }
 void HostPool::begin(const ExpandJob &job, const int64_t *bounds, int n_chunks) {
   std::lock_guard<std::mutex> lk(impl_->mu);
+  if (n_chunks > Impl::MAX_CHUNKS) n_chunks = Impl::MAX_CHUNKS;  // (callers never ask for more)
   impl_->job = job;
-  impl_->bounds.assign(bounds, bounds + n_chunks + 1);
-  impl_->ready.store(0, std::memory_order_release);
-  impl_->done = 0;
-  impl_->done_fast.store(0, std::memory_order_release);
+  impl_->n_chunks = n_chunks;
+  impl_->total_slices = 0;
   impl_->generation += 1;
+  for (int c = 0; c <= n_chunks; ++c) impl_->bounds[c] = bounds[c];
+  for (int c = 0; c < n_chunks; ++c) {
+    impl_->total_slices += Impl::slices_of(bounds[c + 1] - bounds[c]);
+    impl_->next[c].store((impl_->generation & 0xFFFFFFFFu) << 32, std::memory_order_release);
+  }
+  impl_->ready.store(0, std::memory_order_release);
+  impl_->finished.store(0, std::memory_order_release);
   impl_->gen_fast.store(impl_->generation, std::memory_order_release);
   impl_->cv_start.notify_all();
 }
 void HostPool::chunk_ready() { impl_->ready.fetch_add(1, std::memory_order_release); }
 void HostPool::abort_chunks(int n_chunks) { impl_->ready.store(n_chunks, std::memory_order_release); }
 void HostPool::wait() {
-  for (int spins = 0; spins < 200000; ++spins) {  // the workers are a few microseconds from done when this is called
-    if (impl_->done_fast.load(std::memory_order_acquire) == n_threads_) break;
-    _mm_pause();
+  // every chunk has been released: the calling thread takes slices too, then waits for the slices still in other hands
+  const uint64_t gen = impl_->generation;  // (only this thread starts jobs)
+  for (int c = 0; c < impl_->n_chunks; ++c) impl_->drain_chunk(impl_->job, impl_->bounds, c, gen);
+  int spins = 0;
+  while (impl_->finished.load(std::memory_order_acquire) < impl_->total_slices) {
+    if (++spins < 4000) _mm_pause();
+    else { std::this_thread::yield(); spins = 0; }
   }
-  std::unique_lock<std::mutex> lk(impl_->mu);
-  impl_->cv_done.wait(lk, [&] { return impl_->done == n_threads_; });
 }
 
 }  // namespace mg
@@ -305,7 +339,7 @@ extern "C" int mg_expand_packed(const uint8_t *packed, int64_t n_envs, int32_t m
                                 double *reward, uint8_t *terminated, uint8_t *truncated) {
   if (!packed || n_envs < 0 || max_steps < 1) return MG_ERR_INVALID_ARG;
   mg::ExpandJob j{};
-  j.packed = packed; j.max_steps = max_steps; j.reward_lut = nullptr;
+  j.packed = packed; j.max_steps = max_steps; j.reward_lut = nullptr; j.stream = -1;
   j.obs = obs; j.dir = dir; j.reward = reward; j.term = terminated; j.trunc = truncated;
   mg::expand_range(j, 0, n_envs);
   return MG_OK;
@@ -318,7 +352,7 @@ extern "C" int mg_expand_packed_mt(const uint8_t *packed, int64_t n_envs, int32_
   const int want = n_threads > 0 ? n_threads : mg::usable_host_threads();
   if (!pool || pool->threads() != want) { delete pool; pool = new mg::HostPool(want); }
   mg::ExpandJob j{};
-  j.packed = packed; j.max_steps = max_steps; j.reward_lut = nullptr;
+  j.packed = packed; j.max_steps = max_steps; j.reward_lut = nullptr; j.stream = -1;
   j.obs = obs; j.dir = dir; j.reward = reward; j.term = terminated; j.trunc = truncated;
   const int64_t bounds[2] = {0, n_envs};
   pool->begin(j, bounds, 1);

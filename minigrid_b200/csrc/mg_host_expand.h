@@ -12,6 +12,8 @@ struct ExpandJob {
   int32_t *dir;              // [n] or NULL
   double *reward;            // [n] or NULL
   uint8_t *term, *trunc;     // [n] or NULL
+  int stream;                // 1: non-temporal stores through a 64-record staging block (outputs that live in DRAM),
+                             // 0: plain stores (outputs that stay in the last-level cache); -1: MINIGRID_B200_EXPAND_STREAM or plain
 };
 
 // expands records [lo, hi)

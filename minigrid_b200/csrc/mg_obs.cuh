@@ -193,11 +193,12 @@ MG_D void load_view_words(const Geom &g, int ax, int ay, int dirn, ViewWords &vw
   const int lstep = (dirn == 0 || dirn == 3) ? 1 : -1;
   const int abase = useC ? g.offC : 0;
   const int ws = view_first_pos(ax, ay, dirn) >> 2;
-  const int k0 = clampi(ws, 0, WIN_LINE_WORDS - 1), k1 = clampi(ws + 1, 0, WIN_LINE_WORDS - 1), k2 = clampi(ws + 2, 0, WIN_LINE_WORDS - 1);
+  const int lsw = useC ? g.lswC : g.lswR;  // words per line of the array the agent faces along
+  const int k0 = clampi(ws, 0, lsw - 1), k1 = clampi(ws + 1, 0, lsw - 1), k2 = clampi(ws + 2, 0, lsw - 1);
   vw.ws = ws;
 #pragma unroll
   for (int vx = 0; vx < VIEW; ++vx) {
-    const int rw = abase + (lc + lstep * (vx - 3) + g.ring) * WIN_LINE_WORDS;  // ring = 3 lines: lc +- 3 always exists
+    const int rw = abase + (lc + lstep * (vx - 3) + g.ring) * lsw;  // ring = 3 lines: lc +- 3 always exists
     vw.w[vx][0] = load(rw + k0);
     vw.w[vx][1] = load(rw + k1);
     vw.w[vx][2] = load(rw + k2);

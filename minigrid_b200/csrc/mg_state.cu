@@ -9,21 +9,48 @@ __device__ __forceinline__ uint32_t load_code(const Params &p, int env, int x, i
 }
 
 // K3. out[n][W][H][3] = grid.encode(), agent cell = (OBJECT_TO_IDX["agent"], COLOR_TO_IDX["red"], agent_dir).
-// One CTA per tile of 32 environments, whose output block (32 x 3WH bytes) is contiguous. Four consecutive cells are
-// twelve output bytes = three aligned words, so a thread takes a GROUP of four cells of the tile's flat cell sequence
-// (array C is [x][y] ordered like the output; a group may straddle two envs): four code bytes through the read-only
-// path (L1-resident lines), four (type, colour, state) lookups, three byte permutes like K1's image stream, three
-// word stores. One division per group, no staging. HBM-bound: W*H code bytes + the agent record in, 3*W*H out.
+// One CTA per tile of 32 environments, whose output block (32 x 3WH bytes) is contiguous. The tile's array C (lines x,
+// column-major: ordered like the output) is staged in shared memory by TMA bulk copies — one for a tiled block, one per
+// env in the window layout — so that every HBM read of the CTA is in flight at once instead of behind the per-cell
+// dependency chain (offset lookup -> byte load -> table lookup -> store) of the previous version. Four consecutive
+// cells are twelve output bytes = three aligned words: a thread takes a GROUP of four cells of the tile's flat cell
+// sequence (a group may straddle two envs): four code bytes out of the stage, four (type, colour, state) lookups, three
+// byte permutes like K1's image stream, three word stores. HBM-bound: array C + the agent record in, 3*W*H out.
+__device__ __forceinline__ uint32_t k3_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__host__ __device__ inline uint32_t k3_env_bytes(const Geom &g) { return (uint32_t)(g.wpe - g.offC) * 4u; }  // array C of one env (window layout: a multiple of 16)
+__host__ __device__ inline size_t k3_smem_bytes(const Geom &g) {
+  return (size_t)TILE * k3_env_bytes(g) + 256 * 4 + TILE * 4 + (MAX_DIM * MAX_DIM + 2) * 2 + 16;
+}
 __global__ void __launch_bounds__(256)
 k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with_agent) {
-  __shared__ uint32_t s_lut[256];
-  __shared__ uint32_t s_agent[TILE];                // agent cell index x * H + y | dir << 16 (no agent: never matches)
-  __shared__ uint16_t s_off[MAX_DIM * MAX_DIM + 1]; // cell c = x * H + y -> byte offset of the cell inside the env's part of array C
+  extern __shared__ __align__(128) uint8_t k3_raw[];
   const Geom &g = p.g;
+  const uint32_t cbytes = k3_env_bytes(g), stage_bytes = TILE * cbytes;
+  uint8_t *stage = k3_raw;                                               // tiled: [word][lane] words of array C; window: [env][cbytes]
+  uint32_t *s_lut = reinterpret_cast<uint32_t *>(k3_raw + stage_bytes);
+  uint32_t *s_agent = s_lut + 256;                  // agent cell index x * H + y | dir << 16 (no agent: never matches)
+  uint16_t *s_off = reinterpret_cast<uint16_t *>(s_agent + TILE);  // cell c = x * H + y -> byte offset of the cell inside an env's part of the stage
+  uint64_t *bar = reinterpret_cast<uint64_t *>(k3_raw + ((stage_bytes + 256 * 4 + TILE * 4 + (MAX_DIM * MAX_DIM + 2) * 2 + 7) & ~7u));
   const int WH = g.W * g.H, env_bytes = 3 * WH;
   const int tile = blockIdx.x;
   const int nvalid = min(TILE, p.n_envs - tile * TILE);
   const bool tiled = g.layout == LAYOUT_TILED;
+  const uint32_t bar_s = k3_smem(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(stage_bytes) : "memory");
+  }
+  __syncthreads();
+  const uint8_t *tb = reinterpret_cast<const uint8_t *>(p.grid) + (size_t)tile * g.wpe * 128;  // both layouts: 32 envs x wpe words
+  if (tiled) {
+    if (threadIdx.x == 0)  // words offC .. wpe - 1 of all 32 lanes: one contiguous block
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(k3_smem(stage)),
+                   "l"(tb + (size_t)g.offC * 128), "r"(stage_bytes), "r"(bar_s) : "memory");
+  } else if (threadIdx.x < TILE) {  // env-major: array C of env e is cbytes contiguous bytes
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(k3_smem(stage + threadIdx.x * cbytes)),
+                 "l"(tb + (size_t)threadIdx.x * g.wpe * 4 + (size_t)g.offC * 4), "r"(cbytes), "r"(bar_s) : "memory");
+  }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = decode_cell((uint32_t)i);
   if (threadIdx.x < TILE) {
     const uint4 rec = p.agent[tile * TILE + threadIdx.x];
@@ -32,16 +59,19 @@ k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with
   const float inv_h = 1.0f / (float)g.H;
   for (int c = threadIdx.x; c < WH; c += blockDim.x) {
     const int x = (int)(((float)c + 0.5f) * inv_h), y = c - x * g.H;  // exact: (c + 0.5) / H is never within rounding of an integer
-    // tiled: word cw of lane e sits at (cw * 32 + e) * 4 of the tile block; window: env-major words
-    s_off[c] = (uint16_t)(tiled ? c_word(g, x, y) * 128 + (y & 3) : c_word(g, x, y) * 4 + (y & 3));
+    const int cw = c_word(g, x, y) - g.offC;  // word of the cell inside array C
+    s_off[c] = (uint16_t)(tiled ? cw * 128 + (y & 3) : cw * 4 + (y & 3));
   }
   __syncthreads();
-  const uint8_t *tb = reinterpret_cast<const uint8_t *>(p.grid) + (size_t)tile * g.wpe * 128;  // both layouts: 32 envs x wpe words
-  const uint32_t estride = tiled ? 4u : (uint32_t)g.wpe * 4u;
+  {  // the stage has landed
+    asm volatile(
+        "{\n.reg .pred p;\nK3W_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra K3D_%=;\nbra K3W_%=;\nK3D_%=:\n}\n" ::"r"(bar_s), "r"(0) : "memory");
+  }
+  const uint32_t estride = tiled ? 4u : cbytes;
   const float inv_wh = 1.0f / (float)WH;
   auto triple = [&](int e, int c) -> uint32_t {  // type | colour << 8 | state << 16 of cell c of env e
     const uint32_t ag = s_agent[e];
-    const uint32_t t = s_lut[__ldg(tb + (uint32_t)e * estride + s_off[c])];
+    const uint32_t t = s_lut[stage[(uint32_t)e * estride + s_off[c]]];
     return (ag & 0xFFFFu) == (uint32_t)c ? (T_AGENT | (C_RED << 8) | (ag & 0x30000u)) : t;
   };
   uint8_t *dst = out + (size_t)tile * TILE * env_bytes;
@@ -158,7 +188,7 @@ __global__ void k_init(Params p) {
 }
 
 cudaError_t launch_full_obs(const Params &p, uint8_t *out, int with_agent, cudaStream_t stream) {
-  k_full_obs<<<(unsigned)p.n_tiles, 256, 0, stream>>>(p, out, with_agent);
+  k_full_obs<<<(unsigned)p.n_tiles, 256, k3_smem_bytes(p.g), stream>>>(p, out, with_agent);  // <= 35 KB: under the 48 KB default
   return cudaGetLastError();
 }
 cudaError_t launch_get_state(const Params &p, uint8_t *grid, int32_t *agent, uint64_t *rng, uint8_t *pending, cudaStream_t stream) {

@@ -92,6 +92,9 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
   const long long want = ((long long)p.n_tiles + plan->warps - 1) / plan->warps;
   long long grid = (long long)sms * plan->ctas_per_sm;
   if (grid > want) grid = want;
+  // test knob: fewer CTAs than the device offers, so that a SMALL batch gives every warp several tiles (the tile loop's
+  // prefetch / buffer rotation / order list are otherwise only exercised at BASELINE sizes)
+  if (const char *e = getenv("MINIGRID_B200_GRID")) { const long long cap = atoll(e); if (cap >= 1 && cap < grid) grid = cap; }
   plan->grid = (int)(grid < 1 ? 1 : grid);
   return cudaSuccess;
 }

@@ -106,13 +106,36 @@ __device__ __forceinline__ int load_action(const void *actions, int dtype, int e
   return v;
 }
 
-// 1 / math.sqrt(new_count) of ActionBonus / PositionBonus (wrappers.py:122, 180): correctly rounded sqrt and division,
-// like CPython's. Out of line: the wrappers are rare, the hot loop must not carry their registers.
-static __device__ __noinline__ double bonus_of(uint32_t count) { return __ddiv_rn(1.0, __dsqrt_rn((double)count)); }
 // OBJECT_TO_IDX type of a cell code (door states and the key-hiding box folded back)
 __device__ __forceinline__ uint32_t code_type(uint32_t code) {
   const uint32_t t4 = code & 15u;
   return (t4 == T4_DOOR_CLOSED || t4 == T4_DOOR_LOCKED) ? (uint32_t)T_DOOR : (t4 == T4_BOX_WITH_KEY ? (uint32_t)T_BOX : t4);
+}
+// The reference's reward wrappers around one env's step, BonusWrapper(NoDeath(env)).step (wrappers.py:106-125, 163-184,
+// 852-882). Out of line and behind one uniform branch: the hot loop must not carry their registers.
+//   f0   the cell in front BEFORE the env stepped (Dynamic-Obstacles: before its balls moved), cur the cell under the agent after
+struct WrapOut { double reward; uint32_t terminated; };
+static __device__ __noinline__ WrapOut wrap_step(const Params &p, int env, bool active, int action_raw, uint32_t f0, uint32_t cur,
+                                                 int ax, int ay, int dir, double reward, uint32_t terminated) {
+  if (p.no_death_mask) {
+    const bool going_to_death = action_raw == A_FORWARD && f0 != CODE_EMPTY && ((p.no_death_mask >> code_type(f0)) & 1);
+    const bool in_death = cur != CODE_EMPTY && ((p.no_death_mask >> code_type(cur)) & 1);
+    if (terminated && (going_to_death || in_death)) {
+      terminated = 0u;
+      reward = __dadd_rn(reward, p.death_cost);
+    }
+  }
+  if (p.bonus_mode && active && (unsigned)action_raw <= (unsigned)A_DONE) {  // the state after the step keys the count
+    uint32_t key = (uint32_t)(ay * p.g.W + ax);
+    uint32_t per = (uint32_t)(p.g.W * p.g.H);
+    if (p.bonus_mode == 1) { key = (key * 4u + (uint32_t)dir) * 7u + (uint32_t)action_raw; per *= 28u; }
+    uint32_t *cnt = p.counts + (size_t)env * per + key;
+    const uint32_t c = *cnt + 1u;
+    *cnt = c;
+    reward = __dadd_rn(reward, __ddiv_rn(1.0, __dsqrt_rn((double)c)));  // 1 / math.sqrt(new_count): both correctly rounded
+  }
+  WrapOut o = {reward, terminated};
+  return o;
 }
 
 // MiniGridEnv.reset() for the lanes in `pend`. Phase 1: every pending lane replays the numpy-exact draws of ITS
@@ -498,12 +521,7 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       const int fpos = ((dir & 1) ? ay : ax) + ((dir < 2) ? 1 : -1);  // the front cell's position on the agent's own line
       if (WIN) fc = view_words_byte(vw, fpos);  // meaningless after a turn (other array loaded), and then unused
       else fc = (tile_word<true>(base, rw) >> (8 * (fx & 3))) & 0xFFu;
-      // NoDeath.step (wrappers.py:855-861): the cell in front BEFORE the env steps (Dynamic-Obstacles: before its balls move)
-      bool going_to_death = false;
-      if (p.no_death_mask) {
-        const uint32_t f0 = (KIND == KIND_DYNOBS && !WIN) ? fc_before : fc;
-        going_to_death = action_raw == A_FORWARD && f0 != CODE_EMPTY && ((p.no_death_mask >> code_type(f0)) & 1);
-      }
+
       const uint32_t carry_before = carry;
       const int act = pre_filter<KIND>(action);
       const StepOut so = transition(act, fc, fx, fy, ax, ay, dir, carry);
@@ -570,24 +588,15 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
           reward = steps <= p.max_steps ? p.reward_lut[steps]
                                         : __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)p.max_steps)));
       }
-      if (p.no_death_mask) {  // NoDeath.step after env.step (wrappers.py:863-872): also an agent that stays on a death cell
-        uint32_t cur;
-        if (WIN) cur = view_words_byte(vw, (dir & 1) ? ay : ax);
-        else cur = (tile_word<true>(base, r_word(g, ax, ay)) >> (8 * (ax & 3))) & 0xFFu;
-        const bool in_death = cur != CODE_EMPTY && ((p.no_death_mask >> code_type(cur)) & 1);
-        if (terminated && (going_to_death || in_death)) {
-          terminated = 0u;
-          reward = __dadd_rn(reward, p.death_cost);
+      if (p.no_death_mask | p.bonus_mode) {  // the reference's reward wrappers: rare, one uniform branch, out of line
+        uint32_t cur = 0;  // the cell under the agent after the step
+        if (p.no_death_mask) {
+          if (WIN) cur = view_words_byte(vw, (dir & 1) ? ay : ax);
+          else cur = (tile_word<true>(base, r_word(g, ax, ay)) >> (8 * (ax & 3))) & 0xFFu;
         }
-      }
-      if (p.bonus_mode && active && (unsigned)action_raw <= (unsigned)A_DONE) {  // ActionBonus / PositionBonus.step: the state after the step
-        uint32_t key = (uint32_t)(ay * g.W + ax);
-        uint32_t per = (uint32_t)(g.W * g.H);
-        if (p.bonus_mode == 1) { key = (key * 4u + (uint32_t)dir) * 7u + (uint32_t)action_raw; per *= 28u; }
-        uint32_t *cnt = p.counts + (size_t)env * per + key;
-        const uint32_t c = *cnt + 1u;
-        *cnt = c;
-        reward = __dadd_rn(reward, bonus_of(c));
+        const WrapOut wo = wrap_step(p, env, active, action_raw, (KIND == KIND_DYNOBS && !WIN) ? fc_before : fc, cur, ax, ay, dir, reward, terminated);
+        reward = wo.reward;
+        terminated = wo.terminated;
       }
       truncated = steps >= p.max_steps;
       rsteps = steps;

@@ -24,7 +24,7 @@ for l in sass[start:end]:
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", l)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", l)
     if m:
         lines.append((cur, re.sub(r"\s+", " ", m.group(1)).strip()))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
@@ -60,5 +60,5 @@ for (f, l), c in agg.most_common(int(sys.argv[4]) if len(sys.argv) > 4 else 45):
     if f not in files:
         pth = os.path.join(root, "minigrid_b200", "csrc", f)
         files[f] = open(pth).read().split("\n") if os.path.exists(pth) else None
-    text = files[f][l - 1].strip()[:95] if files[f] else ""
+    text = files[f][l - 1].strip()[:95] if files[f] and 0 < l <= len(files[f]) else ""  # (the source may have moved on since the capture)
     print(f"{c / n_tiles:7.1f} {samp[(f, l)]:5d}  {f}:{l}  {text}")

@@ -148,3 +148,36 @@ def test_emu_boxes_hide_keys(env_id, layout):
     for k in ("grid", "agent", "rng", "pending"):
         np.testing.assert_array_equal(es[k], os_[k], err_msg=k)
     assert (os_["agent"][moved, 3] == 5).sum() >= moved.sum() // 4  # keys did come out of boxes
+
+
+def test_expand_pool_matches_the_single_threaded_expander():
+    """The host pool (slices handed out through generation-tagged counters, the caller helping) against the plain
+    single-threaded expander on random records: many back-to-back jobs of changing size and thread count. Host code of
+    the product library, no GPU needed."""
+    import ctypes as C
+
+    from minigrid_b200 import _build
+
+    L = C.CDLL(_build.LIB_PATH)
+    p = C.c_void_p
+    L.mg_expand_packed.argtypes = [p, C.c_int64, C.c_int32, p, p, p, p, p]
+    L.mg_expand_packed_mt.argtypes = [p, C.c_int64, C.c_int32, p, p, p, p, p, C.c_int]
+    rng = np.random.default_rng(3)
+    ptr = lambda a: a.ctypes.data_as(p)
+    for it in range(60):
+        n = int(rng.integers(1, 70000))
+        packed = rng.integers(0, 256, (n, 52), dtype=np.uint8)
+        packed[:, 0:49] = rng.integers(0, 14, (n, 49)) | (rng.integers(0, 6, (n, 49)) << 4)  # plausible cell codes
+        packed[:, 49] &= 0x1F          # step_count < 2^16
+        packed[:, 50:52] = rng.integers(0, 256, (n, 2)); packed[:, 51] &= 0x01  # step_count <= 511
+        outs = []
+        for mt in (0, int(rng.integers(1, 9))):
+            obs = np.zeros((n, 147), np.uint8); d = np.zeros(n, np.int32); r = np.zeros(n, np.float64)
+            te = np.zeros(n, np.uint8); tr = np.zeros(n, np.uint8)
+            if mt == 0:
+                assert L.mg_expand_packed(ptr(packed), n, 640, ptr(obs), ptr(d), ptr(r), ptr(te), ptr(tr)) == 0
+            else:
+                assert L.mg_expand_packed_mt(ptr(packed), n, 640, ptr(obs), ptr(d), ptr(r), ptr(te), ptr(tr), mt) == 0
+            outs.append((obs, d, r, te, tr))
+        for a, b in zip(*outs):
+            assert a.tobytes() == b.tobytes(), f"job {it} n={n}"
