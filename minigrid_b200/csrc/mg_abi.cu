@@ -63,8 +63,10 @@ struct mg_env {
   cudaEvent_t chunk_ev[16];
   int n_chunks;
   // store form of the host expansion (mg_host_expand.cpp: expand_range): calibrated per handle, because it depends on
-  // whether the caller's output arrays stay in the host's last-level cache. Steps 2..13 of a calibration alternate the
-  // two forms and time the whole call; the faster one is kept for the next 8192 steps.
+  // whether the caller's output arrays stay in the host's last-level cache. A calibration is ten steps with plain stores,
+  // then ten with streaming stores (blocks, not alternation: plain stores only win once the arrays ARE cache-resident,
+  // which a streaming step in between undoes); the last six calls of each block are timed and the faster form is kept
+  // for the next 8192 steps.
   int stream_fixed;            // -1 calibrate, 0 / 1 forced by MINIGRID_B200_EXPAND_STREAM
   int stream_mode;             // the form in use outside a calibration
   int64_t packed_steps;        // packed host steps so far
@@ -694,15 +696,18 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   ExpandJob job;
   job.packed = h->h_packed; job.max_steps = h->p.max_steps; job.reward_lut = h->h_reward_lut;
   const int64_t cal_pos = h->packed_steps % 8192;  // a calibration opens every 8192 steps
-  const bool calibrating = h->stream_fixed < 0 && cal_pos < 14;
+  const bool calibrating = h->stream_fixed < 0 && cal_pos < 20;
   if (h->stream_fixed >= 0) job.stream = h->stream_fixed;
-  else if (calibrating) job.stream = (int)(cal_pos & 1);
+  else if (calibrating) job.stream = cal_pos >= 10;
   else job.stream = h->stream_mode;
   if (calibrating && cal_pos == 0) { h->cal_us[0] = h->cal_us[1] = 0.0; h->cal_n[0] = h->cal_n[1] = 0; }
   job.obs = obs_host; job.dir = dir_host; job.reward = reward_host; job.term = term_host; job.trunc = trunc_host;
   int64_t bounds[17];
   const int C = h->n_chunks;
-  for (int c = 0; c <= C; ++c) bounds[c] = (int64_t)((n * (size_t)c / (size_t)C) / 64 * 64);  // whole tiles, and whole cache lines on the host
+  // whole tiles, and whole cache lines on the host. Eight chunks are not equal: a small first one (the expansion starts
+  // sooner), small last ones (less is left to expand once the bus has gone quiet), the bulk in between
+  static const int w8[9] = {0, 1, 3, 6, 9, 12, 14, 15, 16};
+  for (int c = 0; c <= C; ++c) bounds[c] = (int64_t)((C == 8 ? n * (size_t)w8[c] / 16 : n * (size_t)c / (size_t)C) / 64 * 64);
   bounds[C] = (int64_t)n;
   const auto t0 = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
@@ -735,9 +740,9 @@ static int step_host_packed(mg_env *h, const int32_t *src, uint8_t *obs_host, in
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (h->trace) h->tr_total += since();
-  if (calibrating && cal_pos >= 2) {  // (the first two steps warm the buffers up)
+  if (calibrating && cal_pos % 10 >= 4) {  // (the first four steps of a block settle the caches)
     h->cal_us[job.stream] += since(); h->cal_n[job.stream] += 1;
-    if (cal_pos == 13) {
+    if (cal_pos == 19) {
       h->stream_mode = h->cal_us[1] * h->cal_n[0] < h->cal_us[0] * h->cal_n[1] ? 1 : 0;
       if (h->trace) fprintf(stderr, "[minigrid_b200] host expansion: plain %.1f us, streaming %.1f us per step -> %s stores\n",
                             h->cal_us[0] / h->cal_n[0], h->cal_us[1] / h->cal_n[1], h->stream_mode ? "streaming" : "plain");

@@ -35,11 +35,13 @@ static StepKernel step_kernel(int kind, int vis, int mode) {
   return mode == MODE_TILED2 ? pick_vis<MODE_TILED2>(kind, vis) : step_kernel_tiled1(kind, vis);
 }
 
-// Choose the CTA shape once per handle. One persistent CTA of W <= 32 warps per SM; W is taken from the upper half
-// of what shared memory allows so that tiles_per_SM / W lands just below an integer (the last round of tiles is
-// then full: 8192 tiles on 148 SMs is 55.35 per SM, and 19 warps finish in 2.91 rounds). Measured preferences
-// (profiles/r01_sweep_*): the table-driven process_vis (32 KB of shared memory) beats the ALU form, prefetching
-// (two buffers per warp) beats occupancy, and beyond ~20 resident warps nothing is gained.
+// Choose the CTA shape once per handle: one persistent CTA per SM. Measured preferences on the final kernels
+// (profiles/r02o..r02q_gpu_call.log, 262144 envs, desynchronised episodes): for the tiled layout the ONE-buffer kernel
+// at 72 registers with about 22 warps beats the two-buffer kernel at 96 registers with 19 on every kind tried (DoorKey
+// 18.8 against 21.5 us, Empty 18.5 / 19.6, GoToDoor 125 / 157, Fetch 30.4 / 36.8; 20..22 warps is a plateau, 24..28 a
+// little behind, 16 clearly) — round 1's "prefetching beats occupancy" no longer holds now that regenerating tiles go
+// first and the tile loop is shorter; the table-driven process_vis (32 KB of shared memory) beats the ALU form; the
+// window layout wants all 20 warps its 96 registers allow (at 72 registers and 28 warps it spills and loses).
 // MINIGRID_B200_CFG="warps,vis,nbuf" (vis: 1 ALU, 2 table) overrides the choice (tuning knob).
 cudaError_t configure_step(const Params &p, StepPlan *plan) {
   int dev = 0, sms = 148;
@@ -47,7 +49,6 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int want_warps = 0, want_vis = 0, want_nbuf = 0;
   if (const char *cfg = getenv("MINIGRID_B200_CFG")) sscanf(cfg, "%d,%d,%d", &want_warps, &want_vis, &want_nbuf);
-  const double tiles_per_sm = (double)p.n_tiles / sms;
   const bool win = p.g.layout == LAYOUT_WINDOW;
   double best_score = -1.0;
   plan->warps = 0;
@@ -59,7 +60,7 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
       if (!win && want_nbuf && nbuf != want_nbuf) continue;
       const int mode = win ? MODE_WINDOW : (nbuf == 2 ? MODE_TILED2 : MODE_TILED1);
       StepKernel k = step_kernel(p.kind, vis, mode);
-      const int wcap = (nbuf == 2 || win) ? 20 : 32;  // __launch_bounds__ of the variants
+      const int wcap = (nbuf == 2 || win) ? 20 : 28;  // __launch_bounds__ of the variants
       int wmax = 0;
       for (int w = wcap; w >= 1; --w)
         if (step_smem_bytes(p.g, vis, w, nbuf) <= 227 * 1024 - 1024) { wmax = w; break; }
@@ -77,10 +78,9 @@ cudaError_t configure_step(const Params &p, StepPlan *plan) {
         if (ctas * w > wcap) ctas = wcap / w;
         if (ctas < 1) continue;
         const int resident = ctas * w;
-        const double rounds = tiles_per_sm / resident;
-        const double fill = rounds <= 1.0 ? 1.0 : rounds / (double)(long long)(rounds + 0.999999);  // last-round efficiency
-        const int cap = 20;  // the window layout has one exposed HBM round trip per tile to hide
-        const double score = (resident < cap ? resident : cap) * fill * (vis == VIS_TBL ? 1.3 : 1.0) * (nbuf == 2 ? 1.25 : 1.0);
+        const int target = win ? 20 : (nbuf == 1 ? 22 : 14);  // see above
+        const int off = resident > target ? resident - target : target - resident;
+        const double score = (win || nbuf == 1 ? 2.0 : 1.0) * (vis == VIS_TBL ? 1.3 : 1.0) - 0.02 * off;
         if (score > best_score + 1e-9) {
           best_score = score;
           plan->warps = w; plan->vis = vis; plan->nbuf = nbuf; plan->mode = mode; plan->ctas_per_sm = ctas; plan->smem = smem;

@@ -255,7 +255,7 @@ __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int 
 // MODE_TILED2: each warp owns two buffers and prefetches its next tile (TMA + agent records + actions) before it
 // processes the current one, so HBM transfers overlap compute instead of alternating with it in GPU-wide bursts.
 template <int KIND, int VIS, int MODE>
-__global__ void __launch_bounds__(MODE == MODE_TILED2 ? 640 : (MODE == MODE_TILED1 ? 1024 : 640), 1)  // one CTA per SM: <= 20 warps (96 regs; the window mode keeps 21 view words live) or <= 32 (64 regs)
+__global__ void __launch_bounds__(MODE == MODE_TILED2 ? 640 : (MODE == MODE_TILED1 ? 896 : 640), 1)  // one CTA per SM: <= 20 warps (96 regs; the window mode keeps 21 view words live) or <= 28 (72 regs: 7 warps per scheduler)
 k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int act_dtype, uint8_t *__restrict__ obs,
        int32_t *__restrict__ dir_out, double *__restrict__ reward_out, uint8_t *__restrict__ term_out,
        uint8_t *__restrict__ trunc_out, uint32_t *__restrict__ packed_out, int obs_tma_ok) {

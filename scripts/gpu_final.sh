@@ -6,7 +6,7 @@
 tag=${1:-r02_final}
 out=gpurun_out
 mkdir -p $out
-timeout 1500 python -m pytest tests -m gpu -x -q --timeout 120 > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $out/${tag}_pytest.log
+timeout 1500 python -m pytest tests -m gpu -x -q --timeout 300 > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $out/${tag}_pytest.log
 timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"; tail -c 1500 $out/${tag}_bench.json; tail -3 $out/${tag}_bench.err
 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 3 > $out/${tag}_bench_k20.json 2>/dev/null; echo "k20: $(cut -c1-160 $out/${tag}_bench_k20.json)"
@@ -36,6 +36,7 @@ for tool in memcheck racecheck; do
   echo "$tool rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|all cases' $out/${tag}_sanitizer_${tool}.log | tr '\n' ' ')"
 done
 echo "--- one bench line per env family"
+timeout 120 python scripts/k3_time.py 2>&1 | tail -3
 for env in MiniGrid-Empty-8x8-v0 MiniGrid-DoorKey-16x16-v0 MiniGrid-MultiRoom-N6-v0 MiniGrid-LockedRoom-v0 MiniGrid-Playground-v0 MiniGrid-GoToDoor-8x8-v0 MiniGrid-Fetch-8x8-N3-v0 MiniGrid-PutNear-8x8-N3-v0 MiniGrid-RedBlueDoors-8x8-v0 MiniGrid-MemoryS13Random-v0 MiniGrid-GoToObject-8x8-N2-v0 MiniGrid-Dynamic-Obstacles-8x8-v0 MiniGrid-Unlock-v0 MiniGrid-BlockedUnlockPickup-v0 MiniGrid-KeyCorridorS6R3-v0 MiniGrid-ObstructedMaze-Full-v1 MiniGrid-LavaGapS7-v0 MiniGrid-DistShift2-v0; do
   timeout 120 python bench.py --env $env --steps 300 --warmup 20 --no-cpu-baseline --no-configs --e2e-steps 10 > $out/${tag}_bench_$env.json 2>/dev/null
   echo "$env: $(python -c "import json;d=json.load(open('$out/${tag}_bench_$env.json'));print('%.3g'%d['value'], '%.3f'%d['roofline']['frac'], 'autoreset/step %.4f'%d['run']['autoreset_fraction_per_step'], 'e2e %.3g'%d['e2e']['value'])" 2>&1 | tail -1)"
