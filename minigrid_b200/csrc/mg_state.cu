@@ -62,11 +62,11 @@ k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with
     const int cw = c_word(g, x, y) - g.offC;  // word of the cell inside array C
     s_off[c] = (uint16_t)(tiled ? cw * 128 + (y & 3) : cw * 4 + (y & 3));
   }
-  __syncthreads();
-  {  // the stage has landed
+  if (threadIdx.x == 0) {  // the stage has landed: one thread watches the barrier, the CTA barrier passes it on
     asm volatile(
         "{\n.reg .pred p;\nK3W_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra K3D_%=;\nbra K3W_%=;\nK3D_%=:\n}\n" ::"r"(bar_s), "r"(0) : "memory");
   }
+  __syncthreads();
   const uint32_t estride = tiled ? 4u : cbytes;
   const float inv_wh = 1.0f / (float)WH;
   auto triple = [&](int e, int c) -> uint32_t {  // type | colour << 8 | state << 16 of cell c of env e

@@ -149,6 +149,10 @@ template <int KIND>
 __device__ __noinline__ ResetOut warp_reset(const Params &p, unsigned pend, int tile, uint32_t *gtile, int lane) {
   const Geom &g = p.g;
   Level L = blank_level();
+  // SAME_STEP: the lanes have just read (front cell) and possibly written (pickup / drop / toggle) their columns of the
+  // staged tile, and other lanes are about to overwrite the pending envs' columns: the ballot that brought the warp
+  // here synchronises the lanes but orders no memory
+  __syncwarp();
   // pending envs per tile from which every pending lane fills its own env (a truncation wave) instead of the warp going
   // through them one at a time. 8: by chance (LavaCrossing: 0.85 % of the envs end per step) 4 of 32 happen once per
   // step somewhere in a 262144-env batch, and that one tile then cost 35 us and set the step time (profiles/r02d_gpu_call.log)

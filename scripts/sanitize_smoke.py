@@ -12,7 +12,7 @@ import torch
 from minigrid_b200 import MinigridVecEnv
 from oracle.oracle import OracleVecEnv
 
-cases = [("MiniGrid-DoorKey-8x8-v0", None, None), ("MiniGrid-DoorKey-8x8-v0", None, "0,2,1"), ("MiniGrid-DoorKey-8x8-v0", "1", None),
+cases = [("MiniGrid-DoorKey-8x8-v0", None, None), ("MiniGrid-DoorKey-8x8-v0", None, "0,2,2"), ("MiniGrid-DoorKey-8x8-v0", "1", None),
          ("MiniGrid-FourRooms-v0", None, None), ("MiniGrid-LavaCrossingS9N1-v0", None, None), ("MiniGrid-Empty-8x8-v0", None, None),
          ("MiniGrid-Fetch-8x8-N3-v0", None, None), ("MiniGrid-MemoryS13Random-v0", None, None),
          # two CTAs of three warps: every warp goes through several tiles (prefetch, buffer rotation, order list)
