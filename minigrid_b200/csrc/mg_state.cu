@@ -39,9 +39,11 @@ k_full_obs(const __grid_constant__ Params p, uint8_t *__restrict__ out, int with
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(stage_bytes) : "memory");
   }
   __syncthreads();
+  if (threadIdx.x == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(stage_bytes) : "memory");
+  __syncwarp();  // the byte count is armed before any lane of warp 0 issues its copy
   const uint8_t *tb = reinterpret_cast<const uint8_t *>(p.grid) + (size_t)tile * g.wpe * 128;  // both layouts: 32 envs x wpe words
   if (tiled) {
     if (threadIdx.x == 0)  // words offC .. wpe - 1 of all 32 lanes: one contiguous block
