@@ -315,9 +315,12 @@ def main():
         # launch), so it is captured once as a CUDA graph through the same public step() calls and replayed. K steps
         # are still exactly K kernel launches on the device. G = steps per graph: a multiple of R (every batch), at
         # most 128 and at most K, so that a short --steps run replays graphs too.
-        graph, G, graph_error = None, 0, None
-        if want_graph and K >= R:
-            G = R * max(1, min(K // R, 128 // R if R <= 128 else 1))
+        # K <= 128: ONE graph of exactly K steps (a short --steps run, the driver's 20, is then a single graph launch and not
+        # a graph plus a few eager launches with their host gaps); beyond that, graphs of G steps and one graph for the rest.
+        graph, graph_rem, G, graph_error = None, None, 0, None
+        if want_graph and K >= 1:
+            G = K if K <= 128 else R * max(1, 128 // R if R <= 128 else 1)
+            rem = K % G
             try:
                 cap_stream = torch.cuda.Stream(device=dev)
                 cap_stream.wait_stream(torch.cuda.current_stream(dev))
@@ -326,10 +329,14 @@ def main():
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph, stream=cap_stream):
                         eager_run(G)
+                    if rem:
+                        graph_rem = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph_rem, stream=cap_stream):
+                            eager_run(rem, G * (K // G))
                 torch.cuda.current_stream(dev).wait_stream(cap_stream)
                 torch.cuda.synchronize()
             except Exception as exc:  # noqa: BLE001  (fall back to eager launches, and say so)
-                graph, G, graph_error = None, 0, repr(exc)
+                graph, graph_rem, G, graph_error = None, None, 0, repr(exc)
                 torch.cuda.synchronize()
 
         def run(steps, first=0):
@@ -338,7 +345,10 @@ def main():
             for _ in range(steps // G):
                 graph.replay()
             if steps % G:
-                eager_run(steps % G, first)
+                if graph_rem is not None and steps % G == K % G:
+                    graph_rem.replay()
+                else:
+                    eager_run(steps % G, first)
 
         if graph is not None:
             run(G)
@@ -359,6 +369,8 @@ def main():
         launches = sum(b.launch_count for b in batches) - l0
         if graph is not None:
             launches += (K // G) * G  # launches replayed by the graphs (each captured step() is one kernel node)
+            if graph_rem is not None:
+                launches += K % G
         for b in batches:
             b.check_actions()
         # share of envs that were regenerated per timed step (pending flags after the run, averaged over the batches)
@@ -397,7 +409,7 @@ def main():
         pass
 
     # ---- end to end through the host-buffer API: pinned host actions in, pinned host obs/reward/flags out ----
-    Ke = max(1, min(args.e2e_steps, K))
+    Ke = max(1, args.e2e_steps)  # its own count: a short --steps run (the driver's 20) must not shorten this leg
     host_actions = torch.from_numpy(np.random.default_rng(4321 + rank).integers(0, 7, (min(Ke, 64), n)).astype(np.int32)).pin_memory()
     act_views = [host_actions[i] for i in range(host_actions.shape[0])]
 
@@ -405,7 +417,9 @@ def main():
         """Ke synchronous step_host calls (pinned host actions in, host arrays out), three times; the median repetition."""
         for b in batches:
             b.set_host_format(fmt, max(1, usable_cores() // max(1, world)))
-        for t in range(max(3, 2 * R)):  # every batch allocates its pinned staging on first use: keep that out of the timing
+        # every batch allocates its pinned staging on first use, and a handle's first 20 packed steps calibrate the
+        # expander's store form (mg_abi.cu): keep both out of the timing
+        for t in range(max(3, 22 * R)):
             batches[t % R].step_host(act_views[t % len(act_views)])
         reps = []
         for _ in range(3):
