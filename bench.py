@@ -415,8 +415,11 @@ def main():
 
     def e2e_run(fmt):
         """Ke synchronous step_host calls (pinned host actions in, host arrays out), three times; the median repetition."""
+        # expander threads per rank: this rank's share of the host's cores; with several ranks on one host the calling
+        # thread of every rank (it polls the copy events) needs a core of its own as well
+        threads = max(1, usable_cores() // max(1, world) - (1 if world > 1 else 0))
         for b in batches:
-            b.set_host_format(fmt, max(1, usable_cores() // max(1, world)))
+            b.set_host_format(fmt, threads)
         # every batch allocates its pinned staging on first use, and a handle's first 20 packed steps calibrate the
         # expander's store form (mg_abi.cu): keep both out of the timing
         for t in range(max(3, 22 * R)):

@@ -4,18 +4,20 @@
 // One warp = one tile of 32 environments, one lane per environment.
 //   1. lane 0 issues a TMA bulk copy (cp.async.bulk -> SASS UBLKCP) of the tile's interleaved grid words
 //      into shared memory and arms an mbarrier with the byte count; meanwhile every lane loads its
-//      action and 16-byte agent record with coalesced loads. Warps are persistent (one CTA per SM, one wave); each
-//      warp owns two buffers and requests its next tile (copy + records + actions) while it works on the current one.
+//      action and 16-byte agent record with coalesced loads. Warps are persistent (one CTA per SM, one wave). Default
+//      plan: one buffer per warp, 22 warps at 72 registers (mg_step_tiled1.cu); the two-buffer form, in which a warp
+//      requests its next tile (copy + records + actions) while it works on the current one, is this file's (configure_step).
 //   2. autoreset (NEXT_STEP: envs flagged last step, before the transition; SAME_STEP: envs that just ended,
-//      after it): rare, so the whole warp regenerates one environment at a time — every lane replays the
-//      numpy-exact RNG draws (uniform control flow) and fills a 1/32 share of the level's words.
+//      after it): rare; the pending lanes replay their env's numpy-exact RNG draws while the idle lanes copy the level
+//      template over those envs, then the warp patches the few draw-dependent cells (warp_reset).
 //   3. transition: the 7-action rule on (agent, carrying, the one cell in front), predicated, with the
 //      rare cell mutation written to the staged tile and straight back to HBM (2 byte stores).
 //   4. observation in registers (mg_obs.cuh), staged into the consumed tile buffer in output layout, then one
 //      TMA bulk store of the warp's 32 x 147 = 4704 contiguous bytes.
 //   5. coalesced stores of direction / reward / terminated / truncated and the agent record.
-// Large grids (LAYOUT_WINDOW) skip step 1: each lane copies only the 7 lines its view needs (224 B, one bulk copy per
-// lane) into shared memory, in flight together with the one front-cell byte the transition reads from HBM.
+// Large grids (LAYOUT_WINDOW) skip step 1: each lane gathers only the 7 lines its view needs straight into registers
+// (21 independent 4-byte loads, one round trip; mg_obs.cuh: load_view_words), and the transition reads its front cell
+// out of the same words.
 #include "mg_step_kernel.cuh"
 
 namespace mg {

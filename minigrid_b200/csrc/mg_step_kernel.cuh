@@ -1,5 +1,5 @@
 // mg_step_kernel.cuh — K1, the step kernel template (see mg_step.cu for the overview). It is instantiated in three
-// translation units, mg_step.cu (tiled layout, two buffers per warp), mg_step_tiled1.cu (one buffer) and
+// translation units, mg_step.cu (tiled layout, two buffers per warp), mg_step_tiled1.cu (one buffer: the default plan) and
 // mg_step_window.cu (window layout): ptxas's code for the tiled
 // kernels measurably depends on what else it compiles alongside them (profiles/README.md, r01 A/B runs).
 #pragma once
