@@ -186,6 +186,7 @@ int mg_create(int kind, int width, int height, int max_steps, int see_through_wa
   p.mode = autoreset_mode;
   p.kind = kind;
   h->trace = getenv("MINIGRID_B200_HOST_TRACE") != nullptr;
+  { const char *wp = getenv("MINIGRID_B200_WINPREF"); h->p.win_prefetch = !wp || atoi(wp) != 0; }
   h->stream_fixed = -1;
   if (const char *es = getenv("MINIGRID_B200_EXPAND_STREAM")) h->stream_fixed = atoi(es) != 0;
   p.hot_first = 1;

@@ -164,6 +164,7 @@ struct Params {
   int *err;                 // sticky error word
   int hot_first;            // visit the tiles flagged in tile_hot right after a CTA's first round (MINIGRID_B200_HOTFIRST=0 turns it off)
   uint8_t *tile_hot;        // [n_tiles] 1 = an env of the tile ended in the last step (K1's scheduling hint, never semantics)
+  int win_prefetch;         // LAYOUT_WINDOW: L2-prefetch the next tile's view lines (MINIGRID_B200_WINPREF=0 turns it off)
   // the reference's reward wrappers around every env (wrappers.py:68-184, 809-882), 0 = absent
   int no_death_mask;        // NoDeath: bit t = OBJECT_TO_IDX type t is a death cell
   int bonus_mode;           // 1 ActionBonus, 2 PositionBonus

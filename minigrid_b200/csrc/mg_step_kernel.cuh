@@ -422,6 +422,9 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
       rec = ldg_rec(p.agent + env0);
       action = (stepping && env0 < p.n_envs) ? load_action(actions, act_dtype, env0) : A_DONE;
       if (stepping && ((rec.y >> 8) & FLAG_PENDING)) prefetch_rng(p.rng + env0);
+      // (Pulling the next tile's index here and asking L2 for its block a tile ahead was measured and rejected: DoorKey
+      // 18.8 -> 20.2 us, Fetch 30.5 -> 34.1: committing a warp to its next tile one tile early costs more balance than
+      // the shorter copy wins, profiles/r02w_gpu_call.log. The same early commitment is what the two-buffer kernel pays.)
     }
 #ifdef MG_TIMELINE
     const unsigned long long tl_t0 = gtime();
@@ -620,6 +623,23 @@ k_step(const __grid_constant__ Params p, const void *__restrict__ actions, int a
         }
         if (WIN && again) load_view_words(g, ax, ay, dir, vw, ldw);  // the regenerated level replaces the loaded words
       }
+    }
+
+    // LAYOUT_WINDOW: the view gather is one exposed HBM round trip per tile (18 % of the warps' time on FourRooms,
+    // profiles/r02_final_kstep_fourrooms_summary.txt). The next tile's records and actions, requested at the top of
+    // this tile, have arrived by now: ask L2 for the 7 lines that tile's gather will read (contiguous: 7 * lsw words),
+    // so that the gather finds them a few hundred cycles away instead of in HBM. Hints only: a lane that regenerates
+    // its env in the next tile prefetches lines it will not use.
+    if (WIN && PREF && p.win_prefetch && next < p.n_tiles) {
+      const int axn = rec_n.x & 0xFF, ayn = (rec_n.x >> 8) & 0xFF, dn0 = rec_n.y & 3;
+      const int dnn = stepping ? ((dn0 + (action_n == A_LEFT ? 3 : 0) + (action_n == A_RIGHT ? 1 : 0)) & 3) : dn0;
+      const bool useCn = dnn & 1;
+      const int lswn = useCn ? g.lswC : g.lswR;
+      const uint32_t *w0 = p.grid + (size_t)(next * TILE + lane) * g.wpe + (useCn ? g.offC : 0) + ((useCn ? axn : ayn) - 3 + g.ring) * lswn;
+      const int span = 7 * lswn * 4;  // bytes: 140 for FourRooms, at most 196
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(w0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(w0) + span - 4));
+      if (span > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(w0) + 128));
     }
 
     // ---- gen_obs ----
