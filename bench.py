@@ -261,6 +261,7 @@ def main():
     torch.set_num_threads(1)
     # pinned host buffers (the e2e leg) should live on the GPU's own NUMA node: with 8 ranks copying at once, remote
     # pinned memory costs a quarter of the D2H bandwidth (round 1: 37 instead of 50 GB/s per GPU at N = 8)
+    cores_total = usable_cores()  # before the NUMA binding narrows this process's affinity mask to one node's CPUs
     numa = bind_to_gpu_numa_node(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -417,7 +418,7 @@ def main():
         """Ke synchronous step_host calls (pinned host actions in, host arrays out), three times; the median repetition."""
         # expander threads per rank: this rank's share of the host's cores; with several ranks on one host the calling
         # thread of every rank (it polls the copy events) needs a core of its own as well
-        threads = max(1, usable_cores() // max(1, world) - (1 if world > 1 else 0))
+        threads = max(1, min(cores_total // max(1, world), usable_cores()) - (1 if world > 1 else 0))
         for b in batches:
             b.set_host_format(fmt, threads)
         # every batch allocates its pinned staging on first use, and a handle's first 20 packed steps calibrate the
