@@ -13,7 +13,7 @@ from . import specs  # noqa: F401
 from ._lib import MinigridB200Error  # noqa: F401
 from ._numa import bind_to_gpu_numa_node, gpu_numa_node  # noqa: F401
 from .vector_env import MinigridVecEnv, make_sharded, shard_range  # noqa: F401
-from .wrappers import (ActionBonus, FlatObsWrapper, FullyObsWrapper, ImgObsWrapper, NoDeath, OneHotPartialObsWrapper,  # noqa: F401
+from .wrappers import (ActionBonus, DictObservationSpaceWrapper, FlatObsWrapper, FullyObsWrapper, ImgObsWrapper, NoDeath, OneHotPartialObsWrapper,  # noqa: F401
                        PositionBonus, RGBImgObsWrapper, RGBImgPartialObsWrapper, SymbolicObsWrapper, ViewSizeWrapper)
 
 __version__ = "0.1.0"

@@ -12,6 +12,9 @@ RGBImgPartialObsWrapper  :334-380  obs["image"] = the agent's view rendered with
 RGBImgObsWrapper         :287-331  obs["image"] = the whole grid rendered, the agent's view highlighted, (8 H, 8 W, 3).
 The two RGB wrappers copy tiles that the reference's own Grid.render_tile drew (data/tile_atlas.npz).
 
+DictObservationSpaceWrapper :428-554 obs["mission"] = the mission's words as indices into the Minigrid vocabulary, padded to
+                                   max_words_in_mission (host side; ids with a constant mission string only).
+
 Reward wrappers (they act inside the engine's step kernel, because NoDeath decides whether an episode ends):
 NoDeath                  :809-882  a terminated step into / on a death cell continues with reward + death_cost.
 ActionBonus              :68-125   reward += 1 / sqrt(visits of (agent_pos, agent_dir, action)), per env.
@@ -191,6 +194,42 @@ class FlatObsWrapper(_DeviceObsWrapper):
             self._out = torch.empty((img.shape[0], nb + self._mission.numel()), dtype=torch.uint8, device=img.device)
         self._call(_lib.load().mg_obs_flat, self._p(img), nb, self._p(self._mission), int(self._mission.numel()), self._p(self._out))
         return self._out
+
+
+MINIGRID_WORDS = (["red", "green", "blue", "yellow", "purple", "grey"]                                         # wrappers.py:475-531
+                  + ["unseen", "empty", "wall", "floor", "box", "key", "ball", "door", "goal", "agent", "lava"]
+                  + ["pick", "avoid", "get", "find", "put", "use", "open", "go", "fetch", "reach", "unlock", "traverse"]
+                  + ["up", "the", "a", "at", ",", "square", "and", "then", "to", "of", "rooms", "near", "opening", "must", "you",
+                     "matching", "end", "hallway", "object", "from", "room", "maze"])
+
+
+def mission_to_indices(mission: str, max_words_in_mission: int = 50, word_dict=None, offset: int = 1):
+    """DictObservationSpaceWrapper.string_to_indices + observation (wrappers.py:535-554): word indices + 1, zero padded."""
+    wd = word_dict if word_dict is not None else {w: i for i, w in enumerate(MINIGRID_WORDS)}
+    idx = []
+    for word in mission.replace(",", " , ").split():
+        if word not in wd:
+            raise ValueError(f"Unknown word: {word}")
+        idx.append(wd[word] + offset)
+    assert len(idx) < max_words_in_mission
+    return idx + [0] * (max_words_in_mission - len(idx))
+
+
+class DictObservationSpaceWrapper(_VecWrapper):
+    """obs["mission"] as a fixed-length list of vocabulary indices (the same list for every env of the batch: the engine
+    serves ids whose mission string is constant; the others draw it per episode and are refused here)."""
+
+    def __init__(self, env, max_words_in_mission=50, word_dict=None):
+        super().__init__(env)
+        b = self.unwrapped
+        if "{" in b.mission:
+            raise ValueError(f"DictObservationSpaceWrapper needs a constant mission string; {b.env_id} draws its mission per episode")
+        self.max_words_in_mission = max_words_in_mission
+        self.word_dict = word_dict if word_dict is not None else {w: i for i, w in enumerate(MINIGRID_WORDS)}
+        self._mission = mission_to_indices(b.mission, max_words_in_mission, self.word_dict)
+
+    def observation(self, obs):
+        return {**obs, "mission": list(self._mission)}
 
 
 class SymbolicObsWrapper(_DeviceObsWrapper):

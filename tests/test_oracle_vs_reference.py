@@ -164,3 +164,26 @@ def test_reward_wrapper_known_answers():
     r = o.step([2]); assert (float(r[2][0]), bool(r[3][0])) == (-1.0, True)
     o = OracleVecEnv("MiniGrid-Dynamic-Obstacles-5x5-v0", 1); o.set_no_death(("ball",), -1.0); o.reset(seed=2)
     r = o.step([2]); assert (float(r[2][0]), bool(r[3][0])) == (-2.0, False)
+
+
+def test_dict_observation_space_wrapper_mission_indices():
+    """minigrid_b200.wrappers.mission_to_indices against the reference's DictObservationSpaceWrapper (wrappers.py:428-554) on the
+    constant mission strings of the registered ids (its doctest value included: LavaCrossingS11N5 -> [19, 31, 17, 36, 20, 38, ...])."""
+    gym, _ = ref_loader.load()
+    from minigrid.wrappers import DictObservationSpaceWrapper as RefDict
+
+    from minigrid_b200 import specs
+    from minigrid_b200.wrappers import MINIGRID_WORDS, mission_to_indices
+
+    assert {w: i for i, w in enumerate(MINIGRID_WORDS)} == RefDict.get_minigrid_words()
+    seen = 0
+    for env_id in specs.all_ids() if hasattr(specs, "all_ids") else list(ENV_SPECS):
+        mission = specs.get(env_id).mission
+        if "{" in mission:
+            continue
+        e = RefDict(gym.make(env_id))
+        obs, _ = e.reset(seed=0)
+        assert obs["mission"] == mission_to_indices(mission), env_id
+        seen += 1
+    assert seen >= 20
+    assert mission_to_indices("avoid the lava and get to the green goal square")[:10] == [19, 31, 17, 36, 20, 38, 31, 2, 15, 35]
